@@ -1,0 +1,115 @@
+"""Host-side mirror of the reference's case handling (no CUDA involved).
+
+``Case`` wraps include/par2d_host.h: it reads the reference's case directories
+(FV/FileIO.cpp:13-51 block files + FV/main.cpp:117-142 grid.conn), generates the
+synthetic ramp meshes of the benchmark, splits blocks with GridPart's rules and
+assigns blocks to ranks.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _capi
+from ._capi import BlockDesc, Config
+
+
+class Case:
+    def __init__(self, handle: C.c_void_p):
+        self._lib = _capi.load_host()
+        self._h = handle
+
+    # -- constructors -----------------------------------------------------
+    @classmethod
+    def load(cls, directory: str) -> "Case":
+        lib = _capi.load_host()
+        h = C.c_void_p()
+        lib.check(lib.par2d_case_load(os.fsencode(directory), C.byref(h)), "case_load")
+        return cls(h)
+
+    @classmethod
+    def synthetic_ramp(cls, ncx: int, ncy: int, nbx: int, nby: int) -> "Case":
+        lib = _capi.load_host()
+        h = C.c_void_p()
+        lib.check(lib.par2d_case_synthetic_ramp(ncx, ncy, nbx, nby, C.byref(h)), "case_synthetic_ramp")
+        return cls(h)
+
+    def split(self, nbx: int, nby: int) -> "Case":
+        h = C.c_void_p()
+        self._lib.check(self._lib.par2d_case_split(self._h, nbx, nby, C.byref(h)), "case_split")
+        return Case(h)
+
+    # -- queries ----------------------------------------------------------
+    @property
+    def nblocks(self) -> int:
+        return self._lib.par2d_case_num_blocks(self._h)
+
+    @property
+    def ncells(self) -> int:
+        return self._lib.par2d_case_num_cells(self._h)
+
+    def desc(self, b: int) -> BlockDesc:
+        d = BlockDesc()
+        self._lib.check(self._lib.par2d_case_block(self._h, b, C.byref(d)), "case_block")
+        return d
+
+    def descs(self):
+        arr = (BlockDesc * self.nblocks)()
+        for b in range(self.nblocks):
+            self._lib.check(self._lib.par2d_case_block(self._h, b, C.byref(arr[b])), "case_block")
+        return arr
+
+    def shape(self, b: int):
+        d = self.desc(b)
+        return d.nx, d.ny
+
+    def nodes(self, b: int):
+        d = self.desc(b)
+        n = d.nx * d.ny
+        x = np.ctypeslib.as_array(d.x, shape=(n,)).reshape(d.ny, d.nx).copy()
+        y = np.ctypeslib.as_array(d.y, shape=(n,)).reshape(d.ny, d.nx).copy()
+        return x, y
+
+    def ibound(self, b: int):
+        d = self.desc(b)
+        n = 2 * (d.nx - 1) + 2 * (d.ny - 1)
+        return np.ctypeslib.as_array(d.ibound, shape=(n,)).copy()
+
+    def partition(self, nranks: int):
+        self._lib.check(self._lib.par2d_case_partition(self._h, nranks), "case_partition")
+        return [self.desc(b).owner for b in range(self.nblocks)]
+
+    def write(self, directory: str, one_based: bool = False):
+        self._lib.check(self._lib.par2d_case_write(self._h, os.fsencode(directory), int(one_based)), "case_write")
+
+    def close(self):
+        if self._h:
+            self._lib.par2d_case_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def load_thermo(path: str, cfg: Config) -> Config:
+    lib = _capi.load_host()
+    lib.check(lib.par2d_thermo_load(os.fsencode(path), C.byref(cfg)), "thermo_load")
+    return cfg
+
+
+def write_solution(path: str, title: str, cfg: Config, x: np.ndarray, y: np.ndarray, unk: np.ndarray):
+    """solution.b<N>.tec in print_state's byte format (FV/FileIO.cpp:84-115)."""
+    lib = _capi.load_host()
+    ny, nx = x.shape
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    unk = np.ascontiguousarray(unk, dtype=np.float64)
+    dp = C.POINTER(C.c_double)
+    lib.check(lib.par2d_write_solution(os.fsencode(path), title.encode(), C.byref(cfg), nx, ny,
+                                       x.ctypes.data_as(dp), y.ctypes.data_as(dp), unk.ctypes.data_as(dp)),
+              "write_solution")
