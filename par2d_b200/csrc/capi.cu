@@ -1,0 +1,826 @@
+// capi.cu -- implementation of the C ABI in include/par2d_gpu.h over the sm_100a kernels.
+//
+// One par2d_ctx = the blocks one rank owns (the reference: one MPI rank per block,
+// FV/main.cpp:124-128), resident in HBM as padded SoA planes with the ghost ring in place
+// (common.cuh).  A step is three launches on one stream, no host synchronisation:
+//   ghost_kernel -> step_kernel -> finalize_kernel
+// and a batch of steps returns its dt / residual history in one copy at the end.
+// There is no CPU fallback anywhere in this file.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/par2d_gpu.h"
+#include "common.cuh"
+#include "kernels.cuh"
+#include "kernels_common.cuh"
+
+using namespace par2d;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU_TRY(expr)                                                                                     \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) return fail(PAR2D_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct Peer {
+    long long n_send = 0, n_recv = 0;
+    double *d_send = nullptr, *d_recv = nullptr;
+};
+
+int desc_edge(const par2d_block_desc& d, int side) { return (side == PAR2D_BOTTOM || side == PAR2D_TOP) ? d.nx - 1 : d.ny - 1; }
+
+// The side of block nb that faces block `me` (opposite side preferred; the reference pairs
+// sides implicitly through message order, SpatialDiscretization.cpp:227-470).
+int facing_side(const par2d_block_desc& nb, int me, int my_side) {
+    const int opp = (my_side + 2) & 3;
+    if (nb.bid[opp] == me) return opp;
+    for (int s = 0; s < 4; s++)
+        if (nb.bid[s] == me) return s;
+    return -1;
+}
+
+Gas make_gas(const par2d_config& c) {
+    Gas g;
+    memset(&g, 0, sizeof g);
+    g.Rs = c.Rs;
+    g.igam = c.igam;
+    g.gam = fabs(c.igam);
+    g.gamRs = g.gam * g.Rs;
+    g.cpg_den = (1.0 - 1.0 / (c.igam));
+    g.cp_cpg = g.Rs / (1.0 - 1.0 / (c.igam));
+    g.inv_cv_cpg = 1.0 / (g.cp_cpg - g.Rs);
+    for (int k = 0; k < 7; k++) { g.hi[k] = c.thermo_hi[k]; g.lo[k] = c.thermo_lo[k]; }
+    for (int k = 0; k < 4; k++) g.uFS[k] = c.uFS[k];
+    g.p_back = c.p_back;
+    g.cfl = c.cfl;
+    return g;
+}
+
+int flags_to_code(unsigned f) {
+    if (f & 0x80000000u) return PAR2D_ERR_CUDA;  // TMA copy never completed
+    if (f & FLAG_NAN) return PAR2D_ERR_NAN;
+    if (f & FLAG_DENSITY) return PAR2D_ERR_DENSITY;
+    if (f & FLAG_STATE) return PAR2D_ERR_STATE;
+    if (f & FLAG_SINGULAR) return PAR2D_ERR_SINGULAR;
+    if (f & FLAG_THERMO) return PAR2D_ERR_THERMO_RANGE;
+    return PAR2D_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+}  // namespace
+
+struct par2d_ctx {
+    par2d_config cfg;
+    Gas gas;
+    bool tpg = false, axi = true, use_tma = true;
+    const KernelTable* kt = nullptr;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    int nblocks = 0;
+    std::vector<par2d_block_desc> table;  // global, pointers cleared
+    std::vector<int> owned_gid, owned_index;
+    int nowned = 0;
+    std::vector<BlockDev> hblk;
+    std::vector<double*> block_mem;       // one allocation per owned block (10 planes)
+    std::vector<int*> block_ibound;
+    BlockDev* dblk = nullptr;
+    void* dtmaps = nullptr;
+
+    double* dt_table = nullptr;
+    double* partials = nullptr;
+    unsigned* flags = nullptr;
+    int* stop = nullptr;
+    long long* d_iter = nullptr;
+    int* hist_pos = nullptr;
+    unsigned* ticket = nullptr;
+    double* res0 = nullptr;
+    double* blk_norm = nullptr;
+    double* blk_hist = nullptr;
+    double* step_hist = nullptr;
+    int hist_cap = 0;
+    double* staging = nullptr;
+    long long staging_doubles = 0;
+
+    int cur = 0;
+    long long iter = 0;
+    int total_tiles = 0, max_tiles = 0, max_faces = 0;
+    long long owned_cells = 0;
+
+    std::vector<Peer> peers;
+    SendLine* dlines = nullptr;
+    int nlines = 0, max_line = 0;
+
+    // history of the last batch, host copies
+    std::vector<double> h_step_hist, h_blk_hist;
+    int last_steps = 0;
+    long long last_iter0 = 0;
+    int pending_steps = 0;  // begin/end mode: steps queued since the last collect
+
+    StepArgs step_args(int update) const {
+        StepArgs a;
+        a.blocks = dblk;
+        a.nowned = nowned;
+        a.nblocks_global = nblocks;
+        a.cur = cur;
+        a.total_tiles = total_tiles;
+        a.max_tiles = max_tiles;
+        a.max_faces = max_faces;
+        a.tmaps = dtmaps;
+        a.dt_table = dt_table;
+        a.partials = partials;
+        a.flags = flags;
+        a.stop = stop;
+        a.res_out = nullptr;
+        a.res_block = -1;
+        a.update = update;
+        return a;
+    }
+    FinalizeArgs finalize_args(int stop_on_tol) const {
+        FinalizeArgs f;
+        f.blocks = dblk;
+        f.nowned = nowned;
+        f.partials = partials;
+        f.res0 = res0;
+        f.blk_hist = blk_hist;
+        f.step_hist = step_hist;
+        f.iter = d_iter;
+        f.hist_pos = hist_pos;
+        f.stop = stop;
+        f.ticket = ticket;
+        f.dt_table = dt_table;
+        f.nblocks_global = nblocks;
+        f.tol = cfg.tol;
+        f.stop_on_tol = stop_on_tol;
+        f.hist_cap = hist_cap;
+        return f;
+    }
+};
+
+namespace {
+
+int use_device(const par2d_ctx* c) {
+    CU_TRY(cudaSetDevice(c->device));
+    return 0;
+}
+
+int ensure_hist(par2d_ctx* c, int nsteps) {
+    if (nsteps <= c->hist_cap) return 0;
+    const int cap = std::max(nsteps, 64);
+    if (c->blk_hist) cudaFree(c->blk_hist);
+    if (c->step_hist) cudaFree(c->step_hist);
+    c->blk_hist = c->step_hist = nullptr;
+    CU_TRY(cudaMalloc(&c->blk_hist, sizeof(double) * 2 * (size_t)cap * c->nowned));
+    CU_TRY(cudaMalloc(&c->step_hist, sizeof(double) * 4 * (size_t)cap));
+    c->hist_cap = cap;
+    return 0;
+}
+
+int validate_table(int nblocks, const par2d_block_desc* t, int nranks) {
+    for (int g = 0; g < nblocks; g++) {
+        if (t[g].nx < 2 || t[g].ny < 2) return fail(PAR2D_ERR_ARG, "block %d has fewer than 2 nodes in a direction", g);
+        if (t[g].owner < 0 || t[g].owner >= nranks) return fail(PAR2D_ERR_ARG, "block %d: owner %d out of range", g, t[g].owner);
+        for (int s = 0; s < 4; s++) {
+            const int nb = t[g].bid[s];
+            if (nb < 0) continue;
+            if (nb >= nblocks || nb == g) return fail(PAR2D_ERR_ARG, "block %d side %d: neighbour id %d out of range", g, s, nb);
+            const int os = facing_side(t[nb], g, s);
+            if (os < 0) return fail(PAR2D_ERR_ARG, "block %d side %d: neighbour %d does not point back", g, s, nb);
+            if (desc_edge(t[g], s) != desc_edge(t[nb], os)) return fail(PAR2D_ERR_ARG, "block %d side %d: shared edge lengths differ", g, s);
+        }
+    }
+    return 0;
+}
+
+int build_tensor_maps(par2d_ctx* c) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) {
+        c->use_tma = false;
+        return 0;
+    }
+    std::vector<CUtensorMap> maps((size_t)c->nowned * 3);
+    for (int k = 0; k < c->nowned; k++) {
+        const BlockDev& b = c->hblk[k];
+        for (int m = 0; m < 3; m++) {
+            const cuuint32_t planes = m < 2 ? 4 : 2;
+            void* base = m < 2 ? (void*)b.state[m] : (void*)b.nodes;
+            const cuuint64_t dims[3] = {(cuuint64_t)b.pitch, (cuuint64_t)(b.ncy + 2), planes};
+            const cuuint64_t strides[2] = {(cuuint64_t)b.pitch * 8, (cuuint64_t)b.plane * 8};
+            const cuuint32_t box[3] = {(cuuint32_t)HX, (cuuint32_t)HY, planes};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = enc(&maps[(size_t)k * 3 + m], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(PAR2D_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for block %d map %d", (int)r, b.gid, m);
+        }
+    }
+    CU_TRY(cudaMalloc(&c->dtmaps, maps.size() * sizeof(CUtensorMap)));
+    CU_TRY(cudaMemcpy(c->dtmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+void queue_step(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
+    StepArgs a = c->step_args(1);
+    c->kt->ghost(c->stream, a, c->gas, with_ghost_dt ? 1 : 0);
+    c->kt->step(c->stream, a, c->gas, c->tpg, c->axi, c->use_tma);
+    launch_finalize(c->stream, c->finalize_args(stop_on_tol), c->blk_norm);
+    c->cur ^= 1;
+}
+
+// after a synchronise: pull the history of `queued` steps, fix up cur/iter if the batch stopped early
+int harvest(par2d_ctx* c, int queued, int cur0, par2d_step_info* info, int ninfo) {
+    int done = 0;
+    unsigned fl = 0;
+    long long it = 0;
+    CU_TRY(cudaMemcpy(&done, c->hist_pos, sizeof done, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(&fl, c->flags, sizeof fl, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(&it, c->d_iter, sizeof it, cudaMemcpyDeviceToHost));
+    if (done > queued) done = queued;
+    c->cur = cur0 ^ (done & 1);
+    c->last_iter0 = c->iter;
+    c->iter = it;
+    c->last_steps = done;
+    c->h_step_hist.resize((size_t)4 * std::max(done, 1));
+    c->h_blk_hist.resize((size_t)2 * std::max(done, 1) * c->nowned);
+    if (done > 0) {
+        CU_TRY(cudaMemcpy(c->h_step_hist.data(), c->step_hist, sizeof(double) * 4 * done, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(c->h_blk_hist.data(), c->blk_hist, sizeof(double) * 2 * (size_t)done * c->nowned, cudaMemcpyDeviceToHost));
+    }
+    const int code = flags_to_code(fl);
+    if (info) {
+        for (int s = 0; s < ninfo; s++) {
+            par2d_step_info& r = info[s];
+            memset(&r, 0, sizeof r);
+            if (s < done) {
+                const double* h = &c->h_step_hist[4 * (size_t)s];
+                r.iter = c->last_iter0 + s;
+                r.dt = h[0]; r.ressumsum = h[1]; r.res0sum = h[2]; r.relres = h[3];
+                r.status = code;
+            } else {
+                r.iter = -1;
+            }
+        }
+    }
+    if (code) fail(code, "device raised error flags 0x%x during the batch", fl);
+    return code;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* par2d_last_error(void) { return g_err.c_str(); }
+
+void par2d_default_config(par2d_config* c) {
+    // FV/Indexing.h:12-20, FV/main.cpp:77-94, Thermo.h:25,46 and the AIR record of
+    // FV/therm_air.dat in the order Thermo.h:27-29 reads it.
+    static const double hi[7] = {3.08792717E+00, 1.24597184E-03, -4.23718945E-07, 6.74774789E-11, -3.97076972E-15, -9.95262755E+02, 5.95960930E+00};
+    static const double lo[7] = {3.56839620E+00, -6.78729429E-04, 1.55371476E-06, -3.29937060E-12, -4.66395387E-13, -1.06234659E+03, 3.71582965E+00};
+    memset(c, 0, sizeof *c);
+    c->iaxi = 1;
+    c->mode = PAR2D_MODE_FAST;
+    c->igam = 1.4;
+    c->cfl = 0.01;
+    c->tol = 1e-6;
+    c->Rs = 8314.34 / 28.9;
+    c->uFS[0] = 1000.0 / (c->Rs * 300.0);
+    c->uFS[1] = 1736.0;
+    c->uFS[2] = 0.0;
+    c->uFS[3] = 300.0;
+    c->p_back = 101325.0;
+    memcpy(c->thermo_hi, hi, sizeof hi);
+    memcpy(c->thermo_lo, lo, sizeof lo);
+    c->device = -1;
+    c->rank = 0;
+    c->nranks = 1;
+}
+
+int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_desc* blocks, par2d_ctx** out) {
+    if (!cfg || !blocks || !out || nblocks < 1) return fail(PAR2D_ERR_ARG, "create: null argument");
+    if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(PAR2D_ERR_ARG, "create: bad rank %d of %d", cfg->rank, cfg->nranks);
+    if (cfg->mode != PAR2D_MODE_FAST && cfg->mode != PAR2D_MODE_FAITHFUL) return fail(PAR2D_ERR_ARG, "create: unknown mode %d", cfg->mode);
+    int rc = validate_table(nblocks, blocks, cfg->nranks);
+    if (rc) return rc;
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(PAR2D_ERR_CUDA, "no CUDA device available; par2d_b200 has no CPU fallback");
+    int dev = cfg->device;
+    if (dev < 0) CU_TRY(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(PAR2D_ERR_CUDA, "device %d requested but only %d present", dev, ndev);
+    CU_TRY(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return fail(PAR2D_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", dev, prop.major, prop.minor);
+
+    par2d_ctx* c = new par2d_ctx;
+    c->cfg = *cfg;
+    c->gas = make_gas(*cfg);
+    c->tpg = !(cfg->igam > 0);
+    c->axi = cfg->iaxi == 1;
+    c->kt = cfg->mode == PAR2D_MODE_FAITHFUL ? kernels_faithful() : kernels_fast();
+    c->device = dev;
+    const char* no_tma = getenv("PAR2D_NO_TMA");
+    c->use_tma = !(no_tma && atoi(no_tma) != 0);
+    cudaError_t pe = c->kt->prepare();
+    if (pe != cudaSuccess) { delete c; return fail(PAR2D_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(pe)); }
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(PAR2D_ERR_CUDA, "cannot create stream"); }
+    c->own_stream = true;
+
+    c->nblocks = nblocks;
+    c->table.assign(blocks, blocks + nblocks);
+    c->owned_index.assign(nblocks, -1);
+    for (int g = 0; g < nblocks; g++) {
+        c->table[g].x = c->table[g].y = nullptr;
+        c->table[g].ibound = nullptr;
+        if (blocks[g].owner == cfg->rank) {
+            c->owned_index[g] = (int)c->owned_gid.size();
+            c->owned_gid.push_back(g);
+        }
+    }
+    c->nowned = (int)c->owned_gid.size();
+    *out = c;  // from here on failures leave a destroyable ctx behind
+    if (c->nowned == 0) return fail(PAR2D_ERR_ARG, "rank %d owns no block", cfg->rank);
+
+    // peer buffers: lines ordered by (receiving block id, receiving side)
+    c->peers.resize(cfg->nranks);
+    for (int p = 0; p < cfg->nranks; p++) {
+        if (p == cfg->rank) continue;
+        for (int g = 0; g < nblocks; g++)
+            for (int s = 0; s < 4; s++) {
+                const int nb = blocks[g].bid[s];
+                if (nb < 0) continue;
+                if (blocks[g].owner == cfg->rank && blocks[nb].owner == p) c->peers[p].n_recv += 4ll * desc_edge(blocks[g], s);
+                if (blocks[g].owner == p && blocks[nb].owner == cfg->rank) c->peers[p].n_send += 4ll * desc_edge(blocks[g], s);
+            }
+        if (c->peers[p].n_send) { CU_TRY(cudaMalloc(&c->peers[p].d_send, sizeof(double) * c->peers[p].n_send)); CU_TRY(cudaMemset(c->peers[p].d_send, 0, sizeof(double) * c->peers[p].n_send)); }
+        if (c->peers[p].n_recv) { CU_TRY(cudaMalloc(&c->peers[p].d_recv, sizeof(double) * c->peers[p].n_recv)); CU_TRY(cudaMemset(c->peers[p].d_recv, 0, sizeof(double) * c->peers[p].n_recv)); }
+    }
+
+    // per-block device memory
+    c->hblk.resize(c->nowned);
+    c->block_mem.assign(c->nowned, nullptr);
+    c->block_ibound.assign(c->nowned, nullptr);
+    long long max_cells = 0, max_nodes = 0;
+    for (int k = 0; k < c->nowned; k++) {
+        const int g = c->owned_gid[k];
+        const par2d_block_desc& d = blocks[g];
+        if (!d.x || !d.y || !d.ibound) return fail(PAR2D_ERR_ARG, "owned block %d has no coordinates / BC codes", g);
+        BlockDev& b = c->hblk[k];
+        memset(&b, 0, sizeof b);
+        b.gid = g;
+        b.ncx = d.nx - 1;
+        b.ncy = d.ny - 1;
+        b.pitch = ((b.ncx + COL0 + 1 + 15) / 16) * 16;
+        b.plane = (long long)b.pitch * (b.ncy + 2);
+        CU_TRY(cudaMalloc(&c->block_mem[k], sizeof(double) * 10 * b.plane));
+        CU_TRY(cudaMemsetAsync(c->block_mem[k], 0, sizeof(double) * 10 * b.plane, c->stream));
+        b.state[0] = c->block_mem[k];
+        b.state[1] = c->block_mem[k] + 4 * b.plane;
+        b.nodes = c->block_mem[k] + 8 * b.plane;
+        const int nfaces = 2 * (b.ncx + b.ncy);
+        CU_TRY(cudaMalloc(&c->block_ibound[k], sizeof(int) * nfaces));
+        CU_TRY(cudaMemcpyAsync(c->block_ibound[k], d.ibound, sizeof(int) * nfaces, cudaMemcpyHostToDevice, c->stream));
+        b.ibound = c->block_ibound[k];
+        b.tiles_x = (b.ncx + TX - 1) / TX;
+        b.tiles_y = (b.ncy + TY - 1) / TY;
+        b.tile0 = c->total_tiles;
+        c->total_tiles += b.tiles_x * b.tiles_y;
+        c->max_tiles = std::max(c->max_tiles, b.tiles_x * b.tiles_y);
+        c->max_faces = std::max(c->max_faces, nfaces);
+        c->owned_cells += (long long)b.ncx * b.ncy;
+        max_cells = std::max(max_cells, (long long)b.ncx * b.ncy);
+        max_nodes = std::max(max_nodes, (long long)d.nx * d.ny);
+        for (int s = 0; s < 4; s++) {
+            const int nb = d.bid[s];
+            b.nb_kind[s] = NB_NONE;
+            b.nb_block[s] = -1;
+            b.nb_side[s] = -1;
+            b.recv[s] = nullptr;
+            if (nb < 0) continue;
+            b.nb_side[s] = facing_side(blocks[nb], g, s);
+            if (blocks[nb].owner == cfg->rank) {
+                b.nb_kind[s] = NB_LOCAL;
+                b.nb_block[s] = c->owned_index[nb];
+            } else {
+                b.nb_kind[s] = NB_REMOTE;
+                // slot offset inside the peer's receive buffer
+                const int p = blocks[nb].owner;
+                long long off = 0;
+                bool found = false;
+                for (int gg = 0; gg < nblocks && !found; gg++) {
+                    if (blocks[gg].owner != cfg->rank) continue;
+                    for (int ss = 0; ss < 4; ss++) {
+                        const int n2 = blocks[gg].bid[ss];
+                        if (n2 < 0 || blocks[n2].owner != p) continue;
+                        if (gg == g && ss == s) { found = true; break; }
+                        off += 4ll * desc_edge(blocks[gg], ss);
+                    }
+                }
+                b.recv[s] = c->peers[p].d_recv + off;
+            }
+        }
+    }
+    c->staging_doubles = std::max(4 * max_cells, 2 * max_nodes);
+    CU_TRY(cudaMalloc(&c->staging, sizeof(double) * c->staging_doubles));
+
+    // nodes, min_face, initial state
+    std::vector<double> parts(1024);
+    double* dparts = nullptr;
+    CU_TRY(cudaMalloc(&dparts, sizeof(double) * 1024));
+    for (int k = 0; k < c->nowned; k++) {
+        const par2d_block_desc& d = blocks[c->owned_gid[k]];
+        BlockDev& b = c->hblk[k];
+        const long long nn = (long long)d.nx * d.ny;
+        CU_TRY(cudaMemcpyAsync(c->staging, d.x, sizeof(double) * nn, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaMemcpyAsync(c->staging + nn, d.y, sizeof(double) * nn, cudaMemcpyHostToDevice, c->stream));
+        launch_nodes_to_planes(c->stream, b, c->staging, c->staging + nn);
+        const long long cells = (long long)b.ncx * b.ncy;
+        const int nparts = (int)std::min<long long>(1024, (cells + 255) / 256);
+        launch_min_face(c->stream, b, dparts, nparts);
+        CU_TRY(cudaMemcpyAsync(parts.data(), dparts, sizeof(double) * nparts, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        double m = 1.0;
+        for (int q = 0; q < nparts; q++) m = fmin(m, parts[q]);
+        b.min_face = m;
+        launch_fill_uniform(c->stream, b, 0, cfg->uFS);
+    }
+    cudaFree(dparts);
+
+    CU_TRY(cudaMalloc(&c->dblk, sizeof(BlockDev) * c->nowned));
+    CU_TRY(cudaMemcpyAsync(c->dblk, c->hblk.data(), sizeof(BlockDev) * c->nowned, cudaMemcpyHostToDevice, c->stream));
+
+    // send lines for off-rank neighbours
+    std::vector<SendLine> lines;
+    for (int p = 0; p < cfg->nranks; p++) {
+        if (p == cfg->rank) continue;
+        long long off = 0;
+        for (int g = 0; g < nblocks; g++) {
+            if (blocks[g].owner != p) continue;
+            for (int s = 0; s < 4; s++) {
+                const int nb = blocks[g].bid[s];
+                if (nb < 0 || blocks[nb].owner != cfg->rank) continue;
+                SendLine ln;
+                ln.block = c->owned_index[nb];
+                ln.side = facing_side(blocks[nb], g, s);
+                ln.n = desc_edge(blocks[g], s);
+                ln.pad = 0;
+                ln.dst = c->peers[p].d_send + off;
+                off += 4ll * ln.n;
+                lines.push_back(ln);
+                c->max_line = std::max(c->max_line, ln.n);
+            }
+        }
+    }
+    c->nlines = (int)lines.size();
+    if (c->nlines) {
+        CU_TRY(cudaMalloc(&c->dlines, sizeof(SendLine) * c->nlines));
+        CU_TRY(cudaMemcpyAsync(c->dlines, lines.data(), sizeof(SendLine) * c->nlines, cudaMemcpyHostToDevice, c->stream));
+    }
+
+    CU_TRY(cudaMalloc(&c->dt_table, sizeof(double) * nblocks));
+    CU_TRY(cudaMemsetAsync(c->dt_table, 0, sizeof(double) * nblocks, c->stream));
+    CU_TRY(cudaMalloc(&c->partials, sizeof(double) * 4 * (size_t)c->total_tiles));
+    CU_TRY(cudaMalloc(&c->flags, sizeof(unsigned)));
+    CU_TRY(cudaMalloc(&c->stop, sizeof(int)));
+    CU_TRY(cudaMalloc(&c->d_iter, sizeof(long long)));
+    CU_TRY(cudaMalloc(&c->hist_pos, sizeof(int)));
+    CU_TRY(cudaMalloc(&c->ticket, sizeof(unsigned)));
+    CU_TRY(cudaMalloc(&c->res0, sizeof(double) * 4 * c->nowned));
+    CU_TRY(cudaMalloc(&c->blk_norm, sizeof(double) * 4 * c->nowned));
+    CU_TRY(cudaMemsetAsync(c->flags, 0, sizeof(unsigned), c->stream));
+    CU_TRY(cudaMemsetAsync(c->stop, 0, sizeof(int), c->stream));
+    CU_TRY(cudaMemsetAsync(c->d_iter, 0, sizeof(long long), c->stream));
+    CU_TRY(cudaMemsetAsync(c->hist_pos, 0, sizeof(int), c->stream));
+    CU_TRY(cudaMemsetAsync(c->ticket, 0, sizeof(unsigned), c->stream));
+    CU_TRY(cudaMemsetAsync(c->res0, 0, sizeof(double) * 4 * c->nowned, c->stream));
+    rc = ensure_hist(c, 64);
+    if (rc) return rc;
+    rc = build_tensor_maps(c);
+    if (rc) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int par2d_destroy(par2d_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (double* p : c->block_mem) cudaFree(p);
+    for (int* p : c->block_ibound) cudaFree(p);
+    for (Peer& p : c->peers) { cudaFree(p.d_send); cudaFree(p.d_recv); }
+    cudaFree(c->dblk); cudaFree(c->dtmaps); cudaFree(c->dt_table); cudaFree(c->partials); cudaFree(c->flags);
+    cudaFree(c->stop); cudaFree(c->d_iter); cudaFree(c->hist_pos); cudaFree(c->ticket); cudaFree(c->res0);
+    cudaFree(c->blk_norm); cudaFree(c->blk_hist); cudaFree(c->step_hist); cudaFree(c->staging); cudaFree(c->dlines);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+static int owned_k(par2d_ctx* c, int block, const char* what) {
+    if (!c) { fail(PAR2D_ERR_ARG, "%s: null ctx", what); return -1; }
+    if (block < 0 || block >= c->nblocks || c->owned_index[block] < 0) { fail(PAR2D_ERR_ARG, "%s: block %d is not owned by rank %d", what, block, c->cfg.rank); return -1; }
+    return c->owned_index[block];
+}
+
+int par2d_set_state(par2d_ctx* c, int32_t block, const double* unk) {
+    const int k = owned_k(c, block, "set_state");
+    if (k < 0 || !unk) return PAR2D_ERR_ARG;
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    const BlockDev& b = c->hblk[k];
+    const size_t bytes = sizeof(double) * 4 * (size_t)b.ncx * b.ncy;
+    CU_TRY(cudaMemcpyAsync(c->staging, unk, bytes, cudaMemcpyHostToDevice, c->stream));
+    launch_aos_to_planes(c->stream, b, c->cur, c->staging);
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int par2d_get_state(par2d_ctx* c, int32_t block, double* unk) {
+    const int k = owned_k(c, block, "get_state");
+    if (k < 0 || !unk) return PAR2D_ERR_ARG;
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    const BlockDev& b = c->hblk[k];
+    const size_t bytes = sizeof(double) * 4 * (size_t)b.ncx * b.ncy;
+    launch_planes_to_aos(c->stream, b, c->cur, c->staging);
+    CU_TRY(cudaMemcpyAsync(unk, c->staging, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int par2d_get_residual(par2d_ctx* c, int32_t block, double* res) {
+    const int k = owned_k(c, block, "get_residual");
+    if (k < 0 || !res) return PAR2D_ERR_ARG;
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    const BlockDev& b = c->hblk[k];
+    StepArgs a = c->step_args(0);
+    a.res_out = c->staging;
+    a.res_block = k;
+    // with remote neighbours the receive buffers must already hold this state's edge
+    // lines (par2d_step_begin + transport); the dt table is rebuilt here either way
+    c->kt->ghost(c->stream, a, c->gas, 1);
+    c->kt->step(c->stream, a, c->gas, c->tpg, c->axi, c->use_tma);
+    const size_t bytes = sizeof(double) * 4 * (size_t)b.ncx * b.ncy;
+    CU_TRY(cudaMemcpyAsync(res, c->staging, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int par2d_step(par2d_ctx* c, int32_t nsteps, int32_t stop_on_tol, par2d_step_info* info) {
+    if (!c || nsteps < 0) return fail(PAR2D_ERR_ARG, "step: bad argument");
+    if (c->cfg.nranks != 1) return fail(PAR2D_ERR_COMM, "step: nranks > 1 needs step_begin/step_end (external transport) or a connected peer arena");
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    int rc = ensure_hist(c, nsteps);
+    if (rc) return rc;
+    CU_TRY(cudaMemsetAsync(c->hist_pos, 0, sizeof(int), c->stream));
+    CU_TRY(cudaMemsetAsync(c->stop, 0, sizeof(int), c->stream));
+    const int cur0 = c->cur;
+    for (int s = 0; s < nsteps; s++) queue_step(c, stop_on_tol, true);
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(cudaGetLastError());
+    return harvest(c, nsteps, cur0, info, nsteps);
+}
+
+int par2d_get_block_history(par2d_ctx* c, int32_t nsteps, double* out) {
+    if (!c || !out || nsteps < 0 || nsteps > c->last_steps) return fail(PAR2D_ERR_ARG, "get_block_history: only %d steps recorded", c ? c->last_steps : 0);
+    const size_t row = 2 * (size_t)c->nowned;
+    memcpy(out, c->h_blk_hist.data() + row * (size_t)(c->last_steps - nsteps), sizeof(double) * row * nsteps);
+    return 0;
+}
+
+int64_t par2d_iteration(const par2d_ctx* c) { return c ? c->iter : -1; }
+int32_t par2d_num_owned(const par2d_ctx* c) { return c ? c->nowned : 0; }
+int32_t par2d_owned_block(const par2d_ctx* c, int32_t k) { return (c && k >= 0 && k < c->nowned) ? c->owned_gid[k] : -1; }
+int64_t par2d_owned_cells(const par2d_ctx* c) { return c ? c->owned_cells : 0; }
+
+int par2d_exchange_layout(par2d_ctx* c, int32_t peer, int64_t* n_send, int64_t* n_recv, void** dev_send, void** dev_recv) {
+    if (!c || peer < 0 || peer >= c->cfg.nranks) return fail(PAR2D_ERR_ARG, "exchange_layout: bad peer");
+    const Peer& p = c->peers[peer];
+    if (n_send) *n_send = p.n_send;
+    if (n_recv) *n_recv = p.n_recv;
+    if (dev_send) *dev_send = p.d_send;
+    if (dev_recv) *dev_recv = p.d_recv;
+    return 0;
+}
+
+int par2d_dt_table(par2d_ctx* c, void** dev_table, int32_t* n) {
+    if (!c) return fail(PAR2D_ERR_ARG, "dt_table: null ctx");
+    if (dev_table) *dev_table = c->dt_table;
+    if (n) *n = c->nblocks;
+    return 0;
+}
+
+int par2d_step_begin(par2d_ctx* c) {
+    if (!c) return fail(PAR2D_ERR_ARG, "step_begin: null ctx");
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    if (c->pending_steps == 0) {
+        int rc = ensure_hist(c, 4096);
+        if (rc) return rc;
+        CU_TRY(cudaMemsetAsync(c->hist_pos, 0, sizeof(int), c->stream));
+        CU_TRY(cudaMemsetAsync(c->stop, 0, sizeof(int), c->stream));
+    }
+    if (c->pending_steps >= c->hist_cap) return fail(PAR2D_ERR_COMM, "step_begin: %d steps queued without step_collect", c->pending_steps);
+    CU_TRY(cudaMemsetAsync(c->dt_table, 0, sizeof(double) * c->nblocks, c->stream));
+    c->kt->pack(c->stream, c->step_args(1), c->gas, c->dlines, c->nlines, c->max_line);
+    return 0;
+}
+
+int par2d_step_end(par2d_ctx* c) {
+    if (!c) return fail(PAR2D_ERR_ARG, "step_end: null ctx");
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    queue_step(c, 0, false);
+    c->pending_steps++;
+    return 0;
+}
+
+int par2d_step_collect(par2d_ctx* c, int32_t nsteps, par2d_step_info* info) {
+    if (!c) return fail(PAR2D_ERR_ARG, "step_collect: null ctx");
+    if (nsteps > c->pending_steps) return fail(PAR2D_ERR_ARG, "step_collect: %d requested, %d pending", nsteps, c->pending_steps);
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(cudaGetLastError());
+    const int queued = c->pending_steps;
+    const int cur0 = c->cur ^ (queued & 1);
+    std::vector<par2d_step_info> all(queued);
+    const int code = harvest(c, queued, cur0, all.data(), queued);
+    if (info)
+        for (int s = 0; s < nsteps; s++) info[s] = all[queued - nsteps + s];
+    c->pending_steps = 0;
+    return code;
+}
+
+int par2d_peer_export(par2d_ctx*, void*) { return fail(PAR2D_ERR_COMM, "peer-mapped exchange is not built in this round; use step_begin/step_end"); }
+int par2d_peer_connect(par2d_ctx*, const void*) { return fail(PAR2D_ERR_COMM, "peer-mapped exchange is not built in this round; use step_begin/step_end"); }
+
+int par2d_set_stream(par2d_ctx* c, uint64_t stream) {
+    if (!c) return fail(PAR2D_ERR_ARG, "set_stream: null ctx");
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (stream == 0) {
+        CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    } else {
+        c->stream = reinterpret_cast<cudaStream_t>(stream);
+        c->own_stream = false;
+    }
+    return 0;
+}
+
+int par2d_synchronize(par2d_ctx* c) {
+    if (!c) return fail(PAR2D_ERR_ARG, "synchronize: null ctx");
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- point-wise test hooks ------------------------------------------------
+
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8) == cudaSuccess ? 0 : 1; }
+};
+int test_prolog(const par2d_config* cfg, const KernelTable** kt, Gas* g) {
+    if (!cfg) return fail(PAR2D_ERR_ARG, "test hook: null config");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(PAR2D_ERR_CUDA, "no CUDA device available; par2d_b200 has no CPU fallback");
+    if (cfg->device >= 0) CU_TRY(cudaSetDevice(cfg->device));
+    *kt = cfg->mode == PAR2D_MODE_FAITHFUL ? kernels_faithful() : kernels_fast();
+    *g = make_gas(*cfg);
+    return 0;
+}
+}  // namespace
+
+int par2d_test_ldfss(const par2d_config* cfg, int64_t n, const double* face, const double* uL, const double* uR, double* flux, double* parr) {
+    const KernelTable* kt; Gas g;
+    int rc = test_prolog(cfg, &kt, &g);
+    if (rc) return rc;
+    DevBuf dface, dl, dr, dflux, dparr;
+    if (dface.alloc(32 * n) || dl.alloc(32 * n) || dr.alloc(32 * n) || dflux.alloc(32 * n) || dparr.alloc(8 * n)) return fail(PAR2D_ERR_CUDA, "test_ldfss: out of device memory");
+    CU_TRY(cudaMemcpy(dface.p, face, 32 * n, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(dl.p, uL, 32 * n, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(dr.p, uR, 32 * n, cudaMemcpyHostToDevice));
+    kt->test_ldfss(0, g, !(cfg->igam > 0), cfg->iaxi == 1, n, (double*)dface.p, (double*)dl.p, (double*)dr.p, (double*)dflux.p, (double*)dparr.p);
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(flux, dflux.p, 32 * n, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(parr, dparr.p, 8 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int par2d_test_boundary_state(const par2d_config* cfg, int64_t n, const int32_t* btype, const double* norm, const double* uInt, double* uGhost) {
+    const KernelTable* kt; Gas g;
+    int rc = test_prolog(cfg, &kt, &g);
+    if (rc) return rc;
+    DevBuf dbt, dn, di, dg;
+    if (dbt.alloc(4 * n) || dn.alloc(16 * n) || di.alloc(32 * n) || dg.alloc(32 * n)) return fail(PAR2D_ERR_CUDA, "test_boundary_state: out of device memory");
+    CU_TRY(cudaMemcpy(dbt.p, btype, 4 * n, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(dn.p, norm, 16 * n, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(di.p, uInt, 32 * n, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(dg.p, uGhost, 32 * n, cudaMemcpyHostToDevice));
+    kt->test_boundary(0, g, n, (int*)dbt.p, (double*)dn.p, (double*)di.p, (double*)dg.p);
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(uGhost, dg.p, 32 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int par2d_test_update_state(const par2d_config* cfg, int64_t n, double* unk, double* derived) {
+    const KernelTable* kt; Gas g;
+    int rc = test_prolog(cfg, &kt, &g);
+    if (rc) return rc;
+    DevBuf du, dd;
+    if (du.alloc(32 * n) || dd.alloc(64 * n)) return fail(PAR2D_ERR_CUDA, "test_update_state: out of device memory");
+    CU_TRY(cudaMemcpy(du.p, unk, 32 * n, cudaMemcpyHostToDevice));
+    kt->test_update_state(0, g, !(cfg->igam > 0), n, (double*)du.p, (double*)dd.p);
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(unk, du.p, 32 * n, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(derived, dd.p, 64 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int par2d_test_solve(const par2d_config* cfg, int64_t n, const double* dt_ycc, const double* unk, const double* res, double* dv) {
+    const KernelTable* kt; Gas g;
+    int rc = test_prolog(cfg, &kt, &g);
+    if (rc) return rc;
+    DevBuf dy, du, dr, dd;
+    if (dy.alloc(16 * n) || du.alloc(32 * n) || dr.alloc(32 * n) || dd.alloc(32 * n)) return fail(PAR2D_ERR_CUDA, "test_solve: out of device memory");
+    CU_TRY(cudaMemcpy(dy.p, dt_ycc, 16 * n, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(du.p, unk, 32 * n, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(dr.p, res, 32 * n, cudaMemcpyHostToDevice));
+    kt->test_solve(0, g, !(cfg->igam > 0), cfg->iaxi == 1, n, (double*)dy.p, (double*)du.p, (double*)dr.p, (double*)dd.p);
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(dv, dd.p, 32 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int par2d_probe_fp64(int32_t device, double* tflops) {
+    if (!tflops) return fail(PAR2D_ERR_ARG, "probe_fp64: null output");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(PAR2D_ERR_CUDA, "no CUDA device available");
+    if (device >= 0) CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    int dev;
+    CU_TRY(cudaGetDevice(&dev));
+    CU_TRY(cudaGetDeviceProperties(&prop, dev));
+    const int grid = prop.multiProcessorCount * 8, iters = 2048;
+    DevBuf out;
+    if (out.alloc(sizeof(double) * grid * 256)) return fail(PAR2D_ERR_CUDA, "probe_fp64: out of device memory");
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    launch_fp64_probe(0, (double*)out.p, grid, iters);
+    double best = 0.0;
+    for (int rep = 0; rep < 3; rep++) {
+        CU_TRY(cudaEventRecord(e0, 0));
+        launch_fp64_probe(0, (double*)out.p, grid, iters);
+        CU_TRY(cudaEventRecord(e1, 0));
+        CU_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * iters * 256.0 * grid;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+// common.cuh -- host/device shared descriptors of the par2d_b200 CUDA path.
+//
+// HBM layout of one grid block (all planes share one shape):
+//   rows   : ncy+2   (row 0 = bottom ghost line, rows 1..ncy = cells j=0..ncy-1,
+//                     row ncy+1 = top ghost line; nodes j=0..ncy live in rows 1..ncy+1)
+//   pitch  : multiple of 16 doubles (128 B); column COL0-1 = left ghost, COL0+i = cell i,
+//            COL0+ncx = right ghost; node i lives in column COL0+i
+//   planes : state A {rho,u,v,T}, state B {rho,u,v,T} (ping-pong), nodes {x,y}
+// i.e. the reference's AoS unk[(j*(nx-1)+i)*4+k] (FV/Indexing.h:11) becomes four padded SoA
+// planes with the ghost ring (SpatialDiscretization.cpp:182-185 uGBot/uGRight/uGTop/uGLeft)
+// stored in place, so every cell has four in-array neighbours and one TMA box
+// (TX+2)x(TY+2)x4 stages a tile with its halo.
+#pragma once
+#include <stdint.h>
+#include "physics.cuh"
+
+namespace par2d {
+
+constexpr int COL0 = 16;  // column of cell/node i = 0 (keeps row starts 128-byte aligned)
+
+// step-kernel tile: TX x TY cells, one cell per thread
+constexpr int TX = 32;
+constexpr int TY = 8;
+constexpr int STEP_THREADS = TX * TY;
+constexpr int HX = TX + 2, HY = TY + 2;  // haloed tile
+
+enum : int { SIDE_BOTTOM = 0, SIDE_RIGHT = 1, SIDE_TOP = 2, SIDE_LEFT = 3 };
+enum : int { NB_NONE = 0, NB_LOCAL = 1, NB_REMOTE = 2 };
+
+struct BlockDev {
+    int gid;            // global block id
+    int ncx, ncy;       // cells
+    int pitch;          // doubles per row
+    long long plane;    // doubles per plane = pitch*(ncy+2)
+    double* state[2];   // 4 planes each
+    double* nodes;      // 2 planes: x, y
+    const int* ibound;  // BC code per boundary face, CCW (SpatialDiscretization.cpp:27,45,64,84)
+    int nb_kind[4];     // NB_* per side
+    int nb_block[4];    // owned-block index of a same-rank neighbour
+    int nb_side[4];     // the neighbour's side that faces us
+    double* recv[4];    // AoS line [n*4+k] received from an off-rank neighbour
+    int tiles_x, tiles_y;
+    int tile0;          // first tile of this block in the partial-sum array
+    double min_face;    // static part of find_dt (main.cpp:26-32)
+};
+
+// one edge line to pack for an off-rank neighbour (SpatialDiscretization.cpp:236-257)
+struct SendLine {
+    int block;   // owned-block index
+    int side;
+    int n;       // edge cells
+    int pad;
+    double* dst; // AoS [n*4+k] in the peer send buffer (or, peer-mapped, in the peer's arena)
+};
+
+struct StepArgs {
+    const BlockDev* blocks;
+    int nowned;
+    int nblocks_global;
+    int cur;                 // state buffer read this step
+    int total_tiles;         // sum over owned blocks (size of partials)
+    int max_tiles;           // tiles of the largest owned block (grid.x of the step kernel)
+    int max_faces;           // longest block perimeter (grid.x of the ghost kernel)
+    const void* tmaps;       // CUtensorMap[nowned][3]: state A, state B, nodes
+    double* dt_table;        // nblocks_global
+    double* partials;        // [total_tiles][4] sum of res_k^2
+    unsigned* flags;         // device error bits
+    const int* stop;         // non-zero -> batch already converged, kernels return at once
+    double* res_out;         // optional AoS residual dump (get_residual test hook)
+    int res_block;           // owned index whose residual is dumped, or -1
+    int update;              // 0: residual only (test hook), 1: advance the state
+};
+
+struct FinalizeArgs {
+    const BlockDev* blocks;
+    int nowned;
+    const double* partials;
+    double* res0;            // [nowned][4] iteration-0 norms (main.cpp:260,365-374)
+    double* blk_hist;        // [hist_cap][nowned][2]
+    double* step_hist;       // [hist_cap][4] = dt, ressumsum, res0sum, relres
+    long long* iter;         // device iteration counter
+    int* hist_pos;           // next history slot
+    int* stop;
+    unsigned* ticket;        // last-block-done counter
+    const double* dt_table;
+    int nblocks_global;
+    double tol;
+    int stop_on_tol;
+    int hist_cap;
+};
+
+__host__ __device__ inline int edge_cells(int ncx, int ncy, int side) {
+    return (side == SIDE_BOTTOM || side == SIDE_TOP) ? ncx : ncy;
+}
+
+}  // namespace par2d

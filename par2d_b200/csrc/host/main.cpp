@@ -1,0 +1,114 @@
+// main.cpp -- par2d_fv: the reference driver (FV/main.cpp) re-expressed over the C ABI.
+//
+// Same inputs and outputs as the reference executable MPI2DFV, with its hard-coded paths
+// and compile-time switches turned into arguments whose defaults are the shipped values:
+//   inputs : <case>/grid.conn + <case>/subgrids/grid.block<b>.dat  (FV/main.cpp:114-142)
+//            <therm>  NASA-7 record                                 (FV/Thermo.h:16-34)
+//   outputs: stdout line per iteration                              (FV/main.cpp:499)
+//            <out>/res.tec                                          (FV/main.cpp:245-254,495)
+//            <out>/solution.b<b+1>.tec every saveiter iterations and at the end
+//                                                                   (FV/main.cpp:484-491,541-545)
+// All blocks are advanced by one process on one GPU; the multi-GPU launch lives in
+// par2d_b200/dist.py (one process per GPU).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "par2d_gpu.h"
+#include "par2d_host.h"
+
+static void usage() {
+    printf("usage: par2d_fv --case DIR [--out DIR] [--therm FILE] [--niter N] [--iaxi 0|1] [--igam G]\n"
+           "                [--cfl C] [--tol T] [--printiter N] [--saveiter N] [--batch N] [--faithful]\n");
+}
+
+int main(int argc, char** argv) {
+    std::string case_dir = "../Case", out_dir = "../Outputs", therm = "../therm_air.dat";
+    long niter = 5000000;  // NITER, FV/Indexing.h:20
+    int printiter = 1, saveiter = 1000, batch = 100;
+    par2d_config cfg;
+    par2d_default_config(&cfg);
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto next = [&]() -> const char* { if (i + 1 >= argc) { usage(); exit(2); } return argv[++i]; };
+        if (a == "--case") case_dir = next();
+        else if (a == "--out") out_dir = next();
+        else if (a == "--therm") therm = next();
+        else if (a == "--niter") niter = atol(next());
+        else if (a == "--iaxi") cfg.iaxi = atoi(next());
+        else if (a == "--igam") cfg.igam = atof(next());
+        else if (a == "--cfl") cfg.cfl = atof(next());
+        else if (a == "--tol") cfg.tol = atof(next());
+        else if (a == "--printiter") printiter = atoi(next());
+        else if (a == "--saveiter") saveiter = atoi(next());
+        else if (a == "--batch") batch = atoi(next());
+        else if (a == "--faithful") cfg.mode = PAR2D_MODE_FAITHFUL;
+        else { usage(); return 2; }
+    }
+    if (batch < 1) batch = 1;
+
+    printf("==================== Loading Mesh ====================\n");
+    par2d_case* cs = nullptr;
+    if (par2d_case_load(case_dir.c_str(), &cs)) { printf("%s\n", par2d_host_last_error()); return 1; }
+    if (par2d_thermo_load(therm.c_str(), &cfg)) { printf("%s\n", par2d_host_last_error()); return 1; }
+    // free stream from the loaded gas constant, FV/main.cpp:84-88
+    cfg.uFS[0] = 1000.0 / (cfg.Rs * 300.0);
+    const int nb = par2d_case_num_blocks(cs);
+    std::vector<par2d_block_desc> blocks(nb);
+    for (int b = 0; b < nb; b++) par2d_case_block(cs, b, &blocks[b]);
+
+    printf("==================== Initializing ====================\n");
+    par2d_ctx* ctx = nullptr;
+    if (par2d_create(&cfg, nb, blocks.data(), &ctx)) { printf("par2d_create: %s\n", par2d_last_error()); return 1; }
+
+    auto save = [&](const char* title) {
+        for (int b = 0; b < nb; b++) {
+            std::vector<double> unk((size_t)4 * (blocks[b].nx - 1) * (blocks[b].ny - 1));
+            if (par2d_get_state(ctx, b, unk.data())) { printf("get_state: %s\n", par2d_last_error()); exit(1); }
+            const std::string path = out_dir + "/solution.b" + std::to_string(b + 1) + ".tec";  // bnum+1, FileIO.cpp:84
+            if (par2d_write_solution(path.c_str(), title, &cfg, blocks[b].nx, blocks[b].ny, blocks[b].x, blocks[b].y, unk.data()))
+                printf("%s\n", par2d_host_last_error());
+        }
+    };
+    printf("===== Generating Mesh and Initial State Tecplot Files ====\n");
+    save("Initial State");
+
+    FILE* fres = fopen((out_dir + "/res.tec").c_str(), "w");
+    if (!fres) printf("~~~~~~~~~ Failed to save residual file\n");
+    else fprintf(fres, "Residual history\n");
+
+    printf("==================== Starting Solver ====================\n");
+    std::vector<par2d_step_info> info(batch);
+    long iter = 0;
+    bool converged = false;
+    int rc = 0;
+    while (iter < niter && !converged) {
+        // stop at the next save point so the written state is the reference's (iter % saveiter == 0, iter > 0)
+        long n = std::min<long>(batch, niter - iter);
+        if (saveiter > 0) {
+            const long next_save = (iter / saveiter + 1) * (long)saveiter;  // state after iteration next_save is saved
+            n = std::min<long>(n, next_save + 1 - iter);
+        }
+        // the reference only tests the tolerance in multi-block runs (main.cpp:506)
+        rc = par2d_step(ctx, (int)n, nb > 1 ? 1 : 0, info.data());
+        for (long s = 0; s < n; s++) {
+            if (info[s].iter < 0) { converged = true; break; }
+            if (fres) fprintf(fres, "%d,\t%le\n", (int)info[s].iter, info[s].relres);
+            if (info[s].iter % printiter == 0)
+                printf("Iter:%7d\tdt:%7.4e \t\t RelativeTotalResisual:  %8.5e \n", (int)info[s].iter, info[s].dt, info[s].relres);
+            iter = info[s].iter + 1;
+            if (nb > 1 && info[s].relres < cfg.tol) { converged = true; break; }
+        }
+        if (rc) { printf("Failed Assert on the device: %s\n", par2d_last_error()); break; }
+        if (!converged && saveiter > 0 && iter > 1 && (iter - 1) % saveiter == 0) save("Final State");
+    }
+    if (fres) fclose(fres);
+    printf("==================== Calculation Finished ====================\n");
+    save("Final State");
+    par2d_destroy(ctx);
+    par2d_case_free(cs);
+    return rc ? 1 : 0;
+}

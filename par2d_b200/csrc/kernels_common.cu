@@ -1,0 +1,185 @@
+// kernels_common.cu -- mode-independent kernels: residual-norm finalisation and the
+// reference's residual bookkeeping, AoS<->padded-SoA state transposes, the static part
+// of find_dt, and an fp64 FMA throughput probe.  Compiled with -fmad=false: min_face
+// must be the reference's value bit for bit (main.cpp:26-32, MeshModule.cpp:56,74).
+#include <cuda_runtime.h>
+#include "common.cuh"
+#include "kernels_common.cuh"
+
+namespace par2d {
+
+// One CTA per owned block sums the tile partials in a fixed order (thread-strided, then a
+// shared-memory tree), takes the square roots (main.cpp:53-56) and the last CTA to finish
+// does the bookkeeping of main.cpp:365-392,494 in block order.
+__global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a, double* blk_norm) {
+    if (*a.stop) return;
+    __shared__ double red[256][4];
+    __shared__ bool last;
+    const int k = blockIdx.x, tid = threadIdx.x;
+    const BlockDev& b = a.blocks[k];
+    const int ntiles = b.tiles_x * b.tiles_y;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int t = tid; t < ntiles; t += 256) {
+        const double* p = a.partials + 4 * (long long)(b.tile0 + t);
+        s[0] += p[0]; s[1] += p[1]; s[2] += p[2]; s[3] += p[3];
+    }
+    for (int v = 0; v < 4; v++) red[tid][v] = s[v];
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (tid < w)
+            for (int v = 0; v < 4; v++) red[tid][v] += red[tid + w][v];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        for (int v = 0; v < 4; v++) blk_norm[4 * k + v] = sqrt(red[0][v]);
+        __threadfence();
+        last = atomicAdd(a.ticket, 1u) == (unsigned)(a.nowned - 1);
+    }
+    __syncthreads();
+    if (!last || tid != 0) return;
+    __threadfence();
+    const long long it = *a.iter;
+    const int pos = *a.hist_pos;
+    double tot = 0.0, tot0 = 0.0;
+    const volatile double* norms = blk_norm;
+    for (int q = 0; q < a.nowned; q++) {
+        double sum = 0.0, sum0 = 0.0;
+        for (int v = 0; v < 4; v++) {
+            const double rs = norms[4 * q + v];
+            double r0 = a.res0[4 * q + v];
+            if (it == 0) r0 = rs;
+            if (r0 < 1e-16) r0 = fmax(rs, 1e-16);
+            a.res0[4 * q + v] = r0;
+            sum += rs;
+            sum0 += r0;
+        }
+        if (pos < a.hist_cap) {
+            a.blk_hist[2 * ((long long)pos * a.nowned + q) + 0] = sum;
+            a.blk_hist[2 * ((long long)pos * a.nowned + q) + 1] = sum0;
+        }
+        tot += sum;
+        tot0 += sum0;
+    }
+    double dt = 0.0;
+    for (int q = 0; q < a.nblocks_global; q++) dt = fmax(dt, a.dt_table[q]);
+    const double relres = tot / tot0;
+    if (pos < a.hist_cap) {
+        double* h = a.step_hist + 4 * (long long)pos;
+        h[0] = dt; h[1] = tot; h[2] = tot0; h[3] = relres;
+    }
+    *a.iter = it + 1;
+    *a.hist_pos = pos + 1;
+    *a.ticket = 0u;
+    if (a.stop_on_tol && relres < a.tol) *a.stop = 1;
+}
+
+void launch_finalize(cudaStream_t s, const FinalizeArgs& a, double* blk_norm) {
+    finalize_kernel<<<a.nowned, 256, 0, s>>>(a, blk_norm);
+}
+
+// AoS unk[(j*ncx+i)*4+k] (FV/Indexing.h:11) -> padded planes; applies the T clamp that
+// State::UpdateState performs on the initial state (main.cpp:226-238).
+__global__ void aos_to_planes_kernel(BlockDev b, int buf, const double* __restrict__ aos) {
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (c >= (long long)b.ncx * b.ncy) return;
+    const int i = (int)(c % b.ncx), j = (int)(c / b.ncx);
+    const double2 lo = reinterpret_cast<const double2*>(aos)[2 * c], hi = reinterpret_cast<const double2*>(aos)[2 * c + 1];
+    double* S = b.state[buf];
+    const long long o = (long long)(j + 1) * b.pitch + COL0 + i;
+    S[o] = lo.x; S[b.plane + o] = lo.y; S[2 * b.plane + o] = hi.x; S[3 * b.plane + o] = fmax(hi.y, 201.0);
+}
+__global__ void planes_to_aos_kernel(BlockDev b, int buf, double* __restrict__ aos) {
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (c >= (long long)b.ncx * b.ncy) return;
+    const int i = (int)(c % b.ncx), j = (int)(c / b.ncx);
+    const double* S = b.state[buf];
+    const long long o = (long long)(j + 1) * b.pitch + COL0 + i;
+    reinterpret_cast<double2*>(aos)[2 * c] = make_double2(S[o], S[b.plane + o]);
+    reinterpret_cast<double2*>(aos)[2 * c + 1] = make_double2(S[2 * b.plane + o], S[3 * b.plane + o]);
+}
+__global__ void fill_uniform_kernel(BlockDev b, int buf, double r, double u, double v, double T) {
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (c >= (long long)b.ncx * b.ncy) return;
+    const int i = (int)(c % b.ncx), j = (int)(c / b.ncx);
+    double* S = b.state[buf];
+    const long long o = (long long)(j + 1) * b.pitch + COL0 + i;
+    S[o] = r; S[b.plane + o] = u; S[2 * b.plane + o] = v; S[3 * b.plane + o] = fmax(T, 201.0);
+}
+// node coordinates x[j*nx+i] -> padded planes (row j+1, column COL0+i)
+__global__ void nodes_to_planes_kernel(BlockDev b, const double* __restrict__ x, const double* __restrict__ y) {
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int nx = b.ncx + 1, ny = b.ncy + 1;
+    if (c >= (long long)nx * ny) return;
+    const int i = (int)(c % nx), j = (int)(c / nx);
+    const long long o = (long long)(j + 1) * b.pitch + COL0 + i;
+    b.nodes[o] = x[c];
+    b.nodes[b.plane + o] = y[c];
+}
+
+void launch_aos_to_planes(cudaStream_t s, const BlockDev& b, int buf, const double* aos) {
+    const long long n = (long long)b.ncx * b.ncy;
+    aos_to_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(b, buf, aos);
+}
+void launch_planes_to_aos(cudaStream_t s, const BlockDev& b, int buf, double* aos) {
+    const long long n = (long long)b.ncx * b.ncy;
+    planes_to_aos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(b, buf, aos);
+}
+void launch_fill_uniform(cudaStream_t s, const BlockDev& b, int buf, const double u[4]) {
+    const long long n = (long long)b.ncx * b.ncy;
+    fill_uniform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(b, buf, u[0], u[1], u[2], u[3]);
+}
+void launch_nodes_to_planes(cudaStream_t s, const BlockDev& b, const double* x, const double* y) {
+    const long long n = (long long)(b.ncx + 1) * (b.ncy + 1);
+    nodes_to_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(b, x, y);
+}
+
+// min over cells of the two face lengths leaving node (i,j), seeded with 1.0
+// (main.cpp:26-32 over geofa[.,.,0] and geofa[.,.,3], MeshModule.cpp:56,74).  min is
+// order independent, so a parallel reduction reproduces the serial value exactly.
+__global__ void __launch_bounds__(256) min_face_kernel(BlockDev b, double* out) {
+    __shared__ double red[256];
+    const double* X = b.nodes;
+    const double* Y = b.nodes + b.plane;
+    double m = 1.0;
+    const long long n = (long long)b.ncx * b.ncy;
+    for (long long c = blockIdx.x * 256ll + threadIdx.x; c < n; c += 256ll * gridDim.x) {
+        const int i = (int)(c % b.ncx), j = (int)(c / b.ncx);
+        const long long o = (long long)(j + 1) * b.pitch + COL0 + i;
+        const double x0 = X[o], y0 = Y[o];
+        const double xh = X[o + 1], yh = Y[o + 1], xv = X[o + b.pitch], yv = Y[o + b.pitch];
+        const double lh = sqrt(((xh - x0) * (xh - x0)) + ((yh - y0) * (yh - y0)));
+        const double lv = sqrt((xv - x0) * (xv - x0) + (yv - y0) * (yv - y0));
+        m = fmin(m, lh);
+        m = fmin(m, lv);
+    }
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] = fmin(red[threadIdx.x], red[threadIdx.x + w]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+}
+void launch_min_face(cudaStream_t s, const BlockDev& b, double* out, int nparts) {
+    min_face_kernel<<<nparts, 256, 0, s>>>(b, out);
+}
+
+// fp64 FMA throughput probe: 8 independent chains per thread.
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters, double seed) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const double m = 1.0000001, c = 1e-9;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    out[blockIdx.x * 256 + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+void launch_fp64_probe(cudaStream_t s, double* out, int grid, int iters) {
+    fp64_probe_kernel<<<grid, 256, 0, s>>>(out, iters, 0.5);
+}
+
+}  // namespace par2d

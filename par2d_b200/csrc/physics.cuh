@@ -1,0 +1,402 @@
+// physics.cuh -- point-wise device functions of the PAR2D hot path (sm_100a, fp64).
+//
+// Everything is templated on
+//   FAITHFUL : true  -> the reference's operation order, IEEE division/sqrt, pivoted
+//                       LU; the including TU is compiled with -fmad=false so nothing is
+//                       contracted.  Bit-identical to the reference except through pow().
+//              false -> FMA contraction, Newton reciprocals shared between uses,
+//                       closed-form triangular solve.
+//   TPG      : NASA-7 curve-fit thermodynamics (igam <= 0) instead of the calorically
+//              perfect shortcut (Thermo.cpp:14,34).
+//   AXI      : axisymmetric (IAXI == 1) or planar.
+// Reference lines are cited per function.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace par2d {
+
+// Physics constants of one run; lives in kernel parameter space.
+struct Gas {
+    double Rs;         // Thermo.h:31
+    double gam;        // fabs(IGAM), Thermo.h:47
+    double igam;       // signed IGAM
+    double gamRs;      // gam*Rs (same association as StateVariables.h:51: (gam*Rs)*T)
+    double cp_cpg;     // Rs/(1-1/IGAM)             Thermo.cpp:34
+    double cpg_den;    // (1-1/IGAM)                Thermo.cpp:14
+    double inv_cv_cpg; // 1/(cp_cpg-Rs)   (fast path only)
+    double hi[7], lo[7];
+    double uFS[4];
+    double p_back;
+    double cfl;
+};
+
+// error bits raised on the device (mapped to PAR2D_ERR_* on the host)
+enum : unsigned {
+    FLAG_NAN = 1u, FLAG_DENSITY = 2u, FLAG_STATE = 4u, FLAG_SINGULAR = 8u, FLAG_THERMO = 16u
+};
+
+// ---------------------------------------------------------------- fast math
+// rcp.approx.ftz.f64 (MUFU.RCP64H) seeds ~20 bits; two Newton steps reach <= 1 ulp.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+// rsqrt.approx.ftz.f64 (MUFU.RSQ64H) + two Newton steps.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double hx = 0.5 * x;
+    double e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    return y;
+}
+
+// ---------------------------------------------------------------- thermo
+// Thermo::CalcEnthalpy (Thermo.cpp:7-30) and CalcCp (Thermo.cpp:32-48).
+template <bool TPG>
+__device__ __forceinline__ double enthalpy(const Gas& g, double T, unsigned& flags) {
+    if constexpr (!TPG) {
+        return (T * g.Rs / g.cpg_den + g.hi[5]);
+    } else {
+        double T2 = T * T, T3 = T * T2, T4 = T * T3, T5 = T * T4;
+        if (!(T > 200.0) || !(T < 10000.0)) flags |= FLAG_THERMO;
+        const double* q = (T > 1000.0) ? g.hi : g.lo;
+        return (g.Rs) * (q[0] * T + q[1] * T2 * 0.5 + q[2] * T3 / 3.0 + q[3] * T4 * 0.25 + q[4] * T5 * 0.2 + q[5]);
+    }
+}
+template <bool TPG>
+__device__ __forceinline__ double heat_capacity(const Gas& g, double T, unsigned& flags) {
+    if constexpr (!TPG) {
+        return g.cp_cpg;
+    } else {
+        double T2 = T * T, T3 = T * T2, T4 = T * T3;
+        if (!(T > 200.0) || !(T < 10000.0)) flags |= FLAG_THERMO;
+        const double* q = (T >= 1000.0) ? g.hi : g.lo;
+        return (g.Rs) * (q[0] + q[1] * T + q[2] * T2 + q[3] * T3 + q[4] * T4);
+    }
+}
+
+// What a face needs from a cell: State::UpdateState (StateVariables.h:38-68) minus
+// the members the path never reads.  T must already be clamped (>= 201).
+struct FaceState {
+    double rho, u, v, p, a, h0;
+    double ip;  // 1/p, fast path only
+};
+
+template <bool FAITHFUL, bool TPG>
+__device__ __forceinline__ FaceState face_state(const Gas& g, double rho, double u, double v, double T, unsigned& flags) {
+    FaceState s;
+    s.rho = rho; s.u = u; s.v = v;
+    double v2 = u * u + v * v;
+    s.p = fmax(rho * g.Rs * T, 1.0);
+    if constexpr (FAITHFUL) {
+        s.a = sqrt(g.gamRs * T);
+        s.ip = 0.0;
+    } else {
+        double c2 = g.gamRs * T;
+        s.a = c2 * fast_rsqrt(c2);
+        s.ip = fast_rcp(s.p);
+    }
+    s.h0 = enthalpy<TPG>(g, T, flags) + 0.5 * v2;
+    if (!(s.a > 0.0) || !(s.p > 0.0) || isnan(s.p * s.a * T)) flags |= FLAG_STATE;
+    return s;
+}
+
+// ---------------------------------------------------------------- LDFSS
+// EulerFlux.cpp:121-192.  The face is given by its node difference (dx,dy) =
+// (x1-x0, y1-y0); MeshModule.cpp:52-81 defines len = |d|, n = (dy,-dx)/len.
+struct FaceGeom {
+    double dx, dy;    // node difference
+    double len, rl;   // |d| and 1/|d|
+    double nx, ny;    // unit normal (faithful path: the reference's divided values)
+    double yf;        // face mid-point radius (MeshModule.cpp:66,84)
+};
+
+template <bool FAITHFUL>
+__device__ __forceinline__ FaceGeom face_geom(double x0, double y0, double x1, double y1) {
+    FaceGeom f;
+    f.dx = x1 - x0;
+    f.dy = y1 - y0;
+    if constexpr (FAITHFUL) {
+        f.len = sqrt((f.dx * f.dx) + (f.dy * f.dy));
+        f.nx = f.dy / f.len;
+        f.ny = -f.dx / f.len;
+        f.rl = 0.0;
+    } else {
+        double s = fma(f.dx, f.dx, f.dy * f.dy);
+        f.rl = fast_rsqrt(s);
+        f.len = s * f.rl;
+        f.nx = f.dy * f.rl;
+        f.ny = -f.dx * f.rl;
+    }
+    f.yf = 0.5 * (y1 + y0);
+    return f;
+}
+
+struct Flux {
+    double f0, f1, f2, f3, parr;
+};
+
+__device__ __forceinline__ double sgn_bit(double x) { return signbit(x) ? -1.0 : 1.0; }  // Indexing.h:22
+
+template <bool FAITHFUL, bool AXI>
+__device__ __forceinline__ Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) {
+    Flux o;
+    if constexpr (FAITHFUL) {
+        const double normx = fg.nx, normy = fg.ny, len = fg.len;
+        double yface = fg.yf;
+        double ahalf = 0.5 * (L.a + R.a);
+        double xml = (L.u * normx + L.v * normy) / ahalf;
+        double xmr = (R.u * normx + R.v * normy) / ahalf;
+        double all = 0.5 * (1.0 + sgn_bit(xml));
+        double alr = 0.5 * (1.0 - sgn_bit(xmr));
+        double btl = -fmax(0.0, 1.0 - (double)((int)(fabs(xml))));
+        double btr = -fmax(0.0, 1.0 - (double)((int)(fabs(xmr))));
+        double xmml = 0.25 * (xml + 1.0) * (xml + 1.0);
+        double xmmr = -0.25 * (xmr - 1.0) * (xmr - 1.0);
+        double xmhalf = sqrt(0.5 * (xml * xml + xmr * xmr));
+        double xmc = 0.25 * btl * btr * (xmhalf - 1.0) * (xmhalf - 1.0);
+        double delp = L.p - R.p;
+        double psum = L.p + R.p;
+        double xmcp = xmc * fmax(0.0, (1.0 - (delp / psum + 2.0 * fabs(delp) / L.p)));
+        double xmcm = xmc * fmax(0.0, (1.0 + (delp / psum - 2.0 * fabs(delp) / R.p)));
+        double cvlp = all * (1.0 + btl) * xml - btl * xmml;
+        double cvlm = alr * (1.0 + btr) * xmr - btr * xmmr;
+        double cep = cvlp - xmcp;
+        double cem = cvlm + xmcm;
+        double fml = len * L.rho * ahalf * cep;
+        double fmr = len * R.rho * ahalf * cem;
+        double ppl = 0.25 * (xml + 1.0) * (xml + 1.0) * (2.0 - xml);
+        double ppr = 0.25 * (xmr - 1.0) * (xmr - 1.0) * (2.0 + xmr);
+        double pnet = (all * (1.0 + btl) - btl * ppl) * L.p + (alr * (1.0 + btr) - btr * ppr) * R.p;
+        double py_planar;
+        if constexpr (AXI) {
+            o.parr = len * pnet * normy;
+            py_planar = 0.0;
+        } else {
+            yface = 1.0;
+            o.parr = 0.0;
+            py_planar = len * pnet * normy;
+        }
+        o.f0 = yface * (fml + fmr);
+        o.f1 = yface * (fml * L.u + fmr * R.u + len * pnet * normx);
+        o.f2 = yface * (fml * L.v + fmr * R.v + py_planar);
+        o.f3 = yface * (fml * L.h0 + fmr * (R.h0));
+    } else {
+        // lean evaluation: one reciprocal for ahalf, 1/p per cell shared by its
+        // four faces, the pressure-weighted diffusion term only where both sides
+        // are subsonic (it is multiplied by btl*btr = 0 otherwise).
+        const double ahalf = 0.5 * (L.a + R.a);
+        const double q = fast_rcp(ahalf) * fg.rl;
+        const double xml = fma(L.u, fg.dy, -L.v * fg.dx) * q;
+        const double xmr = fma(R.u, fg.dy, -R.v * fg.dx) * q;
+        const bool subL = fabs(xml) < 1.0, subR = fabs(xmr) < 1.0;
+        const double hl = 0.5 * (xml + 1.0), hr = 0.5 * (xmr - 1.0);
+        const double xmml = hl * hl, xmmr = -(hr * hr);
+        // split Mach numbers and pressure weights (EulerFlux.cpp:146-175 with
+        // all/alr in {0,1} and btl/btr in {-1,0} substituted)
+        double cep = subL ? xmml : (signbit(xml) ? 0.0 : xml);
+        double cem = subR ? xmmr : (signbit(xmr) ? xmr : 0.0);
+        const double wl = subL ? xmml * (2.0 - xml) : (signbit(xml) ? 0.0 : 1.0);
+        const double wr = subR ? -xmmr * (2.0 + xmr) : (signbit(xmr) ? 1.0 : 0.0);
+        if (subL && subR) {
+            const double t = 0.5 * fma(xml, xml, xmr * xmr);
+            const double xmhalf = t > 0.0 ? t * fast_rsqrt(t) : 0.0;
+            const double d1 = xmhalf - 1.0;
+            const double xmc = 0.25 * d1 * d1;
+            const double delp = L.p - R.p;
+            const double dps = delp * fast_rcp(L.p + R.p);
+            const double ad2 = 2.0 * fabs(delp);
+            cep -= xmc * fmax(0.0, 1.0 - fma(ad2, L.ip, dps));
+            cem += xmc * fmax(0.0, 1.0 + fma(-ad2, R.ip, dps));
+        }
+        const double la = fg.len * ahalf;
+        const double fml = la * L.rho * cep;
+        const double fmr = la * R.rho * cem;
+        const double pnet = fma(wl, L.p, wr * R.p);
+        const double px = pnet * fg.dy;    // len*pnet*normx
+        const double py = -pnet * fg.dx;   // len*pnet*normy
+        if constexpr (AXI) {
+            o.parr = py;
+            o.f0 = fg.yf * (fml + fmr);
+            o.f1 = fg.yf * (fma(fml, L.u, fma(fmr, R.u, px)));
+            o.f2 = fg.yf * (fma(fml, L.v, fmr * R.v));
+            o.f3 = fg.yf * (fma(fml, L.h0, fmr * R.h0));
+        } else {
+            o.parr = 0.0;
+            o.f0 = fml + fmr;
+            o.f1 = fma(fml, L.u, fma(fmr, R.u, px));
+            o.f2 = fma(fml, L.v, fma(fmr, R.v, py));
+            o.f3 = fma(fml, L.h0, fmr * R.h0);
+        }
+    }
+    return o;
+}
+
+// ---------------------------------------------------------------- boundary conditions
+// boundary_state + SubsonInflo/SubsonOutfl (BoundaryConditions.cpp:12-190), followed by
+// the ghost's UpdateState temperature clamp (SpatialDiscretization.cpp:39).  O(perimeter)
+// work, so a single (reference-ordered) formulation serves both modes.  Returns false when
+// the ghost must stay unwritten (NaN normal Mach number).
+__device__ __forceinline__ bool boundary_state(const Gas& g, int btype, double normx, double normy,
+                                               const double ui[4], double a_int, double p_int, double v2_int,
+                                               double out[4]) {
+    const double uL = ui[1], vL = ui[2];
+    const double vn = uL * normx + vL * normy;
+    const double mn = vn / a_int;
+    if (btype == -1) btype = 3;
+    if (btype == 0) btype = 4;
+    bool wrote = true;
+    if (btype == 4) {
+        out[0] = ui[0];
+        out[3] = ui[3];
+        out[1] = uL - 2 * vn * normx;
+        out[2] = vL - 2 * vn * normy;
+    } else if (btype == 2) {
+        out[0] = g.p_back / (g.Rs * ui[3]);
+        out[1] = fmax(0.0, ui[1]);
+        out[2] = ui[2];
+        out[3] = ui[3];
+    } else if (btype == 3) {
+        out[0] = ui[0]; out[1] = ui[1]; out[2] = ui[2]; out[3] = ui[3];
+    } else if (btype == 5) {
+        double pFS = g.uFS[0] * g.Rs * g.uFS[3];
+        double pB = pFS - 0.5 * ui[0] * v2_int;
+        if (ui[1] <= 0.0) pB = pFS;
+        out[0] = pB / (g.Rs * g.uFS[3]);
+        out[1] = fmax(ui[1], 0.0);
+        out[2] = ui[2];
+        out[3] = ui[3];
+    } else if (btype == 1) {
+        const double gm1 = g.gam - 1;
+        if (mn <= -1) {
+            out[0] = g.uFS[0]; out[1] = g.uFS[1]; out[2] = g.uFS[2]; out[3] = g.uFS[3];
+        } else if (mn <= 0 && mn > -1) {
+            // far state = free stream, var0 = interior state (BoundaryConditions.cpp:163)
+            double vin = (uL * normx) + (vL * normy);
+            double vfn = (g.uFS[1] * normx) + (g.uFS[2] * normy);
+            double vftx = g.uFS[1] - vfn * normx;
+            double vfty = g.uFS[2] - vfn * normy;
+            double vgn = 0.5 * (vin + vfn) + (1 / gm1) * (a_int - a_int);
+            double cg = a_int + 0.5 * gm1 * (vgn - vfn);
+            out[0] = g.uFS[0] * pow(cg * cg / (a_int * a_int), gm1);
+            double pg = p_int * pow(out[0] / g.uFS[0], g.gam);
+            out[1] = (vftx + vgn * normx);
+            out[2] = (vfty + vgn * normy);
+            out[3] = pg / (out[0] * g.Rs);
+        } else if (mn >= 1) {
+            out[0] = ui[0]; out[1] = ui[1]; out[2] = ui[2]; out[3] = ui[3];
+        } else if (mn > 0 && mn < 1) {
+            double vin = (uL * normx) + (vL * normy);
+            double vfn = (g.uFS[1] * normx) + (g.uFS[2] * normy);
+            double vitx = uL - vin * normx;
+            double vity = vL - vin * normy;
+            double vgn = 0.5 * (vin + vfn) + (1 / gm1) * (a_int - a_int);
+            double cg = a_int + 0.5 * gm1 * (vgn - vfn);
+            out[0] = ui[0] * pow(cg * cg / (a_int * a_int), gm1);
+            double pg = p_int * pow(out[0] / ui[0], g.gam);
+            out[1] = (vitx + vgn * normx);
+            out[2] = (vity + vgn * normy);
+            out[3] = pg / (out[0] * g.Rs);
+        } else {
+            wrote = false;  // NaN normal Mach number
+        }
+    } else {
+        wrote = false;  // unknown code: the reference falls through without writing
+    }
+    if (wrote) out[3] = fmax(out[3], 201.0);
+    return wrote;
+}
+
+// ---------------------------------------------------------------- per-cell solve
+// dv = D^-1 res (Jacobian.cpp:7-47, LUtools.cpp:22-90) and the axisymmetric 1/ycc
+// (main.cpp:325-331).  scale = 1/ycc (AXI) or unused.
+template <bool FAITHFUL, bool AXI>
+__device__ __forceinline__ void solve_cell(double dt, double ycc, double rho, double u, double v, double e0, double Cv,
+                                           double inv_cv, const double r[4], double dv[4], unsigned& flags) {
+    if constexpr (FAITHFUL) {
+        double A[4][4];
+        const double dti = 1.0 / dt;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) A[i][j] = 0.0;
+        A[0][0] = dti * 1.0;
+        A[1][0] = dti * u;
+        A[2][0] = dti * v;
+        A[1][1] = dti * rho;
+        A[2][2] = dti * rho;
+        A[3][0] = dti * e0;
+        A[3][1] = dti * rho * u;
+        A[3][2] = dti * rho * v;
+        A[3][3] = dti * rho * Cv;
+        double b[4] = {r[0], r[1], r[2], r[3]};
+        // partial pivoting with physical row swaps (fully unrolled so A stays in registers)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            double big = 0.0;
+            int imax = i;
+#pragma unroll
+            for (int k = i; k < 4; k++) {
+                double val = fabs(A[k][i]);
+                if (val > big) { big = val; imax = k; }
+            }
+            if (big < 1e-16) flags |= FLAG_SINGULAR;
+#pragma unroll
+            for (int k = i + 1; k < 4; k++) {
+                if (imax == k) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) { double t = A[i][c]; A[i][c] = A[k][c]; A[k][c] = t; }
+                    double t = b[i]; b[i] = b[k]; b[k] = t;
+                }
+            }
+#pragma unroll
+            for (int j = i + 1; j < 4; j++) {
+                A[j][i] /= A[i][i];
+#pragma unroll
+                for (int k = i + 1; k < 4; k++) A[j][k] -= A[j][i] * A[i][k];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            dv[i] = b[i];
+#pragma unroll
+            for (int k = 0; k < i; k++) dv[i] -= A[i][k] * dv[k];
+        }
+#pragma unroll
+        for (int i = 3; i >= 0; i--) {
+#pragma unroll
+            for (int k = i + 1; k < 4; k++) dv[i] -= A[i][k] * dv[k];
+            dv[i] /= A[i][i];
+        }
+        if constexpr (AXI) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) dv[k] *= (1.0 / ycc);
+        }
+    } else {
+        // D is lower triangular: forward substitution in closed form
+        const double irho = fast_rcp(rho);
+        const double d0 = dt * r[0];
+        const double d1 = fma(dt, r[1], -u * d0) * irho;
+        const double d2 = fma(dt, r[2], -v * d0) * irho;
+        const double d3 = (fma(dt, r[3], -e0 * d0) - rho * fma(u, d1, v * d2)) * irho * inv_cv;
+        if constexpr (AXI) {
+            const double s = fast_rcp(ycc);
+            dv[0] = d0 * s; dv[1] = d1 * s; dv[2] = d2 * s; dv[3] = d3 * s;
+        } else {
+            dv[0] = d0; dv[1] = d1; dv[2] = d2; dv[3] = d3;
+        }
+        (void)Cv;
+    }
+}
+
+}  // namespace par2d

@@ -1,0 +1,76 @@
+"""Worker for the multi-rank tests (launched by torch.distributed.run).
+
+  --backend gloo --impl oracle : host-side exchange/partition logic on CPU (world_size 2), the
+                                 oracle standing in for the device library (test infrastructure)
+  --backend nccl --impl gpu    : the real thing, one rank per GPU
+Every rank advances its blocks; each rank then checks the blocks it owns against a
+single-process run of the oracle on the same case: states and the residual history must be
+identical (bitwise for the oracle backend, within tolerance for the CUDA path)."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+from par2d_b200 import Case, Solver, _capi, default_config  # noqa: E402
+from par2d_b200.dist import DistSolver  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--backend", default="gloo")
+    ap.add_argument("--impl", default="oracle")
+    ap.add_argument("--case", default="Case_spikefine24")
+    ap.add_argument("--synthetic", default="")      # e.g. 128x128:4x4
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--tol", type=float, default=0.0)
+    a = ap.parse_args()
+    if a.backend == "nccl":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    dist.init_process_group(a.backend)
+    rank = dist.get_rank()
+    lib = _capi.load_gpu() if a.impl == "gpu" else _capi.load_oracle()
+    orc = _capi.load_oracle()
+
+    def make_case():
+        if a.synthetic:
+            cells, blocks = a.synthetic.split(":")
+            cx, cy = map(int, cells.split("x"))
+            bx, by = map(int, blocks.split("x"))
+            return Case.synthetic_ramp(cx, cy, bx, by)
+        return Case.load(os.path.join(REPO, "tests", "golden", "cases", a.case))
+
+    cfg = default_config(lib)
+    ds = DistSolver(make_case(), cfg, lib=lib)
+    dt, relres = ds.step(a.steps)
+
+    single = Solver(make_case(), default_config(orc), lib=orc)
+    info = single.step(a.steps)
+    ref_rel = np.array([i.relres for i in info])
+    ref_dt = np.array([i.dt for i in info])
+    worst = 0.0
+    for b in ds.owned:
+        got, ref = ds.get_state(b), single.get_state(b)
+        if a.tol == 0.0:
+            assert np.array_equal(got, ref), f"rank {rank}: block {b} differs"
+        for k in range(4):
+            worst = max(worst, np.abs(got[..., k] - ref[..., k]).max() / max(np.abs(ref[..., k]).max(), 1e-300))
+    if a.tol == 0.0:
+        assert np.array_equal(relres, ref_rel) and np.array_equal(dt, ref_dt), (relres, ref_rel)
+    else:
+        assert worst <= a.tol, worst
+        assert np.abs(relres / ref_rel - 1).max() <= 1e-9 and np.abs(dt / ref_dt - 1).max() <= 1e-12
+    owned = len(ds.owned)
+    dist.barrier()
+    print(f"RANK{rank} OK owned={owned} worst={worst:.3e}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
