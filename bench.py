@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- cell-updates/s of the explicit FV residual+update path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU implementation
+
+Workload (config.workload): the synthetic 10-degree ramp mesh of BASELINE.json configs[4], weak
+scaling = 8 blocks of 2048x2048 cells per GPU, so that N = 8 is the full 16k x 16k / 64-block mesh
+and N = 1 is its per-GPU share (4x2 blocks, 33.5 M cells, 1.07 GB of state: larger than the 126 MB
+L2, so no flush between steps is needed).  A "step" is one explicit iteration over all blocks:
+ghost fill + dt, residual assembly (LDFSS fluxes), norms, per-cell solve and update.
+
+One JSON line is printed by rank 0 (see README/DESIGN for the keys).  value = device-timed whole-job
+throughput with state resident in HBM; e2e = the same job through the public C ABI starting from
+pinned HOST buffers (state upload, K steps with the per-step dt/relres log read back, state
+download), all inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+BLOCK = 2048                      # cells per block side (BASELINE.json configs[4]: 64 blocks of 2048^2)
+LAYOUT = {1: (4, 2), 2: (4, 4), 4: (8, 4), 8: (8, 8)}   # blocks in x, y for N GPUs (8 per GPU)
+ALGO_BYTES_PER_CELL = 80          # state read 32 + state write 32 + node coordinates 16
+LAUNCHES_PER_STEP = 3             # ghost_kernel, step_kernel, finalize_kernel (+1 pack_kernel for N > 1)
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks line of /opt/skills/guides/B200_PROFILING.md, sampled during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); power.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference / CPU-baseline leg (the one place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+
+def _pow2_floor(n):
+    p = 1
+    while p * 2 <= n:
+        p *= 2
+    return p
+
+
+def cpu_reference_run(iters: int, warm: int, max_ranks: int = 32):
+    """Times the reference's CPU implementation of the path on the host cores on a bounded sample
+    of the benchmark workload: the same ramp generator scaled down to 128x128-cell blocks, one block
+    per reference MPI rank (the reference is one rank per block, FV/main.cpp:125-128), as many ranks
+    as the box has cores (power of two, <= 32).  With oracle/_ref present the UNMODIFIED reference
+    binary runs (kind "reference"); its step loop is isolated by differencing a `warm`-iteration and a
+    `warm+iters`-iteration run (mesh read, metrics and solution writes are identical in both).
+    Otherwise the oracle port (kind "port") is stepped in-process with OpenMP over blocks."""
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import run_ref
+    from par2d_b200 import Case, Solver, _capi, default_config
+    ncores = os.cpu_count() or 1
+    ranks = min(max_ranks, _pow2_floor(ncores))
+    nbx = 1
+    while nbx * nbx * 2 <= ranks:
+        nbx *= 2
+    nby = ranks // nbx
+    side = 128
+    case = Case.synthetic_ramp(side * nbx, side * nby, nbx, nby)
+    cells = case.ncells
+    sample = (f"synthetic ramp {side * nbx}x{side * nby} cells in {nbx}x{nby} blocks of {side}x{side} (benchmark generator, "
+              f"blocks scaled 16x down per side), {iters} iterations after {warm} warm-up")
+    if run_ref.available():
+        tmp = tempfile.mkdtemp(prefix="par2d_bench_case_")
+        case.write(tmp)
+        shapes = [case.shape(b) for b in range(case.nblocks)]
+        therm = os.path.join(REPO, "tests", "golden", "cases", "therm_air.dat")
+        t_warm = run_ref.run(tmp, therm, shapes, warm)["wall"]
+        t_full = run_ref.run(tmp, therm, shapes, warm + iters)["wall"]
+        dt = max(t_full - t_warm, 1e-9)
+        kind, cores = "reference", min(ranks, ncores)
+        sample += f"; unmodified reference binary, SHIM_NP={ranks} (g++ -O2), step loop = t({warm + iters}) - t({warm})"
+    else:
+        os.environ.setdefault("OMP_NUM_THREADS", str(ranks))
+        orc = _capi.load_oracle()
+        s = Solver(case, default_config(orc), lib=orc)
+        s.step(warm)
+        t0 = time.perf_counter()
+        s.step(iters)
+        dt = time.perf_counter() - t0
+        kind, cores = "port", min(ranks, ncores)
+        sample += f"; oracle port (gcc -O2, OpenMP over blocks, {ranks} threads)"
+    return {"value": cells * iters / dt, "unit": "cell-updates/s", "cores": cores, "kind": kind, "sample": sample,
+            "ms_per_iteration": 1e3 * dt / iters, "sample_cells": cells, "host_cores": ncores}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    inner = 25   # reference iterations per bench "step" so that K steps last seconds, not milliseconds
+    res = cpu_reference_run(iters=args.steps * inner, warm=args.warmup * inner)
+    nbx, nby = LAYOUT[args.gpus]
+    line = {
+        "impl": "reference", "metric": "cell-updates/sec (fp64 residual+update)", "value": res["value"],
+        "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["ms_per_iteration"] * inner, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic 10deg ramp, {nbx * nby} blocks of {BLOCK}x{BLOCK} cells (8 per GPU)",
+                   "reference_step": f"{inner} reference iterations on the bounded sample", "l2": "n/a (CPU)"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+
+def run_gpu_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from par2d_b200 import Case, Solver, _capi, default_config
+    from par2d_b200._capi import StepInfo
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    multi = world > 1
+    if multi:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    gpu = _capi.load_gpu()      # raises when the CUDA library is missing: there is no fallback path
+    nbx, nby = LAYOUT[args.gpus]
+    blk = args.block
+    case = Case.synthetic_ramp(blk * nbx, blk * nby, nbx, nby, nranks=world, rank=rank)
+    total_cells = case.ncells
+    cfg = default_config(gpu)
+    cfg.device = local
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    if multi:
+        from par2d_b200.dist import DistSolver
+        solver = DistSolver(case, cfg, lib=gpu)
+        ctx = solver.solver
+    else:
+        solver = ctx = Solver(case, cfg, lib=gpu)
+        gpu.check(gpu.set_stream(ctx.handle, torch.cuda.current_stream().cuda_stream), "set_stream")
+    h = ctx.handle
+    owned_cells = ctx.owned_cells
+
+    def advance(n):
+        if multi:
+            solver.queue_steps(n)
+            return solver.collect(n)
+        return ctx.step(n)
+
+    # ---- device-resident throughput -------------------------------------------------------
+    advance(args.warmup)
+    gpu.check(gpu.kernel_timing(h, 1), "kernel_timing")
+    sampler = ClockSampler(local) if rank == 0 else None
+    sync_all()
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    info = advance(args.steps)
+    ev1.record()
+    sync_all()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    kms, kn = C.c_double(), C.c_int64()
+    gpu.check(gpu.kernel_time(h, C.byref(kms), C.byref(kn)), "kernel_time")
+    gpu.check(gpu.kernel_timing(h, 0), "kernel_timing")
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    if multi:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    assert all(i.status == 0 for i in info), "device raised an error flag during the timed region"
+    value = total_cells * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the C ABI with pinned host buffers ------------------------------
+    shapes = {b: ctx.get_state(b).shape for b in ctx.owned} if False else None
+    host_bufs = {}
+    for b in ctx.owned:
+        nx, ny = ctx.shapes[b]
+        buf = torch.empty((ny - 1, nx - 1, 4), dtype=torch.float64, pin_memory=True)
+        buf[..., 0], buf[..., 1], buf[..., 2], buf[..., 3] = cfg.uFS[0], cfg.uFS[1], cfg.uFS[2], cfg.uFS[3]
+        host_bufs[b] = buf
+    dp = C.POINTER(C.c_double)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for b, buf in host_bufs.items():
+        gpu.check(gpu.set_state(h, b, C.cast(buf.data_ptr(), dp)), "set_state")
+    einfo = advance(args.steps)                    # per-step dt/relres records are copied back
+    for b, buf in host_bufs.items():
+        gpu.check(gpu.get_state(h, b, C.cast(buf.data_ptr(), dp)), "get_state")
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if multi:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    state_bytes = 32 * total_cells
+    log_bytes = (C.sizeof(StepInfo) + 16 * case.nblocks) * args.steps
+    e2e = {"value": total_cells * args.steps / (e2e_ms * 1e-3), "unit": "cell-updates/s",
+           "h2d_bytes_per_step": state_bytes / args.steps, "d2h_bytes_per_step": (state_bytes + log_bytes) / args.steps,
+           "note": "one job = state upload from pinned host memory + K steps with per-step log read-back + state download; "
+                   "bytes are job totals divided by K"}
+    assert all(i.status == 0 for i in einfo)
+
+    if rank != 0:
+        if multi:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -------------------------------------------------
+    peaks, which = measured_peaks()
+    launches = max(int(kn.value), 1)
+    k_ms = kms.value / launches
+    achieved = ALGO_BYTES_PER_CELL * owned_cells / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(REPO, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("step_kernel_dram_bytes_per_launch")
+    fp64 = C.c_double()
+    gpu.check(gpu.probe_fp64(local, C.byref(fp64)), "probe_fp64")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "traffic": traffic, "kernel": "step_kernel (fused residual+update)", "kernel_ms": k_ms, "kernel_share_of_step": kms.value / elapsed_ms,
+                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which}, burst copy)",
+                "algorithmic_bytes_per_cell": ALGO_BYTES_PER_CELL, "cells_per_launch": owned_cells,
+                "fp64_fma_tflops_measured": fp64.value,
+                "cell_updates_per_s_per_gpu": owned_cells / (k_ms * 1e-3)}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        res = cpu_reference_run(iters=500, warm=25)
+        cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {
+        "metric": "cell-updates/sec (fp64 residual+update)", "value": value, "unit": "cell-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic 10deg ramp, {nbx * nby} blocks of {blk}x{blk} cells (8 per GPU), "
+                               f"{total_cells} cells, IAXI=1, CPG, CFL=0.01 (shipped macros)",
+                   "global_cells": total_cells, "parallelism": f"blocks sharded over {args.gpus} GPU(s), 1 process per GPU",
+                   "l2": "state per GPU 1.07 GB read + 1.07 GB written per step >> 126 MB L2; no flush needed",
+                   "arith_mode": "PAR2D_MODE_FAST"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+        "gpu_launches": (LAUNCHES_PER_STEP + (1 if multi else 0)) * args.steps,
+        "relres_last": info[-1].relres if not multi else None, "dt": info[-1].dt,
+    }
+    print(json.dumps(line), flush=True)
+    if multi:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1, choices=sorted(LAYOUT))
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--block", type=int, default=BLOCK, help="cells per block side (default: the benchmark's 2048)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -225,6 +225,12 @@ int par2d_test_update_state(const par2d_config* cfg, int64_t n, double* unk_inou
 int par2d_test_solve(const par2d_config* cfg, int64_t n, const double* dt_ycc /* {dt,ycc} per i */,
                      const double* unk, const double* res, double* dv);
 
+/* Measurement hook: when enabled, every launch of the dominant (residual+update) kernel is
+ * bracketed by CUDA events on the ctx stream; par2d_kernel_time returns and resets the sum of
+ * their durations and the launch count.  bench.py derives roofline.achieved from it. */
+int par2d_kernel_timing(par2d_ctx* ctx, int32_t enable);
+int par2d_kernel_time(par2d_ctx* ctx, double* total_ms, int64_t* launches);
+
 /* Measured fp64 FMA throughput of the device in TFLOP/s (2 flops per FMA);
  * used by bench.py to report the secondary (fp64-pipe) bound. */
 int par2d_probe_fp64(int32_t device, double* tflops);

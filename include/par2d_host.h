@@ -33,6 +33,11 @@ int par2d_case_load(const char* dir, par2d_case** out);
  * blocks (ids jb*nbx+ib), BCs left=1 right=3 bottom=4 top=4.  The +1e-4 y
  * shift is applied, like the loader does. */
 int par2d_case_synthetic_ramp(int32_t ncx, int32_t ncy, int32_t nbx, int32_t nby, par2d_case** out);
+/* Same mesh, partitioned over nranks (par2d_case_partition rules) with node coordinates
+ * generated only for the blocks rank owns (rank < 0: all) -- a 16k x 16k mesh is 4.3 GB of
+ * coordinates, each process of a multi-GPU run materialises only its share. */
+int par2d_case_synthetic_ramp_ranked(int32_t ncx, int32_t ncy, int32_t nbx, int32_t nby, int32_t nranks, int32_t rank,
+                                     par2d_case** out);
 
 /* Splits a single-block case into nbx x nby blocks with GridPart's rules
  * (ceil slicing, shared node lines, conn tuples); used to test block/halo

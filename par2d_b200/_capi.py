@@ -101,6 +101,8 @@ GPU_ONLY_API = {
     "set_stream": (C.c_int, [C.c_void_p, C.c_uint64]),
     "synchronize": (C.c_int, [C.c_void_p]),
     "probe_fp64": (C.c_int, [C.c_int32, _DP]),
+    "kernel_timing": (C.c_int, [C.c_void_p, C.c_int32]),
+    "kernel_time": (C.c_int, [C.c_void_p, _DP, C.POINTER(C.c_int64)]),
 }
 
 # entry points only the oracle has (test hooks)
@@ -112,6 +114,8 @@ ORACLE_ONLY_API = {
 HOST_API = {
     "par2d_case_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "par2d_case_synthetic_ramp": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "par2d_case_synthetic_ramp_ranked": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                   C.POINTER(C.c_void_p)]),
     "par2d_case_split": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "par2d_case_write": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
     "par2d_case_num_blocks": (C.c_int32, [C.c_void_p]),

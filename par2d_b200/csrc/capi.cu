@@ -153,6 +153,13 @@ struct par2d_ctx {
     long long last_iter0 = 0;
     int pending_steps = 0;  // begin/end mode: steps queued since the last collect
 
+    // measurement hook (par2d_kernel_timing)
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;   // pairs
+    int ev_used = 0;
+    double kernel_ms = 0.0;
+    long long kernel_launches = 0;
+
     StepArgs step_args(int update) const {
         StepArgs a;
         a.blocks = dblk;
@@ -258,7 +265,18 @@ int build_tensor_maps(par2d_ctx* c) {
 void queue_step(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
     StepArgs a = c->step_args(1);
     c->kt->ghost(c->stream, a, c->gas, with_ghost_dt ? 1 : 0);
+    if (c->timing) {
+        if ((int)c->ev.size() < 2 * (c->ev_used + 1)) {
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            c->ev.push_back(e0);
+            c->ev.push_back(e1);
+        }
+        cudaEventRecord(c->ev[2 * c->ev_used], c->stream);
+    }
     c->kt->step(c->stream, a, c->gas, c->tpg, c->axi, c->use_tma);
+    if (c->timing) cudaEventRecord(c->ev[2 * c->ev_used++ + 1], c->stream);
     launch_finalize(c->stream, c->finalize_args(stop_on_tol), c->blk_norm);
     c->cur ^= 1;
 }
@@ -272,6 +290,11 @@ int harvest(par2d_ctx* c, int queued, int cur0, par2d_step_info* info, int ninfo
     CU_TRY(cudaMemcpy(&fl, c->flags, sizeof fl, cudaMemcpyDeviceToHost));
     CU_TRY(cudaMemcpy(&it, c->d_iter, sizeof it, cudaMemcpyDeviceToHost));
     if (done > queued) done = queued;
+    for (int q = 0; q < c->ev_used; q++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev[2 * q], c->ev[2 * q + 1]) == cudaSuccess) { c->kernel_ms += ms; c->kernel_launches++; }
+    }
+    c->ev_used = 0;
     c->cur = cur0 ^ (done & 1);
     c->last_iter0 = c->iter;
     c->iter = it;
@@ -548,6 +571,7 @@ int par2d_destroy(par2d_ctx* c) {
     cudaFree(c->dblk); cudaFree(c->dtmaps); cudaFree(c->dt_table); cudaFree(c->partials); cudaFree(c->flags);
     cudaFree(c->stop); cudaFree(c->d_iter); cudaFree(c->hist_pos); cudaFree(c->ticket); cudaFree(c->res0);
     cudaFree(c->blk_norm); cudaFree(c->blk_hist); cudaFree(c->step_hist); cudaFree(c->staging); cudaFree(c->dlines);
+    for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -700,6 +724,23 @@ int par2d_set_stream(par2d_ctx* c, uint64_t stream) {
         c->stream = reinterpret_cast<cudaStream_t>(stream);
         c->own_stream = false;
     }
+    return 0;
+}
+
+int par2d_kernel_timing(par2d_ctx* c, int32_t enable) {
+    if (!c) return fail(PAR2D_ERR_ARG, "kernel_timing: null ctx");
+    c->timing = enable != 0;
+    c->kernel_ms = 0.0;
+    c->kernel_launches = 0;
+    return 0;
+}
+
+int par2d_kernel_time(par2d_ctx* c, double* total_ms, int64_t* launches) {
+    if (!c) return fail(PAR2D_ERR_ARG, "kernel_time: null ctx");
+    if (total_ms) *total_ms = c->kernel_ms;
+    if (launches) *launches = c->kernel_launches;
+    c->kernel_ms = 0.0;
+    c->kernel_launches = 0;
     return 0;
 }
 

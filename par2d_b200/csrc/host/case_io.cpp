@@ -169,23 +169,31 @@ static void ramp_node(int ncx, int ncy, int I, int J, double* x, double* y) {
 }
 
 int par2d_case_synthetic_ramp(int32_t ncx, int32_t ncy, int32_t nbx, int32_t nby, par2d_case** out) {
+    return par2d_case_synthetic_ramp_ranked(ncx, ncy, nbx, nby, 1, -1, out);
+}
+
+int par2d_case_synthetic_ramp_ranked(int32_t ncx, int32_t ncy, int32_t nbx, int32_t nby, int32_t nranks, int32_t rank,
+                                     par2d_case** out) {
     if (!out || ncx < 1 || ncy < 1 || nbx < 1 || nby < 1 || ncx % nbx || ncy % nby)
         return host_fail(PAR2D_ERR_ARG, "synthetic_ramp: cells must divide evenly into blocks");
+    if (nranks < 1 || rank >= nranks) return host_fail(PAR2D_ERR_ARG, "synthetic_ramp: bad rank");
     std::unique_ptr<par2d_case> cs(new par2d_case);
     cs->blocks.resize((size_t)nbx * nby);
     cs->grid_nbx = nbx;
     cs->grid_nby = nby;
     const int bx = ncx / nbx, by = ncy / nby;
+    for (Block& b : cs->blocks) { b.nx = bx + 1; b.ny = by + 1; }
+    if (int rc = par2d_case_partition(cs.get(), nranks)) return rc;
     for (int jb = 0; jb < nby; jb++)
         for (int ib = 0; ib < nbx; ib++) {
             Block& b = cs->blocks[(size_t)jb * nbx + ib];
-            b.nx = bx + 1;
-            b.ny = by + 1;
-            b.x.resize((size_t)b.nx * b.ny);
-            b.y.resize((size_t)b.nx * b.ny);
-            for (int j = 0; j < b.ny; j++)
-                for (int i = 0; i < b.nx; i++)
-                    ramp_node(ncx, ncy, ib * bx + i, jb * by + j, &b.x[(size_t)j * b.nx + i], &b.y[(size_t)j * b.nx + i]);
+            if (rank < 0 || b.owner == rank) {
+                b.x.resize((size_t)b.nx * b.ny);
+                b.y.resize((size_t)b.nx * b.ny);
+                for (int j = 0; j < b.ny; j++)
+                    for (int i = 0; i < b.nx; i++)
+                        ramp_node(ncx, ncy, ib * bx + i, jb * by + j, &b.x[(size_t)j * b.nx + i], &b.y[(size_t)j * b.nx + i]);
+            }
             const int code_left = ib == 0 ? 1 : -1, code_right = ib == nbx - 1 ? 3 : -1;
             const int code_bot = jb == 0 ? 4 : -1, code_top = jb == nby - 1 ? 4 : -1;
             b.ibound.clear();
@@ -297,9 +305,9 @@ int par2d_case_block(const par2d_case* c, int32_t b, par2d_block_desc* out) {
     memset(out, 0, sizeof *out);
     out->nx = k.nx;
     out->ny = k.ny;
-    out->x = k.x.data();
-    out->y = k.y.data();
-    out->ibound = k.ibound.data();
+    out->x = k.x.empty() ? nullptr : k.x.data();
+    out->y = k.y.empty() ? nullptr : k.y.data();
+    out->ibound = k.ibound.empty() ? nullptr : k.ibound.data();
     for (int s = 0; s < 4; s++) {
         out->bid[s] = k.bid[s];
         out->bbound[s] = k.bbound[s];

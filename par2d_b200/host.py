@@ -30,10 +30,12 @@ class Case:
         return cls(h)
 
     @classmethod
-    def synthetic_ramp(cls, ncx: int, ncy: int, nbx: int, nby: int) -> "Case":
+    def synthetic_ramp(cls, ncx: int, ncy: int, nbx: int, nby: int, nranks: int = 1, rank: int = -1) -> "Case":
+        """rank >= 0: node coordinates only for the blocks that rank owns under partition(nranks)."""
         lib = _capi.load_host()
         h = C.c_void_p()
-        lib.check(lib.par2d_case_synthetic_ramp(ncx, ncy, nbx, nby, C.byref(h)), "case_synthetic_ramp")
+        lib.check(lib.par2d_case_synthetic_ramp_ranked(ncx, ncy, nbx, nby, nranks, rank, C.byref(h)),
+                  "case_synthetic_ramp")
         return cls(h)
 
     def split(self, nbx: int, nby: int) -> "Case":

@@ -1,0 +1,292 @@
+"""Parity tests proper: the CUDA path (through the C ABI, libpar2d_gpu.so) against the oracle on the
+same inputs, against the committed golden fixtures, and - at the benchmark's full block size -
+through size-independent properties.
+
+Bars:
+  PAR2D_MODE_FAST     state max|d|/max|var| <= 1e-11 after N steps, residual history <= 1e-9 relative
+  PAR2D_MODE_FAITHFUL state BIT-IDENTICAL wherever pow() is not involved (the forward-step cases);
+                      <= 1e-13 where subsonic far-field BCs call pow (CUDA pow is not correctly rounded)
+  block / halo indexing: bit-exact (split-invariance tests below)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import case_path, load_golden, make_cfg, random_faces, random_states, state_err
+import pointwise as pw
+from par2d_b200 import MODE_FAITHFUL, MODE_FAST, Case, Solver
+
+pytestmark = pytest.mark.gpu
+
+TOL_STATE = 1e-11
+TOL_HIST = 1e-9
+
+
+# ------------------------------------------------------------------ point-wise device functions
+
+@pytest.mark.parametrize("iaxi,igam", [(1, 1.4), (0, 1.4), (1, -1.4)])
+@pytest.mark.parametrize("mode", [MODE_FAST, MODE_FAITHFUL])
+def test_pointwise_device_functions(gpu, oracle, iaxi, igam, mode):
+    rng = np.random.default_rng(1234)
+    n = 20000
+    cfg_g, cfg_o = make_cfg(gpu, iaxi, igam, mode), make_cfg(oracle, iaxi, igam)
+    uL, uR, face = random_states(rng, n), random_states(rng, n), random_faces(rng, n)
+    uR[: n // 3] = uL[: n // 3] * rng.uniform(0.9, 1.1, (n // 3, 4))
+    uL[: n // 3, 1:3] *= 0.1
+    uR[: n // 3, 1:3] *= 0.1
+    exact = mode == MODE_FAITHFUL
+
+    ug, dg = pw.update_state(gpu, cfg_g, uL)
+    uo, do = pw.update_state(oracle, cfg_o, uL)
+    assert np.array_equal(ug, uo)
+    if exact:
+        assert np.array_equal(dg, do)
+    else:
+        assert np.abs(dg / do - 1).max() < 1e-14
+
+    fg, pg = pw.ldfss(gpu, cfg_g, face, uL, uR)
+    fo, po = pw.ldfss(oracle, cfg_o, face, uL, uR)
+    if exact:
+        assert np.array_equal(fg, fo) and np.array_equal(pg, po)
+    else:
+        scale = np.abs(fo).max(axis=1, keepdims=True) + 1e-300
+        assert (np.abs(fg - fo) / scale).max() < 5e-13
+        assert (np.abs(pg - po) / (np.abs(po) + scale[:, 0])).max() < 5e-13
+
+    btype = rng.choice([-1, 0, 1, 2, 3, 4, 5], n).astype(np.int32)
+    ui = uL.copy()
+    ui[::2, 1:3] *= 0.05
+    gg = pw.boundary_state(gpu, cfg_g, btype, face[:, :2], ui)
+    go = pw.boundary_state(oracle, cfg_o, btype, face[:, :2], ui)
+    nopow = btype != 1
+    if exact:
+        assert np.array_equal(gg[nopow], go[nopow])
+    assert np.abs(gg - go).max() / np.abs(go).max() < 1e-12
+    assert (np.abs(gg / np.where(go == 0, 1, go) - 1)[go != 0]).max() < 1e-11
+
+    res = rng.normal(0, 1e3, (n, 4))
+    dty = np.stack([rng.uniform(1e-9, 1e-6, n), rng.uniform(1e-4, 1.0, n)], axis=1)
+    vg = pw.solve(gpu, cfg_g, dty, uL, res)
+    vo = pw.solve(oracle, cfg_o, dty, uL, res)
+    if exact:
+        assert np.array_equal(vg, vo)
+    else:
+        # compare the update relative to the state it is added to
+        assert (np.abs(vg - vo) / np.abs(uL)).max() < 1e-12
+
+
+# ------------------------------------------------------------------ residual (= calc_dudt)
+
+@pytest.mark.parametrize("name,iaxi,igam", [("Case_ffstep1", 1, 1.4), ("Case_ffstep8", 0, 1.4), ("Case_rktnoz9", 1, -1.4)])
+@pytest.mark.parametrize("mode", [MODE_FAST, MODE_FAITHFUL])
+def test_residual_matches_oracle(gpu, oracle, name, iaxi, igam, mode):
+    case = Case.load(case_path(name))
+    dev = Solver(case, make_cfg(gpu, iaxi, igam, mode), lib=gpu)
+    orc = Solver(case, make_cfg(oracle, iaxi, igam), lib=oracle)
+    # a perturbed state so that every flux branch is exercised
+    rng = np.random.default_rng(7)
+    for b in range(case.nblocks):
+        u = orc.get_state(b)
+        u *= rng.uniform(0.8, 1.2, u.shape)
+        u[..., 2] += rng.uniform(-300, 300, u.shape[:2])
+        u[::3, ::2, 1] *= 0.1
+        dev.set_state(b, u)
+        orc.set_state(b, u)
+    for b in range(case.nblocks):
+        rd, ro = dev.get_residual(b), orc.get_residual(b)
+        if mode == MODE_FAITHFUL and igam > 0 and name != "Case_rktnoz9":
+            assert np.array_equal(rd, ro), f"block {b}"
+        else:
+            scale = np.abs(ro).reshape(-1, 4).max(axis=0)
+            assert (np.abs(rd - ro).reshape(-1, 4).max(axis=0) / scale).max() < 1e-11, f"block {b}"
+
+
+# ------------------------------------------------------------------ N-step parity on the shipped configurations
+
+RUNS = [
+    ("Case_ffstep1", "axi_cpg", 60), ("Case_ffstep8", "axi_cpg", 200), ("Case_ffstep8", "planar_cpg", 100),
+    ("Case_rktnoz9", "axi_cpg", 200), ("Case_rktnoz9", "axi_tpg", 200), ("Case_spikefine24", "axi_cpg", 200),
+]
+
+
+@pytest.mark.parametrize("name,variant,steps", RUNS)
+@pytest.mark.parametrize("mode", [MODE_FAST, MODE_FAITHFUL])
+def test_nstep_state_and_history_vs_reference_golden(gpu, name, variant, steps, mode):
+    """Against fixtures produced by the UNMODIFIED reference (tests/golden/make_golden.py)."""
+    g = load_golden(name, variant)
+    case = Case.load(case_path(name))
+    dev = Solver(case, make_cfg(gpu, int(g["iaxi"]), float(g["igam"]), mode), lib=gpu)
+    info = dev.step(steps)
+    assert len(info) == steps and all(i.status == 0 for i in info)
+    worst = max(state_err(dev.get_state(b), g[f"b{b}"]) for b in range(case.nblocks))
+    if mode == MODE_FAITHFUL and name.startswith("Case_ffstep"):
+        for b in range(case.nblocks):
+            assert np.array_equal(dev.get_state(b), g[f"b{b}"]), f"block {b} not bit-identical"
+    else:
+        assert worst <= (1e-13 if mode == MODE_FAITHFUL else TOL_STATE), worst
+    # the reference prints 7 significant digits of relres and 5 of dt
+    rel = np.array([i.relres for i in info])
+    dts = np.array([i.dt for i in info])
+    assert np.abs(rel / g["relres"] - 1).max() < 1e-6
+    assert np.abs(dts / g["dt"] - 1).max() < 1e-4
+    assert ["%le" % v for v in rel] == ["%le" % v for v in g["relres"]]
+
+
+@pytest.mark.parametrize("name,iaxi,igam,steps", [("Case_ffstep8", 1, 1.4, 1000), ("Case_rktnoz9", 1, -1.4, 1000),
+                                                   ("Case_spikefine24", 1, 1.4, 1000)])
+def test_1000_steps_vs_oracle(gpu, oracle, name, iaxi, igam, steps):
+    """The bar of BASELINE.md section 5: N = 1000 steps, per-variable max|d|/max|var| <= 1e-11,
+    residual history <= 1e-9 relative."""
+    case = Case.load(case_path(name))
+    dev = Solver(case, make_cfg(gpu, iaxi, igam, MODE_FAST), lib=gpu)
+    orc = Solver(case, make_cfg(oracle, iaxi, igam), lib=oracle)
+    di, oi = dev.step(steps), orc.step(steps)
+    worst = max(state_err(dev.get_state(b), orc.get_state(b)) for b in range(case.nblocks))
+    assert worst <= TOL_STATE, worst
+    rel = np.array([a.relres / b.relres for a, b in zip(di, oi)])
+    assert np.abs(rel - 1).max() <= TOL_HIST
+    dts = np.array([a.dt / b.dt for a, b in zip(di, oi)])
+    assert np.abs(dts - 1).max() <= 1e-12
+
+
+def test_committed_res_tec_of_the_reference(gpu):
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "ref_committed_res_ffstep8.tec")) as f:
+        lines = f.read().splitlines()[1:]
+    dev = Solver(Case.load(case_path("Case_ffstep8")), make_cfg(gpu), lib=gpu)
+    info = dev.step(2000)
+    assert ["%d,\t%le" % (i.iter, i.relres) for i in info] == lines[:2000]
+
+
+# ------------------------------------------------------------------ block / halo indexing: bit-exact
+
+def _perturbed(shape, seed):
+    rng = np.random.default_rng(seed)
+    u = np.empty(shape)
+    u[..., 0] = rng.uniform(0.005, 0.05, shape[:2])
+    u[..., 1] = rng.uniform(-500, 2500, shape[:2])
+    u[..., 2] = rng.uniform(-800, 800, shape[:2])
+    u[..., 3] = rng.uniform(210, 1500, shape[:2])
+    return u
+
+
+def _assert_residual_split_invariant(gpu, whole, parts, nbx, nby, mode, seed):
+    """calc_dudt on the same (random) field, unsplit vs split: every bit must agree, because ghost
+    lines filled from neighbour blocks carry exactly the cells the unsplit stencil reads.  (N-step
+    states are NOT comparable across decompositions by design: main.cpp:276 takes dt as the max
+    over blocks of a per-block quantity.)"""
+    a = Solver(whole, make_cfg(gpu, mode=mode), lib=gpu)
+    b = Solver(parts, make_cfg(gpu, mode=mode), lib=gpu)
+    full = _perturbed(a.get_state(0).shape, seed)
+    a.set_state(0, full)
+    j0 = 0
+    where = {}
+    for jb in range(nby):
+        i0 = 0
+        for ib in range(nbx):
+            k = jb * nbx + ib
+            h, w = b.get_state(k).shape[:2]
+            b.set_state(k, full[j0:j0 + h, i0:i0 + w])
+            where[k] = (j0, i0, h, w)
+            i0 += w
+        j0 += h
+    ra = a.get_residual(0)
+    for k, (j0, i0, h, w) in where.items():
+        assert np.array_equal(b.get_residual(k), ra[j0:j0 + h, i0:i0 + w]), f"block {k}"
+
+
+@pytest.mark.parametrize("mode", [MODE_FAST, MODE_FAITHFUL])
+@pytest.mark.parametrize("split", [(4, 2), (3, 5), (1, 7)])
+def test_split_invariance_bitwise(gpu, mode, split):
+    one = Case.load(case_path("Case_ffstep1"))
+    _assert_residual_split_invariant(gpu, one, one.split(*split), split[0], split[1], mode, seed=11)
+
+
+def test_set_get_state_roundtrip_and_clamp(gpu):
+    case = Case.load(case_path("Case_rktnoz9"))
+    dev = Solver(case, make_cfg(gpu), lib=gpu)
+    rng = np.random.default_rng(3)
+    for b in (0, 4, 8):
+        u = random_states(rng, dev.ncells_block(b)).reshape(dev.get_state(b).shape)
+        u[0, 0, 3] = 150.0                    # below the 201 K clamp of UpdateState
+        dev.set_state(b, u)
+        back = dev.get_state(b)
+        u[0, 0, 3] = 201.0
+        assert np.array_equal(back, u)
+
+
+def test_device_error_flags(gpu):
+    case = Case.load(case_path("Case_ffstep8"))
+    dev = Solver(case, make_cfg(gpu), lib=gpu)
+    u = dev.get_state(0)
+    u[3, 3, 0] = 1e-12
+    u[3, 3, 1] = 9000.0
+    dev.set_state(0, u)
+    info = dev.step(200, check=False)
+    assert info[-1].status != 0
+
+
+def test_stop_on_tol(gpu, oracle):
+    case = Case.load(case_path("Case_ffstep8"))
+    cfg = make_cfg(gpu)
+    cfg.tol = 0.9999
+    dev = Solver(case, cfg, lib=gpu)
+    info = dev.step(50, stop_on_tol=True)
+    assert len(info) == 2 and info[-1].relres < cfg.tol and dev.iteration == 2
+    # state is the one after the converged iteration
+    ocfg = make_cfg(oracle)
+    orc = Solver(case, ocfg, lib=oracle)
+    orc.step(2)
+    assert max(state_err(dev.get_state(b), orc.get_state(b)) for b in range(8)) < 1e-13
+
+
+def test_tma_and_plain_load_paths_agree_bitwise(gpu):
+    case = Case.load(case_path("Case_spikefine24"))
+    a = Solver(case, make_cfg(gpu), lib=gpu)
+    os.environ["PAR2D_NO_TMA"] = "1"
+    try:
+        b = Solver(case, make_cfg(gpu), lib=gpu)
+    finally:
+        del os.environ["PAR2D_NO_TMA"]
+    a.step(50)
+    b.step(50)
+    for k in range(case.nblocks):
+        assert np.array_equal(a.get_state(k), b.get_state(k))
+
+
+# ------------------------------------------------------------------ benchmark-size properties
+
+def test_synthetic_small_vs_oracle(gpu, oracle):
+    case = Case.synthetic_ramp(256, 256, 4, 4)
+    dev = Solver(case, make_cfg(gpu), lib=gpu)
+    orc = Solver(case, make_cfg(oracle), lib=oracle)
+    di, oi = dev.step(100), orc.step(100)
+    worst = max(state_err(dev.get_state(b), orc.get_state(b)) for b in range(16))
+    assert worst <= TOL_STATE, worst
+    assert max(abs(a.relres / b.relres - 1) for a, b in zip(di, oi)) <= TOL_HIST
+
+
+def test_full_size_blocks_decomposition_invariance(gpu):
+    """At the benchmark's block size (2048^2 cells per block, BASELINE.json configs[4]) the oracle
+    needs minutes per step; instead check the size-independent property that the residual does not
+    depend on the decomposition: one 4096x2048-cell block vs 2x1 blocks of 2048^2 vs 4x2 blocks of
+    1024^2, bit for bit."""
+    whole = Case.synthetic_ramp(4096, 2048, 1, 1)
+    _assert_residual_split_invariant(gpu, whole, Case.synthetic_ramp(4096, 2048, 2, 1), 2, 1, MODE_FAST, seed=5)
+    _assert_residual_split_invariant(gpu, whole, Case.synthetic_ramp(4096, 2048, 4, 2), 4, 2, MODE_FAST, seed=5)
+
+
+def test_full_size_fast_vs_faithful(gpu):
+    """2x2 blocks of 2048^2 cells, 20 steps: the tuned kernel against the reference-ordered kernel
+    (itself bit-identical to the reference on the shipped forward-step cases)."""
+    case = Case.synthetic_ramp(4096, 4096, 2, 2)
+    fast = Solver(case, make_cfg(gpu, mode=MODE_FAST), lib=gpu)
+    slow = Solver(case, make_cfg(gpu, mode=MODE_FAITHFUL), lib=gpu)
+    fi, si = fast.step(20), slow.step(20)
+    assert all(i.status == 0 for i in fi + si)
+    worst = max(state_err(fast.get_state(b), slow.get_state(b)) for b in range(4))
+    assert worst <= TOL_STATE, worst
+    assert max(abs(a.relres / b.relres - 1) for a, b in zip(fi, si)) <= TOL_HIST
+    assert all(a.dt == b.dt for a, b in zip(fi[:1], si[:1]))
