@@ -75,7 +75,9 @@ def run(case_dir: str, therm_path: str, shapes, niter: int, iaxi: int = 1, igam:
     wall = time.perf_counter() - t0
     if proc.returncode != 0:
         raise RuntimeError(f"reference run failed rc={proc.returncode}: {proc.stdout[-2000:]} {proc.stderr[-2000:]}")
-    dts = [float(m.group(1)) for m in re.finditer(r"^Iter:\s*\d+\s+dt:\s*(\S+)", proc.stdout, re.M)]
+    # only rank 0 prints the iteration line, but the ranks share one pipe and their start-up chatter
+    # can land in the middle of it: accept complete %7.4e fields only
+    dts = [float(m.group(1)) for m in re.finditer(r"^Iter:\s*\d+\s+dt:\s*(\d\.\d{4}e[+-]\d{2,3})(?=\s)", proc.stdout, re.M)]
     relres = []
     with open(os.path.join(run_dir, "Outputs", "res.tec")) as f:
         next(f)

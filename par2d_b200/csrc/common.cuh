@@ -23,6 +23,7 @@ constexpr int TX = 32;
 constexpr int TY = 8;
 constexpr int STEP_THREADS = TX * TY;
 constexpr int HX = TX + 2, HY = TY + 2;  // haloed tile
+constexpr int HOFF = 1, HXL = HX + 2;    // staged width: the copy starts HOFF columns early (16-byte rule)
 
 enum : int { SIDE_BOTTOM = 0, SIDE_RIGHT = 1, SIDE_TOP = 2, SIDE_LEFT = 3 };
 enum : int { NB_NONE = 0, NB_LOCAL = 1, NB_REMOTE = 2 };

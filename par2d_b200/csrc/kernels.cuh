@@ -54,6 +54,10 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int c0,
         : "memory");
 }
 
+__device__ __forceinline__ void tmap_acquire(const void* tmap) {
+    asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
+}
+
 // ------------------------------------------------------------------ small helpers
 // (col,row) in the padded arrays of the n-th cell along a side of a block
 __device__ __forceinline__ void edge_cell_pos(int ncx, int ncy, int side, int n, int& col, int& row) {
@@ -172,8 +176,11 @@ __global__ void __launch_bounds__(256) pack_kernel(StepArgs a, Gas g, const Send
 
 // ------------------------------------------------------------------ the step kernel
 struct StepSmem {
-    double U[4][HY][HX];   // TMA destination: rho,u,v,T with halo
-    double N[2][HY][HX];   // TMA destination: node x,y
+    // TMA destinations.  The box starts one column left of the halo (HOFF) because a tiled copy of
+    // 8-byte elements must start on a 16-byte boundary (odd start columns raise an illegal-instruction
+    // fault on sm_100a, see tools/tma_probe): halo column hx lives at [hx + HOFF].
+    double U[4][HY][HXL];  // rho,u,v,T with halo
+    double N[2][HY][HXL];  // node x,y
     double P[HY][HX], A[HY][HX], H[HY][HX], I[HY][HX];  // p, a, h0, 1/p per halo cell
     double F[5][TY][TX + 1];   // i-face fluxes + parr
     double G[5][TY + 1][TX];   // j-face fluxes + parr
@@ -206,15 +213,18 @@ __global__ void __launch_bounds__(STEP_THREADS, 2) step_kernel(const StepArgs a,
         __syncthreads();
         if (tid == 0) {
             const char* maps = static_cast<const char*>(a.tmaps) + (size_t)k * 3 * 128;
+            // descriptors live in global memory: make them visible to the tensor-map proxy
+            tmap_acquire(maps + a.cur * 128);
+            tmap_acquire(maps + 2 * 128);
             mbar_expect_tx(&sm.bar, (uint32_t)(sizeof(sm.U) + sizeof(sm.N)));
-            tma_load_3d(&sm.U[0][0][0], maps + a.cur * 128, i0 + COL0 - 1, j0, 0, &sm.bar);
-            tma_load_3d(&sm.N[0][0][0], maps + 2 * 128, i0 + COL0 - 1, j0, 0, &sm.bar);
+            tma_load_3d(&sm.U[0][0][0], maps + a.cur * 128, i0 + COL0 - 1 - HOFF, j0, 0, &sm.bar);
+            tma_load_3d(&sm.N[0][0][0], maps + 2 * 128, i0 + COL0 - 1 - HOFF, j0, 0, &sm.bar);
         }
     } else {
         const int rows = ncy + 2;
-        for (int idx = tid; idx < 6 * HY * HX; idx += STEP_THREADS) {
-            const int pl = idx / (HY * HX), rem = idx % (HY * HX), hy = rem / HX, hx = rem % HX;
-            const int col = i0 + COL0 - 1 + hx, row = j0 + hy;
+        for (int idx = tid; idx < 6 * HY * HXL; idx += STEP_THREADS) {
+            const int pl = idx / (HY * HXL), rem = idx % (HY * HXL), hy = rem / HXL, hx = rem % HXL;
+            const int col = i0 + COL0 - 1 - HOFF + hx, row = j0 + hy;
             const bool in = col < pitch && row < rows;
             double val = 0.0;
             if (in) val = pl < 4 ? Sin[pl * plane + (long long)row * pitch + col] : b.nodes[(pl - 4) * plane + (long long)row * pitch + col];
@@ -243,7 +253,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 2) step_kernel(const StepArgs a,
         const bool xin = gi >= 0 && gi < ncx, yin = gj >= 0 && gj < ncy;
         const bool real = (xin && gj >= -1 && gj <= ncy) || (yin && gi >= -1 && gi <= ncx);
         unsigned fl = 0;
-        const FaceState s = face_state<FAITHFUL, TPG>(g, sm.U[0][hy][hx], sm.U[1][hy][hx], sm.U[2][hy][hx], sm.U[3][hy][hx], fl);
+        const FaceState s = face_state<FAITHFUL, TPG>(g, sm.U[0][hy][hx + HOFF], sm.U[1][hy][hx + HOFF], sm.U[2][hy][hx + HOFF], sm.U[3][hy][hx + HOFF], fl);
         sm.P[hy][hx] = s.p; sm.A[hy][hx] = s.a; sm.H[hy][hx] = s.h0; sm.I[hy][hx] = s.ip;
         if (real) flags |= fl;
     }
@@ -251,7 +261,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 2) step_kernel(const StepArgs a,
 
     auto load_state = [&](int hx, int hy) {
         FaceState s;
-        s.rho = sm.U[0][hy][hx]; s.u = sm.U[1][hy][hx]; s.v = sm.U[2][hy][hx];
+        s.rho = sm.U[0][hy][hx + HOFF]; s.u = sm.U[1][hy][hx + HOFF]; s.v = sm.U[2][hy][hx + HOFF];
         s.p = sm.P[hy][hx]; s.a = sm.A[hy][hx]; s.h0 = sm.H[hy][hx]; s.ip = sm.I[hy][hx];
         return s;
     };
@@ -260,23 +270,23 @@ __global__ void __launch_bounds__(STEP_THREADS, 2) step_kernel(const StepArgs a,
     const int hx = tx + 1, hy = ty + 1;
     const FaceState own = load_state(hx, hy);
     {   // face between cell (i-1,j) [left state] and (i,j): node (i,j) -> (i,j+1)
-        const FaceGeom fg = face_geom<FAITHFUL>(sm.N[0][hy][hx], sm.N[1][hy][hx], sm.N[0][hy + 1][hx], sm.N[1][hy + 1][hx]);
+        const FaceGeom fg = face_geom<FAITHFUL>(sm.N[0][hy][hx + HOFF], sm.N[1][hy][hx + HOFF], sm.N[0][hy + 1][hx + HOFF], sm.N[1][hy + 1][hx + HOFF]);
         const Flux f = ldfss<FAITHFUL, AXI>(fg, load_state(hx - 1, hy), own);
         sm.F[0][ty][tx] = f.f0; sm.F[1][ty][tx] = f.f1; sm.F[2][ty][tx] = f.f2; sm.F[3][ty][tx] = f.f3; sm.F[4][ty][tx] = f.parr;
     }
     {   // face between cell (i,j) [left state = upper cell] and (i,j-1): node (i,j) -> (i+1,j)
-        const FaceGeom fg = face_geom<FAITHFUL>(sm.N[0][hy][hx], sm.N[1][hy][hx], sm.N[0][hy][hx + 1], sm.N[1][hy][hx + 1]);
+        const FaceGeom fg = face_geom<FAITHFUL>(sm.N[0][hy][hx + HOFF], sm.N[1][hy][hx + HOFF], sm.N[0][hy][hx + 1 + HOFF], sm.N[1][hy][hx + 1 + HOFF]);
         const Flux f = ldfss<FAITHFUL, AXI>(fg, own, load_state(hx, hy - 1));
         sm.G[0][ty][tx] = f.f0; sm.G[1][ty][tx] = f.f1; sm.G[2][ty][tx] = f.f2; sm.G[3][ty][tx] = f.f3; sm.G[4][ty][tx] = f.parr;
     }
     if (tid < TY) {   // closing column of i-faces (warp 0)
         const int r = tid + 1;
-        const FaceGeom fg = face_geom<FAITHFUL>(sm.N[0][r][TX + 1], sm.N[1][r][TX + 1], sm.N[0][r + 1][TX + 1], sm.N[1][r + 1][TX + 1]);
+        const FaceGeom fg = face_geom<FAITHFUL>(sm.N[0][r][TX + 1 + HOFF], sm.N[1][r][TX + 1 + HOFF], sm.N[0][r + 1][TX + 1 + HOFF], sm.N[1][r + 1][TX + 1 + HOFF]);
         const Flux f = ldfss<FAITHFUL, AXI>(fg, load_state(TX, r), load_state(TX + 1, r));
         sm.F[0][tid][TX] = f.f0; sm.F[1][tid][TX] = f.f1; sm.F[2][tid][TX] = f.f2; sm.F[3][tid][TX] = f.f3; sm.F[4][tid][TX] = f.parr;
     } else if (tid >= 32 && tid < 32 + TX) {   // closing row of j-faces (warp 1)
         const int c = tid - 32 + 1;
-        const FaceGeom fg = face_geom<FAITHFUL>(sm.N[0][TY + 1][c], sm.N[1][TY + 1][c], sm.N[0][TY + 1][c + 1], sm.N[1][TY + 1][c + 1]);
+        const FaceGeom fg = face_geom<FAITHFUL>(sm.N[0][TY + 1][c + HOFF], sm.N[1][TY + 1][c + HOFF], sm.N[0][TY + 1][c + 1 + HOFF], sm.N[1][TY + 1][c + 1 + HOFF]);
         const Flux f = ldfss<FAITHFUL, AXI>(fg, load_state(c, TY + 1), load_state(c, TY));
         sm.G[0][TY][c - 1] = f.f0; sm.G[1][TY][c - 1] = f.f1; sm.G[2][TY][c - 1] = f.f2; sm.G[3][TY][c - 1] = f.f3; sm.G[4][TY][c - 1] = f.parr;
     }
@@ -287,10 +297,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 2) step_kernel(const StepArgs a,
     const bool valid = i < ncx && j < ncy;
     double sq[4] = {0.0, 0.0, 0.0, 0.0};
     if (valid) {
-        const double x1 = sm.N[0][hy][hx], x2 = sm.N[0][hy][hx + 1], x3 = sm.N[0][hy + 1][hx + 1], x4 = sm.N[0][hy + 1][hx];
-        const double y1 = sm.N[1][hy][hx], y2 = sm.N[1][hy][hx + 1], y3 = sm.N[1][hy + 1][hx + 1], y4 = sm.N[1][hy + 1][hx];
-        // MeshModule.cpp:34-40
-        const double vol = fabs(0.5 * (x1 * y2 + x2 * y3 + x3 * y4 + x4 * y1 - x2 * y1 - x3 * y2 - x4 * y3 - x1 * y4));
+        const double x1 = sm.N[0][hy][hx + HOFF], x2 = sm.N[0][hy][hx + 1 + HOFF], x3 = sm.N[0][hy + 1][hx + 1 + HOFF], x4 = sm.N[0][hy + 1][hx + HOFF];
+        const double y1 = sm.N[1][hy][hx + HOFF], y2 = sm.N[1][hy][hx + 1 + HOFF], y3 = sm.N[1][hy + 1][hx + 1 + HOFF], y4 = sm.N[1][hy + 1][hx + HOFF];
+        const double vol = cell_volume(x1, y1, x2, y2, x3, y3, x4, y4);
         const double ycc = 0.25 * (y1 + y2 + y3 + y4);
         const double yc = AXI ? ycc : 0.0;
         double r[4];
@@ -333,7 +342,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 2) step_kernel(const StepArgs a,
             o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[3];
         }
         if (a.update) {
-            const double T = sm.U[3][hy][hx];
+            const double T = sm.U[3][hy][hx + HOFF];
             const double v2 = own.u * own.u + own.v * own.v;
             unsigned fl2 = 0;
             const double h = enthalpy<TPG>(g, T, fl2);

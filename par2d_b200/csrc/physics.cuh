@@ -142,6 +142,21 @@ __device__ __forceinline__ FaceGeom face_geom(double x0, double y0, double x1, d
     return f;
 }
 
+// Cell volume, MeshModule.cpp:34-40.  The shoelace sum cancels to ~1e-9 relative on fine meshes, so
+// its ROUNDING is part of the reference's result: both modes evaluate it in the reference's order with
+// individually rounded products and sums (the intrinsics are never contracted into FMAs).
+__device__ __forceinline__ double cell_volume(double x1, double y1, double x2, double y2, double x3, double y3, double x4, double y4) {
+    double s = __dmul_rn(x1, y2);
+    s = __dadd_rn(s, __dmul_rn(x2, y3));
+    s = __dadd_rn(s, __dmul_rn(x3, y4));
+    s = __dadd_rn(s, __dmul_rn(x4, y1));
+    s = __dsub_rn(s, __dmul_rn(x2, y1));
+    s = __dsub_rn(s, __dmul_rn(x3, y2));
+    s = __dsub_rn(s, __dmul_rn(x4, y3));
+    s = __dsub_rn(s, __dmul_rn(x1, y4));
+    return fabs(__dmul_rn(0.5, s));
+}
+
 struct Flux {
     double f0, f1, f2, f3, parr;
 };
@@ -210,7 +225,8 @@ __device__ __forceinline__ Flux ldfss(const FaceGeom& fg, const FaceState& L, co
         const double wr = subR ? -xmmr * (2.0 + xmr) : (signbit(xmr) ? 1.0 : 0.0);
         if (subL && subR) {
             const double t = 0.5 * fma(xml, xml, xmr * xmr);
-            const double xmhalf = t > 0.0 ? t * fast_rsqrt(t) : 0.0;
+            // rsqrt.approx flushes subnormals: below 1e-200 sqrt(t) is 0 to 100 digits of (xmhalf-1)
+            const double xmhalf = t > 1e-200 ? t * fast_rsqrt(t) : 0.0;
             const double d1 = xmhalf - 1.0;
             const double xmc = 0.25 * d1 * d1;
             const double delp = L.p - R.p;
