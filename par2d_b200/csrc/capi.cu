@@ -108,6 +108,8 @@ struct par2d_ctx {
     par2d_config cfg;
     Gas gas;
     bool tpg = false, axi = true, use_tma = true;
+    bool use_march = true;   // marching-strip kernel (march.cuh); false = the TMA tile kernel (PAR2D_KERNEL=tile)
+    int march_rows = 64;
     const KernelTable* kt = nullptr;
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -177,6 +179,7 @@ struct par2d_ctx {
         a.res_out = nullptr;
         a.res_block = -1;
         a.update = update;
+        a.march_rows = march_rows;
         return a;
     }
     FinalizeArgs finalize_args(int stop_on_tol) const {
@@ -262,6 +265,11 @@ int build_tensor_maps(par2d_ctx* c) {
     return 0;
 }
 
+void launch_step(par2d_ctx* c, const StepArgs& a) {
+    if (c->use_march) c->kt->march(c->stream, a, c->gas, c->tpg, c->axi);
+    else c->kt->step(c->stream, a, c->gas, c->tpg, c->axi, c->use_tma);
+}
+
 void queue_step(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
     StepArgs a = c->step_args(1);
     c->kt->ghost(c->stream, a, c->gas, with_ghost_dt ? 1 : 0);
@@ -275,7 +283,7 @@ void queue_step(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
         }
         cudaEventRecord(c->ev[2 * c->ev_used], c->stream);
     }
-    c->kt->step(c->stream, a, c->gas, c->tpg, c->axi, c->use_tma);
+    launch_step(c, a);
     if (c->timing) cudaEventRecord(c->ev[2 * c->ev_used++ + 1], c->stream);
     launch_finalize(c->stream, c->finalize_args(stop_on_tol), c->blk_norm);
     c->cur ^= 1;
@@ -381,6 +389,11 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
     c->device = dev;
     const char* no_tma = getenv("PAR2D_NO_TMA");
     c->use_tma = !(no_tma && atoi(no_tma) != 0);
+    // A/B switches for measurements: the kernel variant and the strip height
+    const char* kern = getenv("PAR2D_KERNEL");
+    c->use_march = !(kern && strcmp(kern, "tile") == 0);
+    const char* mrows = getenv("PAR2D_MARCH_ROWS");
+    if (mrows && atoi(mrows) > 0) c->march_rows = atoi(mrows);
     cudaError_t pe = c->kt->prepare();
     if (pe != cudaSuccess) { delete c; return fail(PAR2D_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(pe)); }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(PAR2D_ERR_CUDA, "cannot create stream"); }
@@ -441,8 +454,13 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
         CU_TRY(cudaMalloc(&c->block_ibound[k], sizeof(int) * nfaces));
         CU_TRY(cudaMemcpyAsync(c->block_ibound[k], d.ibound, sizeof(int) * nfaces, cudaMemcpyHostToDevice, c->stream));
         b.ibound = c->block_ibound[k];
-        b.tiles_x = (b.ncx + TX - 1) / TX;
-        b.tiles_y = (b.ncy + TY - 1) / TY;
+        if (c->use_march) {
+            b.tiles_x = (b.ncx + MCELLS - 1) / MCELLS;
+            b.tiles_y = (b.ncy + c->march_rows - 1) / c->march_rows;
+        } else {
+            b.tiles_x = (b.ncx + TX - 1) / TX;
+            b.tiles_y = (b.ncy + TY - 1) / TY;
+        }
         b.tile0 = c->total_tiles;
         c->total_tiles += b.tiles_x * b.tiles_y;
         c->max_tiles = std::max(c->max_tiles, b.tiles_x * b.tiles_y);
@@ -618,7 +636,7 @@ int par2d_get_residual(par2d_ctx* c, int32_t block, double* res) {
     // with remote neighbours the receive buffers must already hold this state's edge
     // lines (par2d_step_begin + transport); the dt table is rebuilt here either way
     c->kt->ghost(c->stream, a, c->gas, 1);
-    c->kt->step(c->stream, a, c->gas, c->tpg, c->axi, c->use_tma);
+    launch_step(c, a);
     const size_t bytes = sizeof(double) * 4 * (size_t)b.ncx * b.ncy;
     CU_TRY(cudaMemcpyAsync(res, c->staging, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));

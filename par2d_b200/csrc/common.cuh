@@ -25,6 +25,10 @@ constexpr int STEP_THREADS = TX * TY;
 constexpr int HX = TX + 2, HY = TY + 2;  // haloed tile
 constexpr int HOFF = 1, HXL = HX + 2;    // staged width: the copy starts HOFF columns early (16-byte rule)
 
+// marching kernel (march.cuh): a warp strip updates MCELLS cell columns (lanes 1..30; lanes 0 and 31
+// carry the halo columns) over StepArgs::march_rows cell rows
+constexpr int MCELLS = 30;
+
 enum : int { SIDE_BOTTOM = 0, SIDE_RIGHT = 1, SIDE_TOP = 2, SIDE_LEFT = 3 };
 enum : int { NB_NONE = 0, NB_LOCAL = 1, NB_REMOTE = 2 };
 
@@ -40,8 +44,8 @@ struct BlockDev {
     int nb_block[4];    // owned-block index of a same-rank neighbour
     int nb_side[4];     // the neighbour's side that faces us
     double* recv[4];    // AoS line [n*4+k] received from an off-rank neighbour
-    int tiles_x, tiles_y;
-    int tile0;          // first tile of this block in the partial-sum array
+    int tiles_x, tiles_y; // work decomposition: 32x8 tiles (tile kernel) or 30-column strips x row chunks (marching kernel)
+    int tile0;          // first tile/strip of this block in the partial-sum array
     double min_face;    // static part of find_dt (main.cpp:26-32)
 };
 
@@ -70,6 +74,7 @@ struct StepArgs {
     double* res_out;         // optional AoS residual dump (get_residual test hook)
     int res_block;           // owned index whose residual is dumped, or -1
     int update;              // 0: residual only (test hook), 1: advance the state
+    int march_rows;          // cell rows per strip of the marching kernel
 };
 
 struct FinalizeArgs {

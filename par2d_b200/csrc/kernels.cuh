@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include "common.cuh"
 #include "physics.cuh"
+#include "march.cuh"
 
 namespace par2d {
 
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(256) ghost_kernel(StepArgs a, Gas g, int write
         else if (side == SIDE_RIGHT) { p0 = (long long)(n + 1) * b.pitch + COL0; p1 = p0 + b.pitch; sgn = 1.0; code = b.ibound[b.ncx + n]; }
         else if (side == SIDE_TOP) { p0 = (long long)(b.ncy + 1) * b.pitch + COL0 + n; p1 = p0 + 1; sgn = -1.0; code = b.ibound[2 * b.ncx + b.ncy - 1 - n]; }
         else { p0 = (long long)(n + 1) * b.pitch + COL0; p1 = p0 + b.pitch; sgn = -1.0; code = b.ibound[2 * b.ncx + 2 * b.ncy - 1 - n]; }
-        const FaceGeom fg = face_geom<FAITHFUL>(X[p0], Y[p0], X[p1], Y[p1]);
+        const FaceGeom fg = face_geom<true>(X[p0], Y[p0], X[p1], Y[p1]);   // O(perimeter): unit normal as MeshModule.cpp:52-81
         int c, r;
         edge_cell_pos(b.ncx, b.ncy, side, n, c, r);
         const long long io = (long long)r * b.pitch + c;
@@ -390,7 +391,7 @@ __global__ void test_ldfss_kernel(Gas g, long long n, const double* face, const 
     FaceGeom fg;
     fg.nx = nx; fg.ny = ny; fg.len = len; fg.yf = yf;
     // a face with this unit normal and length: d = len*(-ny, nx)
-    fg.dx = -ny * len; fg.dy = nx * len; fg.rl = 1.0 / len;
+    fg.dx = -ny * len; fg.dy = nx * len; fg.rl = 0.0;
     const FaceState L = face_state<FAITHFUL, TPG>(g, uL[4 * i], uL[4 * i + 1], uL[4 * i + 2], fmax(uL[4 * i + 3], 201.0), fl);
     const FaceState R = face_state<FAITHFUL, TPG>(g, uR[4 * i], uR[4 * i + 1], uR[4 * i + 2], fmax(uR[4 * i + 3], 201.0), fl);
     const Flux f = ldfss<FAITHFUL, AXI>(fg, L, R);
@@ -452,6 +453,7 @@ struct KernelTable {
     void (*ghost)(cudaStream_t, const StepArgs&, const Gas&, int write_dt);
     void (*pack)(cudaStream_t, const StepArgs&, const Gas&, const SendLine*, int nlines, int max_n);
     void (*step)(cudaStream_t, const StepArgs&, const Gas&, bool tpg, bool axi, bool use_tma);
+    void (*march)(cudaStream_t, const StepArgs&, const Gas&, bool tpg, bool axi);
     void (*test_ldfss)(cudaStream_t, const Gas&, bool tpg, bool axi, long long n, const double*, const double*, const double*, double*, double*);
     void (*test_boundary)(cudaStream_t, const Gas&, long long n, const int*, const double*, const double*, double*);
     void (*test_update_state)(cudaStream_t, const Gas&, bool tpg, long long n, double*, double*);
@@ -485,6 +487,11 @@ struct Launch {
         if ((e = prep_one<true, false>()) != cudaSuccess) return e;
         return prep_one<true, true>();
     }
+    static void march(cudaStream_t s, const StepArgs& a, const Gas& g, bool tpg, bool axi) {
+        const dim3 grid((a.max_tiles + MARCH_WARPS - 1) / MARCH_WARPS, a.nowned);
+        if (tpg) { if (axi) march_kernel<FAITHFUL, true, true><<<grid, MARCH_THREADS, 0, s>>>(a, g); else march_kernel<FAITHFUL, true, false><<<grid, MARCH_THREADS, 0, s>>>(a, g); }
+        else { if (axi) march_kernel<FAITHFUL, false, true><<<grid, MARCH_THREADS, 0, s>>>(a, g); else march_kernel<FAITHFUL, false, false><<<grid, MARCH_THREADS, 0, s>>>(a, g); }
+    }
     static void ghost(cudaStream_t s, const StepArgs& a, const Gas& g, int write_dt) {
         ghost_kernel<FAITHFUL><<<dim3((a.max_faces + 255) / 256, a.nowned), 256, 0, s>>>(a, g, write_dt);
     }
@@ -511,7 +518,7 @@ struct Launch {
         else { if (axi) test_solve_kernel<FAITHFUL, false, true><<<grid, 128, 0, s>>>(g, n, dy, unk, res, dv); else test_solve_kernel<FAITHFUL, false, false><<<grid, 128, 0, s>>>(g, n, dy, unk, res, dv); }
     }
     static const KernelTable* table() {
-        static const KernelTable t = {sizeof(StepSmem), &prepare, &ghost, &pack, &step, &test_ldfss, &test_boundary, &test_update_state, &test_solve};
+        static const KernelTable t = {sizeof(StepSmem), &prepare, &ghost, &pack, &step, &march, &test_ldfss, &test_boundary, &test_update_state, &test_solve};
         return &t;
     }
 };

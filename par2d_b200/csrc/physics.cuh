@@ -60,6 +60,19 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
     return y;
 }
 
+// sqrt(x), x > 0 normal: coupled (Goldschmidt) iteration from the same seed; the last step corrects
+// the residual x - g*g, so the result is within 1 ulp.
+__device__ __forceinline__ double fast_sqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double gq = x * y, h = 0.5 * y;
+    double r = fma(-gq, h, 0.5);
+    gq = fma(gq, r, gq);
+    h = fma(h, r, h);
+    r = fma(-gq, gq, x);
+    return fma(r, h, gq);
+}
+
 // ---------------------------------------------------------------- thermo
 // Thermo::CalcEnthalpy (Thermo.cpp:7-30) and CalcCp (Thermo.cpp:32-48).
 template <bool TPG>
@@ -101,13 +114,16 @@ __device__ __forceinline__ FaceState face_state(const Gas& g, double rho, double
     if constexpr (FAITHFUL) {
         s.a = sqrt(g.gamRs * T);
         s.ip = 0.0;
+        s.h0 = enthalpy<TPG>(g, T, flags) + 0.5 * v2;
+        if (!(s.a > 0.0) || !(s.p > 0.0) || isnan(s.p * s.a * T)) flags |= FLAG_STATE;
     } else {
-        double c2 = g.gamRs * T;
-        s.a = c2 * fast_rsqrt(c2);
+        // T >= 201 and p >= 1 by the clamps, so a > 0 and p > 0 hold by construction; NaNs surface in
+        // the residual norm (FLAG_NAN) and in the density check of the update
+        s.a = fast_sqrt(g.gamRs * T);
         s.ip = fast_rcp(s.p);
+        if constexpr (TPG) s.h0 = fma(0.5, v2, enthalpy<TPG>(g, T, flags));
+        else s.h0 = fma(0.5, v2, fma(g.cp_cpg, T, g.hi[5]));   // Thermo.cpp:14 with Rs/(1-1/IGAM) folded
     }
-    s.h0 = enthalpy<TPG>(g, T, flags) + 0.5 * v2;
-    if (!(s.a > 0.0) || !(s.p > 0.0) || isnan(s.p * s.a * T)) flags |= FLAG_STATE;
     return s;
 }
 
@@ -132,11 +148,9 @@ __device__ __forceinline__ FaceGeom face_geom(double x0, double y0, double x1, d
         f.ny = -f.dx / f.len;
         f.rl = 0.0;
     } else {
-        double s = fma(f.dx, f.dx, f.dy * f.dy);
-        f.rl = fast_rsqrt(s);
-        f.len = s * f.rl;
-        f.nx = f.dy * f.rl;
-        f.ny = -f.dx * f.rl;
+        // the lean LDFSS works on the node difference itself: len*n = (dy,-dx), and |d| only enters
+        // through len*ahalf, which it gets from one rsqrt (see ldfss)
+        f.len = f.rl = f.nx = f.ny = 0.0;
     }
     f.yf = 0.5 * (y1 + y0);
     return f;
@@ -207,11 +221,13 @@ __device__ __forceinline__ Flux ldfss(const FaceGeom& fg, const FaceState& L, co
         o.f2 = yface * (fml * L.v + fmr * R.v + py_planar);
         o.f3 = yface * (fml * L.h0 + fmr * (R.h0));
     } else {
-        // lean evaluation: one reciprocal for ahalf, 1/p per cell shared by its
-        // four faces, the pressure-weighted diffusion term only where both sides
-        // are subsonic (it is multiplied by btl*btr = 0 otherwise).
+        // lean evaluation: one rsqrt of (|d| ahalf)^2 yields both len*ahalf and its reciprocal, 1/p
+        // comes per cell (shared by its four faces), and the pressure-weighted diffusion term is
+        // evaluated only where both sides are subsonic (it is multiplied by btl*btr = 0 otherwise).
         const double ahalf = 0.5 * (L.a + R.a);
-        const double q = fast_rcp(ahalf) * fg.rl;
+        const double w = fma(fg.dx, fg.dx, fg.dy * fg.dy) * (ahalf * ahalf);
+        const double q = fast_rsqrt(w);          // 1 / (len * ahalf)
+        const double la = w * q;                 // len * ahalf
         const double xml = fma(L.u, fg.dy, -L.v * fg.dx) * q;
         const double xmr = fma(R.u, fg.dy, -R.v * fg.dx) * q;
         const bool subL = fabs(xml) < 1.0, subR = fabs(xmr) < 1.0;
@@ -235,7 +251,6 @@ __device__ __forceinline__ Flux ldfss(const FaceGeom& fg, const FaceState& L, co
             cep -= xmc * fmax(0.0, 1.0 - fma(ad2, L.ip, dps));
             cem += xmc * fmax(0.0, 1.0 + fma(-ad2, R.ip, dps));
         }
-        const double la = fg.len * ahalf;
         const double fml = la * L.rho * cep;
         const double fmr = la * R.rho * cem;
         const double pnet = fma(wl, L.p, wr * R.p);
