@@ -162,7 +162,8 @@ _cache = {}
 def load_gpu() -> _Lib:
     """The product CUDA library.  No fallback: raises if it has not been built."""
     if "gpu" not in _cache:
-        _cache["gpu"] = _Lib(GPU_LIB, "par2d_", [SOLVER_API, GPU_ONLY_API])
+        # PAR2D_GPU_LIB: A/B builds of the same CUDA library (tools/build_variants.sh), measurements only
+        _cache["gpu"] = _Lib(os.environ.get("PAR2D_GPU_LIB", GPU_LIB), "par2d_", [SOLVER_API, GPU_ONLY_API])
     return _cache["gpu"]
 
 

@@ -11,11 +11,54 @@
 //   AXI      : axisymmetric (IAXI == 1) or planar.
 // Reference lines are cited per function.
 #pragma once
-#include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define PAR2D_FN __device__ __forceinline__
+#else
+// Host build of the same formulas, used ONLY by tests/host_physics (CPU-side check of the point-wise
+// functions against the oracle without a GPU).  The MUFU seeds are emulated at their measured accuracy
+// (2^-20) and the never-contracted intrinsics by plain operations (that TU is built with
+// -ffp-contract=off or, for the fast mode, with FMA contraction like nvcc's default).
+#include <cmath>
+#include <cstring>
+#define PAR2D_FN inline
+namespace par2d {
+using std::isnan;
+using std::signbit;
+inline double par2d_trunc20(double v) { uint64_t b; memcpy(&b, &v, 8); b &= 0xffffffff00000000ull; memcpy(&v, &b, 8); return v; }
+inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+}  // namespace par2d
+#endif
 
 namespace par2d {
+
+// seeds of the reciprocal / reciprocal square root (MUFU.RCP64H, MUFU.RSQ64H: 2^-20 relative)
+PAR2D_FN double seed_rcp(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+#elif !defined(__CUDACC__)
+    return par2d_trunc20(1.0 / par2d_trunc20(x));
+#else
+    return 1.0 / x;   // nvcc's host pass only parses this __device__ function
+#endif
+}
+PAR2D_FN double seed_rsqrt(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+#elif !defined(__CUDACC__)
+    return par2d_trunc20(1.0 / sqrt(par2d_trunc20(x)));
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
 
 // Physics constants of one run; lives in kernel parameter space.
 struct Gas {
@@ -38,45 +81,36 @@ enum : unsigned {
 };
 
 // ---------------------------------------------------------------- fast math
-// rcp.approx.ftz.f64 (MUFU.RCP64H) seeds ~20 bits; two Newton steps reach <= 1 ulp.
-__device__ __forceinline__ double fast_rcp(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    return y;
+// MUFU.RCP64H / MUFU.RSQ64H seed 2^-20 relative (measured on B200, profiles/r01_hw_probe_*.txt).
+// One fourth-order step in the seed's residual e reaches e^4 = 2^-80, i.e. rounding-limited
+// (<= 1.1e-16 measured), with a shorter dependency chain than two Newton steps.
+PAR2D_FN double fast_rcp(double x) {
+    const double y = seed_rcp(x);
+    const double e = fma(-x, y, 1.0);          // 1 - x*y0
+    const double y1 = fma(y, e, y);            // y0 (1 + e)
+    const double e2 = e * e;
+    return fma(y1, e2, y1);                    // y0 (1 + e)(1 + e^2) = y0 (1 + e + e^2 + e^3)
 }
-// rsqrt.approx.ftz.f64 (MUFU.RSQ64H) + two Newton steps.
-__device__ __forceinline__ double fast_rsqrt(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double hx = 0.5 * x;
-    double e = fma(-hx * y, y, 0.5);
-    y = fma(y, e, y);
-    e = fma(-hx * y, y, 0.5);
-    y = fma(y, e, y);
-    return y;
+// 1/sqrt(x): y0 (1 + e/2 + 3e^2/8 + 5e^3/16), e = 1 - x*y0^2.
+PAR2D_FN double fast_rsqrt(double x) {
+    const double y = seed_rsqrt(x);
+    const double e = fma(-x, y * y, 1.0);
+    const double p = fma(fma(e, 0.3125, 0.375), e, 0.5);
+    return fma(y * e, p, y);
 }
-
-// sqrt(x), x > 0 normal: coupled (Goldschmidt) iteration from the same seed; the last step corrects
-// the residual x - g*g, so the result is within 1 ulp.
-__device__ __forceinline__ double fast_sqrt(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double gq = x * y, h = 0.5 * y;
-    double r = fma(-gq, h, 0.5);
-    gq = fma(gq, r, gq);
-    h = fma(h, r, h);
-    r = fma(-gq, gq, x);
-    return fma(r, h, gq);
+// sqrt(x), x > 0 normal: g = x*y0 ~ sqrt(x), same series in e = 1 - g*y0.
+PAR2D_FN double fast_sqrt(double x) {
+    const double y = seed_rsqrt(x);
+    const double gq = x * y;
+    const double e = fma(-gq, y, 1.0);
+    const double p = fma(fma(e, 0.3125, 0.375), e, 0.5);
+    return fma(gq * e, p, gq);
 }
 
 // ---------------------------------------------------------------- thermo
 // Thermo::CalcEnthalpy (Thermo.cpp:7-30) and CalcCp (Thermo.cpp:32-48).
 template <bool TPG>
-__device__ __forceinline__ double enthalpy(const Gas& g, double T, unsigned& flags) {
+PAR2D_FN double enthalpy(const Gas& g, double T, unsigned& flags) {
     if constexpr (!TPG) {
         return (T * g.Rs / g.cpg_den + g.hi[5]);
     } else {
@@ -87,7 +121,7 @@ __device__ __forceinline__ double enthalpy(const Gas& g, double T, unsigned& fla
     }
 }
 template <bool TPG>
-__device__ __forceinline__ double heat_capacity(const Gas& g, double T, unsigned& flags) {
+PAR2D_FN double heat_capacity(const Gas& g, double T, unsigned& flags) {
     if constexpr (!TPG) {
         return g.cp_cpg;
     } else {
@@ -106,7 +140,7 @@ struct FaceState {
 };
 
 template <bool FAITHFUL, bool TPG>
-__device__ __forceinline__ FaceState face_state(const Gas& g, double rho, double u, double v, double T, unsigned& flags) {
+PAR2D_FN FaceState face_state(const Gas& g, double rho, double u, double v, double T, unsigned& flags) {
     FaceState s;
     s.rho = rho; s.u = u; s.v = v;
     double v2 = u * u + v * v;
@@ -138,7 +172,7 @@ struct FaceGeom {
 };
 
 template <bool FAITHFUL>
-__device__ __forceinline__ FaceGeom face_geom(double x0, double y0, double x1, double y1) {
+PAR2D_FN FaceGeom face_geom(double x0, double y0, double x1, double y1) {
     FaceGeom f;
     f.dx = x1 - x0;
     f.dy = y1 - y0;
@@ -159,7 +193,7 @@ __device__ __forceinline__ FaceGeom face_geom(double x0, double y0, double x1, d
 // Cell volume, MeshModule.cpp:34-40.  The shoelace sum cancels to ~1e-9 relative on fine meshes, so
 // its ROUNDING is part of the reference's result: both modes evaluate it in the reference's order with
 // individually rounded products and sums (the intrinsics are never contracted into FMAs).
-__device__ __forceinline__ double cell_volume(double x1, double y1, double x2, double y2, double x3, double y3, double x4, double y4) {
+PAR2D_FN double cell_volume(double x1, double y1, double x2, double y2, double x3, double y3, double x4, double y4) {
     double s = __dmul_rn(x1, y2);
     s = __dadd_rn(s, __dmul_rn(x2, y3));
     s = __dadd_rn(s, __dmul_rn(x3, y4));
@@ -175,10 +209,10 @@ struct Flux {
     double f0, f1, f2, f3, parr;
 };
 
-__device__ __forceinline__ double sgn_bit(double x) { return signbit(x) ? -1.0 : 1.0; }  // Indexing.h:22
+PAR2D_FN double sgn_bit(double x) { return signbit(x) ? -1.0 : 1.0; }  // Indexing.h:22
 
 template <bool FAITHFUL, bool AXI>
-__device__ __forceinline__ Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) {
+PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) {
     Flux o;
     if constexpr (FAITHFUL) {
         const double normx = fg.nx, normy = fg.ny, len = fg.len;
@@ -231,7 +265,7 @@ __device__ __forceinline__ Flux ldfss(const FaceGeom& fg, const FaceState& L, co
         const double xml = fma(L.u, fg.dy, -L.v * fg.dx) * q;
         const double xmr = fma(R.u, fg.dy, -R.v * fg.dx) * q;
         const bool subL = fabs(xml) < 1.0, subR = fabs(xmr) < 1.0;
-        const double hl = 0.5 * (xml + 1.0), hr = 0.5 * (xmr - 1.0);
+        const double hl = fma(0.5, xml, 0.5), hr = fma(0.5, xmr, -0.5);
         const double xmml = hl * hl, xmmr = -(hr * hr);
         // split Mach numbers and pressure weights (EulerFlux.cpp:146-175 with
         // all/alr in {0,1} and btl/btr in {-1,0} substituted)
@@ -251,22 +285,25 @@ __device__ __forceinline__ Flux ldfss(const FaceGeom& fg, const FaceState& L, co
             cep -= xmc * fmax(0.0, 1.0 - fma(ad2, L.ip, dps));
             cem += xmc * fmax(0.0, 1.0 + fma(-ad2, R.ip, dps));
         }
-        const double fml = la * L.rho * cep;
-        const double fmr = la * R.rho * cem;
         const double pnet = fma(wl, L.p, wr * R.p);
-        const double px = pnet * fg.dy;    // len*pnet*normx
-        const double py = -pnet * fg.dx;   // len*pnet*normy
         if constexpr (AXI) {
-            o.parr = py;
-            o.f0 = fg.yf * (fml + fmr);
-            o.f1 = fg.yf * (fma(fml, L.u, fma(fmr, R.u, px)));
-            o.f2 = fg.yf * (fma(fml, L.v, fmr * R.v));
-            o.f3 = fg.yf * (fma(fml, L.h0, fmr * R.h0));
-        } else {
-            o.parr = 0.0;
+            // every flux component carries yface (EulerFlux.cpp:178-186): fold it into len*ahalf and pnet
+            const double lay = la * fg.yf;
+            const double fml = lay * L.rho * cep;
+            const double fmr = lay * R.rho * cem;
+            const double px = (pnet * fg.yf) * fg.dy;   // yface*len*pnet*normx
+            o.parr = -pnet * fg.dx;                     // len*pnet*normy, without yface (:181)
             o.f0 = fml + fmr;
             o.f1 = fma(fml, L.u, fma(fmr, R.u, px));
-            o.f2 = fma(fml, L.v, fma(fmr, R.v, py));
+            o.f2 = fma(fml, L.v, fmr * R.v);
+            o.f3 = fma(fml, L.h0, fmr * R.h0);
+        } else {
+            const double fml = la * L.rho * cep;
+            const double fmr = la * R.rho * cem;
+            o.parr = 0.0;
+            o.f0 = fml + fmr;
+            o.f1 = fma(fml, L.u, fma(fmr, R.u, pnet * fg.dy));
+            o.f2 = fma(fml, L.v, fma(fmr, R.v, -pnet * fg.dx));
             o.f3 = fma(fml, L.h0, fmr * R.h0);
         }
     }
@@ -278,7 +315,7 @@ __device__ __forceinline__ Flux ldfss(const FaceGeom& fg, const FaceState& L, co
 // the ghost's UpdateState temperature clamp (SpatialDiscretization.cpp:39).  O(perimeter)
 // work, so a single (reference-ordered) formulation serves both modes.  Returns false when
 // the ghost must stay unwritten (NaN normal Mach number).
-__device__ __forceinline__ bool boundary_state(const Gas& g, int btype, double normx, double normy,
+PAR2D_FN bool boundary_state(const Gas& g, int btype, double normx, double normy,
                                                const double ui[4], double a_int, double p_int, double v2_int,
                                                double out[4]) {
     const double uL = ui[1], vL = ui[2];
@@ -348,11 +385,28 @@ __device__ __forceinline__ bool boundary_state(const Gas& g, int btype, double n
     return wrote;
 }
 
+// Closed-form forward substitution of D dv = res (D lower triangular, Jacobian.cpp:7-47) with every
+// scalar factor folded into one: sc = dt/ycc for a residual r = R/vol, or dt/(vol*ycc) when R is the
+// raw flux sum (planar: without ycc).
+//   drho = sc R0;  du = sc (R1 - u R0)/rho;  dv = sc (R2 - v R0)/rho;
+//   dT   = sc (R3 - e0 R0 - u (R1 - u R0) - v (R2 - v R0)) / (rho Cv)
+PAR2D_FN void solve_lean(double sc, double rho, double u, double v, double e0, double inv_cv,
+                                           const double R[4], double dv[4]) {
+    const double sr = sc * fast_rcp(rho);
+    const double m1 = fma(-u, R[0], R[1]);
+    const double m2 = fma(-v, R[0], R[2]);
+    const double m3 = fma(-v, m2, fma(-u, m1, fma(-e0, R[0], R[3])));
+    dv[0] = sc * R[0];
+    dv[1] = sr * m1;
+    dv[2] = sr * m2;
+    dv[3] = (sr * inv_cv) * m3;
+}
+
 // ---------------------------------------------------------------- per-cell solve
 // dv = D^-1 res (Jacobian.cpp:7-47, LUtools.cpp:22-90) and the axisymmetric 1/ycc
 // (main.cpp:325-331).  scale = 1/ycc (AXI) or unused.
 template <bool FAITHFUL, bool AXI>
-__device__ __forceinline__ void solve_cell(double dt, double ycc, double rho, double u, double v, double e0, double Cv,
+PAR2D_FN void solve_cell(double dt, double ycc, double rho, double u, double v, double e0, double Cv,
                                            double inv_cv, const double r[4], double dv[4], unsigned& flags) {
     if constexpr (FAITHFUL) {
         double A[4][4];
@@ -415,17 +469,9 @@ __device__ __forceinline__ void solve_cell(double dt, double ycc, double rho, do
         }
     } else {
         // D is lower triangular: forward substitution in closed form
-        const double irho = fast_rcp(rho);
-        const double d0 = dt * r[0];
-        const double d1 = fma(dt, r[1], -u * d0) * irho;
-        const double d2 = fma(dt, r[2], -v * d0) * irho;
-        const double d3 = (fma(dt, r[3], -e0 * d0) - rho * fma(u, d1, v * d2)) * irho * inv_cv;
-        if constexpr (AXI) {
-            const double s = fast_rcp(ycc);
-            dv[0] = d0 * s; dv[1] = d1 * s; dv[2] = d2 * s; dv[3] = d3 * s;
-        } else {
-            dv[0] = d0; dv[1] = d1; dv[2] = d2; dv[3] = d3;
-        }
+        double s = dt;
+        if constexpr (AXI) s = dt * fast_rcp(ycc);
+        solve_lean(s, rho, u, v, e0, inv_cv, r, dv);
         (void)Cv;
     }
 }

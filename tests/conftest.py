@@ -65,6 +65,23 @@ def state_err(a, b):
     return max(np.abs(a[:, k] - b[:, k]).max() / scales[k] for k in range(4))
 
 
+def flux_scales(cfg, face, uL, uR):
+    """Characteristic magnitude of the four LDFSS flux components of each face: the Mach-1 mass flux
+    len*yface*ahalf*(rhoL+rhoR) times (1, speed, speed, total enthalpy) plus the pressure force.  A split
+    flux near |M| = 1 or M = 0 is a small difference of O(1) terms - (M -+ 1)^2 in EulerFlux.cpp:152-153 -
+    so rounding differences of 1e-16 in M are 1e-12 of THAT face's flux but 1e-16 of this scale, which is
+    what enters a residual."""
+    T = np.maximum(np.stack([uL[:, 3], uR[:, 3]]), 201.0)
+    a = np.sqrt(abs(cfg.igam) * cfg.Rs * T)
+    rho = np.stack([uL[:, 0], uR[:, 0]])
+    speed = np.maximum(np.sqrt(np.stack([uL[:, 1] ** 2 + uL[:, 2] ** 2, uR[:, 1] ** 2 + uR[:, 2] ** 2])), a).max(axis=0)
+    area = face[:, 2] * (face[:, 3] if cfg.iaxi == 1 else 1.0)
+    mass = area * a.mean(axis=0) * rho.sum(axis=0)
+    p = (rho * cfg.Rs * T).sum(axis=0)
+    h0 = (3.5 * cfg.Rs * T).max(axis=0) + 0.5 * speed ** 2
+    return np.stack([mass, mass * speed + area * p, mass * speed + area * p, mass * h0], axis=1), face[:, 2] * p
+
+
 def make_cfg(lib, iaxi=1, igam=1.4, mode=0):
     from par2d_b200 import default_config
     cfg = default_config(lib)

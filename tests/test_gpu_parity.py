@@ -14,7 +14,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import case_path, load_golden, make_cfg, random_faces, random_states, state_err
+from conftest import case_path, flux_scales, load_golden, make_cfg, random_faces, random_states, state_err
 import pointwise as pw
 from par2d_b200 import MODE_FAITHFUL, MODE_FAST, Case, Solver
 
@@ -54,9 +54,9 @@ def test_pointwise_device_functions(gpu, oracle, iaxi, igam, mode):
     if exact:
         assert np.array_equal(fg, fo) and np.array_equal(pg, po)
     else:
-        scale = np.abs(fo).max(axis=1, keepdims=True) + 1e-300
-        assert (np.abs(fg - fo) / scale).max() < 5e-13
-        assert (np.abs(pg - po) / (np.abs(po) + scale[:, 0])).max() < 5e-13
+        scale, pscale = flux_scales(cfg_o, face, uL, uR)
+        assert (np.abs(fg - fo) / scale).max() < 2e-15
+        assert (np.abs(pg - po) / pscale).max() < 2e-15
 
     btype = rng.choice([-1, 0, 1, 2, 3, 4, 5], n).astype(np.int32)
     ui = uL.copy()
