@@ -182,7 +182,7 @@ struct StepSmem {
     // fault on sm_100a, see tools/tma_probe): halo column hx lives at [hx + HOFF].
     double U[4][HY][HXL];  // rho,u,v,T with halo
     double N[2][HY][HXL];  // node x,y
-    double P[HY][HX], A[HY][HX], H[HY][HX], I[HY][HX];  // p, a, h0, 1/p per halo cell
+    double P[HY][HX], A[HY][HX], H[HY][HX];  // p, a, h0 per halo cell
     double F[5][TY][TX + 1];   // i-face fluxes + parr
     double G[5][TY + 1][TX];   // j-face fluxes + parr
     double red[STEP_THREADS / 32][4];
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 2) step_kernel(const StepArgs a,
         const bool real = (xin && gj >= -1 && gj <= ncy) || (yin && gi >= -1 && gi <= ncx);
         unsigned fl = 0;
         const FaceState s = face_state<FAITHFUL, TPG>(g, sm.U[0][hy][hx + HOFF], sm.U[1][hy][hx + HOFF], sm.U[2][hy][hx + HOFF], sm.U[3][hy][hx + HOFF], fl);
-        sm.P[hy][hx] = s.p; sm.A[hy][hx] = s.a; sm.H[hy][hx] = s.h0; sm.I[hy][hx] = s.ip;
+        sm.P[hy][hx] = s.p; sm.A[hy][hx] = s.a; sm.H[hy][hx] = s.h0;
         if (real) flags |= fl;
     }
     __syncthreads();
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 2) step_kernel(const StepArgs a,
     auto load_state = [&](int hx, int hy) {
         FaceState s;
         s.rho = sm.U[0][hy][hx + HOFF]; s.u = sm.U[1][hy][hx + HOFF]; s.v = sm.U[2][hy][hx + HOFF];
-        s.p = sm.P[hy][hx]; s.a = sm.A[hy][hx]; s.h0 = sm.H[hy][hx]; s.ip = sm.I[hy][hx];
+        s.p = sm.P[hy][hx]; s.a = sm.A[hy][hx]; s.h0 = sm.H[hy][hx];
         return s;
     };
 

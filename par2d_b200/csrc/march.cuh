@@ -1,24 +1,32 @@
 // march.cuh -- the production step kernel: register-marching warp strips.
 //
-// One warp advances a strip of MCELLS (30) cell columns by `rows` cell rows of one block, marching
-// upwards row by row (FV/SpatialDiscretization.cpp:481-1011 + main.cpp:39-57,307-351,394-404 fused):
+// One warp (= one CTA) advances a strip of MCELLS (30) cell columns by `march_rows` cell rows of one
+// block, marching upwards row by row (FV/SpatialDiscretization.cpp:481-1011 + main.cpp:39-57,307-351,
+// 394-404 fused):
 //
 //   lane l holds cell column c0-1+l: lanes 0 and 31 are the strip's left/right halo columns (their
 //   state is loaded and derived, but only lanes 1..30 update a cell), so the 32 lanes of a row are one
 //   fully coalesced 256-byte read per plane, straight from the padded HBM planes (ghost ring in place).
-//   Per row and lane:  load + derive the cell one row up (software-prefetched one further row ahead),
-//   ONE i-face flux (left face; the left cell's state comes from lane l-1 by warp shuffle, the right
-//   face's flux from lane l+1), ONE j-face flux (top face; the bottom face is last row's top face,
-//   carried in registers), residual, norms, Jacobian solve, update, 4 coalesced stores.
-//   Nothing is staged in shared memory: every state value is read from HBM once per strip (plus the
-//   halo column / row re-reads, 2/30 and 1/rows, which hit L2) and every face flux is evaluated once
-//   per strip.  The sum of squares is accumulated per lane over the rows and reduced by warp shuffles
-//   in a fixed order once per strip.
+//   Rows are staged ahead of their use by cp.async (LDGSTS) into a per-warp shared-memory ring of
+//   MARCH_STAGES rows x 6 planes, every lane copying and later reading only its own 8-byte slots: no
+//   registers are held by loads in flight, no barrier is needed, and HBM latency is covered by
+//   MARCH_STAGES-1 rows of compute.
+//   Per row and lane: derive the cell one row up, ONE i-face flux (left face; the left cell's state
+//   comes from lane l-1 by warp shuffle, the right face's flux from lane l+1), ONE j-face flux (top
+//   face; the bottom face is last row's top face, parked in shared memory meanwhile), residual,
+//   norms, Jacobian solve, update, 4 coalesced stores.
+//   Every state value is read from HBM once per strip (plus the halo column / row re-reads, 2/30 and
+//   1/rows, which hit L2) and every face flux is evaluated once per strip.  The sum of squares is
+//   accumulated per lane over the rows and reduced by warp shuffles in a fixed order once per strip.
+//
+// Why one warp per CTA: every loop bound then derives from blockIdx, ptxas proves the shuffles
+// convergent and drops the divergence fallbacks (and their register moves).  Why the ring and the
+// parked flux: the kernel is bound by warps x ILP under the register file; both take live values out
+// of registers (ncu history in DESIGN.md).
 //
 // Compared with the TMA-staged 32x8 tile kernel (kernels.cuh::step_kernel, kept as the A/B baseline,
-// PAR2D_KERNEL=tile): no block-wide barriers, no smem round trips (~70 LDS/STS per cell there), a
-// fifth of the index arithmetic, and global-load latency hidden by the row prefetch instead of by
-// occupancy.  See DESIGN.md for the ncu numbers of both.
+// PAR2D_KERNEL=tile): no block-wide barriers, ~1/6 of the shared-memory traffic, a fifth of the index
+// arithmetic.
 #pragma once
 #include "common.cuh"
 #include "physics.cuh"
@@ -28,14 +36,14 @@ namespace par2d {
 #ifndef MARCH_NWARPS
 #define MARCH_NWARPS 1
 #endif
-constexpr int MARCH_WARPS = MARCH_NWARPS;                    // one strip per CTA: every loop bound derives from blockIdx, so ptxas proves the shuffles convergent
-constexpr int MARCH_THREADS = 32 * MARCH_WARPS;
-#ifndef MARCH_UNROLL2
-#define MARCH_UNROLL2 0
-#endif
 #ifndef MARCH_MINB
-#define MARCH_MINB 12
+#define MARCH_MINB 16
 #endif
+#ifndef MARCH_STAGES
+#define MARCH_STAGES 4
+#endif
+constexpr int MARCH_WARPS = MARCH_NWARPS;         // strips per CTA
+constexpr int MARCH_THREADS = 32 * MARCH_WARPS;
 
 __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ double shfl_down1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
@@ -43,7 +51,7 @@ __device__ __forceinline__ double shfl_down1(double v) { return __shfl_down_sync
 __device__ __forceinline__ FaceState shfl_up1(const FaceState& s) {
     FaceState o;
     o.rho = shfl_up1(s.rho); o.u = shfl_up1(s.u); o.v = shfl_up1(s.v);
-    o.p = shfl_up1(s.p); o.a = shfl_up1(s.a); o.h0 = shfl_up1(s.h0); o.ip = shfl_up1(s.ip);
+    o.p = shfl_up1(s.p); o.a = shfl_up1(s.a); o.h0 = shfl_up1(s.h0);
     return o;
 }
 __device__ __forceinline__ Flux shfl_down1(const Flux& f) {
@@ -53,46 +61,56 @@ __device__ __forceinline__ Flux shfl_down1(const Flux& f) {
     return o;
 }
 
-struct RawRow {   // one cell row as loaded: state of the cell and the node at its lower-left corner
-    double rho, u, v, T, x, y;
+// cp.async (SASS: LDGSTS): 8 bytes global -> shared, tracked per thread
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// per-warp shared memory: the row ring and the parked bottom-face flux
+struct MarchSmem {
+    double ring[MARCH_STAGES][6][32];   // [stage][rho,u,v,T,x,y][lane]
+    double G[5][32];                    // j-face flux at the bottom of the current row
 };
 
-// What a lane carries from one row to the next: the derived state of its cell, the two lower nodes of
-// the cell (own column and, from lane+1, the next column) and the flux through the cell's bottom face.
+// What a lane carries in registers from one row to the next: the derived state of its cell and the two
+// lower nodes of the cell (own column and, from lane+1, the next column).
 struct RowState {
     FaceState s;
     double T;
     double xa, ya, xb, yb;   // node (c, j), node (c+1, j)
-    Flux G;                  // j-face flux at the bottom of the row
 };
 
 struct MarchCtx {
-    int k, c, ncx, ncy, pitch;
+    int k, c, ncx, ncy, pitch, lane;
     long long plane;
     bool writer;
     double dt;
     double* Sout;
 };
 
-// One row of a strip: consumes the carried state `lo` of cell row j and the raw row above it, produces
-// the carried state `hi` of row j+1, updates cell (c, j).  Called alternately with (A,B) and (B,A) so
-// that no register is moved between rows.
+// One row of a strip: consumes the carried state `lo` of cell row j and the staged row above it
+// (ring stage `st`), produces the carried state `hi` of row j+1, updates cell (c, j).
 template <bool FAITHFUL, bool TPG, bool AXI>
-__device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const MarchCtx& m, int j, const RowState& lo, const RawRow& ru,
+__device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const MarchCtx& m, MarchSmem& sm, int j, int st, const RowState& lo,
                                           RowState& hi, double& sq0, double& sq1, double& sq2, double& sq3, unsigned& flags) {
+    const int lane = m.lane;
     unsigned flu = 0;
-    hi.s = face_state<FAITHFUL, TPG>(g, ru.rho, ru.u, ru.v, ru.T, flu);
-    hi.T = ru.T;
-    hi.xa = ru.x; hi.ya = ru.y;                                  // node (c, j+1)
-    hi.xb = shfl_down1(ru.x); hi.yb = shfl_down1(ru.y);          // node (c+1, j+1)
+    hi.T = sm.ring[st][3][lane];
+    hi.s = face_state<FAITHFUL, TPG>(g, sm.ring[st][0][lane], sm.ring[st][1][lane], sm.ring[st][2][lane], hi.T, flu);
+    hi.xa = sm.ring[st][4][lane]; hi.ya = sm.ring[st][5][lane];   // node (c, j+1)
+    hi.xb = shfl_down1(hi.xa); hi.yb = shfl_down1(hi.ya);         // node (c+1, j+1)
 
     // i-face between cell (c-1, j) [left state] and (c, j): node (c, j) -> (c, j+1)
     const Flux Fl = ldfss<FAITHFUL, AXI>(face_geom<FAITHFUL>(lo.xa, lo.ya, hi.xa, hi.ya), shfl_up1(lo.s), lo.s);
-    // j-face between cell (c, j+1) [left state = upper cell] and (c, j): node (c, j+1) -> (c+1, j+1)
-    hi.G = ldfss<FAITHFUL, AXI>(face_geom<FAITHFUL>(hi.xa, hi.ya, hi.xb, hi.yb), hi.s, lo.s);
     const Flux Fr = shfl_down1(Fl);
-    const Flux& Gb = lo.G;
-    const Flux& Gt = hi.G;
+    // j-face between cell (c, j+1) [left state = upper cell] and (c, j): node (c, j+1) -> (c+1, j+1)
+    const Flux Gt = ldfss<FAITHFUL, AXI>(face_geom<FAITHFUL>(hi.xa, hi.ya, hi.xb, hi.yb), hi.s, lo.s);
+    Flux Gb;
+    Gb.f0 = sm.G[0][lane]; Gb.f1 = sm.G[1][lane]; Gb.f2 = sm.G[2][lane]; Gb.f3 = sm.G[3][lane]; Gb.parr = sm.G[4][lane];
+    sm.G[0][lane] = Gt.f0; sm.G[1][lane] = Gt.f1; sm.G[2][lane] = Gt.f2; sm.G[3][lane] = Gt.f3; sm.G[4][lane] = Gt.parr;
 
     if (m.writer) {
         flags |= flu;
@@ -179,23 +197,45 @@ __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const
 
 template <bool FAITHFUL, bool TPG, bool AXI>
 __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) march_kernel(const StepArgs a, const Gas g) {
+    __shared__ MarchSmem smem[MARCH_WARPS];
     if (*a.stop) return;
     const int lane = threadIdx.x & 31;
+    MarchSmem& sm = smem[threadIdx.x >> 5];
     const int k = blockIdx.y;                      // grid.y = owned blocks, grid.x covers the block with most strips
     const BlockDev& b = a.blocks[k];
     const int strip = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
     if (strip >= b.tiles_x * b.tiles_y) return;    // warp-uniform
     MarchCtx m;
-    m.k = k; m.ncx = b.ncx; m.ncy = b.ncy; m.pitch = b.pitch; m.plane = b.plane;
+    m.k = k; m.ncx = b.ncx; m.ncy = b.ncy; m.pitch = b.pitch; m.plane = b.plane; m.lane = lane;
     const int c0 = (strip % b.tiles_x) * MCELLS;   // first updated cell column
     const int j0 = (strip / b.tiles_x) * a.march_rows;
     const int j1 = min(j0 + a.march_rows, m.ncy);
     m.c = c0 - 1 + lane;                           // this lane's cell column (-1 and ncx are the ghost columns)
     m.writer = lane >= 1 && lane <= MCELLS && m.c < m.ncx;
     m.Sout = b.state[a.cur ^ 1];
-    const double* __restrict__ Sin = b.state[a.cur];
-    const double* __restrict__ X = b.nodes;
     const long long plane = m.plane;
+
+    // lanes right of the right ghost column re-read that column (never used, never stored)
+    const double* src = b.state[a.cur] + (COL0 + min(m.c, m.ncx));
+    const double* nsrc = b.nodes + (COL0 + min(m.c, m.ncx));
+    // array row `arow` holds cell row arow-1 and node row arow-1; rows past the strip's last one are
+    // not fetched (the group is still committed so that the wait counts stay uniform)
+    const int arow_end = j1 + 1;                   // last array row this strip reads (cell row j1 = row above the last)
+    auto stage_row = [&](int arow, int st) {
+        if (arow <= arow_end) {
+            const long long o = (long long)arow * m.pitch;
+            cp_async8(&sm.ring[st][0][lane], src + o);
+            cp_async8(&sm.ring[st][1][lane], src + plane + o);
+            cp_async8(&sm.ring[st][2][lane], src + 2 * plane + o);
+            cp_async8(&sm.ring[st][3][lane], src + 3 * plane + o);
+            cp_async8(&sm.ring[st][4][lane], nsrc + o);
+            cp_async8(&sm.ring[st][5][lane], nsrc + plane + o);
+        }
+        cp_async_commit();
+    };
+    // ---- fill the ring: array rows j0 (cell row below), j0+1 (first cell row), j0+2, ...
+#pragma unroll
+    for (int s = 0; s < MARCH_STAGES; s++) stage_row(j0 + s, s);
 
     // global dt = max over blocks (main.cpp:270-292); the table was written by the ghost kernel
     double dt = 0.0;
@@ -204,57 +244,39 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
     for (int s = 16; s > 0; s >>= 1) dt = fmax(dt, __shfl_xor_sync(0xffffffffu, dt, s));
     m.dt = dt;
 
-    // lanes right of the right ghost column re-read that column (never used, never stored)
-    const double* src = Sin + (COL0 + min(m.c, m.ncx));
-    const double* nsrc = X + (COL0 + min(m.c, m.ncx));
-    auto load_row = [&](int arow) {   // array row: cell row j and node row j both live in array row j+1
-        RawRow r;
-        const long long o = (long long)arow * m.pitch;
-        r.rho = __ldg(src + o); r.u = __ldg(src + plane + o); r.v = __ldg(src + 2 * plane + o); r.T = __ldg(src + 3 * plane + o);
-        r.x = __ldg(nsrc + o); r.y = __ldg(nsrc + plane + o);
-        return r;
-    };
-
     unsigned flags = 0;
-    // ---- prologue: cell rows j0-1 (below) and j0, node row j0, bottom-face flux of row j0
+    // ---- prologue: cell rows j0-1 (stage 0) and j0 (stage 1), node row j0, bottom-face flux of row j0
     RowState A, B;
-    RawRow ra, rb;
+    cp_async_wait<MARCH_STAGES - 2>();
     {
-        const RawRow below = load_row(j0), rc = load_row(j0 + 1);
-        ra = load_row(j0 + 2);
         unsigned fl0 = 0;
-        A.s = face_state<FAITHFUL, TPG>(g, rc.rho, rc.u, rc.v, rc.T, fl0);
-        A.T = rc.T;
-        A.xa = rc.x; A.ya = rc.y;
-        A.xb = shfl_down1(rc.x); A.yb = shfl_down1(rc.y);
-        const FaceState lo = face_state<FAITHFUL, TPG>(g, below.rho, below.u, below.v, below.T, fl0);
+        A.T = sm.ring[1][3][lane];
+        A.s = face_state<FAITHFUL, TPG>(g, sm.ring[1][0][lane], sm.ring[1][1][lane], sm.ring[1][2][lane], A.T, fl0);
+        A.xa = sm.ring[1][4][lane]; A.ya = sm.ring[1][5][lane];
+        A.xb = shfl_down1(A.xa); A.yb = shfl_down1(A.ya);
+        const FaceState lo = face_state<FAITHFUL, TPG>(g, sm.ring[0][0][lane], sm.ring[0][1][lane], sm.ring[0][2][lane], sm.ring[0][3][lane], fl0);
         // j-face: left state = upper cell, right state = lower cell (SpatialDiscretization.cpp:556-625)
-        A.G = ldfss<FAITHFUL, AXI>(face_geom<FAITHFUL>(A.xa, A.ya, A.xb, A.yb), A.s, lo);
+        const Flux G0 = ldfss<FAITHFUL, AXI>(face_geom<FAITHFUL>(A.xa, A.ya, A.xb, A.yb), A.s, lo);
+        sm.G[0][lane] = G0.f0; sm.G[1][lane] = G0.f1; sm.G[2][lane] = G0.f2; sm.G[3][lane] = G0.f3; sm.G[4][lane] = G0.parr;
         if (m.writer) flags |= fl0;
     }
     double sq0 = 0.0, sq1 = 0.0, sq2 = 0.0, sq3 = 0.0;
 
-#if MARCH_UNROLL2
-    // ---- two rows per trip, (A -> B) then (B -> A); raw rows prefetched one row ahead of their use
-    int j = j0;
-#pragma unroll 1
-    for (; j + 1 < j1; j += 2) {
-        rb = load_row(j + 3);
-        march_row<FAITHFUL, TPG, AXI>(a, g, m, j, A, ra, B, sq0, sq1, sq2, sq3, flags);
-        if (j + 2 < j1) ra = load_row(j + 4);
-        march_row<FAITHFUL, TPG, AXI>(a, g, m, j + 1, B, rb, A, sq0, sq1, sq2, sq3, flags);
-    }
-    if (j < j1) march_row<FAITHFUL, TPG, AXI>(a, g, m, j, A, ra, B, sq0, sq1, sq2, sq3, flags);
-#else
-    // ---- one row per trip; the raw row above is prefetched one row ahead of its use
+    // ---- march: row j consumes array row j+2 (ring stage (j-j0+2) % STAGES), then refills the stage that
+    //      held array row j+1-... with array row j+2+STAGES-... ; stages 0 and 1 are free after the prologue
+    stage_row(j0 + MARCH_STAGES, 0);
+    stage_row(j0 + MARCH_STAGES + 1, 1);
+    int st = 2 % MARCH_STAGES;                     // stage of array row j+2
 #pragma unroll 1
     for (int j = j0; j < j1; j++) {
-        rb = ra;
-        if (j + 1 < j1) ra = load_row(j + 3);
-        march_row<FAITHFUL, TPG, AXI>(a, g, m, j, A, rb, B, sq0, sq1, sq2, sq3, flags);
+        // groups committed so far: array rows <= j+1+STAGES; the row needed now is j+2
+        cp_async_wait<MARCH_STAGES - 1>();
+        march_row<FAITHFUL, TPG, AXI>(a, g, m, sm, j, st, A, B, sq0, sq1, sq2, sq3, flags);
         A = B;
+        stage_row(j + 2 + MARCH_STAGES, st);       // this stage is consumed: refill it
+        st = (st + 1 == MARCH_STAGES) ? 0 : st + 1;
     }
-#endif
+    cp_async_wait<0>();
 
     // ---- sum of squares of this strip, fixed order: lanes (xor tree)
     double sq[4] = {sq0, sq1, sq2, sq3};

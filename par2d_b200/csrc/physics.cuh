@@ -136,7 +136,6 @@ PAR2D_FN double heat_capacity(const Gas& g, double T, unsigned& flags) {
 // the members the path never reads.  T must already be clamped (>= 201).
 struct FaceState {
     double rho, u, v, p, a, h0;
-    double ip;  // 1/p, fast path only
 };
 
 template <bool FAITHFUL, bool TPG>
@@ -147,14 +146,12 @@ PAR2D_FN FaceState face_state(const Gas& g, double rho, double u, double v, doub
     s.p = fmax(rho * g.Rs * T, 1.0);
     if constexpr (FAITHFUL) {
         s.a = sqrt(g.gamRs * T);
-        s.ip = 0.0;
         s.h0 = enthalpy<TPG>(g, T, flags) + 0.5 * v2;
         if (!(s.a > 0.0) || !(s.p > 0.0) || isnan(s.p * s.a * T)) flags |= FLAG_STATE;
     } else {
         // T >= 201 and p >= 1 by the clamps, so a > 0 and p > 0 hold by construction; NaNs surface in
         // the residual norm (FLAG_NAN) and in the density check of the update
         s.a = fast_sqrt(g.gamRs * T);
-        s.ip = fast_rcp(s.p);
         if constexpr (TPG) s.h0 = fma(0.5, v2, enthalpy<TPG>(g, T, flags));
         else s.h0 = fma(0.5, v2, fma(g.cp_cpg, T, g.hi[5]));   // Thermo.cpp:14 with Rs/(1-1/IGAM) folded
     }
@@ -255,8 +252,8 @@ PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) 
         o.f2 = yface * (fml * L.v + fmr * R.v + py_planar);
         o.f3 = yface * (fml * L.h0 + fmr * (R.h0));
     } else {
-        // lean evaluation: one rsqrt of (|d| ahalf)^2 yields both len*ahalf and its reciprocal, 1/p
-        // comes per cell (shared by its four faces), and the pressure-weighted diffusion term is
+        // lean evaluation: one rsqrt of (|d| ahalf)^2 yields both len*ahalf and its reciprocal, and
+        // the pressure-weighted diffusion term (with its three divisions) is
         // evaluated only where both sides are subsonic (it is multiplied by btl*btr = 0 otherwise).
         const double ahalf = 0.5 * (L.a + R.a);
         const double w = fma(fg.dx, fg.dx, fg.dy * fg.dy) * (ahalf * ahalf);
@@ -279,11 +276,16 @@ PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) 
             const double xmhalf = t > 1e-200 ? t * fast_rsqrt(t) : 0.0;
             const double d1 = xmhalf - 1.0;
             const double xmc = 0.25 * d1 * d1;
-            const double delp = L.p - R.p;
-            const double dps = delp * fast_rcp(L.p + R.p);
+            // delp/psum, 2|delp|/pL, 2|delp|/pR (EulerFlux.cpp:157-160) from ONE reciprocal,
+            // w = 1/(pL pR psum):  1/psum = pL pR w,  1/pL = pR psum w,  1/pR = pL psum w
+            const double delp = L.p - R.p, psum = L.p + R.p;
+            const double plr = L.p * R.p;
+            const double w3 = fast_rcp(plr * psum);
+            const double tw = psum * w3;
+            const double dps = delp * (plr * w3);
             const double ad2 = 2.0 * fabs(delp);
-            cep -= xmc * fmax(0.0, 1.0 - fma(ad2, L.ip, dps));
-            cem += xmc * fmax(0.0, 1.0 + fma(-ad2, R.ip, dps));
+            cep -= xmc * fmax(0.0, 1.0 - fma(ad2, R.p * tw, dps));
+            cem += xmc * fmax(0.0, 1.0 + fma(-ad2, L.p * tw, dps));
         }
         const double pnet = fma(wl, L.p, wr * R.p);
         if constexpr (AXI) {
