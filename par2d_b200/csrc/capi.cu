@@ -3,7 +3,7 @@
 // One par2d_ctx = the blocks one rank owns (the reference: one MPI rank per block,
 // FV/main.cpp:124-128), resident in HBM as padded SoA planes with the ghost ring in place
 // (common.cuh).  A step is three launches on one stream, no host synchronisation:
-//   ghost_kernel -> step_kernel -> finalize_kernel
+//   ghost_kernel -> march_kernel -> finalize_kernel
 // and a batch of steps returns its dt / residual history in one copy at the end.
 // There is no CPU fallback anywhere in this file.
 #include <cuda.h>
@@ -107,9 +107,8 @@ EncodeTiledFn tensor_map_encoder() {
 struct par2d_ctx {
     par2d_config cfg;
     Gas gas;
-    bool tpg = false, axi = true, use_tma = true;
-    bool use_march = true;   // marching-strip kernel (march.cuh); false = the TMA tile kernel (PAR2D_KERNEL=tile)
-    int march_rows = 64;
+    bool tpg = false, axi = true;
+    int march_rows = 64;     // cell rows per warp strip of the march kernel (PAR2D_MARCH_ROWS overrides, measurements only)
     const KernelTable* kt = nullptr;
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -120,7 +119,7 @@ struct par2d_ctx {
     std::vector<int> owned_gid, owned_index;
     int nowned = 0;
     std::vector<BlockDev> hblk;
-    std::vector<double*> block_mem;       // one allocation per owned block (10 planes)
+    std::vector<double*> block_mem;       // one allocation per owned block (11 planes: 2 x 4 state, x, y, metric)
     std::vector<int*> block_ibound;
     BlockDev* dblk = nullptr;
     void* dtmaps = nullptr;
@@ -240,22 +239,20 @@ int validate_table(int nblocks, const par2d_block_desc* t, int nranks) {
 
 int build_tensor_maps(par2d_ctx* c) {
     EncodeTiledFn enc = tensor_map_encoder();
-    if (!enc) {
-        c->use_tma = false;
-        return 0;
-    }
+    if (!enc) return fail(PAR2D_ERR_CUDA, "cuTensorMapEncodeTiled is not exported by this driver; the row staging of the march kernel needs it");
     std::vector<CUtensorMap> maps((size_t)c->nowned * 3);
     for (int k = 0; k < c->nowned; k++) {
         const BlockDev& b = c->hblk[k];
         for (int m = 0; m < 3; m++) {
-            const cuuint32_t planes = m < 2 ? 4 : 2;
+            // state A, state B: 4 planes; nodes: x, y, metric.  One box = 32 columns of one row of all planes
+            const cuuint32_t planes = m < 2 ? 4 : 3;
             void* base = m < 2 ? (void*)b.state[m] : (void*)b.nodes;
             const cuuint64_t dims[3] = {(cuuint64_t)b.pitch, (cuuint64_t)(b.ncy + 2), planes};
             const cuuint64_t strides[2] = {(cuuint64_t)b.pitch * 8, (cuuint64_t)b.plane * 8};
-            const cuuint32_t box[3] = {(cuuint32_t)HXL, (cuuint32_t)HY, planes};
+            const cuuint32_t box[3] = {32u, 1u, planes};
             const cuuint32_t estr[3] = {1, 1, 1};
             CUresult r = enc(&maps[(size_t)k * 3 + m], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return fail(PAR2D_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for block %d map %d", (int)r, b.gid, m);
         }
@@ -265,10 +262,7 @@ int build_tensor_maps(par2d_ctx* c) {
     return 0;
 }
 
-void launch_step(par2d_ctx* c, const StepArgs& a) {
-    if (c->use_march) c->kt->march(c->stream, a, c->gas, c->tpg, c->axi);
-    else c->kt->step(c->stream, a, c->gas, c->tpg, c->axi, c->use_tma);
-}
+void launch_step(par2d_ctx* c, const StepArgs& a) { c->kt->march(c->stream, a, c->gas, c->tpg, c->axi); }
 
 void queue_step(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
     StepArgs a = c->step_args(1);
@@ -387,15 +381,8 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
     c->axi = cfg->iaxi == 1;
     c->kt = cfg->mode == PAR2D_MODE_FAITHFUL ? kernels_faithful() : kernels_fast();
     c->device = dev;
-    const char* no_tma = getenv("PAR2D_NO_TMA");
-    c->use_tma = !(no_tma && atoi(no_tma) != 0);
-    // A/B switches for measurements: the kernel variant and the strip height
-    const char* kern = getenv("PAR2D_KERNEL");
-    c->use_march = !(kern && strcmp(kern, "tile") == 0);
     const char* mrows = getenv("PAR2D_MARCH_ROWS");
     if (mrows && atoi(mrows) > 0) c->march_rows = atoi(mrows);
-    cudaError_t pe = c->kt->prepare();
-    if (pe != cudaSuccess) { delete c; return fail(PAR2D_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(pe)); }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(PAR2D_ERR_CUDA, "cannot create stream"); }
     c->own_stream = true;
 
@@ -445,8 +432,8 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
         b.ncy = d.ny - 1;
         b.pitch = ((b.ncx + COL0 + 1 + 15) / 16) * 16;
         b.plane = (long long)b.pitch * (b.ncy + 2);
-        CU_TRY(cudaMalloc(&c->block_mem[k], sizeof(double) * 10 * b.plane));
-        CU_TRY(cudaMemsetAsync(c->block_mem[k], 0, sizeof(double) * 10 * b.plane, c->stream));
+        CU_TRY(cudaMalloc(&c->block_mem[k], sizeof(double) * 11 * b.plane));
+        CU_TRY(cudaMemsetAsync(c->block_mem[k], 0, sizeof(double) * 11 * b.plane, c->stream));
         b.state[0] = c->block_mem[k];
         b.state[1] = c->block_mem[k] + 4 * b.plane;
         b.nodes = c->block_mem[k] + 8 * b.plane;
@@ -454,13 +441,8 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
         CU_TRY(cudaMalloc(&c->block_ibound[k], sizeof(int) * nfaces));
         CU_TRY(cudaMemcpyAsync(c->block_ibound[k], d.ibound, sizeof(int) * nfaces, cudaMemcpyHostToDevice, c->stream));
         b.ibound = c->block_ibound[k];
-        if (c->use_march) {
-            b.tiles_x = (b.ncx + MCELLS - 1) / MCELLS;
-            b.tiles_y = (b.ncy + c->march_rows - 1) / c->march_rows;
-        } else {
-            b.tiles_x = (b.ncx + TX - 1) / TX;
-            b.tiles_y = (b.ncy + TY - 1) / TY;
-        }
+        b.tiles_x = (b.ncx + MCELLS - 1) / MCELLS;
+        b.tiles_y = (b.ncy + c->march_rows - 1) / c->march_rows;
         b.tile0 = c->total_tiles;
         c->total_tiles += b.tiles_x * b.tiles_y;
         c->max_tiles = std::max(c->max_tiles, b.tiles_x * b.tiles_y);
@@ -512,6 +494,7 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
         CU_TRY(cudaMemcpyAsync(c->staging, d.x, sizeof(double) * nn, cudaMemcpyHostToDevice, c->stream));
         CU_TRY(cudaMemcpyAsync(c->staging + nn, d.y, sizeof(double) * nn, cudaMemcpyHostToDevice, c->stream));
         launch_nodes_to_planes(c->stream, b, c->staging, c->staging + nn);
+        launch_cell_metric(c->stream, b, c->axi ? 1 : 0);
         const long long cells = (long long)b.ncx * b.ncy;
         const int nparts = (int)std::min<long long>(1024, (cells + 255) / 256);
         launch_min_face(c->stream, b, dparts, nparts);

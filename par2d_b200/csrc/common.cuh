@@ -5,25 +5,19 @@
 //                     row ncy+1 = top ghost line; nodes j=0..ncy live in rows 1..ncy+1)
 //   pitch  : multiple of 16 doubles (128 B); column COL0-1 = left ghost, COL0+i = cell i,
 //            COL0+ncx = right ghost; node i lives in column COL0+i
-//   planes : state A {rho,u,v,T}, state B {rho,u,v,T} (ping-pong), nodes {x,y}
+//   planes : state A {rho,u,v,T}, state B {rho,u,v,T} (ping-pong), nodes {x, y, metric} where
+//            metric[cell (i,j)] = 1/(vol*ycc) (axisymmetric) or 1/vol (planar), stored at node (i,j)'s slot
 // i.e. the reference's AoS unk[(j*(nx-1)+i)*4+k] (FV/Indexing.h:11) becomes four padded SoA
 // planes with the ghost ring (SpatialDiscretization.cpp:182-185 uGBot/uGRight/uGTop/uGLeft)
-// stored in place, so every cell has four in-array neighbours and one TMA box
-// (TX+2)x(TY+2)x4 stages a tile with its halo.
+// stored in place, so every cell has four in-array neighbours and one TMA box of 32 columns x
+// 4 planes stages a strip row with its two halo columns.
 #pragma once
 #include <stdint.h>
 #include "physics.cuh"
 
 namespace par2d {
 
-constexpr int COL0 = 16;  // column of cell/node i = 0 (keeps row starts 128-byte aligned)
-
-// step-kernel tile: TX x TY cells, one cell per thread
-constexpr int TX = 32;
-constexpr int TY = 8;
-constexpr int STEP_THREADS = TX * TY;
-constexpr int HX = TX + 2, HY = TY + 2;  // haloed tile
-constexpr int HOFF = 1, HXL = HX + 2;    // staged width: the copy starts HOFF columns early (16-byte rule)
+constexpr int COL0 = 17;  // column of cell/node i = 0; odd, so that a strip's first staged column COL0+30k-1 is even (TMA 16-byte rule)
 
 // marching kernel (march.cuh): a warp strip updates MCELLS cell columns (lanes 1..30; lanes 0 and 31
 // carry the halo columns) over StepArgs::march_rows cell rows
@@ -38,13 +32,13 @@ struct BlockDev {
     int pitch;          // doubles per row
     long long plane;    // doubles per plane = pitch*(ncy+2)
     double* state[2];   // 4 planes each
-    double* nodes;      // 2 planes: x, y
+    double* nodes;      // 3 planes: x, y, cell metric
     const int* ibound;  // BC code per boundary face, CCW (SpatialDiscretization.cpp:27,45,64,84)
     int nb_kind[4];     // NB_* per side
     int nb_block[4];    // owned-block index of a same-rank neighbour
     int nb_side[4];     // the neighbour's side that faces us
     double* recv[4];    // AoS line [n*4+k] received from an off-rank neighbour
-    int tiles_x, tiles_y; // work decomposition: 32x8 tiles (tile kernel) or 30-column strips x row chunks (marching kernel)
+    int tiles_x, tiles_y; // work decomposition: 30-column strips x row chunks (marching kernel)
     int tile0;          // first tile/strip of this block in the partial-sum array
     double min_face;    // static part of find_dt (main.cpp:26-32)
 };
@@ -64,9 +58,9 @@ struct StepArgs {
     int nblocks_global;
     int cur;                 // state buffer read this step
     int total_tiles;         // sum over owned blocks (size of partials)
-    int max_tiles;           // tiles of the largest owned block (grid.x of the step kernel)
+    int max_tiles;           // strips of the largest owned block (grid.x of the march kernel)
     int max_faces;           // longest block perimeter (grid.x of the ghost kernel)
-    const void* tmaps;       // CUtensorMap[nowned][3]: state A, state B, nodes
+    const void* tmaps;       // CUtensorMap[nowned][3]: state A, state B, nodes+metric; boxes of 32 columns x 1 row x all planes
     double* dt_table;        // nblocks_global
     double* partials;        // [total_tiles][4] sum of res_k^2
     unsigned* flags;         // device error bits

@@ -116,6 +116,29 @@ __global__ void nodes_to_planes_kernel(BlockDev b, const double* __restrict__ x,
     b.nodes[b.plane + o] = y[c];
 }
 
+// Static cell metric of the fast path, third node plane: 1/(vol*ycc) (axisymmetric: the residual's 1/vol,
+// MeshModule.cpp:34-36 + SpatialDiscretization.cpp:980-1011, times the 1/ycc of main.cpp:325-331) or 1/vol
+// (planar), of cell (i,j) stored in node (i,j)'s slot.  vol is evaluated in the reference's order with
+// individually rounded operations (this TU is compiled with -fmad=false, and cell_volume uses
+// never-contracted intrinsics), the division is IEEE.
+__global__ void cell_metric_kernel(BlockDev b, int axi) {
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (c >= (long long)b.ncx * b.ncy) return;
+    const int i = (int)(c % b.ncx), j = (int)(c / b.ncx);
+    const double* X = b.nodes;
+    const double* Y = b.nodes + b.plane;
+    const long long o = (long long)(j + 1) * b.pitch + COL0 + i;
+    const double x1 = X[o], x2 = X[o + 1], x3 = X[o + b.pitch + 1], x4 = X[o + b.pitch];
+    const double y1 = Y[o], y2 = Y[o + 1], y3 = Y[o + b.pitch + 1], y4 = Y[o + b.pitch];
+    const double vol = cell_volume(x1, y1, x2, y2, x3, y3, x4, y4);
+    const double ycc = 0.25 * (y1 + y2 + y3 + y4);
+    b.nodes[2 * b.plane + o] = axi ? 1.0 / (vol * ycc) : 1.0 / vol;
+}
+void launch_cell_metric(cudaStream_t s, const BlockDev& b, int axi) {
+    const long long n = (long long)b.ncx * b.ncy;
+    cell_metric_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(b, axi);
+}
+
 void launch_aos_to_planes(cudaStream_t s, const BlockDev& b, int buf, const double* aos) {
     const long long n = (long long)b.ncx * b.ncy;
     aos_to_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(b, buf, aos);

@@ -7,10 +7,13 @@
 //   lane l holds cell column c0-1+l: lanes 0 and 31 are the strip's left/right halo columns (their
 //   state is loaded and derived, but only lanes 1..30 update a cell), so the 32 lanes of a row are one
 //   fully coalesced 256-byte read per plane, straight from the padded HBM planes (ghost ring in place).
-//   Rows are staged ahead of their use by cp.async (LDGSTS) into a per-warp shared-memory ring of
-//   MARCH_STAGES rows x 6 planes, every lane copying and later reading only its own 8-byte slots: no
-//   registers are held by loads in flight, no barrier is needed, and HBM latency is covered by
-//   MARCH_STAGES-1 rows of compute.
+//   Rows are staged ahead of their use by TMA (cp.async.bulk.tensor, SASS UTMALDG): lane 0 issues two
+//   tiled copies per row - a 32-column x 4-plane box of the state and a 32-column x 3-plane box of
+//   the node coordinates + cell metric - into a per-warp shared-memory ring of MARCH_STAGES rows, each
+//   stage completing on its own mbarrier.  No registers are held by loads in flight, no address
+//   arithmetic is spent per plane, and HBM latency is covered by MARCH_STAGES-1 rows of compute.
+//   (A tiled copy of 8-byte elements must start on a 16-byte boundary - tools/tma_probe - which is why
+//   cell column 0 sits in the odd array column COL0 = 17: every strip's box starts in an even column.)
 //   Per row and lane: derive the cell one row up, ONE i-face flux (left face; the left cell's state
 //   comes from lane l-1 by warp shuffle, the right face's flux from lane l+1), ONE j-face flux (top
 //   face; the bottom face is last row's top face, parked in shared memory meanwhile), residual,
@@ -28,22 +31,62 @@
 // PAR2D_KERNEL=tile): no block-wide barriers, ~1/6 of the shared-memory traffic, a fifth of the index
 // arithmetic.
 #pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
 #include "common.cuh"
 #include "physics.cuh"
 
 namespace par2d {
 
-#ifndef MARCH_NWARPS
-#define MARCH_NWARPS 1
-#endif
 #ifndef MARCH_MINB
 #define MARCH_MINB 16
 #endif
 #ifndef MARCH_STAGES
 #define MARCH_STAGES 4
 #endif
-constexpr int MARCH_WARPS = MARCH_NWARPS;         // strips per CTA
-constexpr int MARCH_THREADS = 32 * MARCH_WARPS;
+#ifndef MARCH_UNROLL2
+#define MARCH_UNROLL2 0
+#endif
+constexpr int MARCH_THREADS = 32;                 // one warp strip per CTA
+
+// ------------------------------------------------------------------ PTX helpers (TMA + mbarrier)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a mis-programmed copy must surface as an error, never as a hung GPU.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+    for (int spin = 0; spin < (1 << 22); spin++) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+// 3-D tiled bulk tensor load global -> shared, completion on an mbarrier (SASS: UTMALDG).
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+// descriptors live in global memory: make them visible to the tensor-map proxy before first use
+__device__ __forceinline__ void tmap_acquire(const void* tmap) {
+    asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
+}
 
 __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ double shfl_down1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
@@ -61,25 +104,21 @@ __device__ __forceinline__ Flux shfl_down1(const Flux& f) {
     return o;
 }
 
-// cp.async (SASS: LDGSTS): 8 bytes global -> shared, tracked per thread
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// per-warp shared memory: the row ring and the parked bottom-face flux
+// per-warp shared memory: the row ring (TMA destination), its barriers and the parked bottom-face flux
+constexpr int RING_PLANES = 7;                     // rho,u,v,T | x,y,metric
 struct MarchSmem {
-    double ring[MARCH_STAGES][6][32];   // [stage][rho,u,v,T,x,y][lane]
-    double G[5][32];                    // j-face flux at the bottom of the current row
+    double ring[MARCH_STAGES][RING_PLANES][32];    // [stage][plane][lane]; a stage is 1792 B = 14 x 128 B
+    double G[5][32];                               // j-face flux at the bottom of the current row
+    uint64_t bar[MARCH_STAGES];
 };
+constexpr uint32_t STAGE_BYTES = RING_PLANES * 32 * sizeof(double);
 
-// What a lane carries in registers from one row to the next: the derived state of its cell and the two
-// lower nodes of the cell (own column and, from lane+1, the next column).
+// What a lane carries in registers from one row to the next: the derived state of its cell, the cell's
+// metric and the two lower nodes of the cell (own column and, from lane+1, the next column).
 struct RowState {
     FaceState s;
     double T;
+    double im;               // 1/(vol*ycc) (axisymmetric) or 1/vol (planar) of cell (c, j): cell_metric_kernel
     double xa, ya, xb, yb;   // node (c, j), node (c+1, j)
 };
 
@@ -101,6 +140,7 @@ __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const
     hi.T = sm.ring[st][3][lane];
     hi.s = face_state<FAITHFUL, TPG>(g, sm.ring[st][0][lane], sm.ring[st][1][lane], sm.ring[st][2][lane], hi.T, flu);
     hi.xa = sm.ring[st][4][lane]; hi.ya = sm.ring[st][5][lane];   // node (c, j+1)
+    hi.im = sm.ring[st][6][lane];
     hi.xb = shfl_down1(hi.xa); hi.yb = shfl_down1(hi.ya);         // node (c+1, j+1)
 
     // i-face between cell (c-1, j) [left state] and (c, j): node (c, j) -> (c, j+1)
@@ -115,7 +155,6 @@ __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const
     if (m.writer) {
         flags |= flu;
         // cell (c, j): nodes 1..4 = (c,j), (c+1,j), (c+1,j+1), (c,j+1)  (MeshModule.cpp:28-40)
-        const double vol = cell_volume(lo.xa, lo.ya, lo.xb, lo.yb, hi.xb, hi.yb, hi.xa, hi.ya);
         const double ycc = 0.25 * (lo.ya + lo.yb + hi.yb + hi.ya);
         const FaceState& cur = lo.s;
         double r[4];        // residual = calc_dudt's dudt
@@ -123,6 +162,7 @@ __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const
         if constexpr (FAITHFUL) {
             // accumulation order of SpatialDiscretization.cpp:481-625 (interior faces: left, right,
             // bottom, top) then :643-977 (block-boundary faces: left, right, bottom, top)
+            const double vol = cell_volume(lo.xa, lo.ya, lo.xb, lo.yb, hi.xb, hi.yb, hi.xa, hi.ya);
             const double yc = AXI ? ycc : 0.0;
             const bool bl = m.c == 0, br = m.c == m.ncx - 1, bb = j == 0, bt = j == m.ncy - 1;
             const double fl[4] = {Fl.f0, Fl.f1, Fl.f2 + (yc * Fl.parr), Fl.f3};
@@ -155,19 +195,17 @@ __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const
             R[1] = (Fl.f1 - Fr.f1) + (Gt.f1 - Gb.f1);
             R[2] = (Fl.f2 - Fr.f2) + (Gt.f2 - Gb.f2);
             R[3] = (Fl.f3 - Fr.f3) + (Gt.f3 - Gb.f3);
-            double ivol, sc;
+            double ivol;
             if constexpr (AXI) {
                 // axisymmetric source: the y-momentum pressure term carries the cell's own radius
-                // (SpatialDiscretization.cpp:521-523,595-597); 1/vol and 1/ycc (main.cpp:325-331) share
-                // one reciprocal
+                // (SpatialDiscretization.cpp:521-523,595-597); 1/vol and 1/ycc (main.cpp:325-331) come
+                // from the stored metric 1/(vol*ycc)
                 R[2] = fma(ycc, (Fl.parr - Fr.parr) + (Gt.parr - Gb.parr), R[2]);
-                const double im = fast_rcp(vol * ycc);
-                ivol = im * ycc;
-                sc = m.dt * im;
+                ivol = lo.im * ycc;
             } else {
-                ivol = fast_rcp(vol);
-                sc = m.dt * ivol;
+                ivol = lo.im;
             }
+            const double sc = m.dt * lo.im;
 #pragma unroll
             for (int v = 0; v < 4; v++) r[v] = R[v] * ivol;
             if (a.update) {
@@ -197,14 +235,13 @@ __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const
 
 template <bool FAITHFUL, bool TPG, bool AXI>
 __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) march_kernel(const StepArgs a, const Gas g) {
-    __shared__ MarchSmem smem[MARCH_WARPS];
+    __shared__ __align__(128) MarchSmem sm;
     if (*a.stop) return;
-    const int lane = threadIdx.x & 31;
-    MarchSmem& sm = smem[threadIdx.x >> 5];
+    const int lane = threadIdx.x;
     const int k = blockIdx.y;                      // grid.y = owned blocks, grid.x covers the block with most strips
     const BlockDev& b = a.blocks[k];
-    const int strip = blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
-    if (strip >= b.tiles_x * b.tiles_y) return;    // warp-uniform
+    const int strip = blockIdx.x;
+    if (strip >= b.tiles_x * b.tiles_y) return;    // CTA-uniform
     MarchCtx m;
     m.k = k; m.ncx = b.ncx; m.ncy = b.ncy; m.pitch = b.pitch; m.plane = b.plane; m.lane = lane;
     const int c0 = (strip % b.tiles_x) * MCELLS;   // first updated cell column
@@ -213,29 +250,31 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
     m.c = c0 - 1 + lane;                           // this lane's cell column (-1 and ncx are the ghost columns)
     m.writer = lane >= 1 && lane <= MCELLS && m.c < m.ncx;
     m.Sout = b.state[a.cur ^ 1];
-    const long long plane = m.plane;
 
-    // lanes right of the right ghost column re-read that column (never used, never stored)
-    const double* src = b.state[a.cur] + (COL0 + min(m.c, m.ncx));
-    const double* nsrc = b.nodes + (COL0 + min(m.c, m.ncx));
-    // array row `arow` holds cell row arow-1 and node row arow-1; rows past the strip's last one are
-    // not fetched (the group is still committed so that the wait counts stay uniform)
-    const int arow_end = j1 + 1;                   // last array row this strip reads (cell row j1 = row above the last)
-    auto stage_row = [&](int arow, int st) {
+    // ---- TMA row ring.  Array row `arow` holds cell row arow-1, node row arow-1 and the metric of cell
+    // row arow-1; this strip reads array rows j0 (cell row below) .. j1+1 (cell row above the last).
+    const char* maps = static_cast<const char*>(a.tmaps) + (size_t)k * 3 * 128;
+    const void* map_state = maps + a.cur * 128;
+    const void* map_nodes = maps + 2 * 128;
+    const int col0 = COL0 + c0 - 1;                // even: the 16-byte rule of tiled copies
+    const int arow_end = j1 + 1;
+    auto stage_row = [&](int arow, int st) {       // lane 0 only
         if (arow <= arow_end) {
-            const long long o = (long long)arow * m.pitch;
-            cp_async8(&sm.ring[st][0][lane], src + o);
-            cp_async8(&sm.ring[st][1][lane], src + plane + o);
-            cp_async8(&sm.ring[st][2][lane], src + 2 * plane + o);
-            cp_async8(&sm.ring[st][3][lane], src + 3 * plane + o);
-            cp_async8(&sm.ring[st][4][lane], nsrc + o);
-            cp_async8(&sm.ring[st][5][lane], nsrc + plane + o);
+            mbar_expect_tx(&sm.bar[st], STAGE_BYTES);
+            tma_load_3d(&sm.ring[st][0][0], map_state, col0, arow, 0, &sm.bar[st]);
+            tma_load_3d(&sm.ring[st][4][0], map_nodes, col0, arow, 0, &sm.bar[st]);
         }
-        cp_async_commit();
     };
-    // ---- fill the ring: array rows j0 (cell row below), j0+1 (first cell row), j0+2, ...
+    if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < MARCH_STAGES; s++) stage_row(j0 + s, s);
+        for (int s = 0; s < MARCH_STAGES; s++) mbar_init(&sm.bar[s], 1);
+        mbar_init_fence();
+        tmap_acquire(map_state);
+        tmap_acquire(map_nodes);
+#pragma unroll
+        for (int s = 0; s < MARCH_STAGES; s++) stage_row(j0 + s, s);
+    }
+    __syncwarp();
 
     // global dt = max over blocks (main.cpp:270-292); the table was written by the ghost kernel
     double dt = 0.0;
@@ -245,14 +284,17 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
     m.dt = dt;
 
     unsigned flags = 0;
+    bool ok = true;
     // ---- prologue: cell rows j0-1 (stage 0) and j0 (stage 1), node row j0, bottom-face flux of row j0
     RowState A, B;
-    cp_async_wait<MARCH_STAGES - 2>();
+    ok &= mbar_wait(&sm.bar[0], 0);
+    ok &= mbar_wait(&sm.bar[1], 0);
     {
         unsigned fl0 = 0;
         A.T = sm.ring[1][3][lane];
         A.s = face_state<FAITHFUL, TPG>(g, sm.ring[1][0][lane], sm.ring[1][1][lane], sm.ring[1][2][lane], A.T, fl0);
         A.xa = sm.ring[1][4][lane]; A.ya = sm.ring[1][5][lane];
+        A.im = sm.ring[1][6][lane];
         A.xb = shfl_down1(A.xa); A.yb = shfl_down1(A.ya);
         const FaceState lo = face_state<FAITHFUL, TPG>(g, sm.ring[0][0][lane], sm.ring[0][1][lane], sm.ring[0][2][lane], sm.ring[0][3][lane], fl0);
         // j-face: left state = upper cell, right state = lower cell (SpatialDiscretization.cpp:556-625)
@@ -261,22 +303,46 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
         if (m.writer) flags |= fl0;
     }
     double sq0 = 0.0, sq1 = 0.0, sq2 = 0.0, sq3 = 0.0;
+    // stages 0 and 1 are consumed: refill them with the next two rows
+    __syncwarp();
+    if (lane == 0) {
+        stage_row(j0 + MARCH_STAGES, 0);
+        stage_row(j0 + MARCH_STAGES + 1, 1);
+    }
 
-    // ---- march: row j consumes array row j+2 (ring stage (j-j0+2) % STAGES), then refills the stage that
-    //      held array row j+1-... with array row j+2+STAGES-... ; stages 0 and 1 are free after the prologue
-    stage_row(j0 + MARCH_STAGES, 0);
-    stage_row(j0 + MARCH_STAGES + 1, 1);
-    int st = 2 % MARCH_STAGES;                     // stage of array row j+2
+    // ---- march: row j consumes array row j+2 = ring use n = j-j0+2 (stage n % STAGES, parity (n / STAGES) & 1)
+    //      and then refills that stage with array row j+2+STAGES
+    int st = 2 % MARCH_STAGES;
+    uint32_t ph = (2 / MARCH_STAGES) & 1;
+    auto advance = [&](int j) {
+        __syncwarp();                              // every lane has read stage st
+        if (lane == 0) stage_row(j + 2 + MARCH_STAGES, st);
+        if (++st == MARCH_STAGES) { st = 0; ph ^= 1u; }
+    };
+#if MARCH_UNROLL2
+    int j = j0;
+#pragma unroll 1
+    for (; j + 1 < j1; j += 2) {
+        ok &= mbar_wait(&sm.bar[st], ph);
+        march_row<FAITHFUL, TPG, AXI>(a, g, m, sm, j, st, A, B, sq0, sq1, sq2, sq3, flags);
+        advance(j);
+        ok &= mbar_wait(&sm.bar[st], ph);
+        march_row<FAITHFUL, TPG, AXI>(a, g, m, sm, j + 1, st, B, A, sq0, sq1, sq2, sq3, flags);
+        advance(j + 1);
+    }
+    if (j < j1) {
+        ok &= mbar_wait(&sm.bar[st], ph);
+        march_row<FAITHFUL, TPG, AXI>(a, g, m, sm, j, st, A, B, sq0, sq1, sq2, sq3, flags);
+    }
+#else
 #pragma unroll 1
     for (int j = j0; j < j1; j++) {
-        // groups committed so far: array rows <= j+1+STAGES; the row needed now is j+2
-        cp_async_wait<MARCH_STAGES - 1>();
+        ok &= mbar_wait(&sm.bar[st], ph);
         march_row<FAITHFUL, TPG, AXI>(a, g, m, sm, j, st, A, B, sq0, sq1, sq2, sq3, flags);
         A = B;
-        stage_row(j + 2 + MARCH_STAGES, st);       // this stage is consumed: refill it
-        st = (st + 1 == MARCH_STAGES) ? 0 : st + 1;
+        advance(j);
     }
-    cp_async_wait<0>();
+#endif
 
     // ---- sum of squares of this strip, fixed order: lanes (xor tree)
     double sq[4] = {sq0, sq1, sq2, sq3};
@@ -286,6 +352,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
         for (int s = 16; s > 0; s >>= 1) sq[v] += __shfl_xor_sync(0xffffffffu, sq[v], s);
     }
     if (isnan(sq[0]) || isnan(sq[1]) || isnan(sq[2]) || isnan(sq[3])) flags |= FLAG_NAN;   // SpatialDiscretization.cpp:1008
+    if (!ok) flags |= FLAG_NAN | 0x80000000u;      // a staged row never arrived
     if (lane < 4) {
         const double s = lane == 0 ? sq[0] : lane == 1 ? sq[1] : lane == 2 ? sq[2] : sq[3];
         a.partials[4 * (long long)(b.tile0 + strip) + lane] = s;

@@ -258,20 +258,6 @@ def test_stop_on_tol(gpu, oracle):
     assert max(state_err(dev.get_state(b), orc.get_state(b)) for b in range(8)) < 1e-13
 
 
-def test_tma_and_plain_load_paths_agree_bitwise(gpu):
-    case = Case.load(case_path("Case_spikefine24"))
-    a = Solver(case, make_cfg(gpu), lib=gpu)
-    os.environ["PAR2D_NO_TMA"] = "1"
-    try:
-        b = Solver(case, make_cfg(gpu), lib=gpu)
-    finally:
-        del os.environ["PAR2D_NO_TMA"]
-    a.step(50)
-    b.step(50)
-    for k in range(case.nblocks):
-        assert np.array_equal(a.get_state(k), b.get_state(k))
-
-
 # ------------------------------------------------------------------ benchmark-size properties
 
 def test_synthetic_small_vs_oracle(gpu, oracle):
