@@ -244,12 +244,12 @@ int build_tensor_maps(par2d_ctx* c) {
     for (int k = 0; k < c->nowned; k++) {
         const BlockDev& b = c->hblk[k];
         for (int m = 0; m < 3; m++) {
-            // state A, state B: 4 planes; nodes: x, y, metric.  One box = 32 columns of one row of all planes
+            // state A, state B: 4 planes; nodes: x, y, metric.  One box = the 32*MARCH_CPL staged columns of one row of all planes
             const cuuint32_t planes = m < 2 ? 4 : 3;
             void* base = m < 2 ? (void*)b.state[m] : (void*)b.nodes;
             const cuuint64_t dims[3] = {(cuuint64_t)b.pitch, (cuuint64_t)(b.ncy + 2), planes};
             const cuuint64_t strides[2] = {(cuuint64_t)b.pitch * 8, (cuuint64_t)b.plane * 8};
-            const cuuint32_t box[3] = {32u, 1u, planes};
+            const cuuint32_t box[3] = {(cuuint32_t)(32 * MARCH_CPL), 1u, planes};
             const cuuint32_t estr[3] = {1, 1, 1};
             CUresult r = enc(&maps[(size_t)k * 3 + m], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

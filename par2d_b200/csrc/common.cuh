@@ -19,9 +19,13 @@ namespace par2d {
 
 constexpr int COL0 = 17;  // column of cell/node i = 0; odd, so that a strip's first staged column COL0+30k-1 is even (TMA 16-byte rule)
 
-// marching kernel (march.cuh): a warp strip updates MCELLS cell columns (lanes 1..30; lanes 0 and 31
-// carry the halo columns) over StepArgs::march_rows cell rows
-constexpr int MCELLS = 30;
+// marching kernel (march.cuh): a warp strip updates MCELLS cell columns - MARCH_CPL columns per lane, the
+// first and the last of the 32*MARCH_CPL staged columns being halo columns - over StepArgs::march_rows
+// cell rows
+#ifndef MARCH_CPL
+#define MARCH_CPL 1   // measured on B200: 2 columns per lane need ~200 registers (10 warps/SM) and lose to 1 column at 16 warps/SM
+#endif
+constexpr int MCELLS = 32 * MARCH_CPL - 2;
 
 enum : int { SIDE_BOTTOM = 0, SIDE_RIGHT = 1, SIDE_TOP = 2, SIDE_LEFT = 3 };
 enum : int { NB_NONE = 0, NB_LOCAL = 1, NB_REMOTE = 2 };

@@ -1,12 +1,13 @@
 // march.cuh -- the production step kernel: register-marching warp strips.
 //
-// One warp (= one CTA) advances a strip of MCELLS (30) cell columns by `march_rows` cell rows of one
-// block, marching upwards row by row (FV/SpatialDiscretization.cpp:481-1011 + main.cpp:39-57,307-351,
-// 394-404 fused):
+// One warp (= one CTA) advances a strip of MCELLS = 32*CPL-2 cell columns by `march_rows` cell rows of
+// one block, marching upwards row by row (FV/SpatialDiscretization.cpp:481-1011 + main.cpp:39-57,
+// 307-351,394-404 fused):
 //
-//   lane l holds cell column c0-1+l: lanes 0 and 31 are the strip's left/right halo columns (their
-//   state is loaded and derived, but only lanes 1..30 update a cell), so the 32 lanes of a row are one
-//   fully coalesced 256-byte read per plane, straight from the padded HBM planes (ghost ring in place).
+//   lane l holds CPL (= MARCH_CPL, 1 or 2) adjacent cell columns c0-1+CPL*l ..: the first and the last
+//   column of the warp are the strip's left/right halo columns (their state is loaded and derived,
+//   but never updated), so a row is one contiguous 256*CPL-byte read per plane from the padded HBM
+//   planes (ghost ring in place).
 //   Rows are staged ahead of their use by TMA (cp.async.bulk.tensor, SASS UTMALDG): lane 0 issues two
 //   tiled copies per row - a 32-column x 4-plane box of the state and a 32-column x 3-plane box of
 //   the node coordinates + cell metric - into a per-warp shared-memory ring of MARCH_STAGES rows, each
@@ -14,10 +15,10 @@
 //   arithmetic is spent per plane, and HBM latency is covered by MARCH_STAGES-1 rows of compute.
 //   (A tiled copy of 8-byte elements must start on a 16-byte boundary - tools/tma_probe - which is why
 //   cell column 0 sits in the odd array column COL0 = 17: every strip's box starts in an even column.)
-//   Per row and lane: derive the cell one row up, ONE i-face flux (left face; the left cell's state
-//   comes from lane l-1 by warp shuffle, the right face's flux from lane l+1), ONE j-face flux (top
-//   face; the bottom face is last row's top face, parked in shared memory meanwhile), residual,
-//   norms, Jacobian solve, update, 4 coalesced stores.
+//   Per row and cell: derive the cell one row up, ONE i-face flux (left face; across lanes the left
+//   cell's state comes from lane l-1 by warp shuffle and the right face's flux from lane l+1), ONE
+//   j-face flux (top face; the bottom face is last row's top face, parked in shared memory
+//   meanwhile), residual, norms, Jacobian solve, update, coalesced (CPL=2: 16-byte) stores.
 //   Every state value is read from HBM once per strip (plus the halo column / row re-reads, 2/30 and
 //   1/rows, which hit L2) and every face flux is evaluated once per strip.  The sum of squares is
 //   accumulated per lane over the rows and reduced by warp shuffles in a fixed order once per strip.
@@ -38,14 +39,20 @@
 
 namespace par2d {
 
+#ifndef MARCH_CPL
+#define MARCH_CPL 1
+#endif
 #ifndef MARCH_MINB
-#define MARCH_MINB 16
+#define MARCH_MINB (MARCH_CPL == 2 ? 8 : 16)
+#endif
+#ifndef MARCH_NODE_LDS
+#define MARCH_NODE_LDS 0
 #endif
 #ifndef MARCH_STAGES
 #define MARCH_STAGES 4
 #endif
 #ifndef MARCH_UNROLL2
-#define MARCH_UNROLL2 0
+#define MARCH_UNROLL2 1   // two rows per trip with the carried state swapping roles: no register moves between rows
 #endif
 constexpr int MARCH_THREADS = 32;                 // one warp strip per CTA
 
@@ -105,130 +112,202 @@ __device__ __forceinline__ Flux shfl_down1(const Flux& f) {
 }
 
 // per-warp shared memory: the row ring (TMA destination), its barriers and the parked bottom-face flux
+constexpr int CPL = MARCH_CPL;                     // cell columns per lane
+constexpr int WCOLS = 32 * CPL;                    // columns staged per row
 constexpr int RING_PLANES = 7;                     // rho,u,v,T | x,y,metric
 struct MarchSmem {
-    double ring[MARCH_STAGES][RING_PLANES][32];    // [stage][plane][lane]; a stage is 1792 B = 14 x 128 B
-    double G[5][32];                               // j-face flux at the bottom of the current row
+    double ring[MARCH_STAGES][RING_PLANES][WCOLS]; // [stage][plane][column]; a stage is a multiple of 128 B
+    double G[5][WCOLS];                            // j-face flux at the bottom of the current row
     uint64_t bar[MARCH_STAGES];
 };
-constexpr uint32_t STAGE_BYTES = RING_PLANES * 32 * sizeof(double);
+constexpr uint32_t STAGE_BYTES = RING_PLANES * WCOLS * sizeof(double);
 
-// What a lane carries in registers from one row to the next: the derived state of its cell, the cell's
-// metric and the two lower nodes of the cell (own column and, from lane+1, the next column).
+// What a lane carries in registers from one row to the next, per cell column: the derived state of the
+// cell, its metric and the node at its lower-left corner; plus the node right of the last column.
 struct RowState {
-    FaceState s;
-    double T;
-    double im;               // 1/(vol*ycc) (axisymmetric) or 1/vol (planar) of cell (c, j): cell_metric_kernel
-    double xa, ya, xb, yb;   // node (c, j), node (c+1, j)
+    FaceState s[CPL];
+    double T[CPL];
+    double im[CPL];          // 1/(vol*ycc) (axisymmetric) or 1/vol (planar) of cell (c, j): cell_metric_kernel
+    double x[CPL + 1], y[CPL + 1];   // nodes (c, j) .. (c+CPL, j)
 };
 
 struct MarchCtx {
-    int k, c, ncx, ncy, pitch, lane;
+    int k, c, ncx, ncy, pitch, lane;   // c = first cell column of this lane
     long long plane;
-    bool writer;
+    bool writer[CPL];
     double dt;
     double* Sout;
 };
 
+// Residual, norms, solve and new state of one cell from its four face fluxes (left, right, bottom, top).
+// (xa,ya)..(xd,yd) = nodes (c,j), (c+1,j), (c+1,j+1), (c,j+1)  (MeshModule.cpp:28-40).  Returns the new
+// state in out[4] when a.update.
+template <bool FAITHFUL, bool TPG, bool AXI>
+__device__ __forceinline__ void cell_update(const StepArgs& a, const Gas& g, const MarchCtx& m, int c, int j, const FaceState& cur, double T, double im,
+                                            double xa, double ya, double xb, double yb, double xc, double yc_, double xd, double yd,
+                                            const Flux& Fl, const Flux& Fr, const Flux& Gb, const Flux& Gt,
+                                            double out[4], double& sq0, double& sq1, double& sq2, double& sq3, unsigned& flags) {
+    const double ycc = 0.25 * (ya + yb + yc_ + yd);
+    double r[4];        // residual = calc_dudt's dudt
+    double dv[4];
+    if constexpr (FAITHFUL) {
+        // accumulation order of SpatialDiscretization.cpp:481-625 (interior faces: left, right,
+        // bottom, top) then :643-977 (block-boundary faces: left, right, bottom, top)
+        const double vol = cell_volume(xa, ya, xb, yb, xc, yc_, xd, yd);
+        const double yc = AXI ? ycc : 0.0;
+        const bool bl = c == 0, br = c == m.ncx - 1, bb = j == 0, bt = j == m.ncy - 1;
+        const double fl[4] = {Fl.f0, Fl.f1, Fl.f2 + (yc * Fl.parr), Fl.f3};
+        const double fr[4] = {Fr.f0, Fr.f1, Fr.f2 + (yc * Fr.parr), Fr.f3};
+        const double gb[4] = {Gb.f0, Gb.f1, Gb.f2 + (yc * Gb.parr), Gb.f3};
+        const double gt[4] = {Gt.f0, Gt.f1, Gt.f2 + (yc * Gt.parr), Gt.f3};
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            double acc = 0.0;
+            if (!bl) acc += fl[v];
+            if (!br) acc -= fr[v];
+            if (!bb) acc -= gb[v];
+            if (!bt) acc += gt[v];
+            if (bl) acc += fl[v];
+            if (br) acc -= fr[v];
+            if (bb) acc -= gb[v];
+            if (bt) acc += gt[v];
+            r[v] = acc / vol;
+        }
+        if (a.update) {
+            unsigned fl2 = 0;
+            const double v2 = cur.u * cur.u + cur.v * cur.v;
+            const double e0 = enthalpy<TPG>(g, T, fl2) - g.Rs * T + 0.5 * v2;   // StateVariables.h:62
+            const double Cv = heat_capacity<TPG>(g, T, fl2) - g.Rs;
+            solve_cell<true, AXI>(m.dt, ycc, cur.rho, cur.u, cur.v, e0, Cv, 0.0, r, dv, flags);
+        }
+    } else {
+        double R[4];    // raw flux sums
+        R[0] = (Fl.f0 - Fr.f0) + (Gt.f0 - Gb.f0);
+        R[1] = (Fl.f1 - Fr.f1) + (Gt.f1 - Gb.f1);
+        R[2] = (Fl.f2 - Fr.f2) + (Gt.f2 - Gb.f2);
+        R[3] = (Fl.f3 - Fr.f3) + (Gt.f3 - Gb.f3);
+        double ivol;
+        if constexpr (AXI) {
+            // axisymmetric source: the y-momentum pressure term carries the cell's own radius
+            // (SpatialDiscretization.cpp:521-523,595-597); 1/vol and 1/ycc (main.cpp:325-331) come
+            // from the stored metric 1/(vol*ycc)
+            R[2] = fma(ycc, (Fl.parr - Fr.parr) + (Gt.parr - Gb.parr), R[2]);
+            ivol = im * ycc;
+        } else {
+            ivol = im;
+        }
+        const double sc = m.dt * im;
+#pragma unroll
+        for (int v = 0; v < 4; v++) r[v] = R[v] * ivol;
+        if (a.update) {
+            unsigned fl2 = 0;
+            const double e0 = fma(-g.Rs, T, cur.h0);   // h - Rs T + v2/2 with h0 = h + v2/2 at hand
+            double inv_cv = g.inv_cv_cpg;
+            if constexpr (TPG) inv_cv = fast_rcp(heat_capacity<TPG>(g, T, fl2) - g.Rs);
+            solve_lean(sc, cur.rho, cur.u, cur.v, e0, inv_cv, R, dv);
+        }
+    }
+    sq0 = fma(r[0], r[0], sq0); sq1 = fma(r[1], r[1], sq1); sq2 = fma(r[2], r[2], sq2); sq3 = fma(r[3], r[3], sq3);
+    if (a.res_out != nullptr && a.res_block == m.k) {
+        double* o = a.res_out + 4 * ((long long)j * m.ncx + c);
+        o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[3];
+    }
+    if (a.update) {
+        // main.cpp:394-404: unk += dv, rho > 0, UpdateState's T clamp
+        out[0] = cur.rho + dv[0]; out[1] = cur.u + dv[1]; out[2] = cur.v + dv[2];
+        out[3] = fmax(T + dv[3], 201.0);
+        if (!(out[0] > 0.0)) flags |= FLAG_DENSITY;
+        if constexpr (CPL == 1) {
+            double* o = m.Sout + ((long long)(j + 1) * m.pitch + COL0 + c);
+            __stcg(o, out[0]); __stcg(o + m.plane, out[1]); __stcg(o + 2 * m.plane, out[2]); __stcg(o + 3 * m.plane, out[3]);
+        }
+    }
+}
+
 // One row of a strip: consumes the carried state `lo` of cell row j and the staged row above it
-// (ring stage `st`), produces the carried state `hi` of row j+1, updates cell (c, j).
+// (ring stage `st`), produces the carried state `hi` of row j+1, updates this lane's cells of row j.
 template <bool FAITHFUL, bool TPG, bool AXI>
 __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const MarchCtx& m, MarchSmem& sm, int j, int st, const RowState& lo,
                                           RowState& hi, double& sq0, double& sq1, double& sq2, double& sq3, unsigned& flags) {
-    const int lane = m.lane;
-    unsigned flu = 0;
-    hi.T = sm.ring[st][3][lane];
-    hi.s = face_state<FAITHFUL, TPG>(g, sm.ring[st][0][lane], sm.ring[st][1][lane], sm.ring[st][2][lane], hi.T, flu);
-    hi.xa = sm.ring[st][4][lane]; hi.ya = sm.ring[st][5][lane];   // node (c, j+1)
-    hi.im = sm.ring[st][6][lane];
-    hi.xb = shfl_down1(hi.xa); hi.yb = shfl_down1(hi.ya);         // node (c+1, j+1)
-
-    // i-face between cell (c-1, j) [left state] and (c, j): node (c, j) -> (c, j+1)
-    const Flux Fl = ldfss<FAITHFUL, AXI>(face_geom<FAITHFUL>(lo.xa, lo.ya, hi.xa, hi.ya), shfl_up1(lo.s), lo.s);
-    const Flux Fr = shfl_down1(Fl);
-    // j-face between cell (c, j+1) [left state = upper cell] and (c, j): node (c, j+1) -> (c+1, j+1)
-    const Flux Gt = ldfss<FAITHFUL, AXI>(face_geom<FAITHFUL>(hi.xa, hi.ya, hi.xb, hi.yb), hi.s, lo.s);
-    Flux Gb;
-    Gb.f0 = sm.G[0][lane]; Gb.f1 = sm.G[1][lane]; Gb.f2 = sm.G[2][lane]; Gb.f3 = sm.G[3][lane]; Gb.parr = sm.G[4][lane];
-    sm.G[0][lane] = Gt.f0; sm.G[1][lane] = Gt.f1; sm.G[2][lane] = Gt.f2; sm.G[3][lane] = Gt.f3; sm.G[4][lane] = Gt.parr;
-
-    if (m.writer) {
-        flags |= flu;
-        // cell (c, j): nodes 1..4 = (c,j), (c+1,j), (c+1,j+1), (c,j+1)  (MeshModule.cpp:28-40)
-        const double ycc = 0.25 * (lo.ya + lo.yb + hi.yb + hi.ya);
-        const FaceState& cur = lo.s;
-        double r[4];        // residual = calc_dudt's dudt
-        double dv[4];
-        if constexpr (FAITHFUL) {
-            // accumulation order of SpatialDiscretization.cpp:481-625 (interior faces: left, right,
-            // bottom, top) then :643-977 (block-boundary faces: left, right, bottom, top)
-            const double vol = cell_volume(lo.xa, lo.ya, lo.xb, lo.yb, hi.xb, hi.yb, hi.xa, hi.ya);
-            const double yc = AXI ? ycc : 0.0;
-            const bool bl = m.c == 0, br = m.c == m.ncx - 1, bb = j == 0, bt = j == m.ncy - 1;
-            const double fl[4] = {Fl.f0, Fl.f1, Fl.f2 + (yc * Fl.parr), Fl.f3};
-            const double fr[4] = {Fr.f0, Fr.f1, Fr.f2 + (yc * Fr.parr), Fr.f3};
-            const double gb[4] = {Gb.f0, Gb.f1, Gb.f2 + (yc * Gb.parr), Gb.f3};
-            const double gt[4] = {Gt.f0, Gt.f1, Gt.f2 + (yc * Gt.parr), Gt.f3};
+    const int q = CPL * m.lane;                    // this lane's first column in the staged row
+    unsigned flu[CPL];
+    double raw[RING_PLANES][CPL];
+    if constexpr (CPL == 2) {
 #pragma unroll
-            for (int v = 0; v < 4; v++) {
-                double acc = 0.0;
-                if (!bl) acc += fl[v];
-                if (!br) acc -= fr[v];
-                if (!bb) acc -= gb[v];
-                if (!bt) acc += gt[v];
-                if (bl) acc += fl[v];
-                if (br) acc -= fr[v];
-                if (bb) acc -= gb[v];
-                if (bt) acc += gt[v];
-                r[v] = acc / vol;
-            }
-            if (a.update) {
-                unsigned fl2 = 0;
-                const double v2 = cur.u * cur.u + cur.v * cur.v;
-                const double e0 = enthalpy<TPG>(g, lo.T, fl2) - g.Rs * lo.T + 0.5 * v2;   // StateVariables.h:62
-                const double Cv = heat_capacity<TPG>(g, lo.T, fl2) - g.Rs;
-                solve_cell<true, AXI>(m.dt, ycc, cur.rho, cur.u, cur.v, e0, Cv, 0.0, r, dv, flags);
-            }
-        } else {
-            double R[4];    // raw flux sums
-            R[0] = (Fl.f0 - Fr.f0) + (Gt.f0 - Gb.f0);
-            R[1] = (Fl.f1 - Fr.f1) + (Gt.f1 - Gb.f1);
-            R[2] = (Fl.f2 - Fr.f2) + (Gt.f2 - Gb.f2);
-            R[3] = (Fl.f3 - Fr.f3) + (Gt.f3 - Gb.f3);
-            double ivol;
-            if constexpr (AXI) {
-                // axisymmetric source: the y-momentum pressure term carries the cell's own radius
-                // (SpatialDiscretization.cpp:521-523,595-597); 1/vol and 1/ycc (main.cpp:325-331) come
-                // from the stored metric 1/(vol*ycc)
-                R[2] = fma(ycc, (Fl.parr - Fr.parr) + (Gt.parr - Gb.parr), R[2]);
-                ivol = lo.im * ycc;
-            } else {
-                ivol = lo.im;
-            }
-            const double sc = m.dt * lo.im;
+        for (int v = 0; v < RING_PLANES; v++) {
+            const double2 t = *reinterpret_cast<const double2*>(&sm.ring[st][v][q]);
+            raw[v][0] = t.x; raw[v][1] = t.y;
+        }
+    } else {
 #pragma unroll
-            for (int v = 0; v < 4; v++) r[v] = R[v] * ivol;
-            if (a.update) {
-                unsigned fl2 = 0;
-                const double e0 = fma(-g.Rs, lo.T, cur.h0);   // h - Rs T + v2/2 with h0 = h + v2/2 at hand
-                double inv_cv = g.inv_cv_cpg;
-                if constexpr (TPG) inv_cv = fast_rcp(heat_capacity<TPG>(g, lo.T, fl2) - g.Rs);
-                solve_lean(sc, cur.rho, cur.u, cur.v, e0, inv_cv, R, dv);
-            }
-        }
-        sq0 = fma(r[0], r[0], sq0); sq1 = fma(r[1], r[1], sq1); sq2 = fma(r[2], r[2], sq2); sq3 = fma(r[3], r[3], sq3);
+        for (int v = 0; v < RING_PLANES; v++) raw[v][0] = sm.ring[st][v][q];
+    }
+#pragma unroll
+    for (int e = 0; e < CPL; e++) {
+        flu[e] = 0;
+        hi.T[e] = raw[3][e];
+        hi.s[e] = face_state<FAITHFUL, TPG>(g, raw[0][e], raw[1][e], raw[2][e], raw[3][e], flu[e]);
+        hi.x[e] = raw[4][e]; hi.y[e] = raw[5][e];  // node (c+e, j+1)
+        hi.im[e] = raw[6][e];
+    }
+    // node right of this lane's last column = first node of lane+1 (for lane 31 it is never used)
+#if MARCH_NODE_LDS
+    hi.x[CPL] = sm.ring[st][4][q + CPL]; hi.y[CPL] = sm.ring[st][5][q + CPL];   // lane 31 reads the next plane's first slot: unused
+#else
+    hi.x[CPL] = shfl_down1(hi.x[0]); hi.y[CPL] = shfl_down1(hi.y[0]);
+#endif
 
-        if (a.res_out != nullptr && a.res_block == m.k) {
-            double* o = a.res_out + 4 * ((long long)j * m.ncx + m.c);
-            o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[3];
+    // i-faces of row j: face e between cell (c+e-1, j) [left state] and (c+e, j): node (c+e, j) -> (c+e, j+1);
+    // the left state of face 0 is the last cell of lane-1, the flux of face CPL is face 0 of lane+1
+    Flux F[CPL + 1];
+    F[0] = ldfss<FAITHFUL, AXI>(face_geom<FAITHFUL>(lo.x[0], lo.y[0], hi.x[0], hi.y[0]), shfl_up1(lo.s[CPL - 1]), lo.s[0]);
+#pragma unroll
+    for (int e = 1; e < CPL; e++)
+        F[e] = ldfss<FAITHFUL, AXI>(face_geom<FAITHFUL>(lo.x[e], lo.y[e], hi.x[e], hi.y[e]), lo.s[e - 1], lo.s[e]);
+    F[CPL] = shfl_down1(F[0]);
+    // j-faces: between cell (c+e, j+1) [left state = upper cell] and (c+e, j): node (c+e, j+1) -> (c+e+1, j+1)
+    Flux Gt[CPL], Gb[CPL];
+#pragma unroll
+    for (int e = 0; e < CPL; e++)
+        Gt[e] = ldfss<FAITHFUL, AXI>(face_geom<FAITHFUL>(hi.x[e], hi.y[e], hi.x[e + 1], hi.y[e + 1]), hi.s[e], lo.s[e]);
+    // swap the parked bottom fluxes with the new top fluxes
+    if constexpr (CPL == 2) {
+        double2* G2 = reinterpret_cast<double2*>(&sm.G[0][q]);
+        constexpr int stride = WCOLS / 2;
+        double2 t;
+        t = G2[0 * stride]; Gb[0].f0 = t.x; Gb[1].f0 = t.y; G2[0 * stride] = make_double2(Gt[0].f0, Gt[1].f0);
+        t = G2[1 * stride]; Gb[0].f1 = t.x; Gb[1].f1 = t.y; G2[1 * stride] = make_double2(Gt[0].f1, Gt[1].f1);
+        t = G2[2 * stride]; Gb[0].f2 = t.x; Gb[1].f2 = t.y; G2[2 * stride] = make_double2(Gt[0].f2, Gt[1].f2);
+        t = G2[3 * stride]; Gb[0].f3 = t.x; Gb[1].f3 = t.y; G2[3 * stride] = make_double2(Gt[0].f3, Gt[1].f3);
+        t = G2[4 * stride]; Gb[0].parr = t.x; Gb[1].parr = t.y; G2[4 * stride] = make_double2(Gt[0].parr, Gt[1].parr);
+    } else {
+        Gb[0].f0 = sm.G[0][q]; Gb[0].f1 = sm.G[1][q]; Gb[0].f2 = sm.G[2][q]; Gb[0].f3 = sm.G[3][q]; Gb[0].parr = sm.G[4][q];
+        sm.G[0][q] = Gt[0].f0; sm.G[1][q] = Gt[0].f1; sm.G[2][q] = Gt[0].f2; sm.G[3][q] = Gt[0].f3; sm.G[4][q] = Gt[0].parr;
+    }
+
+    double out[CPL][4];
+#pragma unroll
+    for (int e = 0; e < CPL; e++) {
+        if (m.writer[e]) {
+            flags |= flu[e];   // state checks of the cell above: a real cell or a filled ghost
+            cell_update<FAITHFUL, TPG, AXI>(a, g, m, m.c + e, j, lo.s[e], lo.T[e], lo.im[e], lo.x[e], lo.y[e], lo.x[e + 1], lo.y[e + 1],
+                                            hi.x[e + 1], hi.y[e + 1], hi.x[e], hi.y[e], F[e], F[e + 1], Gb[e], Gt[e], out[e], sq0, sq1, sq2, sq3, flags);
         }
+    }
+    if constexpr (CPL == 2) {
         if (a.update) {
-            // main.cpp:394-404: unk += dv, rho > 0, UpdateState's T clamp
-            const double nrho = cur.rho + dv[0], nu = cur.u + dv[1], nv = cur.v + dv[2];
-            const double nT = fmax(lo.T + dv[3], 201.0);
-            if (!(nrho > 0.0)) flags |= FLAG_DENSITY;
             double* o = m.Sout + ((long long)(j + 1) * m.pitch + COL0 + m.c);
-            __stcg(o, nrho); __stcg(o + m.plane, nu); __stcg(o + 2 * m.plane, nv); __stcg(o + 3 * m.plane, nT);
+            if (m.writer[0] && m.writer[1]) {      // 16-byte stores: COL0 + c is even for every lane
+#pragma unroll
+                for (int v = 0; v < 4; v++) __stcg(reinterpret_cast<double2*>(o + v * m.plane), make_double2(out[0][v], out[1][v]));
+            } else {
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+                    if (m.writer[e]) {
+#pragma unroll
+                        for (int v = 0; v < 4; v++) __stcg(o + v * m.plane + e, out[e][v]);
+                    }
+            }
         }
     }
 }
@@ -247,8 +326,12 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
     const int c0 = (strip % b.tiles_x) * MCELLS;   // first updated cell column
     const int j0 = (strip / b.tiles_x) * a.march_rows;
     const int j1 = min(j0 + a.march_rows, m.ncy);
-    m.c = c0 - 1 + lane;                           // this lane's cell column (-1 and ncx are the ghost columns)
-    m.writer = lane >= 1 && lane <= MCELLS && m.c < m.ncx;
+    m.c = c0 - 1 + CPL * lane;                     // this lane's first cell column (-1 and ncx are the ghost columns)
+#pragma unroll
+    for (int e = 0; e < CPL; e++) {
+        const int w = CPL * lane + e;              // column within the staged row: 0 and WCOLS-1 are the halo columns
+        m.writer[e] = w >= 1 && w <= MCELLS && m.c + e < m.ncx;
+    }
     m.Sout = b.state[a.cur ^ 1];
 
     // ---- TMA row ring.  Array row `arow` holds cell row arow-1, node row arow-1 and the metric of cell
@@ -278,29 +361,37 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
 
     // global dt = max over blocks (main.cpp:270-292); the table was written by the ghost kernel
     double dt = 0.0;
-    for (int q = lane; q < a.nblocks_global; q += 32) dt = fmax(dt, a.dt_table[q]);
+    for (int t = lane; t < a.nblocks_global; t += 32) dt = fmax(dt, a.dt_table[t]);
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) dt = fmax(dt, __shfl_xor_sync(0xffffffffu, dt, s));
     m.dt = dt;
 
     unsigned flags = 0;
     bool ok = true;
-    // ---- prologue: cell rows j0-1 (stage 0) and j0 (stage 1), node row j0, bottom-face flux of row j0
+    // ---- prologue: cell rows j0-1 (stage 0) and j0 (stage 1), node row j0, bottom-face fluxes of row j0
     RowState A, B;
     ok &= mbar_wait(&sm.bar[0], 0);
     ok &= mbar_wait(&sm.bar[1], 0);
     {
-        unsigned fl0 = 0;
-        A.T = sm.ring[1][3][lane];
-        A.s = face_state<FAITHFUL, TPG>(g, sm.ring[1][0][lane], sm.ring[1][1][lane], sm.ring[1][2][lane], A.T, fl0);
-        A.xa = sm.ring[1][4][lane]; A.ya = sm.ring[1][5][lane];
-        A.im = sm.ring[1][6][lane];
-        A.xb = shfl_down1(A.xa); A.yb = shfl_down1(A.ya);
-        const FaceState lo = face_state<FAITHFUL, TPG>(g, sm.ring[0][0][lane], sm.ring[0][1][lane], sm.ring[0][2][lane], sm.ring[0][3][lane], fl0);
-        // j-face: left state = upper cell, right state = lower cell (SpatialDiscretization.cpp:556-625)
-        const Flux G0 = ldfss<FAITHFUL, AXI>(face_geom<FAITHFUL>(A.xa, A.ya, A.xb, A.yb), A.s, lo);
-        sm.G[0][lane] = G0.f0; sm.G[1][lane] = G0.f1; sm.G[2][lane] = G0.f2; sm.G[3][lane] = G0.f3; sm.G[4][lane] = G0.parr;
-        if (m.writer) flags |= fl0;
+        unsigned fl0[CPL];
+        const int q = CPL * lane;
+#pragma unroll
+        for (int e = 0; e < CPL; e++) {
+            fl0[e] = 0;
+            A.T[e] = sm.ring[1][3][q + e];
+            A.s[e] = face_state<FAITHFUL, TPG>(g, sm.ring[1][0][q + e], sm.ring[1][1][q + e], sm.ring[1][2][q + e], A.T[e], fl0[e]);
+            A.x[e] = sm.ring[1][4][q + e]; A.y[e] = sm.ring[1][5][q + e];
+            A.im[e] = sm.ring[1][6][q + e];
+        }
+        A.x[CPL] = shfl_down1(A.x[0]); A.y[CPL] = shfl_down1(A.y[0]);
+#pragma unroll
+        for (int e = 0; e < CPL; e++) {
+            const FaceState lo = face_state<FAITHFUL, TPG>(g, sm.ring[0][0][q + e], sm.ring[0][1][q + e], sm.ring[0][2][q + e], sm.ring[0][3][q + e], fl0[e]);
+            // j-face: left state = upper cell, right state = lower cell (SpatialDiscretization.cpp:556-625)
+            const Flux G0 = ldfss<FAITHFUL, AXI>(face_geom<FAITHFUL>(A.x[e], A.y[e], A.x[e + 1], A.y[e + 1]), A.s[e], lo);
+            sm.G[0][q + e] = G0.f0; sm.G[1][q + e] = G0.f1; sm.G[2][q + e] = G0.f2; sm.G[3][q + e] = G0.f3; sm.G[4][q + e] = G0.parr;
+            if (m.writer[e]) flags |= fl0[e];
+        }
     }
     double sq0 = 0.0, sq1 = 0.0, sq2 = 0.0, sq3 = 0.0;
     // stages 0 and 1 are consumed: refill them with the next two rows
