@@ -58,7 +58,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -68,6 +68,9 @@ class ClockSampler:
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
+
+    def count(self):
+        return len(self.rows)
 
     def stop(self):
         if not self.proc:
@@ -235,7 +238,6 @@ def run_gpu_arm(args):
     ev1.record()
     sync_all()
     elapsed_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if sampler else None
     kms, kn = C.c_double(), C.c_int64()
     gpu.check(gpu.kernel_time(h, C.byref(kms), C.byref(kn)), "kernel_time")
     gpu.check(gpu.kernel_timing(h, 0), "kernel_timing")
@@ -243,11 +245,24 @@ def run_gpu_arm(args):
     if multi:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
+    clock_window = "timed region"
+    if elapsed_ms < 1500.0:
+        # nvidia-smi samples every 50 ms: a timed region of a few ms cannot be sampled on its own, so every
+        # rank keeps running the same step loop (untimed, not part of the metric) for ~1.5 s of device time
+        extra = int(1500.0 / max(elapsed_ms / args.steps, 1e-3)) + 1
+        while extra > 0:
+            n = min(extra, 500)
+            advance(n)
+            extra -= n
+        sync_all()
+        clock_window = "timed region + ~1.5 s untimed continuation of the same step loop (the timed region is shorter than the sampling period)"
+    clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["window"] = clock_window
     assert all(i.status == 0 for i in info), "device raised an error flag during the timed region"
     value = total_cells * args.steps / (elapsed_ms * 1e-3)
 
     # ---- end to end through the C ABI with pinned host buffers ------------------------------
-    shapes = {b: ctx.get_state(b).shape for b in ctx.owned} if False else None
     host_bufs = {}
     for b in ctx.owned:
         nx, ny = ctx.shapes[b]
@@ -327,8 +342,8 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1, choices=sorted(LAYOUT))
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--block", type=int, default=BLOCK, help="cells per block side (default: the benchmark's 2048)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
