@@ -211,18 +211,21 @@ def run_gpu_arm(args):
 
     if multi:
         from par2d_b200.dist import DistSolver
-        solver = DistSolver(case, cfg, lib=gpu)
+        solver = DistSolver(case, cfg, lib=gpu, transport=args.transport)
         ctx = solver.solver
     else:
         solver = ctx = Solver(case, cfg, lib=gpu)
-        gpu.check(gpu.set_stream(ctx.handle, torch.cuda.current_stream().cuda_stream), "set_stream")
+    # the library's work and the timing events share one real torch stream
+    stream = solver.stream if multi else torch.cuda.Stream()
+    if not multi:
+        gpu.check(gpu.set_stream(ctx.handle, stream.cuda_stream), "set_stream")
+    torch.cuda.set_stream(stream)
     h = ctx.handle
     owned_cells = ctx.owned_cells
 
     def advance(n):
         if multi:
-            solver.queue_steps(n)
-            return solver.collect(n)
+            return solver.advance(n)
         return ctx.step(n)
 
     # ---- device-resident throughput -------------------------------------------------------
@@ -291,6 +294,8 @@ def run_gpu_arm(args):
            "note": "one job = state upload from pinned host memory + K steps with per-step log read-back + state download; "
                    "bytes are job totals divided by K"}
     assert all(i.status == 0 for i in einfo)
+    transport = solver.transport if multi else None
+    solver.close()        # collective for the peer-mapped transport: arenas are unmapped before anybody frees
 
     if rank != 0:
         if multi:
@@ -328,10 +333,12 @@ def run_gpu_arm(args):
         "config": {"workload": f"synthetic 10deg ramp, {nbx * nby} blocks of {blk}x{blk} cells (8 per GPU), "
                                f"{total_cells} cells, IAXI=1, CPG, CFL=0.01 (shipped macros)",
                    "global_cells": total_cells, "parallelism": f"blocks sharded over {args.gpus} GPU(s), 1 process per GPU",
+                   "halo_exchange": (f"{transport} (" + ("kernel stores into NVLink peer-mapped arenas + sequence flags, no host transport"
+                                     if transport == "peer" else "NCCL send/recv + all-reduce(MAX) per step") + ")") if multi else "none (single GPU)",
                    "l2": "state per GPU 1.07 GB read + 1.07 GB written per step >> 126 MB L2; no flush needed",
                    "arith_mode": "PAR2D_MODE_FAST"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-        "gpu_launches": (LAUNCHES_PER_STEP + (1 if multi else 0)) * args.steps,
+        "gpu_launches": (LAUNCHES_PER_STEP + (1 if multi else 0)) * args.steps + (1 if transport == "peer" else 0),
         "relres_last": info[-1].relres if not multi else None, "dt": info[-1].dt,
     }
     print(json.dumps(line), flush=True)
@@ -347,6 +354,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--block", type=int, default=BLOCK, help="cells per block side (default: the benchmark's 2048)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="auto", choices=["auto", "peer", "external"],
+                    help="multi-GPU halo exchange: NVLink peer-mapped arenas (default) or NCCL send/recv per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -193,14 +193,24 @@ int par2d_step_end(par2d_ctx* ctx);
 int par2d_step_collect(par2d_ctx* ctx, int32_t nsteps, par2d_step_info* info);
 
 /* Peer-mapped mode (NVLink P2P between the processes of one box): each rank
- * exports a 64-byte handle to its receive arena, the host all-gathers the
- * handles with whatever it has (torch.distributed, MPI, a file), and after
- * par2d_peer_connect() par2d_step() pushes edge lines and dt_b straight into
- * the neighbours' arenas from inside the kernels; no host transport remains
- * on the data path. */
+ * exports a 64-byte handle to its receive arena (cudaIpcMemHandle_t), the host
+ * all-gathers the handles with whatever it has (torch.distributed, MPI, a file),
+ * and after par2d_peer_connect() par2d_step() becomes a COLLECTIVE over the
+ * ranks (same nsteps everywhere, stop_on_tol ignored) that needs no host
+ * transport: the put kernel stores edge lines and dt_b straight into the
+ * neighbours' arenas over NVLink and raises a per-source sequence flag there;
+ * the ghost kernel of the consuming step waits on those flags (bounded:
+ * PAR2D_PEER_TIMEOUT_MS, default 20000, then PAR2D_ERR_COMM).  A whole batch
+ * of steps is queued without host synchronisation.  info[] carries this rank's
+ * local sums (use par2d_get_block_history for the global-order relres).
+ * par2d_get_residual() uses the halos left by the last par2d_step(); after
+ * par2d_set_state() call par2d_step(ctx, 0, 0, NULL) on every rank first.
+ * par2d_peer_disconnect() unmaps the peers' arenas; call it on every rank
+ * (and synchronise the ranks) before any rank destroys its ctx. */
 #define PAR2D_PEER_HANDLE_BYTES 64
 int par2d_peer_export(par2d_ctx* ctx, void* handle_out);
 int par2d_peer_connect(par2d_ctx* ctx, const void* all_handles /* nranks*64 bytes */);
+int par2d_peer_disconnect(par2d_ctx* ctx);
 
 /* All device work of this ctx is issued on one CUDA stream.  stream is a
  * cudaStream_t passed as an integer (0 = a private non-blocking stream). */

@@ -98,6 +98,7 @@ SOLVER_API = {
 GPU_ONLY_API = {
     "peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "peer_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "peer_disconnect": (C.c_int, [C.c_void_p]),
     "set_stream": (C.c_int, [C.c_void_p, C.c_uint64]),
     "synchronize": (C.c_int, [C.c_void_p]),
     "probe_fp64": (C.c_int, [C.c_int32, _DP]),

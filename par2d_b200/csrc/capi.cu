@@ -60,6 +60,43 @@ int facing_side(const par2d_block_desc& nb, int me, int my_side) {
     return -1;
 }
 
+// Arena layout of rank r, a pure function of the global block table (so every rank can address every
+// other rank's arena without asking): see common.cuh PutArgs.
+struct ArenaLayout {
+    size_t flags_off = 0, dt_off = 0, lines_off = 0, bytes = 0;
+    long long dt_stride = 0;     // doubles
+    long long lines_stride = 0;  // doubles = everything rank r receives per event
+};
+long long recv_count(const par2d_block_desc* t, int nblocks, int r, int src) {  // doubles rank r receives from rank src
+    long long n = 0;
+    for (int g = 0; g < nblocks; g++) {
+        if (t[g].owner != r) continue;
+        for (int s = 0; s < 4; s++) {
+            const int nb = t[g].bid[s];
+            if (nb >= 0 && t[nb].owner == src) n += 4ll * desc_edge(t[g], s);
+        }
+    }
+    return n;
+}
+long long recv_segment_off(const par2d_block_desc* t, int nblocks, int r, int src) {  // where src's segment starts in r's lines
+    long long off = 0;
+    for (int p = 0; p < src; p++)
+        if (p != r) off += recv_count(t, nblocks, r, p);
+    return off;
+}
+ArenaLayout arena_layout(const par2d_block_desc* t, int nblocks, int nranks, int r) {
+    ArenaLayout L;
+    auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+    L.flags_off = 0;
+    L.dt_off = up(sizeof(unsigned long long) * 16 * (size_t)nranks);
+    L.dt_stride = (long long)((nblocks + 31) / 32 * 32);
+    L.lines_off = up(L.dt_off + sizeof(double) * 2 * (size_t)L.dt_stride);
+    for (int p = 0; p < nranks; p++)
+        if (p != r) L.lines_stride += recv_count(t, nblocks, r, p);
+    L.bytes = up(L.lines_off + sizeof(double) * 2 * (size_t)std::max<long long>(L.lines_stride, 1));
+    return L;
+}
+
 Gas make_gas(const par2d_config& c) {
     Gas g;
     memset(&g, 0, sizeof g);
@@ -79,6 +116,7 @@ Gas make_gas(const par2d_config& c) {
 
 int flags_to_code(unsigned f) {
     if (f & 0x80000000u) return PAR2D_ERR_CUDA;  // TMA copy never completed
+    if (f & FLAG_COMM) return PAR2D_ERR_COMM;    // a peer's exchange flag never arrived
     if (f & FLAG_NAN) return PAR2D_ERR_NAN;
     if (f & FLAG_DENSITY) return PAR2D_ERR_DENSITY;
     if (f & FLAG_STATE) return PAR2D_ERR_STATE;
@@ -119,7 +157,7 @@ struct par2d_ctx {
     std::vector<int> owned_gid, owned_index;
     int nowned = 0;
     std::vector<BlockDev> hblk;
-    std::vector<double*> block_mem;       // one allocation per owned block (11 planes: 2 x 4 state, x, y, metric)
+    std::vector<double*> block_mem;       // one allocation per owned block: 11 planes [state A x4][x y metric][state B x4]
     std::vector<int*> block_ibound;
     BlockDev* dblk = nullptr;
     void* dtmaps = nullptr;
@@ -145,8 +183,23 @@ struct par2d_ctx {
     long long owned_cells = 0;
 
     std::vector<Peer> peers;
-    SendLine* dlines = nullptr;
+    SendLine* dlines = nullptr;      // external transport: destinations in the local send buffers
+    SendLine* dlines_peer = nullptr; // peer-mapped: destinations in the neighbours' arenas
+    std::vector<SendLine> hlines;
+    std::vector<int> hline_peer;     // destination rank of each line
+    std::vector<long long> hline_off;// offset of each line inside that rank's segment for this source
     int nlines = 0, max_line = 0;
+
+    // arena of this rank (nranks > 1): flags | dt[2] | lines[2]   (common.cuh, PutArgs)
+    char* arena = nullptr;
+    ArenaLayout lay;
+    bool peer_connected = false;
+    std::vector<char*> peer_base;    // mapped arena of every rank (own: arena)
+    double** d_dt_dst = nullptr;
+    unsigned long long** d_flag_dst = nullptr;
+    unsigned* put_ticket = nullptr;
+    unsigned long long seq = 0;      // exchange events produced so far (identical on every rank)
+    long long timeout_ns = 20000000000ll;
 
     // history of the last batch, host copies
     std::vector<double> h_step_hist, h_blk_hist;
@@ -179,6 +232,20 @@ struct par2d_ctx {
         a.res_block = -1;
         a.update = update;
         a.march_rows = march_rows;
+        a.wait_flags = nullptr;
+        a.wait_seq = 0;
+        a.recv_off = 0;
+        a.nranks = cfg.nranks;
+        a.rank = cfg.rank;
+        a.timeout_ns = timeout_ns;
+        if (peer_connected) {
+            // consume the latest exchange event (parity seq & 1) from this rank's arena
+            const int par = (int)(seq & 1);
+            a.wait_flags = reinterpret_cast<const unsigned long long*>(arena + lay.flags_off);
+            a.wait_seq = seq;
+            a.recv_off = par * lay.lines_stride;
+            a.dt_table = reinterpret_cast<double*>(arena + lay.dt_off) + par * lay.dt_stride;
+        }
         return a;
     }
     FinalizeArgs finalize_args(int stop_on_tol) const {
@@ -193,7 +260,7 @@ struct par2d_ctx {
         f.hist_pos = hist_pos;
         f.stop = stop;
         f.ticket = ticket;
-        f.dt_table = dt_table;
+        f.dt_table = peer_connected ? reinterpret_cast<double*>(arena + lay.dt_off) + (long long)(seq & 1) * lay.dt_stride : dt_table;
         f.nblocks_global = nblocks;
         f.tol = cfg.tol;
         f.stop_on_tol = stop_on_tol;
@@ -240,22 +307,20 @@ int validate_table(int nblocks, const par2d_block_desc* t, int nranks) {
 int build_tensor_maps(par2d_ctx* c) {
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return fail(PAR2D_ERR_CUDA, "cuTensorMapEncodeTiled is not exported by this driver; the row staging of the march kernel needs it");
-    std::vector<CUtensorMap> maps((size_t)c->nowned * 3);
+    std::vector<CUtensorMap> maps((size_t)c->nowned);
     for (int k = 0; k < c->nowned; k++) {
         const BlockDev& b = c->hblk[k];
-        for (int m = 0; m < 3; m++) {
-            // state A, state B: 4 planes; nodes: x, y, metric.  One box = the 32*MARCH_CPL staged columns of one row of all planes
-            const cuuint32_t planes = m < 2 ? 4 : 3;
-            void* base = m < 2 ? (void*)b.state[m] : (void*)b.nodes;
-            const cuuint64_t dims[3] = {(cuuint64_t)b.pitch, (cuuint64_t)(b.ncy + 2), planes};
-            const cuuint64_t strides[2] = {(cuuint64_t)b.pitch * 8, (cuuint64_t)b.plane * 8};
-            const cuuint32_t box[3] = {(cuuint32_t)(32 * MARCH_CPL), 1u, planes};
-            const cuuint32_t estr[3] = {1, 1, 1};
-            CUresult r = enc(&maps[(size_t)k * 3 + m], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) return fail(PAR2D_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for block %d map %d", (int)r, b.gid, m);
-        }
+        // one map over the block's 11 planes [state A x4][x y metric][state B x4]; one box = the 32*MARCH_CPL
+        // staged columns x 2 rows x the 7 consecutive planes a step reads (march.cuh)
+        void* base = (void*)c->block_mem[k];
+        const cuuint64_t dims[3] = {(cuuint64_t)b.pitch, (cuuint64_t)(b.ncy + 2), 11};
+        const cuuint64_t strides[2] = {(cuuint64_t)b.pitch * 8, (cuuint64_t)b.plane * 8};
+        const cuuint32_t box[3] = {(cuuint32_t)(32 * MARCH_CPL), 2u, 7u};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&maps[(size_t)k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(PAR2D_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for block %d", (int)r, b.gid);
     }
     CU_TRY(cudaMalloc(&c->dtmaps, maps.size() * sizeof(CUtensorMap)));
     CU_TRY(cudaMemcpy(c->dtmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
@@ -263,6 +328,25 @@ int build_tensor_maps(par2d_ctx* c) {
 }
 
 void launch_step(par2d_ctx* c, const StepArgs& a) { c->kt->march(c->stream, a, c->gas, c->tpg, c->axi); }
+
+// peer-mapped mode: produce the next exchange event from the current state
+void queue_put(par2d_ctx* c) {
+    c->seq++;
+    PutArgs put;
+    memset(&put, 0, sizeof put);
+    put.peer_mode = 1;
+    put.parity = (int)(c->seq & 1);
+    put.seq = c->seq;
+    put.dt_dst = c->d_dt_dst;
+    put.dt_stride = c->lay.dt_stride;
+    put.flag_dst = c->d_flag_dst;
+    put.ticket = c->put_ticket;
+    put.local_flags = reinterpret_cast<const unsigned long long*>(c->arena + c->lay.flags_off);
+    put.nranks = c->cfg.nranks;
+    put.rank = c->cfg.rank;
+    put.timeout_ns = c->timeout_ns;
+    c->kt->pack(c->stream, c->step_args(1), c->gas, c->dlines_peer, c->nlines, c->max_line, put);
+}
 
 void queue_step(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
     StepArgs a = c->step_args(1);
@@ -413,7 +497,20 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
                 if (blocks[g].owner == p && blocks[nb].owner == cfg->rank) c->peers[p].n_send += 4ll * desc_edge(blocks[g], s);
             }
         if (c->peers[p].n_send) { CU_TRY(cudaMalloc(&c->peers[p].d_send, sizeof(double) * c->peers[p].n_send)); CU_TRY(cudaMemset(c->peers[p].d_send, 0, sizeof(double) * c->peers[p].n_send)); }
-        if (c->peers[p].n_recv) { CU_TRY(cudaMalloc(&c->peers[p].d_recv, sizeof(double) * c->peers[p].n_recv)); CU_TRY(cudaMemset(c->peers[p].d_recv, 0, sizeof(double) * c->peers[p].n_recv)); }
+    }
+    if (cfg->nranks > 1) {
+        // the receive side lives in one exportable allocation (the arena); with the external transport
+        // only parity 0 of it is used
+        c->lay = arena_layout(blocks, nblocks, cfg->nranks, cfg->rank);
+        CU_TRY(cudaMalloc(&c->arena, c->lay.bytes));
+        CU_TRY(cudaMemset(c->arena, 0, c->lay.bytes));
+        double* lines0 = reinterpret_cast<double*>(c->arena + c->lay.lines_off);
+        for (int p = 0; p < cfg->nranks; p++)
+            if (p != cfg->rank && c->peers[p].n_recv) c->peers[p].d_recv = lines0 + recv_segment_off(blocks, nblocks, cfg->rank, p);
+        CU_TRY(cudaMalloc(&c->put_ticket, sizeof(unsigned)));
+        CU_TRY(cudaMemset(c->put_ticket, 0, sizeof(unsigned)));
+        const char* tmo = getenv("PAR2D_PEER_TIMEOUT_MS");
+        if (tmo && atoll(tmo) > 0) c->timeout_ns = atoll(tmo) * 1000000ll;
     }
 
     // per-block device memory
@@ -434,9 +531,9 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
         b.plane = (long long)b.pitch * (b.ncy + 2);
         CU_TRY(cudaMalloc(&c->block_mem[k], sizeof(double) * 11 * b.plane));
         CU_TRY(cudaMemsetAsync(c->block_mem[k], 0, sizeof(double) * 11 * b.plane, c->stream));
-        b.state[0] = c->block_mem[k];
-        b.state[1] = c->block_mem[k] + 4 * b.plane;
-        b.nodes = c->block_mem[k] + 8 * b.plane;
+        b.state[0] = c->block_mem[k];                  // planes 0..3
+        b.nodes = c->block_mem[k] + 4 * b.plane;       // planes 4..6: x, y, metric
+        b.state[1] = c->block_mem[k] + 7 * b.plane;    // planes 7..10
         const int nfaces = 2 * (b.ncx + b.ncy);
         CU_TRY(cudaMalloc(&c->block_ibound[k], sizeof(int) * nfaces));
         CU_TRY(cudaMemcpyAsync(c->block_ibound[k], d.ibound, sizeof(int) * nfaces, cudaMemcpyHostToDevice, c->stream));
@@ -526,6 +623,9 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
                 ln.n = desc_edge(blocks[g], s);
                 ln.pad = 0;
                 ln.dst = c->peers[p].d_send + off;
+                ln.parity_stride = 0;
+                c->hline_peer.push_back(p);
+                c->hline_off.push_back(off);
                 off += 4ll * ln.n;
                 lines.push_back(ln);
                 c->max_line = std::max(c->max_line, ln.n);
@@ -533,13 +633,18 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
         }
     }
     c->nlines = (int)lines.size();
+    c->hlines = lines;
     if (c->nlines) {
         CU_TRY(cudaMalloc(&c->dlines, sizeof(SendLine) * c->nlines));
         CU_TRY(cudaMemcpyAsync(c->dlines, lines.data(), sizeof(SendLine) * c->nlines, cudaMemcpyHostToDevice, c->stream));
     }
 
-    CU_TRY(cudaMalloc(&c->dt_table, sizeof(double) * nblocks));
-    CU_TRY(cudaMemsetAsync(c->dt_table, 0, sizeof(double) * nblocks, c->stream));
+    if (c->arena) {
+        c->dt_table = reinterpret_cast<double*>(c->arena + c->lay.dt_off);   // parity 0
+    } else {
+        CU_TRY(cudaMalloc(&c->dt_table, sizeof(double) * nblocks));
+        CU_TRY(cudaMemsetAsync(c->dt_table, 0, sizeof(double) * nblocks, c->stream));
+    }
     CU_TRY(cudaMalloc(&c->partials, sizeof(double) * 4 * (size_t)c->total_tiles));
     CU_TRY(cudaMalloc(&c->flags, sizeof(unsigned)));
     CU_TRY(cudaMalloc(&c->stop, sizeof(int)));
@@ -568,8 +673,11 @@ int par2d_destroy(par2d_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (double* p : c->block_mem) cudaFree(p);
     for (int* p : c->block_ibound) cudaFree(p);
-    for (Peer& p : c->peers) { cudaFree(p.d_send); cudaFree(p.d_recv); }
-    cudaFree(c->dblk); cudaFree(c->dtmaps); cudaFree(c->dt_table); cudaFree(c->partials); cudaFree(c->flags);
+    par2d_peer_disconnect(c);
+    for (Peer& p : c->peers) cudaFree(p.d_send);
+    if (c->arena) cudaFree(c->arena); else cudaFree(c->dt_table);
+    cudaFree(c->put_ticket); cudaFree(c->dlines_peer); cudaFree(c->d_dt_dst); cudaFree(c->d_flag_dst);
+    cudaFree(c->dblk); cudaFree(c->dtmaps); cudaFree(c->partials); cudaFree(c->flags);
     cudaFree(c->stop); cudaFree(c->d_iter); cudaFree(c->hist_pos); cudaFree(c->ticket); cudaFree(c->res0);
     cudaFree(c->blk_norm); cudaFree(c->blk_hist); cudaFree(c->step_hist); cudaFree(c->staging); cudaFree(c->dlines);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
@@ -618,7 +726,9 @@ int par2d_get_residual(par2d_ctx* c, int32_t block, double* res) {
     a.res_block = k;
     // with remote neighbours the receive buffers must already hold this state's edge
     // lines (par2d_step_begin + transport); the dt table is rebuilt here either way
-    c->kt->ghost(c->stream, a, c->gas, 1);
+    // peer-mapped mode: the arenas hold the lines and dt of the state left by the last par2d_step
+    // (after par2d_set_state, call par2d_step(ctx, 0, 0, NULL) on every rank to refresh them)
+    c->kt->ghost(c->stream, a, c->gas, c->peer_connected ? 0 : 1);
     launch_step(c, a);
     const size_t bytes = sizeof(double) * 4 * (size_t)b.ncx * b.ncy;
     CU_TRY(cudaMemcpyAsync(res, c->staging, bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -629,14 +739,27 @@ int par2d_get_residual(par2d_ctx* c, int32_t block, double* res) {
 
 int par2d_step(par2d_ctx* c, int32_t nsteps, int32_t stop_on_tol, par2d_step_info* info) {
     if (!c || nsteps < 0) return fail(PAR2D_ERR_ARG, "step: bad argument");
-    if (c->cfg.nranks != 1) return fail(PAR2D_ERR_COMM, "step: nranks > 1 needs step_begin/step_end (external transport) or a connected peer arena");
+    if (c->cfg.nranks != 1 && !c->peer_connected)
+        return fail(PAR2D_ERR_COMM, "step: nranks > 1 needs step_begin/step_end (external transport) or par2d_peer_connect");
+    if (c->pending_steps) return fail(PAR2D_ERR_COMM, "step: %d begin/end steps are waiting for step_collect", c->pending_steps);
     if (use_device(c)) return PAR2D_ERR_CUDA;
     int rc = ensure_hist(c, nsteps);
     if (rc) return rc;
     CU_TRY(cudaMemsetAsync(c->hist_pos, 0, sizeof(int), c->stream));
     CU_TRY(cudaMemsetAsync(c->stop, 0, sizeof(int), c->stream));
     const int cur0 = c->cur;
-    for (int s = 0; s < nsteps; s++) queue_step(c, stop_on_tol, true);
+    if (c->peer_connected) {
+        // collective batch, no host transport: every step is  put (edge lines + dt_b into the neighbours'
+        // arenas, flag) -> ghost (waits for the flags) -> march -> finalize.  The trailing put leaves the
+        // final state's lines in the arenas for par2d_get_residual.
+        for (int s = 0; s < nsteps; s++) {
+            queue_put(c);
+            queue_step(c, 0, false);
+        }
+        queue_put(c);
+    } else {
+        for (int s = 0; s < nsteps; s++) queue_step(c, stop_on_tol, true);
+    }
     CU_TRY(cudaStreamSynchronize(c->stream));
     CU_TRY(cudaGetLastError());
     return harvest(c, nsteps, cur0, info, nsteps);
@@ -681,8 +804,11 @@ int par2d_step_begin(par2d_ctx* c) {
         CU_TRY(cudaMemsetAsync(c->stop, 0, sizeof(int), c->stream));
     }
     if (c->pending_steps >= c->hist_cap) return fail(PAR2D_ERR_COMM, "step_begin: %d steps queued without step_collect", c->pending_steps);
+    if (c->peer_connected) return fail(PAR2D_ERR_COMM, "step_begin: this ctx exchanges over peer-mapped memory; use par2d_step");
     CU_TRY(cudaMemsetAsync(c->dt_table, 0, sizeof(double) * c->nblocks, c->stream));
-    c->kt->pack(c->stream, c->step_args(1), c->gas, c->dlines, c->nlines, c->max_line);
+    PutArgs put;
+    memset(&put, 0, sizeof put);
+    c->kt->pack(c->stream, c->step_args(1), c->gas, c->dlines, c->nlines, c->max_line, put);
     return 0;
 }
 
@@ -710,8 +836,77 @@ int par2d_step_collect(par2d_ctx* c, int32_t nsteps, par2d_step_info* info) {
     return code;
 }
 
-int par2d_peer_export(par2d_ctx*, void*) { return fail(PAR2D_ERR_COMM, "peer-mapped exchange is not built in this round; use step_begin/step_end"); }
-int par2d_peer_connect(par2d_ctx*, const void*) { return fail(PAR2D_ERR_COMM, "peer-mapped exchange is not built in this round; use step_begin/step_end"); }
+int par2d_peer_export(par2d_ctx* c, void* handle_out) {
+    if (!c || !handle_out) return fail(PAR2D_ERR_ARG, "peer_export: null argument");
+    if (!c->arena) return fail(PAR2D_ERR_COMM, "peer_export: this ctx was created with nranks == 1");
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    static_assert(sizeof(cudaIpcMemHandle_t) == PAR2D_PEER_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, c->arena));
+    memcpy(handle_out, &h, sizeof h);
+    return 0;
+}
+
+int par2d_peer_connect(par2d_ctx* c, const void* all_handles) {
+    if (!c || !all_handles) return fail(PAR2D_ERR_ARG, "peer_connect: null argument");
+    if (!c->arena) return fail(PAR2D_ERR_COMM, "peer_connect: this ctx was created with nranks == 1");
+    if (c->peer_connected) return fail(PAR2D_ERR_COMM, "peer_connect: already connected");
+    if (c->pending_steps) return fail(PAR2D_ERR_COMM, "peer_connect: begin/end steps are pending");
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    const int nr = c->cfg.nranks, me = c->cfg.rank;
+    c->peer_base.assign(nr, nullptr);
+    c->peer_base[me] = c->arena;
+    for (int p = 0; p < nr; p++) {
+        if (p == me) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(all_handles) + (size_t)p * PAR2D_PEER_HANDLE_BYTES, sizeof h);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            par2d_peer_disconnect(c);
+            return fail(PAR2D_ERR_COMM, "peer_connect: cannot map the arena of rank %d (%s); no peer access between the GPUs?", p, cudaGetErrorString(e));
+        }
+        c->peer_base[p] = static_cast<char*>(ptr);
+    }
+    // destinations: dt tables and flag slots in every arena, edge lines in the neighbours' arenas
+    std::vector<double*> dt_dst(nr);
+    std::vector<unsigned long long*> flag_dst(nr);
+    std::vector<ArenaLayout> lay(nr);
+    for (int p = 0; p < nr; p++) {
+        lay[p] = arena_layout(c->table.data(), c->nblocks, nr, p);
+        dt_dst[p] = reinterpret_cast<double*>(c->peer_base[p] + lay[p].dt_off);
+        flag_dst[p] = reinterpret_cast<unsigned long long*>(c->peer_base[p] + lay[p].flags_off) + 16 * me;
+    }
+    std::vector<SendLine> lines = c->hlines;
+    for (size_t l = 0; l < lines.size(); l++) {
+        const int p = c->hline_peer[l];
+        lines[l].dst = reinterpret_cast<double*>(c->peer_base[p] + lay[p].lines_off) + recv_segment_off(c->table.data(), c->nblocks, p, me) + c->hline_off[l];
+        lines[l].parity_stride = lay[p].lines_stride;
+    }
+    CU_TRY(cudaMalloc(&c->d_dt_dst, sizeof(double*) * nr));
+    CU_TRY(cudaMalloc(&c->d_flag_dst, sizeof(unsigned long long*) * nr));
+    CU_TRY(cudaMemcpy(c->d_dt_dst, dt_dst.data(), sizeof(double*) * nr, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(c->d_flag_dst, flag_dst.data(), sizeof(unsigned long long*) * nr, cudaMemcpyHostToDevice));
+    if (!lines.empty()) {
+        CU_TRY(cudaMalloc(&c->dlines_peer, sizeof(SendLine) * lines.size()));
+        CU_TRY(cudaMemcpy(c->dlines_peer, lines.data(), sizeof(SendLine) * lines.size(), cudaMemcpyHostToDevice));
+    }
+    c->seq = 0;
+    c->peer_connected = true;
+    return 0;
+}
+
+int par2d_peer_disconnect(par2d_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (size_t p = 0; p < c->peer_base.size(); p++)
+        if ((int)p != c->cfg.rank && c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
+    c->peer_base.clear();
+    c->peer_connected = false;
+    return 0;
+}
 
 int par2d_set_stream(par2d_ctx* c, uint64_t stream) {
     if (!c) return fail(PAR2D_ERR_ARG, "set_stream: null ctx");

@@ -5,7 +5,8 @@
 //                     row ncy+1 = top ghost line; nodes j=0..ncy live in rows 1..ncy+1)
 //   pitch  : multiple of 16 doubles (128 B); column COL0-1 = left ghost, COL0+i = cell i,
 //            COL0+ncx = right ghost; node i lives in column COL0+i
-//   planes : state A {rho,u,v,T}, state B {rho,u,v,T} (ping-pong), nodes {x, y, metric} where
+//   planes : state A {rho,u,v,T}, nodes {x, y, metric}, state B {rho,u,v,T} (ping-pong; the 7 planes a step
+//            reads are always consecutive: A+nodes or nodes+B), where
 //            metric[cell (i,j)] = 1/(vol*ycc) (axisymmetric) or 1/vol (planar), stored at node (i,j)'s slot
 // i.e. the reference's AoS unk[(j*(nx-1)+i)*4+k] (FV/Indexing.h:11) becomes four padded SoA
 // planes with the ghost ring (SpatialDiscretization.cpp:182-185 uGBot/uGRight/uGTop/uGLeft)
@@ -41,7 +42,7 @@ struct BlockDev {
     int nb_kind[4];     // NB_* per side
     int nb_block[4];    // owned-block index of a same-rank neighbour
     int nb_side[4];     // the neighbour's side that faces us
-    double* recv[4];    // AoS line [n*4+k] received from an off-rank neighbour
+    double* recv[4];    // AoS line [n*4+k] received from an off-rank neighbour (parity 0 of this rank's arena)
     int tiles_x, tiles_y; // work decomposition: 30-column strips x row chunks (marching kernel)
     int tile0;          // first tile/strip of this block in the partial-sum array
     double min_face;    // static part of find_dt (main.cpp:26-32)
@@ -53,7 +54,28 @@ struct SendLine {
     int side;
     int n;       // edge cells
     int pad;
-    double* dst; // AoS [n*4+k] in the peer send buffer (or, peer-mapped, in the peer's arena)
+    double* dst; // AoS [n*4+k] in the peer send buffer (or, peer-mapped, in the peer's arena, parity 0)
+    long long parity_stride;  // doubles between the two parities of the destination (peer-mapped mode), else 0
+};
+
+// Peer-mapped exchange (NVLink P2P): every rank owns one "arena" (a single cudaMalloc, exported by
+// cudaIpcGetMemHandle) that its neighbours write into:
+//   flags[nranks][16]   u64, slot src*16 = number of exchange events rank src has completed into this arena
+//   dt[2][nblocks_pad]  per-block time steps of the event's state, written by each block's owner
+//   lines[2][total]     received edge lines, per source rank in rank order, per (receiving block, side)
+// Event e (1-based) lives in parity e&1.  A producer may write event e only after every peer has produced
+// event e-1 (which, in stream order, follows that peer's consumption of event e-2 from the same parity).
+struct PutArgs {
+    int peer_mode;                       // 0: external transport (plain pack into local send buffers)
+    int parity;                          // parity written by this event
+    unsigned long long seq;              // event number being produced
+    double* const* dt_dst;               // [nranks] dt table (parity 0) of every rank's arena, own included
+    long long dt_stride;                 // doubles between dt parities
+    unsigned long long* const* flag_dst; // [nranks] this rank's flag slot in every peer's arena (own: unused)
+    unsigned* ticket;                    // CTA completion counter of the producing kernel
+    const unsigned long long* local_flags; // this rank's own flag array (for the pre-wait)
+    int nranks, rank;
+    long long timeout_ns;
 };
 
 struct StepArgs {
@@ -64,7 +86,7 @@ struct StepArgs {
     int total_tiles;         // sum over owned blocks (size of partials)
     int max_tiles;           // strips of the largest owned block (grid.x of the march kernel)
     int max_faces;           // longest block perimeter (grid.x of the ghost kernel)
-    const void* tmaps;       // CUtensorMap[nowned][3]: state A, state B, nodes+metric; boxes of 32 columns x 1 row x all planes
+    const void* tmaps;       // CUtensorMap[nowned] over each block's 11 planes; boxes of 32 columns x 2 rows x 7 planes
     double* dt_table;        // nblocks_global
     double* partials;        // [total_tiles][4] sum of res_k^2
     unsigned* flags;         // device error bits
@@ -73,6 +95,12 @@ struct StepArgs {
     int res_block;           // owned index whose residual is dumped, or -1
     int update;              // 0: residual only (test hook), 1: advance the state
     int march_rows;          // cell rows per strip of the marching kernel
+    // peer-mapped mode: the ghost kernel consumes exchange event wait_seq from this rank's arena
+    const unsigned long long* wait_flags;  // null: nothing to wait for
+    unsigned long long wait_seq;
+    long long recv_off;      // doubles added to BlockDev::recv[] (parity of the consumed event)
+    int nranks, rank;
+    long long timeout_ns;
 };
 
 struct FinalizeArgs {

@@ -39,9 +39,38 @@ __device__ __forceinline__ void ghost_cell_pos(int ncx, int ncy, int side, int n
     }
 }
 
+// ------------------------------------------------------------------ peer-mapped exchange: flags
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Waits until every other rank has completed exchange event `need` into this rank's arena.  Bounded: a
+// peer that never arrives surfaces as FLAG_COMM (PAR2D_ERR_COMM), never as a hung GPU.
+static __device__ __noinline__ bool wait_peers(const unsigned long long* flags, int nranks, int rank, unsigned long long need, long long timeout_ns) {
+    if (need == 0) return true;
+    const unsigned long long t0 = global_ns();
+    for (int r = 0; r < nranks; r++) {
+        if (r == rank) continue;
+        while (ld_acquire_sys(flags + 16 * r) < need) {
+            if ((long long)(global_ns() - t0) > timeout_ns) return false;
+            __nanosleep(200);
+        }
+    }
+    return true;
+}
+
 // per-block time step from cell (0,0): find_dt, main.cpp:19-37
 template <bool FAITHFUL>
-__device__ __forceinline__ void block_dt(const StepArgs& a, const Gas& g, const BlockDev& b) {
+__device__ __forceinline__ double block_dt_value(const StepArgs& a, const Gas& g, const BlockDev& b) {
     const double* S = b.state[a.cur];
     const long long o = (long long)b.pitch + COL0;
     const double u = S[b.plane + o], v = S[2 * b.plane + o], T = S[3 * b.plane + o];
@@ -49,13 +78,27 @@ __device__ __forceinline__ void block_dt(const StepArgs& a, const Gas& g, const 
     const double vmax = sqrt(v2) + sqrt(g.gamRs * T);
     const double dt = g.cfl * b.min_face / vmax;
     if (isnan(dt)) atomicOr(a.flags, FLAG_NAN);
-    a.dt_table[b.gid] = dt;
+    return dt;
+}
+template <bool FAITHFUL>
+__device__ __forceinline__ void block_dt(const StepArgs& a, const Gas& g, const BlockDev& b) {
+    a.dt_table[b.gid] = block_dt_value<FAITHFUL>(a, g, b);
 }
 
 // ------------------------------------------------------------------ ghost fill
 template <bool FAITHFUL>
 __global__ void __launch_bounds__(256) ghost_kernel(StepArgs a, Gas g, int write_dt) {
     if (*a.stop) return;
+    if (a.wait_flags != nullptr) {
+        // peer-mapped mode: the neighbours' edge lines and every block's dt of this step's state are
+        // written into this rank's arena by the other GPUs; wait for their completion flags
+        __shared__ int arrived;
+        if (threadIdx.x == 0) {
+            arrived = wait_peers(a.wait_flags, a.nranks, a.rank, a.wait_seq, a.timeout_ns) ? 1 : 0;
+            if (!arrived) atomicOr(a.flags, FLAG_COMM);
+        }
+        __syncthreads();
+    }
     const BlockDev b = a.blocks[blockIdx.y];   // grid.y = owned blocks, grid.x covers the longest perimeter
     int n = blockIdx.x * blockDim.x + threadIdx.x, side;
     if (n >= 2 * (b.ncx + b.ncy)) return;
@@ -83,9 +126,9 @@ __global__ void __launch_bounds__(256) ghost_kernel(StepArgs a, Gas g, int write
         for (int v = 0; v < 4; v++) gh[v] = So[v * o.plane + oo];
         gh[3] = fmax(gh[3], 201.0);
     } else if (b.nb_kind[side] == NB_REMOTE) {
-        const double* line = b.recv[side] + 4 * (long long)n;
+        const double* line = b.recv[side] + a.recv_off + 4 * (long long)n;
 #pragma unroll
-        for (int v = 0; v < 4; v++) gh[v] = line[v];
+        for (int v = 0; v < 4; v++) gh[v] = __ldcg(line + v);   // written by another GPU: read at L2
         gh[3] = fmax(gh[3], 201.0);
     } else {
         // outward normal of the boundary face (SpatialDiscretization.cpp:33-34,51-52,71-72,91-92);
@@ -119,19 +162,56 @@ __global__ void __launch_bounds__(256) ghost_kernel(StepArgs a, Gas g, int write
 
 // ------------------------------------------------------------------ pack (multi-rank send side)
 template <bool FAITHFUL>
-__global__ void __launch_bounds__(256) pack_kernel(StepArgs a, Gas g, const SendLine* lines, int nlines) {
+__global__ void __launch_bounds__(256) pack_kernel(StepArgs a, Gas g, const SendLine* lines, int nlines, PutArgs put) {
     if (*a.stop) return;
-    if (blockIdx.x == 0 && threadIdx.x < a.nowned) block_dt<FAITHFUL>(a, g, a.blocks[threadIdx.x]);
+    if (put.peer_mode) {
+        // producing event seq: every peer must have produced event seq-1 (see PutArgs)
+        __shared__ int arrived;
+        if (threadIdx.x == 0) {
+            arrived = wait_peers(put.local_flags, put.nranks, put.rank, put.seq - 1, put.timeout_ns) ? 1 : 0;
+            if (!arrived) atomicOr(a.flags, FLAG_COMM);
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        for (int k = threadIdx.x; k < a.nowned; k += blockDim.x) {
+            const BlockDev& b = a.blocks[k];
+            const double dt = block_dt_value<FAITHFUL>(a, g, b);
+            if (put.peer_mode) {
+                for (int r = 0; r < put.nranks; r++) put.dt_dst[r][put.parity * put.dt_stride + b.gid] = dt;
+            } else {
+                a.dt_table[b.gid] = dt;
+            }
+        }
+    }
     for (int l = blockIdx.y; l < nlines; l += gridDim.y) {
         const SendLine ln = lines[l];
         const BlockDev& b = a.blocks[ln.block];
         const double* S = b.state[a.cur];
+        double* dst = ln.dst + put.parity * ln.parity_stride;
         for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < ln.n; n += gridDim.x * blockDim.x) {
             int c, r;
             edge_cell_pos(b.ncx, b.ncy, ln.side, n, c, r);
             const long long o = (long long)r * b.pitch + c;
-#pragma unroll
-            for (int v = 0; v < 4; v++) ln.dst[4 * (long long)n + v] = S[v * b.plane + o];
+            // one 32-byte AoS record per edge cell (usend[k + NVAR*j], SpatialDiscretization.cpp:241)
+            double2* d2 = reinterpret_cast<double2*>(dst + 4 * (long long)n);
+            d2[0] = make_double2(S[o], S[b.plane + o]);
+            d2[1] = make_double2(S[2 * b.plane + o], S[3 * b.plane + o]);
+        }
+    }
+    if (put.peer_mode) {
+        // all stores of this CTA are ordered before its ticket; the last CTA raises this rank's flag in
+        // every peer's arena (release at system scope)
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned total = gridDim.x * gridDim.y;
+            if (atomicAdd(put.ticket, 1u) == total - 1) {
+                *put.ticket = 0u;
+                __threadfence_system();
+                for (int r = 0; r < put.nranks; r++)
+                    if (r != put.rank) st_release_sys(put.flag_dst[r], put.seq);
+            }
         }
     }
 }
@@ -204,7 +284,7 @@ __global__ void test_solve_kernel(Gas g, long long n, const double* dt_ycc, cons
 // ------------------------------------------------------------------ launch table of one arithmetic mode
 struct KernelTable {
     void (*ghost)(cudaStream_t, const StepArgs&, const Gas&, int write_dt);
-    void (*pack)(cudaStream_t, const StepArgs&, const Gas&, const SendLine*, int nlines, int max_n);
+    void (*pack)(cudaStream_t, const StepArgs&, const Gas&, const SendLine*, int nlines, int max_n, const PutArgs&);
     void (*march)(cudaStream_t, const StepArgs&, const Gas&, bool tpg, bool axi);
     void (*test_ldfss)(cudaStream_t, const Gas&, bool tpg, bool axi, long long n, const double*, const double*, const double*, double*, double*);
     void (*test_boundary)(cudaStream_t, const Gas&, long long n, const int*, const double*, const double*, double*);
@@ -222,9 +302,9 @@ struct Launch {
     static void ghost(cudaStream_t s, const StepArgs& a, const Gas& g, int write_dt) {
         ghost_kernel<FAITHFUL><<<dim3((a.max_faces + 255) / 256, a.nowned), 256, 0, s>>>(a, g, write_dt);
     }
-    static void pack(cudaStream_t s, const StepArgs& a, const Gas& g, const SendLine* lines, int nlines, int max_n) {
+    static void pack(cudaStream_t s, const StepArgs& a, const Gas& g, const SendLine* lines, int nlines, int max_n, const PutArgs& put) {
         dim3 grid((unsigned)((max_n + 255) / 256 > 0 ? (max_n + 255) / 256 : 1), (unsigned)(nlines > 0 ? nlines : 1));
-        pack_kernel<FAITHFUL><<<grid, 256, 0, s>>>(a, g, lines, nlines);
+        pack_kernel<FAITHFUL><<<grid, 256, 0, s>>>(a, g, lines, nlines, put);
     }
     static void test_ldfss(cudaStream_t s, const Gas& g, bool tpg, bool axi, long long n, const double* face, const double* uL, const double* uR, double* flux, double* parr) {
         const int grid = (int)((n + 127) / 128);

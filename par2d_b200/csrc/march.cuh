@@ -8,10 +8,10 @@
 //   column of the warp are the strip's left/right halo columns (their state is loaded and derived,
 //   but never updated), so a row is one contiguous 256*CPL-byte read per plane from the padded HBM
 //   planes (ghost ring in place).
-//   Rows are staged ahead of their use by TMA (cp.async.bulk.tensor, SASS UTMALDG): lane 0 issues two
-//   tiled copies per row - a 32-column x 4-plane box of the state and a 32-column x 3-plane box of
-//   the node coordinates + cell metric - into a per-warp shared-memory ring of MARCH_STAGES rows, each
-//   stage completing on its own mbarrier.  No registers are held by loads in flight, no address
+//   Rows are staged ahead of their use by TMA (cp.async.bulk.tensor, SASS UTMALDG): lane 0 issues ONE
+//   tiled copy per two rows - a box of 32 columns x 2 rows x 7 planes (state + node coordinates + cell
+//   metric) - into a per-warp shared-memory ring of MARCH_STAGES stages, each completing on its own
+//   mbarrier.  No registers are held by loads in flight, no address
 //   arithmetic is spent per plane, and HBM latency is covered by MARCH_STAGES-1 rows of compute.
 //   (A tiled copy of 8-byte elements must start on a 16-byte boundary - tools/tma_probe - which is why
 //   cell column 0 sits in the odd array column COL0 = 17: every strip's box starts in an even column.)
@@ -49,10 +49,7 @@ namespace par2d {
 #define MARCH_NODE_LDS 0
 #endif
 #ifndef MARCH_STAGES
-#define MARCH_STAGES 4
-#endif
-#ifndef MARCH_UNROLL2
-#define MARCH_UNROLL2 1   // two rows per trip with the carried state swapping roles: no register moves between rows
+#define MARCH_STAGES 3    // ring stages of two rows each
 #endif
 constexpr int MARCH_THREADS = 32;                 // one warp strip per CTA
 
@@ -111,16 +108,24 @@ __device__ __forceinline__ Flux shfl_down1(const Flux& f) {
     return o;
 }
 
-// per-warp shared memory: the row ring (TMA destination), its barriers and the parked bottom-face flux
+// per-warp shared memory: the row ring (TMA destination), its barriers and the parked bottom-face flux.
+// One ring stage = ONE tiled copy of 2 array rows x 7 planes x WCOLS columns: the block's 11 planes are laid
+// out [state A x4][x y metric][state B x4] so that the state being read and the node planes are always 7
+// consecutive planes (A+nodes = planes 0..6, nodes+B = planes 4..10).  One copy per two rows instead of
+// two copies per row: the lane-0 issue sequence (about 36 issue slots the whole warp pays for) runs a
+// quarter as often.
 constexpr int CPL = MARCH_CPL;                     // cell columns per lane
 constexpr int WCOLS = 32 * CPL;                    // columns staged per row
-constexpr int RING_PLANES = 7;                     // rho,u,v,T | x,y,metric
+constexpr int RING_PLANES = 7;                     // rho,u,v,T + x,y,metric in either order (see above)
+constexpr int STAGE_ROWS = 2;
+constexpr int PLANE_D = STAGE_ROWS * WCOLS;        // doubles between planes of a stage
+constexpr int STAGE_D = RING_PLANES * PLANE_D;     // doubles per stage
 struct MarchSmem {
-    double ring[MARCH_STAGES][RING_PLANES][WCOLS]; // [stage][plane][column]; a stage is a multiple of 128 B
+    double ring[MARCH_STAGES][RING_PLANES][STAGE_ROWS][WCOLS];   // TMA box layout: [plane][row][column]
     double G[5][WCOLS];                            // j-face flux at the bottom of the current row
     uint64_t bar[MARCH_STAGES];
 };
-constexpr uint32_t STAGE_BYTES = RING_PLANES * WCOLS * sizeof(double);
+constexpr uint32_t STAGE_BYTES = STAGE_D * sizeof(double);
 
 // What a lane carries in registers from one row to the next, per cell column: the derived state of the
 // cell, its metric and the node at its lower-left corner; plus the node right of the last column.
@@ -215,7 +220,8 @@ __device__ __forceinline__ void cell_update(const StepArgs& a, const Gas& g, con
     if (a.update) {
         // main.cpp:394-404: unk += dv, rho > 0, UpdateState's T clamp
         out[0] = cur.rho + dv[0]; out[1] = cur.u + dv[1]; out[2] = cur.v + dv[2];
-        out[3] = fmax(T + dv[3], 201.0);
+        if constexpr (FAITHFUL) out[3] = fmax(T + dv[3], 201.0);
+        else out[3] = max_sel(T + dv[3], 201.0);
         if (!(out[0] > 0.0)) flags |= FLAG_DENSITY;
         if constexpr (CPL == 1) {
             double* o = m.Sout + ((long long)(j + 1) * m.pitch + COL0 + c);
@@ -224,23 +230,31 @@ __device__ __forceinline__ void cell_update(const StepArgs& a, const Gas& g, con
     }
 }
 
-// One row of a strip: consumes the carried state `lo` of cell row j and the staged row above it
-// (ring stage `st`), produces the carried state `hi` of row j+1, updates this lane's cells of row j.
+// One row of a strip: consumes the carried state `lo` of cell row j and the staged row above it (srow/nrow
+// = this lane's first column of the state / node planes of that row in the ring), produces the carried
+// state `hi` of row j+1, updates this lane's cells of row j.
 template <bool FAITHFUL, bool TPG, bool AXI>
-__device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const MarchCtx& m, MarchSmem& sm, int j, int st, const RowState& lo,
-                                          RowState& hi, double& sq0, double& sq1, double& sq2, double& sq3, unsigned& flags) {
+__device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const MarchCtx& m, MarchSmem& sm, int j, const double* srow, const double* nrow,
+                                          const RowState& lo, RowState& hi, double& sq0, double& sq1, double& sq2, double& sq3, unsigned& flags) {
     const int q = CPL * m.lane;                    // this lane's first column in the staged row
     unsigned flu[CPL];
-    double raw[RING_PLANES][CPL];
+    double raw[RING_PLANES][CPL];                  // 0..3 state, 4..6 x, y, metric
     if constexpr (CPL == 2) {
 #pragma unroll
-        for (int v = 0; v < RING_PLANES; v++) {
-            const double2 t = *reinterpret_cast<const double2*>(&sm.ring[st][v][q]);
+        for (int v = 0; v < 4; v++) {
+            const double2 t = *reinterpret_cast<const double2*>(srow + v * PLANE_D);
             raw[v][0] = t.x; raw[v][1] = t.y;
+        }
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+            const double2 t = *reinterpret_cast<const double2*>(nrow + v * PLANE_D);
+            raw[4 + v][0] = t.x; raw[4 + v][1] = t.y;
         }
     } else {
 #pragma unroll
-        for (int v = 0; v < RING_PLANES; v++) raw[v][0] = sm.ring[st][v][q];
+        for (int v = 0; v < 4; v++) raw[v][0] = srow[v * PLANE_D];
+#pragma unroll
+        for (int v = 0; v < 3; v++) raw[4 + v][0] = nrow[v * PLANE_D];
     }
 #pragma unroll
     for (int e = 0; e < CPL; e++) {
@@ -252,7 +266,7 @@ __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const
     }
     // node right of this lane's last column = first node of lane+1 (for lane 31 it is never used)
 #if MARCH_NODE_LDS
-    hi.x[CPL] = sm.ring[st][4][q + CPL]; hi.y[CPL] = sm.ring[st][5][q + CPL];   // lane 31 reads the next plane's first slot: unused
+    hi.x[CPL] = nrow[CPL]; hi.y[CPL] = nrow[PLANE_D + CPL];   // lane 31 reads one slot past its row: unused
 #else
     hi.x[CPL] = shfl_down1(hi.x[0]); hi.y[CPL] = shfl_down1(hi.y[0]);
 #endif
@@ -336,57 +350,60 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
 
     // ---- TMA row ring.  Array row `arow` holds cell row arow-1, node row arow-1 and the metric of cell
     // row arow-1; this strip reads array rows j0 (cell row below) .. j1+1 (cell row above the last).
-    const char* maps = static_cast<const char*>(a.tmaps) + (size_t)k * 3 * 128;
-    const void* map_state = maps + a.cur * 128;
-    const void* map_nodes = maps + 2 * 128;
+    // Ring use n holds array rows j0+2n, j0+2n+1 (rows past the array end are zero-filled by TMA).
+    const void* tmap = static_cast<const char*>(a.tmaps) + (size_t)k * 128;
+    const int plane0 = a.cur ? 4 : 0;              // first of the 7 planes read this step
     const int col0 = COL0 + c0 - 1;                // even: the 16-byte rule of tiled copies
     const int arow_end = j1 + 1;
-    auto stage_row = [&](int arow, int st) {       // lane 0 only
+    auto stage_rows = [&](int n, int slot) {       // lane 0 only
+        const int arow = j0 + 2 * n;
         if (arow <= arow_end) {
-            mbar_expect_tx(&sm.bar[st], STAGE_BYTES);
-            tma_load_3d(&sm.ring[st][0][0], map_state, col0, arow, 0, &sm.bar[st]);
-            tma_load_3d(&sm.ring[st][4][0], map_nodes, col0, arow, 0, &sm.bar[st]);
+            mbar_expect_tx(&sm.bar[slot], STAGE_BYTES);
+            tma_load_3d(&sm.ring[slot][0][0][0], tmap, col0, arow, plane0, &sm.bar[slot]);
         }
     };
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < MARCH_STAGES; s++) mbar_init(&sm.bar[s], 1);
         mbar_init_fence();
-        tmap_acquire(map_state);
-        tmap_acquire(map_nodes);
+        tmap_acquire(tmap);
 #pragma unroll
-        for (int s = 0; s < MARCH_STAGES; s++) stage_row(j0 + s, s);
+        for (int s = 0; s < MARCH_STAGES; s++) stage_rows(s, s);
     }
     __syncwarp();
+    // this lane's first column of the state planes / node planes in stage 0, row 0
+    const double* rs = &sm.ring[0][a.cur ? 3 : 0][0][CPL * lane];
+    const double* rn = &sm.ring[0][a.cur ? 0 : 4][0][CPL * lane];
 
     // global dt = max over blocks (main.cpp:270-292); the table was written by the ghost kernel
     double dt = 0.0;
-    for (int t = lane; t < a.nblocks_global; t += 32) dt = fmax(dt, a.dt_table[t]);
+    for (int t = lane; t < a.nblocks_global; t += 32) dt = fmax(dt, __ldcg(a.dt_table + t));   // peer-mapped mode: written by other GPUs
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) dt = fmax(dt, __shfl_xor_sync(0xffffffffu, dt, s));
     m.dt = dt;
 
     unsigned flags = 0;
     bool ok = true;
-    // ---- prologue: cell rows j0-1 (stage 0) and j0 (stage 1), node row j0, bottom-face fluxes of row j0
+    // ---- prologue (ring use 0): cell rows j0-1 (row 0) and j0 (row 1), node row j0, bottom-face fluxes of row j0
     RowState A, B;
     ok &= mbar_wait(&sm.bar[0], 0);
-    ok &= mbar_wait(&sm.bar[1], 0);
     {
         unsigned fl0[CPL];
         const int q = CPL * lane;
+        const double* s1 = rs + WCOLS;             // row 1 of stage 0
+        const double* n1 = rn + WCOLS;
 #pragma unroll
         for (int e = 0; e < CPL; e++) {
             fl0[e] = 0;
-            A.T[e] = sm.ring[1][3][q + e];
-            A.s[e] = face_state<FAITHFUL, TPG>(g, sm.ring[1][0][q + e], sm.ring[1][1][q + e], sm.ring[1][2][q + e], A.T[e], fl0[e]);
-            A.x[e] = sm.ring[1][4][q + e]; A.y[e] = sm.ring[1][5][q + e];
-            A.im[e] = sm.ring[1][6][q + e];
+            A.T[e] = s1[3 * PLANE_D + e];
+            A.s[e] = face_state<FAITHFUL, TPG>(g, s1[e], s1[PLANE_D + e], s1[2 * PLANE_D + e], A.T[e], fl0[e]);
+            A.x[e] = n1[e]; A.y[e] = n1[PLANE_D + e];
+            A.im[e] = n1[2 * PLANE_D + e];
         }
         A.x[CPL] = shfl_down1(A.x[0]); A.y[CPL] = shfl_down1(A.y[0]);
 #pragma unroll
         for (int e = 0; e < CPL; e++) {
-            const FaceState lo = face_state<FAITHFUL, TPG>(g, sm.ring[0][0][q + e], sm.ring[0][1][q + e], sm.ring[0][2][q + e], sm.ring[0][3][q + e], fl0[e]);
+            const FaceState lo = face_state<FAITHFUL, TPG>(g, rs[e], rs[PLANE_D + e], rs[2 * PLANE_D + e], rs[3 * PLANE_D + e], fl0[e]);
             // j-face: left state = upper cell, right state = lower cell (SpatialDiscretization.cpp:556-625)
             const Flux G0 = ldfss<FAITHFUL, AXI>(face_geom<FAITHFUL>(A.x[e], A.y[e], A.x[e + 1], A.y[e + 1]), A.s[e], lo);
             sm.G[0][q + e] = G0.f0; sm.G[1][q + e] = G0.f1; sm.G[2][q + e] = G0.f2; sm.G[3][q + e] = G0.f3; sm.G[4][q + e] = G0.parr;
@@ -394,46 +411,31 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
         }
     }
     double sq0 = 0.0, sq1 = 0.0, sq2 = 0.0, sq3 = 0.0;
-    // stages 0 and 1 are consumed: refill them with the next two rows
+    // stage 0 is consumed: refill it
     __syncwarp();
-    if (lane == 0) {
-        stage_row(j0 + MARCH_STAGES, 0);
-        stage_row(j0 + MARCH_STAGES + 1, 1);
-    }
+    if (lane == 0) stage_rows(MARCH_STAGES, 0);
 
-    // ---- march: row j consumes array row j+2 = ring use n = j-j0+2 (stage n % STAGES, parity (n / STAGES) & 1)
-    //      and then refills that stage with array row j+2+STAGES
-    int st = 2 % MARCH_STAGES;
-    uint32_t ph = (2 / MARCH_STAGES) & 1;
-    auto advance = [&](int j) {
-        __syncwarp();                              // every lane has read stage st
-        if (lane == 0) stage_row(j + 2 + MARCH_STAGES, st);
-        if (++st == MARCH_STAGES) { st = 0; ph ^= 1u; }
-    };
-#if MARCH_UNROLL2
+    // ---- march, two rows per trip (the carried state swaps roles, no register moves between rows): rows
+    //      j, j+1 consume ring use n = (j-j0)/2 + 1, which is then refilled with use n + MARCH_STAGES
+    int n = 1, slot = 1 % MARCH_STAGES;
+    uint32_t ph = (1 / MARCH_STAGES) & 1;
     int j = j0;
 #pragma unroll 1
     for (; j + 1 < j1; j += 2) {
-        ok &= mbar_wait(&sm.bar[st], ph);
-        march_row<FAITHFUL, TPG, AXI>(a, g, m, sm, j, st, A, B, sq0, sq1, sq2, sq3, flags);
-        advance(j);
-        ok &= mbar_wait(&sm.bar[st], ph);
-        march_row<FAITHFUL, TPG, AXI>(a, g, m, sm, j + 1, st, B, A, sq0, sq1, sq2, sq3, flags);
-        advance(j + 1);
+        ok &= mbar_wait(&sm.bar[slot], ph);
+        const double* s0 = rs + slot * STAGE_D;
+        const double* n0 = rn + slot * STAGE_D;
+        march_row<FAITHFUL, TPG, AXI>(a, g, m, sm, j, s0, n0, A, B, sq0, sq1, sq2, sq3, flags);
+        march_row<FAITHFUL, TPG, AXI>(a, g, m, sm, j + 1, s0 + WCOLS, n0 + WCOLS, B, A, sq0, sq1, sq2, sq3, flags);
+        __syncwarp();                              // every lane has read this stage
+        if (lane == 0) stage_rows(n + MARCH_STAGES, slot);
+        n++;
+        if (++slot == MARCH_STAGES) { slot = 0; ph ^= 1u; }
     }
     if (j < j1) {
-        ok &= mbar_wait(&sm.bar[st], ph);
-        march_row<FAITHFUL, TPG, AXI>(a, g, m, sm, j, st, A, B, sq0, sq1, sq2, sq3, flags);
+        ok &= mbar_wait(&sm.bar[slot], ph);
+        march_row<FAITHFUL, TPG, AXI>(a, g, m, sm, j, rs + slot * STAGE_D, rn + slot * STAGE_D, A, B, sq0, sq1, sq2, sq3, flags);
     }
-#else
-#pragma unroll 1
-    for (int j = j0; j < j1; j++) {
-        ok &= mbar_wait(&sm.bar[st], ph);
-        march_row<FAITHFUL, TPG, AXI>(a, g, m, sm, j, st, A, B, sq0, sq1, sq2, sq3, flags);
-        A = B;
-        advance(j);
-    }
-#endif
 
     // ---- sum of squares of this strip, fixed order: lanes (xor tree)
     double sq[4] = {sq0, sq1, sq2, sq3};

@@ -81,8 +81,21 @@ struct Gas {
 
 // error bits raised on the device (mapped to PAR2D_ERR_* on the host)
 enum : unsigned {
-    FLAG_NAN = 1u, FLAG_DENSITY = 2u, FLAG_STATE = 4u, FLAG_SINGULAR = 8u, FLAG_THERMO = 16u
+    FLAG_NAN = 1u, FLAG_DENSITY = 2u, FLAG_STATE = 4u, FLAG_SINGULAR = 8u, FLAG_THERMO = 16u, FLAG_COMM = 32u
 };
+
+// max(x, lo) for a non-NaN bound lo, as compare + select (3 instructions).  sm_100 has no fp64 max
+// instruction: fmax() expands to DSETP.MAX + selects + NaN fix-up (7 instructions).  Same result as
+// fmax(x, lo) for every x including NaN (-> lo).
+PAR2D_FN double max_sel(double x, double lo) {
+#ifdef __CUDA_ARCH__
+    double r;   // spelled in PTX: nvcc canonicalises the C++ ternary back into fmax()
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(x), "d"(lo));
+    return r;
+#else
+    return x > lo ? x : lo;
+#endif
+}
 
 // ---------------------------------------------------------------- fast math
 // MUFU.RCP64H / MUFU.RSQ64H seed 2^-20 relative (measured on B200, profiles/r01_hw_probe_*.txt).
@@ -147,7 +160,8 @@ PAR2D_FN FaceState face_state(const Gas& g, double rho, double u, double v, doub
     FaceState s;
     s.rho = rho; s.u = u; s.v = v;
     double v2 = u * u + v * v;
-    s.p = fmax(rho * g.Rs * T, 1.0);
+    if constexpr (FAITHFUL) s.p = fmax(rho * g.Rs * T, 1.0);
+    else s.p = max_sel(rho * g.Rs * T, 1.0);
     if constexpr (FAITHFUL) {
         s.a = sqrt(g.gamRs * T);
         s.h0 = enthalpy<TPG>(g, T, flags) + 0.5 * v2;
@@ -294,8 +308,8 @@ PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) 
             const double tw = psum * w3;
             const double dps = delp * (plr * w3);
             const double ad2 = 2.0 * fabs(delp);
-            cep -= xmc * fmax(0.0, 1.0 - fma(ad2, R.p * tw, dps));
-            cem += xmc * fmax(0.0, 1.0 + fma(-ad2, L.p * tw, dps));
+            cep -= xmc * max_sel(1.0 - fma(ad2, R.p * tw, dps), 0.0);
+            cem += xmc * max_sel(1.0 + fma(-ad2, L.p * tw, dps), 0.0);
         }
         const double pnet = fma(wl, L.p, wr * R.p);
         if constexpr (AXI) {

@@ -1,11 +1,16 @@
 """One-process-per-GPU driver: GridPart-decomposed blocks sharded over the ranks of one box.
 
-Replaces the reference's MPI plumbing (one rank per block, FV/main.cpp:68-74,125-128):
+Replaces the reference's MPI plumbing (one rank per block, FV/main.cpp:68-74,125-128).  Two transports:
+  "peer" (default on GPUs): every rank exports its receive arena (cudaIpc handle, all-gathered here
+                     once), then the library's own kernels store edge lines and dt_b into the neighbours'
+                     arenas over NVLink and a whole batch of steps runs without the host (par2d_peer_*);
+  "nccl"/"gloo"    : external transport per step -
   * halo exchange  : the four MPI_Sendrecv sites (SpatialDiscretization.cpp:259,320,380,441)
                      become one grouped NCCL send/recv per neighbouring rank on the device
                      buffers the C ABI exposes (par2d_exchange_layout);
   * dt sync        : the gather/fmax/bcast chain (main.cpp:270-292) becomes one all-reduce(MAX)
                      over the per-block dt table (par2d_dt_table);
+and for both
   * residual gather: main.cpp:379-392 becomes a gather of per-block sums after the batch, added
                      in global block order so relres is independent of the number of GPUs.
 torch.distributed is plumbing only; every byte of compute is in libpar2d_gpu.so.  The same class
@@ -24,6 +29,14 @@ from . import _capi
 from ._capi import Config, StepInfo
 from .host import Case
 from .solver import Solver, default_config
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
 
 
 class _DevPtr:
@@ -47,7 +60,10 @@ def _alias(ptr: int, n: int, cuda: bool) -> Optional[torch.Tensor]:
 class DistSolver:
     """All ranks construct this collectively with the same case; each advances the blocks it owns."""
 
-    def __init__(self, case: Case, cfg: Optional[Config] = None, lib=None, group=None):
+    def __init__(self, case: Case, cfg: Optional[Config] = None, lib=None, group=None, transport: str = "auto"):
+        """transport: "peer" (NVLink peer-mapped arenas; raises if the GPUs have no peer access),
+        "external" (torch.distributed send/recv per step) or "auto" (peer on GPUs, falling back to
+        external with a printed note; always external for the CPU oracle used by the gloo tests)."""
         self.lib = lib or _capi.load_gpu()
         self.group = group
         self.rank = dist.get_rank(group)
@@ -60,8 +76,14 @@ class DistSolver:
         self.owners = case.partition(self.world)
         self.solver = Solver(case, cfg, lib=self.lib, owners=self.owners)
         h = self.solver.handle
+        self.stream = None
         if self.cuda:
-            self.lib.check(self.lib.set_stream(h, torch.cuda.current_stream().cuda_stream), "set_stream")
+            # The external transport interleaves library kernels with NCCL operations, which torch orders
+            # against the CURRENT torch stream: the library must therefore run on a real torch stream (the
+            # legacy default stream's handle is 0 = "private stream" for par2d_set_stream and would not be
+            # ordered with the NCCL work at all).
+            self.stream = torch.cuda.Stream()
+            self.lib.check(self.lib.set_stream(h, self.stream.cuda_stream), "set_stream")
         # exchange buffers per neighbouring rank
         self.send, self.recv = {}, {}
         for p in range(self.world):
@@ -78,8 +100,38 @@ class DistSolver:
         self.dt_table = _alias(pt.value, n.value, self.cuda)
         self.nblocks = case.nblocks
         self.total_cells = case.ncells
+        self.transport = "external"
+        if self.cuda and transport in ("auto", "peer"):
+            self._connect_peers(strict=(transport == "peer"))
+
+    def _connect_peers(self, strict: bool):
+        h = self.solver.handle
+        mine = (C.c_ubyte * 64)()
+        rc = self.lib.peer_export(h, mine)
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device="cuda")
+        handles = torch.zeros(self.world, 64, dtype=torch.uint8, device="cuda")
+        handles[self.rank] = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device="cuda")
+        dist.all_reduce(handles, op=dist.ReduceOp.SUM, group=self.group)      # disjoint rows: an all-gather
+        if rc == 0:
+            buf = (C.c_ubyte * (64 * self.world)).from_buffer_copy(bytes(handles.cpu().numpy().tobytes()))
+            rc = self.lib.peer_connect(h, buf)
+            ok[0] = 1 if rc == 0 else 0
+        err = self.lib.last_error()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)            # all or nobody
+        if int(ok.item()) == 1:
+            self.transport = "peer"
+            return
+        self.lib.peer_disconnect(h)
+        msg = f"peer-mapped exchange unavailable ({err.decode() if err else 'a peer failed'})"
+        if strict:
+            raise RuntimeError(msg)
+        if self.rank == 0:
+            print(f"par2d_b200.dist: {msg}; using the external NCCL transport", flush=True)
 
     # -- one explicit step: pack -> transport -> ghost/residual/update ----------------------
+    def _on_stream(self):
+        return torch.cuda.stream(self.stream) if self.stream is not None else _NullCtx()
+
     def _transport(self):
         dist.all_reduce(self.dt_table, op=dist.ReduceOp.MAX, group=self.group)
         ops = []
@@ -92,12 +144,24 @@ class DistSolver:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
 
+    def advance(self, nsteps: int, check: bool = True) -> List[StepInfo]:
+        """Advance nsteps on every rank (collective); returns this rank's log records (local sums)."""
+        if self.transport == "peer":
+            info = (StepInfo * nsteps)()
+            rc = self.lib.step(self.solver.handle, nsteps, 0, info)
+            if check:
+                self.lib.check(rc, "step")
+            return list(info)
+        self.queue_steps(nsteps)
+        return self.collect(nsteps, check=check)
+
     def queue_steps(self, nsteps: int):
         h = self.solver.handle
-        for _ in range(nsteps):
-            self.lib.check(self.lib.step_begin(h), "step_begin")
-            self._transport()
-            self.lib.check(self.lib.step_end(h), "step_end")
+        with self._on_stream():
+            for _ in range(nsteps):
+                self.lib.check(self.lib.step_begin(h), "step_begin")
+                self._transport()
+                self.lib.check(self.lib.step_end(h), "step_end")
 
     def collect(self, nsteps: int, check: bool = True) -> List[StepInfo]:
         info = (StepInfo * nsteps)()
@@ -109,8 +173,7 @@ class DistSolver:
     def step(self, nsteps: int, check: bool = True):
         """Advance nsteps; returns (dt[nsteps], relres[nsteps]) with relres summed over ALL blocks
         in global block order on every rank."""
-        self.queue_steps(nsteps)
-        info = self.collect(nsteps, check=check)
+        info = self.advance(nsteps, check=check)
         hist = self.solver.block_history(nsteps)            # (nsteps, nowned, 2)
         table = torch.zeros(nsteps, self.nblocks, 2, dtype=torch.float64)
         for k, g in enumerate(self.solver.owned):
@@ -134,4 +197,9 @@ class DistSolver:
         return self.solver.owned
 
     def close(self):
+        if self.transport == "peer":
+            # unmap the peers' arenas everywhere before anybody frees its own
+            self.lib.peer_disconnect(self.solver.handle)
+            dist.barrier(group=self.group)
+            self.transport = "external"
         self.solver.close()

@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--synthetic", default="")      # e.g. 128x128:4x4
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--tol", type=float, default=0.0)
+    ap.add_argument("--transport", default="auto")
+    ap.add_argument("--batches", type=int, default=1)   # the steps are taken in this many par2d_step batches
     a = ap.parse_args()
     if a.backend == "nccl":
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
@@ -47,8 +49,15 @@ def main():
         return Case.load(os.path.join(REPO, "tests", "golden", "cases", a.case))
 
     cfg = default_config(lib)
-    ds = DistSolver(make_case(), cfg, lib=lib)
-    dt, relres = ds.step(a.steps)
+    if a.impl == "gpu":
+        cfg.device = torch.cuda.current_device()
+    ds = DistSolver(make_case(), cfg, lib=lib, transport=a.transport)
+    if a.transport in ("peer", "external"):
+        assert ds.transport == a.transport, ds.transport
+    per = a.steps // a.batches
+    parts = [ds.step(per) for _ in range(a.batches)]
+    dt = np.concatenate([p[0] for p in parts])
+    relres = np.concatenate([p[1] for p in parts])
 
     single = Solver(make_case(), default_config(orc), lib=orc)
     info = single.step(a.steps)
@@ -67,9 +76,21 @@ def main():
     else:
         assert worst <= a.tol, worst
         assert np.abs(relres / ref_rel - 1).max() <= 1e-9 and np.abs(dt / ref_dt - 1).max() <= 1e-12
+    if a.impl == "gpu":
+        # the same case advanced by ONE process on this rank's GPU: sharding over GPUs must not change a bit
+        one = Solver(make_case(), cfg, lib=lib)
+        oinfo = one.step(a.steps)
+        for b in ds.owned:
+            assert np.array_equal(ds.get_state(b), one.get_state(b)), f"rank {rank}: block {b} differs from the single-GPU run"
+            if ds.transport == "peer":   # the arenas hold the final state's halos (trailing put of par2d_step)
+                assert np.array_equal(ds.solver.get_residual(b), one.get_residual(b)), f"rank {rank}: residual of block {b} differs"
+        assert np.array_equal(dt, np.array([i.dt for i in oinfo]))
+        assert np.array_equal(relres, np.array([i.relres for i in oinfo])), (relres, [i.relres for i in oinfo])
+        one.close()
     owned = len(ds.owned)
     dist.barrier()
-    print(f"RANK{rank} OK owned={owned} worst={worst:.3e}", flush=True)
+    print(f"RANK{rank} OK owned={owned} worst={worst:.3e} transport={ds.transport}", flush=True)
+    ds.close()
     dist.destroy_process_group()
 
 
