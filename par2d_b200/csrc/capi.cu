@@ -104,6 +104,7 @@ Gas make_gas(const par2d_config& c) {
     g.igam = c.igam;
     g.gam = fabs(c.igam);
     g.gamRs = g.gam * g.Rs;
+    g.gamRs4 = 0.25 * g.gamRs;
     g.cpg_den = (1.0 - 1.0 / (c.igam));
     g.cp_cpg = g.Rs / (1.0 - 1.0 / (c.igam));
     g.inv_cv_cpg = 1.0 / (g.cp_cpg - g.Rs);

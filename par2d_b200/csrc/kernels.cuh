@@ -260,7 +260,8 @@ __global__ void test_update_state_kernel(Gas g, long long n, double* unk, double
     const double h = enthalpy<TPG>(g, T, fl);
     const double Cp = heat_capacity<TPG>(g, T, fl);
     double* o = derived + 8 * i;
-    o[0] = s.p; o[1] = s.a; o[2] = h; o[3] = s.h0; o[4] = h - g.Rs * T + 0.5 * v2; o[5] = v2; o[6] = Cp; o[7] = Cp - g.Rs;
+    o[0] = s.p; o[1] = FAITHFUL ? s.a : 2.0 * s.a;   // the lean FaceState carries a/2
+    o[2] = h; o[3] = s.h0; o[4] = h - g.Rs * T + 0.5 * v2; o[5] = v2; o[6] = Cp; o[7] = Cp - g.Rs;
 }
 
 template <bool FAITHFUL, bool TPG, bool AXI>
@@ -294,10 +295,16 @@ struct KernelTable {
 
 template <bool FAITHFUL>
 struct Launch {
-    static void march(cudaStream_t s, const StepArgs& a, const Gas& g, bool tpg, bool axi) {
+    template <bool HOOKS>
+    static void march_h(cudaStream_t s, const StepArgs& a, const Gas& g, bool tpg, bool axi) {
         const dim3 grid(a.max_tiles, a.nowned);   // one warp strip per CTA
-        if (tpg) { if (axi) march_kernel<FAITHFUL, true, true><<<grid, MARCH_THREADS, 0, s>>>(a, g); else march_kernel<FAITHFUL, true, false><<<grid, MARCH_THREADS, 0, s>>>(a, g); }
-        else { if (axi) march_kernel<FAITHFUL, false, true><<<grid, MARCH_THREADS, 0, s>>>(a, g); else march_kernel<FAITHFUL, false, false><<<grid, MARCH_THREADS, 0, s>>>(a, g); }
+        if (tpg) { if (axi) march_kernel<FAITHFUL, true, true, HOOKS><<<grid, MARCH_THREADS, 0, s>>>(a, g); else march_kernel<FAITHFUL, true, false, HOOKS><<<grid, MARCH_THREADS, 0, s>>>(a, g); }
+        else { if (axi) march_kernel<FAITHFUL, false, true, HOOKS><<<grid, MARCH_THREADS, 0, s>>>(a, g); else march_kernel<FAITHFUL, false, false, HOOKS><<<grid, MARCH_THREADS, 0, s>>>(a, g); }
+    }
+    // the production step (advancing, no residual dump) runs the instantiation without the test hooks
+    static void march(cudaStream_t s, const StepArgs& a, const Gas& g, bool tpg, bool axi) {
+        if (a.update && a.res_out == nullptr) march_h<false>(s, a, g, tpg, axi);
+        else march_h<true>(s, a, g, tpg, axi);
     }
     static void ghost(cudaStream_t s, const StepArgs& a, const Gas& g, int write_dt) {
         ghost_kernel<FAITHFUL><<<dim3((a.max_faces + 255) / 256, a.nowned), 256, 0, s>>>(a, g, write_dt);

@@ -147,11 +147,12 @@ struct MarchCtx {
 // Residual, norms, solve and new state of one cell from its four face fluxes (left, right, bottom, top).
 // (xa,ya)..(xd,yd) = nodes (c,j), (c+1,j), (c+1,j+1), (c,j+1)  (MeshModule.cpp:28-40).  Returns the new
 // state in out[4] when a.update.
-template <bool FAITHFUL, bool TPG, bool AXI>
+template <bool FAITHFUL, bool TPG, bool AXI, bool HOOKS>
 __device__ __forceinline__ void cell_update(const StepArgs& a, const Gas& g, const MarchCtx& m, int c, int j, const FaceState& cur, double T, double im,
                                             double xa, double ya, double xb, double yb, double xc, double yc_, double xd, double yd,
                                             const Flux& Fl, const Flux& Fr, const Flux& Gb, const Flux& Gt,
                                             double out[4], double& sq0, double& sq1, double& sq2, double& sq3, unsigned& flags) {
+    const bool update = HOOKS ? a.update != 0 : true;   // HOOKS = false: the production step (no residual dump, always advancing)
     const double ycc = 0.25 * (ya + yb + yc_ + yd);
     double r[4];        // residual = calc_dudt's dudt
     double dv[4];
@@ -178,7 +179,7 @@ __device__ __forceinline__ void cell_update(const StepArgs& a, const Gas& g, con
             if (bt) acc += gt[v];
             r[v] = acc / vol;
         }
-        if (a.update) {
+        if (update) {
             unsigned fl2 = 0;
             const double v2 = cur.u * cur.u + cur.v * cur.v;
             const double e0 = enthalpy<TPG>(g, T, fl2) - g.Rs * T + 0.5 * v2;   // StateVariables.h:62
@@ -204,7 +205,7 @@ __device__ __forceinline__ void cell_update(const StepArgs& a, const Gas& g, con
         const double sc = m.dt * im;
 #pragma unroll
         for (int v = 0; v < 4; v++) r[v] = R[v] * ivol;
-        if (a.update) {
+        if (update) {
             unsigned fl2 = 0;
             const double e0 = fma(-g.Rs, T, cur.h0);   // h - Rs T + v2/2 with h0 = h + v2/2 at hand
             double inv_cv = g.inv_cv_cpg;
@@ -213,11 +214,13 @@ __device__ __forceinline__ void cell_update(const StepArgs& a, const Gas& g, con
         }
     }
     sq0 = fma(r[0], r[0], sq0); sq1 = fma(r[1], r[1], sq1); sq2 = fma(r[2], r[2], sq2); sq3 = fma(r[3], r[3], sq3);
-    if (a.res_out != nullptr && a.res_block == m.k) {
-        double* o = a.res_out + 4 * ((long long)j * m.ncx + c);
-        o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[3];
+    if constexpr (HOOKS) {
+        if (a.res_out != nullptr && a.res_block == m.k) {
+            double* o = a.res_out + 4 * ((long long)j * m.ncx + c);
+            o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[3];
+        }
     }
-    if (a.update) {
+    if (update) {
         // main.cpp:394-404: unk += dv, rho > 0, UpdateState's T clamp
         out[0] = cur.rho + dv[0]; out[1] = cur.u + dv[1]; out[2] = cur.v + dv[2];
         if constexpr (FAITHFUL) out[3] = fmax(T + dv[3], 201.0);
@@ -233,7 +236,7 @@ __device__ __forceinline__ void cell_update(const StepArgs& a, const Gas& g, con
 // One row of a strip: consumes the carried state `lo` of cell row j and the staged row above it (srow/nrow
 // = this lane's first column of the state / node planes of that row in the ring), produces the carried
 // state `hi` of row j+1, updates this lane's cells of row j.
-template <bool FAITHFUL, bool TPG, bool AXI>
+template <bool FAITHFUL, bool TPG, bool AXI, bool HOOKS>
 __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const MarchCtx& m, MarchSmem& sm, int j, const double* srow, const double* nrow,
                                           const RowState& lo, RowState& hi, double& sq0, double& sq1, double& sq2, double& sq3, unsigned& flags) {
     const int q = CPL * m.lane;                    // this lane's first column in the staged row
@@ -304,12 +307,12 @@ __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const
     for (int e = 0; e < CPL; e++) {
         if (m.writer[e]) {
             flags |= flu[e];   // state checks of the cell above: a real cell or a filled ghost
-            cell_update<FAITHFUL, TPG, AXI>(a, g, m, m.c + e, j, lo.s[e], lo.T[e], lo.im[e], lo.x[e], lo.y[e], lo.x[e + 1], lo.y[e + 1],
+            cell_update<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, m.c + e, j, lo.s[e], lo.T[e], lo.im[e], lo.x[e], lo.y[e], lo.x[e + 1], lo.y[e + 1],
                                             hi.x[e + 1], hi.y[e + 1], hi.x[e], hi.y[e], F[e], F[e + 1], Gb[e], Gt[e], out[e], sq0, sq1, sq2, sq3, flags);
         }
     }
     if constexpr (CPL == 2) {
-        if (a.update) {
+        if (HOOKS ? a.update != 0 : true) {
             double* o = m.Sout + ((long long)(j + 1) * m.pitch + COL0 + m.c);
             if (m.writer[0] && m.writer[1]) {      // 16-byte stores: COL0 + c is even for every lane
 #pragma unroll
@@ -326,7 +329,7 @@ __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const
     }
 }
 
-template <bool FAITHFUL, bool TPG, bool AXI>
+template <bool FAITHFUL, bool TPG, bool AXI, bool HOOKS>
 __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) march_kernel(const StepArgs a, const Gas g) {
     __shared__ __align__(128) MarchSmem sm;
     if (*a.stop) return;
@@ -425,8 +428,8 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
         ok &= mbar_wait(&sm.bar[slot], ph);
         const double* s0 = rs + slot * STAGE_D;
         const double* n0 = rn + slot * STAGE_D;
-        march_row<FAITHFUL, TPG, AXI>(a, g, m, sm, j, s0, n0, A, B, sq0, sq1, sq2, sq3, flags);
-        march_row<FAITHFUL, TPG, AXI>(a, g, m, sm, j + 1, s0 + WCOLS, n0 + WCOLS, B, A, sq0, sq1, sq2, sq3, flags);
+        march_row<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, sm, j, s0, n0, A, B, sq0, sq1, sq2, sq3, flags);
+        march_row<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, sm, j + 1, s0 + WCOLS, n0 + WCOLS, B, A, sq0, sq1, sq2, sq3, flags);
         __syncwarp();                              // every lane has read this stage
         if (lane == 0) stage_rows(n + MARCH_STAGES, slot);
         n++;
@@ -434,7 +437,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
     }
     if (j < j1) {
         ok &= mbar_wait(&sm.bar[slot], ph);
-        march_row<FAITHFUL, TPG, AXI>(a, g, m, sm, j, rs + slot * STAGE_D, rn + slot * STAGE_D, A, B, sq0, sq1, sq2, sq3, flags);
+        march_row<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, sm, j, rs + slot * STAGE_D, rn + slot * STAGE_D, A, B, sq0, sq1, sq2, sq3, flags);
     }
 
     // ---- sum of squares of this strip, fixed order: lanes (xor tree)

@@ -37,6 +37,9 @@ inline double __dsub_rn(double a, double b) { volatile double r = a - b; return 
 #ifndef LDFSS_SQRT
 #define LDFSS_SQRT 0
 #endif
+#ifndef LDFSS_PRESSURE_V1
+#define LDFSS_PRESSURE_V1 0   // 1: the earlier evaluation of the subsonic diffusion term (A/B runs)
+#endif
 
 namespace par2d {
 
@@ -70,6 +73,7 @@ struct Gas {
     double gam;        // fabs(IGAM), Thermo.h:47
     double igam;       // signed IGAM
     double gamRs;      // gam*Rs (same association as StateVariables.h:51: (gam*Rs)*T)
+    double gamRs4;     // gam*Rs/4: sqrt(gamRs4*T) = a/2 (fast path only)
     double cp_cpg;     // Rs/(1-1/IGAM)             Thermo.cpp:34
     double cpg_den;    // (1-1/IGAM)                Thermo.cpp:14
     double inv_cv_cpg; // 1/(cp_cpg-Rs)   (fast path only)
@@ -99,20 +103,32 @@ PAR2D_FN double max_sel(double x, double lo) {
 
 // ---------------------------------------------------------------- fast math
 // MUFU.RCP64H / MUFU.RSQ64H seed 2^-20 relative (measured on B200, profiles/r01_hw_probe_*.txt).
-// One fourth-order step in the seed's residual e reaches e^4 = 2^-80, i.e. rounding-limited
-// (<= 1.1e-16 measured), with a shorter dependency chain than two Newton steps.
+// One third-order step in the seed's residual e (|e| <= 2^-19) leaves a truncation error of e^3 <= 2^-57,
+// a sixteenth of the rounding error of the last operation; shorter (in operations and in dependency
+// chain) than two Newton steps.  PAR2D_SERIES4 = 1 keeps one more term (e^4 = 2^-76), for A/B runs.
+#ifndef PAR2D_SERIES4
+#define PAR2D_SERIES4 0
+#endif
 PAR2D_FN double fast_rcp(double x) {
     const double y = seed_rcp(x);
     const double e = fma(-x, y, 1.0);          // 1 - x*y0
+#if PAR2D_SERIES4
     const double y1 = fma(y, e, y);            // y0 (1 + e)
     const double e2 = e * e;
     return fma(y1, e2, y1);                    // y0 (1 + e)(1 + e^2) = y0 (1 + e + e^2 + e^3)
+#else
+    return fma(y, fma(e, e, e), y);            // y0 (1 + e + e^2)
+#endif
 }
-// 1/sqrt(x): y0 (1 + e/2 + 3e^2/8 + 5e^3/16), e = 1 - x*y0^2.
+// 1/sqrt(x): y0 (1 + e/2 + 3e^2/8 [+ 5e^3/16]), e = 1 - x*y0^2.
 PAR2D_FN double fast_rsqrt(double x) {
     const double y = seed_rsqrt(x);
     const double e = fma(-x, y * y, 1.0);
+#if PAR2D_SERIES4
     const double p = fma(fma(e, 0.3125, 0.375), e, 0.5);
+#else
+    const double p = fma(e, 0.375, 0.5);
+#endif
     return fma(y * e, p, y);
 }
 // sqrt(x), x > 0 normal: g = x*y0 ~ sqrt(x), same series in e = 1 - g*y0.
@@ -120,7 +136,11 @@ PAR2D_FN double fast_sqrt(double x) {
     const double y = seed_rsqrt(x);
     const double gq = x * y;
     const double e = fma(-gq, y, 1.0);
+#if PAR2D_SERIES4
     const double p = fma(fma(e, 0.3125, 0.375), e, 0.5);
+#else
+    const double p = fma(e, 0.375, 0.5);
+#endif
     return fma(gq * e, p, gq);
 }
 
@@ -152,7 +172,9 @@ PAR2D_FN double heat_capacity(const Gas& g, double T, unsigned& flags) {
 // What a face needs from a cell: State::UpdateState (StateVariables.h:38-68) minus
 // the members the path never reads.  T must already be clamped (>= 201).
 struct FaceState {
-    double rho, u, v, p, a, h0;
+    double rho, u, v, p;
+    double a;          // speed of sound; the lean path (FAITHFUL = false) carries a/2, see ldfss
+    double h0;
 };
 
 template <bool FAITHFUL, bool TPG>
@@ -169,7 +191,7 @@ PAR2D_FN FaceState face_state(const Gas& g, double rho, double u, double v, doub
     } else {
         // T >= 201 and p >= 1 by the clamps, so a > 0 and p > 0 hold by construction; NaNs surface in
         // the residual norm (FLAG_NAN) and in the density check of the update
-        s.a = fast_sqrt(g.gamRs * T);
+        s.a = fast_sqrt(g.gamRs4 * T);             // a/2: ldfss only ever needs (aL + aR)/2
         if constexpr (TPG) s.h0 = fma(0.5, v2, enthalpy<TPG>(g, T, flags));
         else s.h0 = fma(0.5, v2, fma(g.cp_cpg, T, g.hi[5]));   // Thermo.cpp:14 with Rs/(1-1/IGAM) folded
     }
@@ -273,7 +295,7 @@ PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) 
         // lean evaluation: one rsqrt of (|d| ahalf)^2 yields both len*ahalf and its reciprocal, and
         // the pressure-weighted diffusion term (with its three divisions) is
         // evaluated only where both sides are subsonic (it is multiplied by btl*btr = 0 otherwise).
-        const double ahalf = 0.5 * (L.a + R.a);
+        const double ahalf = L.a + R.a;          // the lean FaceState carries a/2
         const double w = fma(fg.dx, fg.dx, fg.dy * fg.dy) * (ahalf * ahalf);
         const double q = fast_rsqrt(w);          // 1 / (len * ahalf)
         const double la = w * q;                 // len * ahalf
@@ -291,6 +313,7 @@ PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) 
         const double wl = subL ? xmml * (2.0 - xml) : (signbit(xml) ? 0.0 : 1.0);
         const double wr = subR ? -xmmr * (2.0 + xmr) : (signbit(xmr) ? 1.0 : 0.0);
         if (subL && subR) {
+#if LDFSS_PRESSURE_V1
             const double t = 0.5 * fma(xml, xml, xmr * xmr);
             // rsqrt.approx flushes subnormals: below 1e-200 sqrt(t) is 0 to 100 digits of (xmhalf-1)
 #if LDFSS_SQRT
@@ -310,6 +333,27 @@ PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) 
             const double ad2 = 2.0 * fabs(delp);
             cep -= xmc * max_sel(1.0 - fma(ad2, R.p * tw, dps), 0.0);
             cem += xmc * max_sel(1.0 + fma(-ad2, L.p * tw, dps), 0.0);
+#else
+            // xmc = (xmhalf-1)^2/4 with xmhalf = sqrt((xml^2+xmr^2)/2) (EulerFlux.cpp:152-154).  Here
+            // xs = xmhalf/sqrt(2) and d = xs - 1/sqrt(2), so d*d = 2 xmc.  The 1e-199 keeps the argument of
+            // rsqrt.approx (which flushes subnormals) normal: it vanishes in the sum unless both Mach
+            // numbers are below 1e-92, where xs is 0 to 90 digits of d either way.  No branch, no compare.
+            const double t = 0.25 * fma(xml, xml, fma(xmr, xmr, 1e-199));
+            const double xs = t * fast_rsqrt(t);
+            const double d = xs - 0.70710678118654752440;
+            // pressure switches (EulerFlux.cpp:157-160) over their common denominator: with delp = pL - pR,
+            // psum = pL + pR and N = pL pR - |delp| psum,
+            //   1 - (delp/psum + 2|delp|/pL) = 2 N / (pL psum),   1 + (delp/psum - 2|delp|/pR) = 2 N / (pR psum)
+            // (psum -+ delp = 2 pR, 2 pL), so ONE reciprocal w3 = 1/(pL pR psum) and ONE max(.,0) serve both:
+            //   xmcp = xmc max(0, 2 N pR w3) = (2 xmc) max(0,N) w3 pR,   xmcm = (2 xmc) max(0,N) w3 pL
+            const double delp = L.p - R.p, psum = L.p + R.p;
+            const double plr = L.p * R.p;
+            const double w3 = fast_rcp(plr * psum);
+            const double N = max_sel(fma(-fabs(delp), psum, plr), 0.0);
+            const double k = ((d * d) * w3) * N;
+            cep = fma(-k, R.p, cep);
+            cem = fma(k, L.p, cem);
+#endif
         }
         const double pnet = fma(wl, L.p, wr * R.p);
         if constexpr (AXI) {

@@ -20,7 +20,7 @@ constexpr bool FAITH = HP_MODE == 1;
 
 static Gas make_gas(const par2d_config& c) {   // same as capi.cu::make_gas
     Gas g{};
-    g.Rs = c.Rs; g.igam = c.igam; g.gam = std::fabs(c.igam); g.gamRs = g.gam * g.Rs;
+    g.Rs = c.Rs; g.igam = c.igam; g.gam = std::fabs(c.igam); g.gamRs = g.gam * g.Rs; g.gamRs4 = 0.25 * g.gamRs;
     g.cpg_den = (1.0 - 1.0 / (c.igam)); g.cp_cpg = g.Rs / (1.0 - 1.0 / (c.igam)); g.inv_cv_cpg = 1.0 / (g.cp_cpg - g.Rs);
     for (int k = 0; k < 7; k++) { g.hi[k] = c.thermo_hi[k]; g.lo[k] = c.thermo_lo[k]; }
     for (int k = 0; k < 4; k++) g.uFS[k] = c.uFS[k];
@@ -96,7 +96,7 @@ int HP(test_update_state)(const par2d_config* cfg, int64_t n, double* unk, doubl
         const double h = tpg ? enthalpy<true>(g, T, fl) : enthalpy<false>(g, T, fl);
         const double Cp = tpg ? heat_capacity<true>(g, T, fl) : heat_capacity<false>(g, T, fl);
         double* o = derived + 8 * i;
-        o[0] = s.p; o[1] = s.a; o[2] = h; o[3] = s.h0; o[4] = h - g.Rs * T + 0.5 * v2; o[5] = v2; o[6] = Cp; o[7] = Cp - g.Rs;
+        o[0] = s.p; o[1] = FAITH ? s.a : 2.0 * s.a; o[2] = h; o[3] = s.h0; o[4] = h - g.Rs * T + 0.5 * v2; o[5] = v2; o[6] = Cp; o[7] = Cp - g.Rs;
     }
     return 0;
 }
