@@ -34,7 +34,7 @@ sys.path.insert(0, REPO)
 BLOCK = 2048                      # cells per block side (BASELINE.json configs[4]: 64 blocks of 2048^2)
 LAYOUT = {1: (4, 2), 2: (4, 4), 4: (8, 4), 8: (8, 8)}   # blocks in x, y for N GPUs (8 per GPU)
 ALGO_BYTES_PER_CELL = 80          # state read 32 + state write 32 + node coordinates 16
-LAUNCHES_PER_STEP = 3             # ghost_kernel, step_kernel, finalize_kernel (+1 pack_kernel for N > 1)
+LAUNCHES_PER_STEP = 2             # ghost_kernel (carries the previous step's residual bookkeeping), march_kernel (+1 pack_kernel for N > 1); +1 finalize_kernel per batch
 
 
 def measured_peaks():
@@ -315,7 +315,7 @@ def run_gpu_arm(args):
     fp64 = C.c_double()
     gpu.check(gpu.probe_fp64(local, C.byref(fp64)), "probe_fp64")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": traffic, "kernel": "step_kernel (fused residual+update)", "kernel_ms": k_ms, "kernel_share_of_step": kms.value / elapsed_ms,
+                "traffic": traffic, "kernel": "march_kernel (fused residual assembly + norms + per-cell solve + update)", "kernel_ms": k_ms, "kernel_share_of_step": kms.value / elapsed_ms,
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which}, burst copy)",
                 "algorithmic_bytes_per_cell": ALGO_BYTES_PER_CELL, "cells_per_launch": owned_cells,
                 "fp64_fma_tflops_measured": fp64.value,
@@ -338,7 +338,7 @@ def run_gpu_arm(args):
                    "l2": "state per GPU 1.07 GB read + 1.07 GB written per step >> 126 MB L2; no flush needed",
                    "arith_mode": "PAR2D_MODE_FAST"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-        "gpu_launches": (LAUNCHES_PER_STEP + (1 if multi else 0)) * args.steps + (1 if transport == "peer" else 0),
+        "gpu_launches": (LAUNCHES_PER_STEP + (1 if multi else 0)) * args.steps + 1 + (1 if transport == "peer" else 0),
         "relres_last": info[-1].relres if not multi else None, "dt": info[-1].dt,
     }
     print(json.dumps(line), flush=True)

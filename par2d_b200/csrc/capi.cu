@@ -3,7 +3,7 @@
 // One par2d_ctx = the blocks one rank owns (the reference: one MPI rank per block,
 // FV/main.cpp:124-128), resident in HBM as padded SoA planes with the ghost ring in place
 // (common.cuh).  A step is three launches on one stream, no host synchronisation:
-//   ghost_kernel -> march_kernel -> finalize_kernel
+//   ghost_kernel (+ the previous step's residual bookkeeping) -> march_kernel [-> finalize_kernel at the end of a batch]
 // and a batch of steps returns its dt / residual history in one copy at the end.
 // There is no CPU fallback anywhere in this file.
 #include <cuda.h>
@@ -164,6 +164,9 @@ struct par2d_ctx {
     void* dtmaps = nullptr;
 
     double* dt_table = nullptr;
+    double* dt_used = nullptr;       // [2]: the dt of the step in flight / of the step whose bookkeeping is pending
+    bool fin_pending = false;        // the last queued step's bookkeeping has not been launched yet
+    FinalizeArgs fin_args;
     double* partials = nullptr;
     unsigned* flags = nullptr;
     int* stop = nullptr;
@@ -207,6 +210,7 @@ struct par2d_ctx {
     int last_steps = 0;
     long long last_iter0 = 0;
     int pending_steps = 0;  // begin/end mode: steps queued since the last collect
+    long long iter_queued = 0;  // steps queued so far (parity of the dt_used slot)
 
     // measurement hook (par2d_kernel_timing)
     bool timing = false;
@@ -226,6 +230,7 @@ struct par2d_ctx {
         a.max_faces = max_faces;
         a.tmaps = dtmaps;
         a.dt_table = dt_table;
+        a.dt_used = dt_used + (iter_queued & 1);
         a.partials = partials;
         a.flags = flags;
         a.stop = stop;
@@ -261,8 +266,8 @@ struct par2d_ctx {
         f.hist_pos = hist_pos;
         f.stop = stop;
         f.ticket = ticket;
-        f.dt_table = peer_connected ? reinterpret_cast<double*>(arena + lay.dt_off) + (long long)(seq & 1) * lay.dt_stride : dt_table;
-        f.nblocks_global = nblocks;
+        f.dt_used = dt_used + (iter_queued & 1);
+        f.blk_norm = blk_norm;
         f.tol = cfg.tol;
         f.stop_on_tol = stop_on_tol;
         f.hist_cap = hist_cap;
@@ -349,9 +354,18 @@ void queue_put(par2d_ctx* c) {
     c->kt->pack(c->stream, c->step_args(1), c->gas, c->dlines_peer, c->nlines, c->max_line, put);
 }
 
+// The bookkeeping of a step (finalize) is deferred into the NEXT step's ghost launch, where it overlaps
+// the ghost fill; flush_finalize() launches it on its own at the end of a batch.
+void flush_finalize(par2d_ctx* c) {
+    if (!c->fin_pending) return;
+    launch_finalize(c->stream, c->fin_args);
+    c->fin_pending = false;
+}
+
 void queue_step(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
     StepArgs a = c->step_args(1);
-    c->kt->ghost(c->stream, a, c->gas, with_ghost_dt ? 1 : 0);
+    c->kt->ghost(c->stream, a, c->gas, with_ghost_dt ? 1 : 0, c->fin_pending ? &c->fin_args : nullptr);
+    c->fin_pending = false;
     if (c->timing) {
         if ((int)c->ev.size() < 2 * (c->ev_used + 1)) {
             cudaEvent_t e0, e1;
@@ -364,7 +378,9 @@ void queue_step(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
     }
     launch_step(c, a);
     if (c->timing) cudaEventRecord(c->ev[2 * c->ev_used++ + 1], c->stream);
-    launch_finalize(c->stream, c->finalize_args(stop_on_tol), c->blk_norm);
+    c->fin_args = c->finalize_args(stop_on_tol);
+    c->fin_pending = true;
+    c->iter_queued++;
     c->cur ^= 1;
 }
 
@@ -654,6 +670,8 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
     CU_TRY(cudaMalloc(&c->ticket, sizeof(unsigned)));
     CU_TRY(cudaMalloc(&c->res0, sizeof(double) * 4 * c->nowned));
     CU_TRY(cudaMalloc(&c->blk_norm, sizeof(double) * 4 * c->nowned));
+    CU_TRY(cudaMalloc(&c->dt_used, sizeof(double) * 2));
+    CU_TRY(cudaMemsetAsync(c->dt_used, 0, sizeof(double) * 2, c->stream));
     CU_TRY(cudaMemsetAsync(c->flags, 0, sizeof(unsigned), c->stream));
     CU_TRY(cudaMemsetAsync(c->stop, 0, sizeof(int), c->stream));
     CU_TRY(cudaMemsetAsync(c->d_iter, 0, sizeof(long long), c->stream));
@@ -680,7 +698,7 @@ int par2d_destroy(par2d_ctx* c) {
     cudaFree(c->put_ticket); cudaFree(c->dlines_peer); cudaFree(c->d_dt_dst); cudaFree(c->d_flag_dst);
     cudaFree(c->dblk); cudaFree(c->dtmaps); cudaFree(c->partials); cudaFree(c->flags);
     cudaFree(c->stop); cudaFree(c->d_iter); cudaFree(c->hist_pos); cudaFree(c->ticket); cudaFree(c->res0);
-    cudaFree(c->blk_norm); cudaFree(c->blk_hist); cudaFree(c->step_hist); cudaFree(c->staging); cudaFree(c->dlines);
+    cudaFree(c->blk_norm); cudaFree(c->dt_used); cudaFree(c->blk_hist); cudaFree(c->step_hist); cudaFree(c->staging); cudaFree(c->dlines);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -729,7 +747,8 @@ int par2d_get_residual(par2d_ctx* c, int32_t block, double* res) {
     // lines (par2d_step_begin + transport); the dt table is rebuilt here either way
     // peer-mapped mode: the arenas hold the lines and dt of the state left by the last par2d_step
     // (after par2d_set_state, call par2d_step(ctx, 0, 0, NULL) on every rank to refresh them)
-    c->kt->ghost(c->stream, a, c->gas, c->peer_connected ? 0 : 1);
+    flush_finalize(c);
+    c->kt->ghost(c->stream, a, c->gas, c->peer_connected ? 0 : 1, nullptr);
     launch_step(c, a);
     const size_t bytes = sizeof(double) * 4 * (size_t)b.ncx * b.ncy;
     CU_TRY(cudaMemcpyAsync(res, c->staging, bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -761,6 +780,7 @@ int par2d_step(par2d_ctx* c, int32_t nsteps, int32_t stop_on_tol, par2d_step_inf
     } else {
         for (int s = 0; s < nsteps; s++) queue_step(c, stop_on_tol, true);
     }
+    flush_finalize(c);
     CU_TRY(cudaStreamSynchronize(c->stream));
     CU_TRY(cudaGetLastError());
     return harvest(c, nsteps, cur0, info, nsteps);
@@ -825,6 +845,7 @@ int par2d_step_collect(par2d_ctx* c, int32_t nsteps, par2d_step_info* info) {
     if (!c) return fail(PAR2D_ERR_ARG, "step_collect: null ctx");
     if (nsteps > c->pending_steps) return fail(PAR2D_ERR_ARG, "step_collect: %d requested, %d pending", nsteps, c->pending_steps);
     if (use_device(c)) return PAR2D_ERR_CUDA;
+    flush_finalize(c);
     CU_TRY(cudaStreamSynchronize(c->stream));
     CU_TRY(cudaGetLastError());
     const int queued = c->pending_steps;

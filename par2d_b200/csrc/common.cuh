@@ -88,6 +88,7 @@ struct StepArgs {
     int max_faces;           // longest block perimeter (grid.x of the ghost kernel)
     const void* tmaps;       // CUtensorMap[nowned] over each block's 11 planes; boxes of 32 columns x 2 rows x 7 planes
     double* dt_table;        // nblocks_global
+    double* dt_used;         // the global dt this step advanced with (written by the march kernel, read by finalize)
     double* partials;        // [total_tiles][4] sum of res_k^2
     unsigned* flags;         // device error bits
     const int* stop;         // non-zero -> batch already converged, kernels return at once
@@ -114,8 +115,8 @@ struct FinalizeArgs {
     int* hist_pos;           // next history slot
     int* stop;
     unsigned* ticket;        // last-block-done counter
-    const double* dt_table;
-    int nblocks_global;
+    const double* dt_used;   // StepArgs::dt_used of the step being finalised
+    double* blk_norm;        // [nowned][4] per-block residual norms (scratch between the block CTAs and the last one)
     double tol;
     int stop_on_tol;
     int hist_cap;

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "physics.cuh"
 #include "march.cuh"
+#include "kernels_common.cuh"
 
 namespace par2d {
 
@@ -87,8 +88,16 @@ __device__ __forceinline__ void block_dt(const StepArgs& a, const Gas& g, const 
 
 // ------------------------------------------------------------------ ghost fill
 template <bool FAITHFUL>
-__global__ void __launch_bounds__(256) ghost_kernel(StepArgs a, Gas g, int write_dt) {
+__global__ void __launch_bounds__(256) ghost_kernel(StepArgs a, Gas g, int write_dt, FinalizeArgs fin, int nfin) {
     if (*a.stop) return;
+    // rows 0..nfin-1 of the grid: the residual bookkeeping of the PREVIOUS step (nfin = owned blocks, or 0
+    // when nothing is pending), overlapped with this step's ghost fill
+    if ((int)blockIdx.y < nfin) {
+        __shared__ double red[256][4];
+        __shared__ bool last;
+        if (blockIdx.x == 0) finalize_block(fin, blockIdx.y, red, &last);
+        return;
+    }
     if (a.wait_flags != nullptr) {
         // peer-mapped mode: the neighbours' edge lines and every block's dt of this step's state are
         // written into this rank's arena by the other GPUs; wait for their completion flags
@@ -99,7 +108,7 @@ __global__ void __launch_bounds__(256) ghost_kernel(StepArgs a, Gas g, int write
         }
         __syncthreads();
     }
-    const BlockDev b = a.blocks[blockIdx.y];   // grid.y = owned blocks, grid.x covers the longest perimeter
+    const BlockDev b = a.blocks[blockIdx.y - nfin];   // grid.y = [pending finalize rows +] owned blocks, grid.x covers the longest perimeter
     int n = blockIdx.x * blockDim.x + threadIdx.x, side;
     if (n >= 2 * (b.ncx + b.ncy)) return;
     if (n < b.ncx) side = SIDE_BOTTOM;
@@ -284,7 +293,7 @@ __global__ void test_solve_kernel(Gas g, long long n, const double* dt_ycc, cons
 
 // ------------------------------------------------------------------ launch table of one arithmetic mode
 struct KernelTable {
-    void (*ghost)(cudaStream_t, const StepArgs&, const Gas&, int write_dt);
+    void (*ghost)(cudaStream_t, const StepArgs&, const Gas&, int write_dt, const FinalizeArgs* pending);
     void (*pack)(cudaStream_t, const StepArgs&, const Gas&, const SendLine*, int nlines, int max_n, const PutArgs&);
     void (*march)(cudaStream_t, const StepArgs&, const Gas&, bool tpg, bool axi);
     void (*test_ldfss)(cudaStream_t, const Gas&, bool tpg, bool axi, long long n, const double*, const double*, const double*, double*, double*);
@@ -306,8 +315,12 @@ struct Launch {
         if (a.update && a.res_out == nullptr) march_h<false>(s, a, g, tpg, axi);
         else march_h<true>(s, a, g, tpg, axi);
     }
-    static void ghost(cudaStream_t s, const StepArgs& a, const Gas& g, int write_dt) {
-        ghost_kernel<FAITHFUL><<<dim3((a.max_faces + 255) / 256, a.nowned), 256, 0, s>>>(a, g, write_dt);
+    static void ghost(cudaStream_t s, const StepArgs& a, const Gas& g, int write_dt, const FinalizeArgs* pending) {
+        FinalizeArgs fin;
+        memset(&fin, 0, sizeof fin);
+        if (pending) fin = *pending;
+        const int nfin = pending ? a.nowned : 0;
+        ghost_kernel<FAITHFUL><<<dim3((a.max_faces + 255) / 256, a.nowned + nfin), 256, 0, s>>>(a, g, write_dt, fin, nfin);
     }
     static void pack(cudaStream_t s, const StepArgs& a, const Gas& g, const SendLine* lines, int nlines, int max_n, const PutArgs& put) {
         dim3 grid((unsigned)((max_n + 255) / 256 > 0 ? (max_n + 255) / 256 : 1), (unsigned)(nlines > 0 ? nlines : 1));

@@ -8,73 +8,16 @@
 
 namespace par2d {
 
-// One CTA per owned block sums the tile partials in a fixed order (thread-strided, then a
-// shared-memory tree), takes the square roots (main.cpp:53-56) and the last CTA to finish
-// does the bookkeeping of main.cpp:365-392,494 in block order.
-__global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a, double* blk_norm) {
+// Stand-alone launch of the step bookkeeping (end of a batch; see finalize_block in kernels_common.cuh).
+__global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
     if (*a.stop) return;
     __shared__ double red[256][4];
     __shared__ bool last;
-    const int k = blockIdx.x, tid = threadIdx.x;
-    const BlockDev& b = a.blocks[k];
-    const int ntiles = b.tiles_x * b.tiles_y;
-    double s[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int t = tid; t < ntiles; t += 256) {
-        const double* p = a.partials + 4 * (long long)(b.tile0 + t);
-        s[0] += p[0]; s[1] += p[1]; s[2] += p[2]; s[3] += p[3];
-    }
-    for (int v = 0; v < 4; v++) red[tid][v] = s[v];
-    __syncthreads();
-    for (int w = 128; w > 0; w >>= 1) {
-        if (tid < w)
-            for (int v = 0; v < 4; v++) red[tid][v] += red[tid + w][v];
-        __syncthreads();
-    }
-    if (tid == 0) {
-        for (int v = 0; v < 4; v++) blk_norm[4 * k + v] = sqrt(red[0][v]);
-        __threadfence();
-        last = atomicAdd(a.ticket, 1u) == (unsigned)(a.nowned - 1);
-    }
-    __syncthreads();
-    if (!last || tid != 0) return;
-    __threadfence();
-    const long long it = *a.iter;
-    const int pos = *a.hist_pos;
-    double tot = 0.0, tot0 = 0.0;
-    const volatile double* norms = blk_norm;
-    for (int q = 0; q < a.nowned; q++) {
-        double sum = 0.0, sum0 = 0.0;
-        for (int v = 0; v < 4; v++) {
-            const double rs = norms[4 * q + v];
-            double r0 = a.res0[4 * q + v];
-            if (it == 0) r0 = rs;
-            if (r0 < 1e-16) r0 = fmax(rs, 1e-16);
-            a.res0[4 * q + v] = r0;
-            sum += rs;
-            sum0 += r0;
-        }
-        if (pos < a.hist_cap) {
-            a.blk_hist[2 * ((long long)pos * a.nowned + q) + 0] = sum;
-            a.blk_hist[2 * ((long long)pos * a.nowned + q) + 1] = sum0;
-        }
-        tot += sum;
-        tot0 += sum0;
-    }
-    double dt = 0.0;
-    for (int q = 0; q < a.nblocks_global; q++) dt = fmax(dt, a.dt_table[q]);
-    const double relres = tot / tot0;
-    if (pos < a.hist_cap) {
-        double* h = a.step_hist + 4 * (long long)pos;
-        h[0] = dt; h[1] = tot; h[2] = tot0; h[3] = relres;
-    }
-    *a.iter = it + 1;
-    *a.hist_pos = pos + 1;
-    *a.ticket = 0u;
-    if (a.stop_on_tol && relres < a.tol) *a.stop = 1;
+    finalize_block(a, blockIdx.x, red, &last);
 }
 
-void launch_finalize(cudaStream_t s, const FinalizeArgs& a, double* blk_norm) {
-    finalize_kernel<<<a.nowned, 256, 0, s>>>(a, blk_norm);
+void launch_finalize(cudaStream_t s, const FinalizeArgs& a) {
+    finalize_kernel<<<a.nowned, 256, 0, s>>>(a);
 }
 
 // AoS unk[(j*ncx+i)*4+k] (FV/Indexing.h:11) -> padded planes; applies the T clamp that

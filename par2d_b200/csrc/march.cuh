@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) dt = fmax(dt, __shfl_xor_sync(0xffffffffu, dt, s));
     m.dt = dt;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) *a.dt_used = dt;   // for the step's history record
 
     unsigned flags = 0;
     bool ok = true;
