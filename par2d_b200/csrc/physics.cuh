@@ -248,7 +248,14 @@ struct Flux {
 
 PAR2D_FN double sgn_bit(double x) { return signbit(x) ? -1.0 : 1.0; }  // Indexing.h:22
 
-template <bool FAITHFUL, bool AXI>
+// WARP_VOTE (device, lean path, all 32 lanes of the warp calling together): when EVERY face of the warp is
+// supersonic in the same direction the flux is fully upwind - cep = xml, cem = 0, pnet = pL (or the mirror
+// image) - and the split polynomials, their selects and the dead side's terms are skipped.  The result is
+// bit-identical to the general path (the skipped terms are exact zeros there).
+#ifndef LDFSS_UPWIND_VOTE
+#define LDFSS_UPWIND_VOTE 1
+#endif
+template <bool FAITHFUL, bool AXI, bool WARP_VOTE = false>
 PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) {
     Flux o;
     if constexpr (FAITHFUL) {
@@ -301,6 +308,46 @@ PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) 
         const double la = w * q;                 // len * ahalf
         const double xml = fma(L.u, fg.dy, -L.v * fg.dx) * q;
         const double xmr = fma(R.u, fg.dy, -R.v * fg.dx) * q;
+#if defined(__CUDA_ARCH__) && LDFSS_UPWIND_VOTE
+        if constexpr (WARP_VOTE) {
+            if (__all_sync(0xffffffffu, xml >= 1.0 && xmr >= 1.0)) {          // all/alr = 1/0, btl = btr = 0
+                if constexpr (AXI) {
+                    const double fml = ((la * fg.yf) * L.rho) * xml;
+                    o.parr = -L.p * fg.dx;
+                    o.f0 = fml;
+                    o.f1 = fma(fml, L.u, (L.p * fg.yf) * fg.dy);
+                    o.f2 = fml * L.v;
+                    o.f3 = fml * L.h0;
+                } else {
+                    const double fml = (la * L.rho) * xml;
+                    o.parr = 0.0;
+                    o.f0 = fml;
+                    o.f1 = fma(fml, L.u, L.p * fg.dy);
+                    o.f2 = fma(fml, L.v, -L.p * fg.dx);
+                    o.f3 = fml * L.h0;
+                }
+                return o;
+            }
+            if (__all_sync(0xffffffffu, xml <= -1.0 && xmr <= -1.0)) {        // all/alr = 0/1
+                if constexpr (AXI) {
+                    const double fmr = ((la * fg.yf) * R.rho) * xmr;
+                    o.parr = -R.p * fg.dx;
+                    o.f0 = fmr;
+                    o.f1 = fma(fmr, R.u, (R.p * fg.yf) * fg.dy);
+                    o.f2 = fmr * R.v;
+                    o.f3 = fmr * R.h0;
+                } else {
+                    const double fmr = (la * R.rho) * xmr;
+                    o.parr = 0.0;
+                    o.f0 = fmr;
+                    o.f1 = fma(fmr, R.u, R.p * fg.dy);
+                    o.f2 = fma(fmr, R.v, -R.p * fg.dx);
+                    o.f3 = fmr * R.h0;
+                }
+                return o;
+            }
+        }
+#endif
         const bool subL = fabs(xml) < 1.0, subR = fabs(xmr) < 1.0;
         // split Mach numbers and pressure weights (EulerFlux.cpp:146-175 with all/alr in {0,1} and
         // btl/btr in {-1,0} substituted).  Selects, not branches: skipping the polynomials on
