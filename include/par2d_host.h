@@ -67,6 +67,11 @@ int par2d_thermo_load(const char* path, par2d_config* cfg);
 int par2d_write_solution(const char* path, const char* title, const par2d_config* cfg,
                          int32_t nx, int32_t ny, const double* x, const double* y, const double* unk);
 
+/* Restart reader for the same file format (the reference writes these files, FV/FileIO.cpp:78-116,
+ * but cannot read them back): fills unk[(j*(nx-1)+i)*4+k] = rho,u,v,T and, when non-null,
+ * the cell centroids xc/yc[(j*(nx-1)+i)].  The zone header must match nx-1 x ny-1 cells. */
+int par2d_read_solution(const char* path, int32_t nx, int32_t ny, double* unk, double* xc, double* yc);
+
 const char* par2d_host_last_error(void);
 
 #ifdef __cplusplus

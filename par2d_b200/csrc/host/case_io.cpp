@@ -404,4 +404,36 @@ int par2d_write_solution(const char* path, const char* title, const par2d_config
     return 0;
 }
 
+// Restart reader (the reference has none): parses a solution.b<N>.tec written by print_state
+// (FV/FileIO.cpp:84-115) or by par2d_write_solution back into the state layout unk[(j*(nx-1)+i)*4+k].
+// The zone header must match the block's cell counts; %.16e round-trips every double exactly.
+int par2d_read_solution(const char* path, int32_t nx, int32_t ny, double* unk, double* xc, double* yc) {
+    if (!path || !unk || nx < 2 || ny < 2) return host_fail(PAR2D_ERR_ARG, "read_solution: bad argument");
+    FILE* f = fopen(path, "r");
+    if (!f) return host_fail(PAR2D_ERR_ARG, "cannot read %s", path);
+    char line[1024];
+    int zi = -1, zj = -1;
+    for (int h = 0; h < 3; h++) {
+        if (!fgets(line, sizeof line, f)) { fclose(f); return host_fail(PAR2D_ERR_ARG, "%s: truncated header", path); }
+        if (h == 2 && sscanf(line, "ZONE I=%d, J=%d", &zi, &zj) != 2) { fclose(f); return host_fail(PAR2D_ERR_ARG, "%s: no ZONE I=, J= line", path); }
+    }
+    if (zi != nx - 1 || zj != ny - 1) {
+        fclose(f);
+        return host_fail(PAR2D_ERR_ARG, "%s: zone is %d x %d cells, the block has %d x %d", path, zi, zj, nx - 1, ny - 1);
+    }
+    const size_t ncell = (size_t)zi * zj;
+    for (size_t c = 0; c < ncell; c++) {
+        double v[9];
+        if (fscanf(f, " %lf , %lf , %lf , %lf , %lf , %lf , %lf , %lf , %lf", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7], &v[8]) != 9) {
+            fclose(f);
+            return host_fail(PAR2D_ERR_ARG, "%s: cell %zu of %zu unreadable", path, c, ncell);
+        }
+        if (xc) xc[c] = v[0];
+        if (yc) yc[c] = v[1];
+        unk[4 * c + 0] = v[2]; unk[4 * c + 1] = v[3]; unk[4 * c + 2] = v[4]; unk[4 * c + 3] = v[5];
+    }
+    fclose(f);
+    return 0;
+}
+
 }  // extern "C"

@@ -115,3 +115,16 @@ def write_solution(path: str, title: str, cfg: Config, x: np.ndarray, y: np.ndar
     lib.check(lib.par2d_write_solution(os.fsencode(path), title.encode(), C.byref(cfg), nx, ny,
                                        x.ctypes.data_as(dp), y.ctypes.data_as(dp), unk.ctypes.data_as(dp)),
               "write_solution")
+
+
+def read_solution(path: str, nx: int, ny: int):
+    """Restart reader for solution.b<N>.tec (reference print_state format, FV/FileIO.cpp:84-115):
+    returns (unk[ny-1, nx-1, 4], xc[ny-1, nx-1], yc[ny-1, nx-1])."""
+    lib = _capi.load_host()
+    unk = np.empty((ny - 1, nx - 1, 4), dtype=np.float64)
+    xc = np.empty((ny - 1, nx - 1), dtype=np.float64)
+    yc = np.empty((ny - 1, nx - 1), dtype=np.float64)
+    dp = C.POINTER(C.c_double)
+    lib.check(lib.par2d_read_solution(os.fsencode(path), nx, ny, unk.ctypes.data_as(dp), xc.ctypes.data_as(dp),
+                                      yc.ctypes.data_as(dp)), "read_solution")
+    return unk, xc, yc

@@ -168,6 +168,26 @@ def test_committed_res_tec_of_the_reference(gpu):
 
 # ------------------------------------------------------------------ block / halo indexing: bit-exact
 
+@pytest.mark.parametrize("mode", [MODE_FAST, MODE_FAITHFUL])
+def test_references_converged_state_sits_at_its_committed_residual(gpu, oracle, mode):
+    """Restart from the reference's own converged solution files (FV/Outputs/solution.b1..8.tec after
+    497 227 iterations): the residual the CUDA path evaluates on that state continues the reference's
+    committed residual history (res.tec ends 497226: 1.000012e-06, 497227: 9.999939e-07), and equals the
+    oracle's to the history tolerance.  Pins residual assembly + norms at a developed, shock-carrying state
+    against outputs the reference itself committed."""
+    import restart
+    g, relres, _ = restart.converged_state_relres(gpu, mode)
+    _, ref, _ = restart.converged_state_relres(oracle)
+    slope = g["res_tail_relres"][2] - g["res_tail_relres"][1]
+    expect = g["res_tail_relres"][2] + slope
+    assert abs(relres[0] - expect) < 2e-11, (relres, expect)
+    assert abs((relres[1] - relres[0]) - slope) < 0.2 * abs(slope)
+    if mode == MODE_FAITHFUL:
+        assert relres == ref                                  # bit-identical (no pow() on the forward step's faces)
+    else:
+        assert max(abs(a / b - 1.0) for a, b in zip(relres, ref)) < TOL_HIST
+
+
 def _perturbed(shape, seed):
     rng = np.random.default_rng(seed)
     u = np.empty(shape)

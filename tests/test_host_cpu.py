@@ -178,3 +178,24 @@ def test_create_rejects_inconsistent_tables(oracle):
     h = C.c_void_p()
     cfg = default_config(oracle)
     assert oracle.create(C.byref(cfg), 8, descs, C.byref(h)) == 1
+
+
+def test_solution_reader_round_trips_the_writer(tmp_path):
+    """par2d_read_solution (restart reader) inverts par2d_write_solution / print_state
+    (FV/FileIO.cpp:84-115) exactly: %.16e round-trips doubles; a wrong zone size is refused."""
+    from par2d_b200.host import read_solution, write_solution
+    from par2d_b200._capi import Par2dError
+    rng = np.random.default_rng(7)
+    case = Case.load(case_path("Case_spikefine24"))
+    x, y = case.nodes(3)
+    ny, nx = x.shape
+    unk = rng.uniform(0.1, 3000.0, size=(ny - 1, nx - 1, 4))
+    unk[..., 3] = rng.uniform(250.0, 3000.0, size=(ny - 1, nx - 1))    # T above the 201 K clamp the writer applies
+    cfg = make_cfg(_capi.load_oracle())
+    path = str(tmp_path / "solution.b4.tec")
+    write_solution(path, "Final State", cfg, x, y, unk)
+    back, xc, yc = read_solution(path, nx, ny)
+    assert np.array_equal(back, unk)
+    assert np.array_equal(xc, 0.25 * (x[:-1, :-1] + x[:-1, 1:] + x[1:, 1:] + x[1:, :-1]))
+    with pytest.raises(Par2dError):
+        read_solution(path, nx + 1, ny)

@@ -202,3 +202,16 @@ def test_synthetic_ramp_port_vs_live_reference_bitwise(oracle, tmp_path):
     for b in range(4):
         assert np.array_equal(s.get_state(b), out["states"][b])
     assert [fmt_le(i.relres) for i in info] == [fmt_le(v) for v in out["relres"]]
+
+
+def test_references_converged_state_sits_at_its_committed_residual(oracle):
+    """The reference's own converged solution files (497 227 iterations, FV/Outputs/solution.b*.tec) read back
+    by the restart reader: its residual, evaluated by the port, continues the committed res.tec
+    (..., 497226: 1.000012e-06, 497227: 9.999939e-07, falling 1.8e-11 per iteration)."""
+    import restart
+    g, relres, _ = restart.converged_state_relres(oracle)
+    assert list(g["res_tail_iter"]) == [497225, 497226, 497227]
+    slope = g["res_tail_relres"][2] - g["res_tail_relres"][1]          # per iteration, ~ -1.8e-11
+    expect = g["res_tail_relres"][2] + slope                           # the state was written after update 497227
+    assert abs(relres[0] - expect) < 2e-11, (relres, expect)
+    assert abs((relres[1] - relres[0]) - slope) < 0.2 * abs(slope)     # and keeps converging at the same rate
