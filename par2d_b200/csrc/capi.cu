@@ -482,6 +482,20 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
     c->axi = cfg->iaxi == 1;
     c->kt = cfg->mode == PAR2D_MODE_FAITHFUL ? kernels_faithful() : kernels_fast();
     c->device = dev;
+    {
+        // Rows per warp strip.  A strip is marched by ONE warp, row after row (~1 us per row), so small meshes
+        // need short strips to expose enough warps (the shipped cases hold ~50 k cells: 64-row strips would be
+        // 40 warps on 148 SMs); large meshes keep the measured optimum of 64 rows, where the per-strip prologue
+        // and the two halo rows are amortised.  The rule looks at the GLOBAL mesh only, so the strip
+        // decomposition - and with it the summation order of the residual norms - does not depend on how the
+        // blocks are spread over ranks (relres stays bit-identical for any number of GPUs).
+        long long global_cells = 0;
+        for (int g = 0; g < nblocks; g++) global_cells += (long long)(blocks[g].nx - 1) * (blocks[g].ny - 1);
+        const long long want_strips = (long long)prop.multiProcessorCount * 16;   // one full residency of 16 warps per SM
+        long long rows = global_cells / (MCELLS * want_strips);
+        rows -= rows & 1;
+        c->march_rows = (int)std::min<long long>(64, std::max<long long>(4, rows));
+    }
     const char* mrows = getenv("PAR2D_MARCH_ROWS");
     if (mrows && atoi(mrows) > 0) c->march_rows = atoi(mrows);
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(PAR2D_ERR_CUDA, "cannot create stream"); }

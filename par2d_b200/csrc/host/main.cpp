@@ -22,11 +22,12 @@
 
 static void usage() {
     printf("usage: par2d_fv --case DIR [--out DIR] [--therm FILE] [--niter N] [--iaxi 0|1] [--igam G]\n"
-           "                [--cfl C] [--tol T] [--printiter N] [--saveiter N] [--batch N] [--faithful]\n");
+           "                [--cfl C] [--tol T] [--printiter N] [--saveiter N] [--batch N] [--faithful]\n"
+           "                [--restart DIR]   start from DIR/solution.b<b+1>.tec instead of the uniform state\n");
 }
 
 int main(int argc, char** argv) {
-    std::string case_dir = "../Case", out_dir = "../Outputs", therm = "../therm_air.dat";
+    std::string case_dir = "../Case", out_dir = "../Outputs", therm = "../therm_air.dat", restart_dir;
     long niter = 5000000;  // NITER, FV/Indexing.h:20
     int printiter = 1, saveiter = 1000, batch = 100;
     par2d_config cfg;
@@ -46,6 +47,7 @@ int main(int argc, char** argv) {
         else if (a == "--saveiter") saveiter = atoi(next());
         else if (a == "--batch") batch = atoi(next());
         else if (a == "--faithful") cfg.mode = PAR2D_MODE_FAITHFUL;
+        else if (a == "--restart") restart_dir = next();
         else { usage(); return 2; }
     }
     if (batch < 1) batch = 1;
@@ -63,6 +65,17 @@ int main(int argc, char** argv) {
     printf("==================== Initializing ====================\n");
     par2d_ctx* ctx = nullptr;
     if (par2d_create(&cfg, nb, blocks.data(), &ctx)) { printf("par2d_create: %s\n", par2d_last_error()); return 1; }
+
+    if (!restart_dir.empty()) {
+        // restart (the reference writes solution.b<N>.tec every saveiter iterations but cannot read them back)
+        for (int b = 0; b < nb; b++) {
+            std::vector<double> unk((size_t)4 * (blocks[b].nx - 1) * (blocks[b].ny - 1));
+            const std::string path = restart_dir + "/solution.b" + std::to_string(b + 1) + ".tec";
+            if (par2d_read_solution(path.c_str(), blocks[b].nx, blocks[b].ny, unk.data(), nullptr, nullptr)) { printf("%s\n", par2d_host_last_error()); return 1; }
+            if (par2d_set_state(ctx, b, unk.data())) { printf("set_state: %s\n", par2d_last_error()); return 1; }
+        }
+        printf("restarted from %s\n", restart_dir.c_str());
+    }
 
     auto save = [&](const char* title) {
         for (int b = 0; b < nb; b++) {

@@ -35,30 +35,41 @@ __device__ __forceinline__ void finalize_block(const FinalizeArgs& a, int k, dou
         *last = atomicAdd(a.ticket, 1u) == (unsigned)(a.nowned - 1);
     }
     __syncthreads();
-    if (!*last || tid != 0) return;
+    if (!*last) return;
     __threadfence();
+    // last CTA: per-block sums by one thread per block (the global loads overlap), then thread 0 adds the
+    // blocks in block order (main.cpp:379-392 gathers in rank order)
     const long long it = *a.iter;
     const int pos = *a.hist_pos;
     double tot = 0.0, tot0 = 0.0;
-    const volatile double* norms = a.blk_norm;
-    for (int q = 0; q < a.nowned; q++) {
-        double sum = 0.0, sum0 = 0.0;
-        for (int v = 0; v < 4; v++) {
-            const double rs = norms[4 * q + v];
-            double r0 = a.res0[4 * q + v];
-            if (it == 0) r0 = rs;
-            if (r0 < 1e-16) r0 = fmax(rs, 1e-16);
-            a.res0[4 * q + v] = r0;
-            sum += rs;
-            sum0 += r0;
+    for (int q0 = 0; q0 < a.nowned; q0 += 256) {
+        const int q = q0 + tid;
+        if (q < a.nowned) {
+            double sum = 0.0, sum0 = 0.0;
+            for (int v = 0; v < 4; v++) {
+                const double rs = __ldcg(a.blk_norm + 4 * q + v);
+                double r0 = a.res0[4 * q + v];
+                if (it == 0) r0 = rs;
+                if (r0 < 1e-16) r0 = fmax(rs, 1e-16);
+                a.res0[4 * q + v] = r0;
+                sum += rs;
+                sum0 += r0;
+            }
+            if (pos < a.hist_cap) {
+                a.blk_hist[2 * ((long long)pos * a.nowned + q) + 0] = sum;
+                a.blk_hist[2 * ((long long)pos * a.nowned + q) + 1] = sum0;
+            }
+            red[tid][0] = sum;
+            red[tid][1] = sum0;
         }
-        if (pos < a.hist_cap) {
-            a.blk_hist[2 * ((long long)pos * a.nowned + q) + 0] = sum;
-            a.blk_hist[2 * ((long long)pos * a.nowned + q) + 1] = sum0;
+        __syncthreads();
+        if (tid == 0) {
+            const int n = min(256, a.nowned - q0);
+            for (int r = 0; r < n; r++) { tot += red[r][0]; tot0 += red[r][1]; }
         }
-        tot += sum;
-        tot0 += sum0;
+        __syncthreads();
     }
+    if (tid != 0) return;
     const double relres = tot / tot0;
     if (pos < a.hist_cap) {
         double* h = a.step_hist + 4 * (long long)pos;

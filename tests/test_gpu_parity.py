@@ -183,9 +183,13 @@ def test_references_converged_state_sits_at_its_committed_residual(gpu, oracle, 
     assert abs(relres[0] - expect) < 2e-11, (relres, expect)
     assert abs((relres[1] - relres[0]) - slope) < 0.2 * abs(slope)
     if mode == MODE_FAITHFUL:
-        assert relres == ref                                  # bit-identical (no pow() on the forward step's faces)
+        # the per-cell residuals are bit-identical (no pow() on the forward step's faces); the norms are summed
+        # per strip instead of serially (hard part 5)
+        assert max(abs(a / b - 1.0) for a, b in zip(relres, ref)) < 1e-12
     else:
-        assert max(abs(a / b - 1.0) for a, b in zip(relres, ref)) < TOL_HIST
+        # the converged residual is the 1e-6 remainder of cancelling O(1) fluxes: rounding differences scale with
+        # the fluxes, i.e. with the initial residual relres is normalised by (measured: 2e-15 absolute)
+        assert max(abs(a - b) for a, b in zip(relres, ref)) < 1e-13
 
 
 def _perturbed(shape, seed):
