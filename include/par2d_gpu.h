@@ -80,7 +80,9 @@ typedef struct par2d_config {
     int32_t device;        /* CUDA device ordinal; -1 = current device                   */
     int32_t rank;          /* this process's rank  (0 for single process)                */
     int32_t nranks;        /* number of processes sharing the block table (1 = single)   */
-    int32_t reserved;
+    int32_t accur;         /* 0: first-order FV (shipped); 1: the reference's DG(P1) second-order branch
+                              (cell mean + xi/eta slopes, 2 Gauss points per face, damped + limited
+                              slopes)                                  Indexing.h:17     */
 } par2d_config;
 
 /* One grid block = what one MPI rank of the reference holds after read_mesh()

@@ -4,7 +4,7 @@
 # Compiles the UNMODIFIED reference solver sources where they lie under
 # /root/reference/FV (never copied into this repo) against oracle/shim/mpi.h,
 # with outputs only into oracle/_ref/ (git-ignored, travels to the GPU box):
-#   _ref/MPI2DFV          run-time configurable binary (ORACLE_NITER/IAXI/IGAM)
+#   _ref/MPI2DFV          run-time configurable binary (ORACLE_NITER/IAXI/IGAM/ACCUR)
 #   _ref/MPI2DFV_strict   header differs from the reference's only in NITER
 #   _ref/libpar2d_ref.so  reference functions behind extern "C" (ref_wrap.cpp)
 # Usage: oracle/build_ref.sh [build|verify]
@@ -27,6 +27,7 @@ mkdir -p "$OUT/gen_rt" "$OUT/gen_strict"
     echo '#include "ref_runtime_config.h"'
     sed -e 's|^#define IGAM .*|#define IGAM (oracle_ref_config().igam)|' \
         -e 's|^#define IAXI .*|#define IAXI (oracle_ref_config().iaxi)|' \
+        -e 's|^#define ACCUR .*|#define ACCUR (oracle_ref_config().accur)|' \
         -e 's|^#define NITER .*|#define NITER (oracle_ref_config().niter)|' "$REF/Indexing.h"
 } > "$OUT/gen_rt/Indexing.h"
 sed -e 's|^#define NITER .*|#define NITER (25)|' "$REF/Indexing.h" > "$OUT/gen_strict/Indexing.h"

@@ -51,6 +51,12 @@ typedef struct {
     orc_derived* gder[4];
     double res0[NV];    /* iteration-0 norms (main.cpp:260,365-369) */
     double dt_b;
+    /* second-order branch (cfg.accur == 1, par2d_oracle_dg.inc) */
+    double* xfa;        /* face mid-point x (MeshModule.cpp:67,85) */
+    double *ux, *uy;    /* xi / eta slopes (main.cpp:169-172) */
+    double *resx, *resy, *dvx, *dvy;
+    double* ghost2[4];  /* two Gauss-point ghost states per boundary face, [(2n+pt)*4+k] */
+    orc_derived* gder2[4];
 } orc_block;
 
 typedef struct {
@@ -346,8 +352,9 @@ static void metrics(orc_block* b) {
     b->geoel = (double*)malloc(sizeof(double) * 3 * b->ncx * b->ncy);
     b->geofa = (double*)malloc(sizeof(double) * 6 * nx * ny);
     b->yfa = (double*)malloc(sizeof(double) * 2 * nx * ny);
+    b->xfa = (double*)malloc(sizeof(double) * 2 * nx * ny);
     for (int k = 0; k < 6 * nx * ny; k++) b->geofa[k] = NAN;
-    for (int k = 0; k < 2 * nx * ny; k++) b->yfa[k] = NAN;
+    for (int k = 0; k < 2 * nx * ny; k++) b->yfa[k] = b->xfa[k] = NAN;
     for (int j = 0; j < b->ncy; j++)
         for (int i = 0; i < b->ncx; i++) {
             int p1 = NIDX(b, i, j), p2 = NIDX(b, i + 1, j), p3 = NIDX(b, i + 1, j + 1), p4 = NIDX(b, i, j + 1);
@@ -369,6 +376,7 @@ static void metrics(orc_block* b) {
                 f[1] = (y[q] - y[p0]) / len;
                 f[2] = -(x[q] - x[p0]) / len;
                 b->yfa[2 * p0 + 0] = 0.5 * (y[q] + y[p0]);
+                b->xfa[2 * p0 + 0] = 0.5 * (x[q] + x[p0]);
             }
             if (j < ny - 1) { /* face towards +j ("vertical") */
                 int q = NIDX(b, i, j + 1);
@@ -377,6 +385,7 @@ static void metrics(orc_block* b) {
                 f[4] = (y[q] - y[p0]) / len;
                 f[5] = -(x[q] - x[p0]) / len;
                 b->yfa[2 * p0 + 1] = 0.5 * (y[q] + y[p0]);
+                b->xfa[2 * p0 + 1] = 0.5 * (x[q] + x[p0]);
             }
         }
     /* static part of find_dt, main.cpp:26-32 */
@@ -544,11 +553,11 @@ static void residual(orc_ctx* c, orc_block* b) {
 }
 
 /* calculate_residual, main.cpp:39-57 (i outer, j inner) */
-static void residual_norms(orc_ctx* c, const orc_block* b, double* ressum) {
+static void residual_norms(orc_ctx* c, const orc_block* b, const double* res, double* ressum) {
     double s[NV] = {0.0, 0.0, 0.0, 0.0};
     for (int i = 0; i < b->ncx; i++)
         for (int j = 0; j < b->ncy; j++) {
-            const double* r = b->res + NV * CIDX(b, i, j);
+            const double* r = res + NV * CIDX(b, i, j);
             for (int k = 0; k < NV; k++) {
                 if (isnan(r[k])) c->error = c->error ? c->error : PAR2D_ERR_NAN;
                 s[k] += r[k] * r[k];
@@ -579,6 +588,9 @@ static void update_block(orc_ctx* c, orc_block* b) {
 static void refresh_derived(orc_ctx* c, orc_block* b) {
     for (int e = 0; e < b->ncx * b->ncy; e++) update_state(&c->cfg, b->unk + NV * e, &b->der[e], &c->error);
 }
+
+/* ------------------------------------------------ second-order branch */
+#include "par2d_oracle_dg.inc"
 
 /* ------------------------------------------------------------ exchange */
 
@@ -667,6 +679,8 @@ static int validate_table(int nblocks, const par2d_block_desc* t, int nranks) {
 int orc_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_desc* blocks, orc_ctx** out) {
     if (!cfg || !blocks || !out || nblocks < 1) return fail(PAR2D_ERR_ARG, "null argument");
     if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(PAR2D_ERR_ARG, "bad rank");
+    if (cfg->accur != 0 && cfg->accur != 1) return fail(PAR2D_ERR_ARG, "accur must be 0 or 1 (SpatialDiscretization.cpp:204)");
+    if (cfg->accur == 1 && cfg->nranks != 1) return fail(PAR2D_ERR_ARG, "the second-order branch of the oracle is single-rank");
     int rc = validate_table(nblocks, blocks, cfg->nranks);
     if (rc) return rc;
     orc_ctx* c = (orc_ctx*)calloc(1, sizeof *c);
@@ -706,6 +720,16 @@ int orc_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_desc*
             b->ghost[s] = (double*)calloc(NV * n, sizeof(double));
             b->gder[s] = (orc_derived*)calloc(n, sizeof(orc_derived));
         }
+        if (cfg->accur == 1) {
+            b->ux = (double*)calloc(NV * nc, sizeof(double)); b->uy = (double*)calloc(NV * nc, sizeof(double));  /* main.cpp:199-209 */
+            b->resx = (double*)calloc(NV * nc, sizeof(double)); b->resy = (double*)calloc(NV * nc, sizeof(double));
+            b->dvx = (double*)calloc(NV * nc, sizeof(double)); b->dvy = (double*)calloc(NV * nc, sizeof(double));
+            for (int s = 0; s < 4; s++) {
+                int n = edge_len(b, s);
+                b->ghost2[s] = (double*)calloc(2 * NV * n, sizeof(double));
+                b->gder2[s] = (orc_derived*)calloc(2 * n, sizeof(orc_derived));
+            }
+        }
         for (size_t e = 0; e < nc; e++) memcpy(b->unk + NV * e, cfg->uFS, sizeof(double) * NV); /* main.cpp:193-197 */
         refresh_derived(c, b);
     }
@@ -733,8 +757,9 @@ int orc_destroy(orc_ctx* c) {
     for (int k = 0; k < c->nowned; k++) {
         orc_block* b = &c->blk[k];
         free(b->x); free(b->y); free(b->ibound); free(b->geoel); free(b->geofa); free(b->yfa);
-        free(b->unk); free(b->res); free(b->dv); free(b->der);
-        for (int s = 0; s < 4; s++) { free(b->ghost[s]); free(b->gder[s]); }
+        free(b->unk); free(b->res); free(b->dv); free(b->der); free(b->xfa);
+        free(b->ux); free(b->uy); free(b->resx); free(b->resy); free(b->dvx); free(b->dvy);
+        for (int s = 0; s < 4; s++) { free(b->ghost[s]); free(b->gder[s]); free(b->ghost2[s]); free(b->gder2[s]); }
     }
     for (int p = 0; p < c->cfg.nranks; p++) { free(c->peers[p].send); free(c->peers[p].recv); }
     free(c->peers); free(c->blk); free(c->table); free(c->owned_index); free(c->dt_table);
@@ -814,14 +839,15 @@ int orc_step_end(orc_ctx* c) {
         else dt = fmax(dt, c->dt_table[g]);
     }
     c->dt = dt;
+    const int dg = c->cfg.accur == 1;
 #pragma omp parallel for schedule(dynamic)
-    for (int k = 0; k < c->nowned; k++) ghost_from_bc(c, &c->blk[k]);
+    for (int k = 0; k < c->nowned; k++) { if (dg) dg_ghost_from_bc(c, &c->blk[k]); else ghost_from_bc(c, &c->blk[k]); }
 #pragma omp parallel for schedule(dynamic)
-    for (int k = 0; k < c->nowned; k++) ghost_from_neighbours(c, &c->blk[k]);
+    for (int k = 0; k < c->nowned; k++) { if (dg) dg_ghost_from_neighbours(c, &c->blk[k]); else ghost_from_neighbours(c, &c->blk[k]); }
 #pragma omp parallel for schedule(dynamic)
     for (int k = 0; k < c->nowned; k++) {
-        residual(c, &c->blk[k]);
-        solve_block(c, &c->blk[k]);
+        if (dg) { dg_residual(c, &c->blk[k]); dg_solve_block(c, &c->blk[k]); }
+        else { residual(c, &c->blk[k]); solve_block(c, &c->blk[k]); }
     }
     ensure_hist(c, c->hist_len + 1);
     par2d_step_info* h = &c->hist[c->hist_len];
@@ -829,7 +855,13 @@ int orc_step_end(orc_ctx* c) {
     for (int k = 0; k < c->nowned; k++) { /* main.cpp:365-392 */
         orc_block* b = &c->blk[k];
         double ressum[NV];
-        residual_norms(c, b, ressum);
+        residual_norms(c, b, b->res, ressum);
+        if (dg) { /* main.cpp:300-302, 360-364 */
+            double rx[NV], ry[NV];
+            residual_norms(c, b, b->resx, rx);
+            residual_norms(c, b, b->resy, ry);
+            for (int v = 0; v < NV; v++) ressum[v] += rx[v] + ry[v];
+        }
         double a = 0.0, z = 0.0;
         for (int v = 0; v < NV; v++) {
             if (c->iter == 0) b->res0[v] = ressum[v];
@@ -844,7 +876,7 @@ int orc_step_end(orc_ctx* c) {
     }
     h->relres = h->ressumsum / h->res0sum;
 #pragma omp parallel for schedule(dynamic)
-    for (int k = 0; k < c->nowned; k++) update_block(c, &c->blk[k]);
+    for (int k = 0; k < c->nowned; k++) { if (dg) dg_update_block(c, &c->blk[k]); else update_block(c, &c->blk[k]); }
     h->status = c->error;
     h->reserved = 0;
     c->hist_len++;
@@ -892,6 +924,33 @@ int orc_get_residual(orc_ctx* c, int32_t block, double* res) {
     for (int k = 0; k < c->nowned; k++) ghost_from_neighbours(c, &c->blk[k]);
     residual(c, b);
     memcpy(res, b->res, sizeof(double) * NV * b->ncx * b->ncy);
+    return 0;
+}
+
+/* second-order branch: slopes in / out and the three right-hand sides of one calc_dudt evaluation */
+int orc_set_slopes(orc_ctx* c, int32_t block, const double* ux, const double* uy) {
+    orc_block* b = owned(c, block);
+    if (!b || !ux || !uy || c->cfg.accur != 1) return fail(PAR2D_ERR_ARG, "set_slopes: block not owned or accur != 1");
+    memcpy(b->ux, ux, sizeof(double) * NV * b->ncx * b->ncy);
+    memcpy(b->uy, uy, sizeof(double) * NV * b->ncx * b->ncy);
+    return 0;
+}
+int orc_get_slopes(orc_ctx* c, int32_t block, double* ux, double* uy) {
+    orc_block* b = owned(c, block);
+    if (!b || !ux || !uy || c->cfg.accur != 1) return fail(PAR2D_ERR_ARG, "get_slopes: block not owned or accur != 1");
+    memcpy(ux, b->ux, sizeof(double) * NV * b->ncx * b->ncy);
+    memcpy(uy, b->uy, sizeof(double) * NV * b->ncx * b->ncy);
+    return 0;
+}
+int orc_get_residual_dg(orc_ctx* c, int32_t block, double* res, double* resx, double* resy) {
+    orc_block* b = owned(c, block);
+    if (!b || !res || !resx || !resy || c->cfg.accur != 1) return fail(PAR2D_ERR_ARG, "get_residual_dg: block not owned or accur != 1");
+    for (int k = 0; k < c->nowned; k++) dg_ghost_from_bc(c, &c->blk[k]);
+    for (int k = 0; k < c->nowned; k++) dg_ghost_from_neighbours(c, &c->blk[k]);
+    dg_residual(c, b);
+    memcpy(res, b->res, sizeof(double) * NV * b->ncx * b->ncy);
+    memcpy(resx, b->resx, sizeof(double) * NV * b->ncx * b->ncy);
+    memcpy(resy, b->resy, sizeof(double) * NV * b->ncx * b->ncy);
     return 0;
 }
 

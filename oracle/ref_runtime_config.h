@@ -8,7 +8,7 @@
  * into the git-ignored oracle/_ref/ -- a copy of the reference header in which
  * just those three #defines read this struct instead.  One oracle binary then
  * serves the planar/axisymmetric and CPG/TPG variants:
- *     ORACLE_NITER (default 10)  ORACLE_IAXI (default 1)  ORACLE_IGAM (default 1.4)
+ *     ORACLE_NITER (default 10)  ORACLE_IAXI (default 1)  ORACLE_IGAM (default 1.4)  ORACLE_ACCUR (default 0)
  * A second, "strict" binary whose header differs from the reference's only in
  * the NITER literal is built alongside and must produce bitwise identical
  * solution files (checked by oracle/build_ref.sh verify).
@@ -19,12 +19,14 @@
 struct OracleRefConfig {
     int niter;
     int iaxi;
+    int accur;   /* Indexing.h:17 ACCUR: every use is a run-time expression as well (if (ACCUR == 1), ntrans *= (ACCUR + 1)) */
     double igam;
     OracleRefConfig() {
         const char* s;
         niter = (s = getenv("ORACLE_NITER")) ? atoi(s) : 10;
         iaxi  = (s = getenv("ORACLE_IAXI"))  ? atoi(s) : 1;
         igam  = (s = getenv("ORACLE_IGAM"))  ? atof(s) : 1.4;
+        accur = (s = getenv("ORACLE_ACCUR")) ? atoi(s) : 0;
     }
 };
 inline OracleRefConfig& oracle_ref_config() { static OracleRefConfig c; return c; }

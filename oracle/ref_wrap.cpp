@@ -109,4 +109,22 @@ void ref_calc_dudt(int nx, int ny, double* x, double* y, int* ibound, double* uF
     free(ev); free(geoel); free(geofa); free(yfa); free(xfa);
 }
 
+/* The same with the second-order branch switched on (ACCUR == 1): dudt, duxdt, duydt of one calc_dudt
+ * evaluation for given means and slopes (SpatialDiscretization.cpp:159-1050, DGP1Tools.cpp). */
+void ref_calc_dudt_dg(int nx, int ny, double* x, double* y, int* ibound, double* uFS,
+                      double* unk, double* ux, double* uy, double* dudt, double* duxdt, double* duydt) {
+    const int keep = oracle_ref_config().accur;
+    oracle_ref_config().accur = 1;
+    double *geoel, *geofa, *yfa, *xfa;
+    calc_geoel_geofa(nx, ny, x, y, &geoel, &geofa, &yfa, &xfa);
+    int nelem = (nx - 1) * (ny - 1);
+    State* ev = (State*)malloc(sizeof(State) * nelem);
+    for (int e = 0; e < nelem; e++) { ev[e] = State(); ev[e].Initialize(unk + NVAR * e); ev[e].UpdateState(*g_air); }
+    int bbounds[4] = {0, 0, 0, 0}, bids[4] = {-1, -1, -1, -1};
+    calc_dudt(bbounds, bids, nx, ny, *g_air, ev, uFS, ibound, geoel, geofa, yfa, xfa,
+              unk, ux, uy, dudt, duxdt, duydt);
+    free(ev); free(geoel); free(geofa); free(yfa); free(xfa);
+    oracle_ref_config().accur = keep;
+}
+
 }  /* extern "C" */

@@ -62,13 +62,22 @@ def read_solution(path: str, nx: int, ny: int) -> np.ndarray:
     return data[:, 2:6].reshape(ny - 1, nx - 1, 4).copy()
 
 
+def read_nodal_dgp1(path: str, nx: int, ny: int) -> np.ndarray:
+    """print_state_DGP1 file (FileIO.cpp:117-217): rho,u,v,T reconstructed at the nx*ny NODES."""
+    data = np.loadtxt(path, delimiter=",", skiprows=3, dtype=np.float64)
+    assert data.shape == (nx * ny, 9), (data.shape, nx, ny)
+    return data[:, 2:6].reshape(ny, nx, 4).copy()
+
+
 def run(case_dir: str, therm_path: str, shapes, niter: int, iaxi: int = 1, igam: float = 1.4,
-        keep: bool = False, timeout: float = 3600.0):
-    """Returns dict(relres=[...], dt=[...], states=[(ny-1,nx-1,4) per block], wall=seconds)."""
+        keep: bool = False, timeout: float = 3600.0, accur: int = 0):
+    """Returns dict(relres=[...], dt=[...], states=[(ny-1,nx-1,4) per block], wall=seconds).
+    accur=1 (the second-order branch): states are replaced by `nodal`, the node-averaged reconstruction
+    print_state_DGP1 writes to ../Outputs/time/solution.b%03d.it%05d.tec (ny, nx, 4 per block)."""
     nblocks = len(shapes)
     run_dir = _stage(case_dir, therm_path, nblocks)
     env = dict(os.environ, SHIM_NP=str(nblocks), ORACLE_NITER=str(niter), ORACLE_IAXI=str(iaxi),
-               ORACLE_IGAM=repr(float(igam)))
+               ORACLE_IGAM=repr(float(igam)), ORACLE_ACCUR=str(int(accur)))
     t0 = time.perf_counter()
     proc = subprocess.run([REF_BIN], cwd=os.path.join(run_dir, "build"), env=env, capture_output=True,
                           text=True, timeout=timeout)
@@ -83,10 +92,16 @@ def run(case_dir: str, therm_path: str, shapes, niter: int, iaxi: int = 1, igam:
         next(f)
         for line in f:
             relres.append(float(line.split(",")[1]))
-    states = [read_solution(os.path.join(run_dir, "Outputs", f"solution.b{b + 1}.tec"), nx, ny)
-              for b, (nx, ny) in enumerate(shapes)]
+    nodal = None
+    if accur == 1:
+        states = None
+        nodal = [read_nodal_dgp1(os.path.join(run_dir, "Outputs", "time", "solution.b%03d.it%05d.tec" % (b + 1, niter)), nx, ny)
+                 for b, (nx, ny) in enumerate(shapes)]
+    else:
+        states = [read_solution(os.path.join(run_dir, "Outputs", f"solution.b{b + 1}.tec"), nx, ny)
+                  for b, (nx, ny) in enumerate(shapes)]
     failed = "Failed Assert" in proc.stdout
-    out = dict(relres=np.array(relres), dt=np.array(dts), states=states, wall=wall, failed=failed,
+    out = dict(relres=np.array(relres), dt=np.array(dts), states=states, nodal=nodal, wall=wall, failed=failed,
                stdout_tail=proc.stdout[-500:])
     if keep:
         out["run_dir"] = run_dir

@@ -36,7 +36,7 @@ class Config(C.Structure):
         ("igam", C.c_double), ("cfl", C.c_double), ("tol", C.c_double),
         ("uFS", C.c_double * NVAR), ("p_back", C.c_double), ("Rs", C.c_double),
         ("thermo_hi", C.c_double * 7), ("thermo_lo", C.c_double * 7),
-        ("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("reserved", C.c_int32),
+        ("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("accur", C.c_int32),
     ]
 
     def copy(self) -> "Config":
@@ -76,6 +76,9 @@ SOLVER_API = {
     "set_state": (C.c_int, [C.c_void_p, C.c_int32, _DP]),
     "get_state": (C.c_int, [C.c_void_p, C.c_int32, _DP]),
     "get_residual": (C.c_int, [C.c_void_p, C.c_int32, _DP]),
+    "set_slopes": (C.c_int, [C.c_void_p, C.c_int32, _DP, _DP]),
+    "get_slopes": (C.c_int, [C.c_void_p, C.c_int32, _DP, _DP]),
+    "get_residual_dg": (C.c_int, [C.c_void_p, C.c_int32, _DP, _DP, _DP]),
     "step": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(StepInfo)]),
     "get_block_history": (C.c_int, [C.c_void_p, C.c_int32, _DP]),
     "iteration": (C.c_int64, [C.c_void_p]),

@@ -128,3 +128,26 @@ def read_solution(path: str, nx: int, ny: int):
     lib.check(lib.par2d_read_solution(os.fsencode(path), nx, ny, unk.ctypes.data_as(dp), xc.ctypes.data_as(dp),
                                       yc.ctypes.data_as(dp)), "read_solution")
     return unk, xc, yc
+
+
+def nodal_dgp1(unk: np.ndarray, ux: np.ndarray, uy: np.ndarray) -> np.ndarray:
+    """Node values of the DG(P1) representation as print_state_DGP1 averages them (FV/FileIO.cpp:139-201):
+    every node takes the mean of the standard reconstruction unk + xsi*ux + eta*uy of its 1, 2 or 4
+    adjacent cells at their corner facing the node.  unk/ux/uy: (ncy, ncx, 4); returns (ncy+1, ncx+1, 4)."""
+    ncy, ncx, _ = unk.shape
+    out = np.zeros((ncy + 1, ncx + 1, 4))
+    for j in range(ncy + 1):
+        for i in range(ncx + 1):
+            # the reference's summation order: pp, pm, mp, mm (interior), see the branches of FileIO.cpp:147-199
+            terms = []
+            for (di, dj, xsi, eta) in ((0, 0, -1.0, -1.0), (0, -1, -1.0, 1.0), (-1, 0, 1.0, -1.0), (-1, -1, 1.0, 1.0)):
+                ci, cj = i + di, j + dj
+                if 0 <= ci < ncx and 0 <= cj < ncy:
+                    terms.append(unk[cj, ci] + (xsi * ux[cj, ci]) + (eta * uy[cj, ci]))
+            if len(terms) == 1:
+                out[j, i] = terms[0]
+            elif len(terms) == 2:
+                out[j, i] = 0.5 * (terms[0] + terms[1])
+            else:
+                out[j, i] = 0.25 * (terms[0] + terms[1] + terms[2] + terms[3])
+    return out

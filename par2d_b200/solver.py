@@ -65,6 +65,33 @@ class Solver:
         self.lib.check(self.lib.get_residual(self._h, b, out.ctypes.data_as(_DP)), "get_residual")
         return out
 
+    # -- second-order branch (cfg.accur == 1): xi / eta slopes of the DG(P1) representation -----------
+    def get_slopes(self, b: int):
+        nx, ny = self.shapes[b]
+        ux = np.empty((ny - 1, nx - 1, 4), dtype=np.float64)
+        uy = np.empty((ny - 1, nx - 1, 4), dtype=np.float64)
+        self.lib.check(self.lib.get_slopes(self._h, b, ux.ctypes.data_as(_DP), uy.ctypes.data_as(_DP)), "get_slopes")
+        return ux, uy
+
+    def set_slopes(self, b: int, ux: np.ndarray, uy: np.ndarray):
+        nx, ny = self.shapes[b]
+        ux = np.ascontiguousarray(ux, dtype=np.float64).reshape(ny - 1, nx - 1, 4)
+        uy = np.ascontiguousarray(uy, dtype=np.float64).reshape(ny - 1, nx - 1, 4)
+        self.lib.check(self.lib.set_slopes(self._h, b, ux.ctypes.data_as(_DP), uy.ctypes.data_as(_DP)), "set_slopes")
+
+    def get_residual_dg(self, b: int):
+        """dudt, duxdt, duydt of one calc_dudt evaluation with ACCUR == 1."""
+        nx, ny = self.shapes[b]
+        out = [np.empty((ny - 1, nx - 1, 4), dtype=np.float64) for _ in range(3)]
+        self.lib.check(self.lib.get_residual_dg(self._h, b, *[o.ctypes.data_as(_DP) for o in out]), "get_residual_dg")
+        return out
+
+    def nodal_dgp1(self, b: int) -> np.ndarray:
+        """The node-averaged reconstruction print_state_DGP1 writes (FileIO.cpp:139-201): (ny, nx, 4)."""
+        from .host import nodal_dgp1
+        ux, uy = self.get_slopes(b)
+        return nodal_dgp1(self.get_state(b), ux, uy)
+
     # -- stepping ---------------------------------------------------------
     def step(self, nsteps: int, stop_on_tol: bool = False, check: bool = True) -> List[StepInfo]:
         info = (StepInfo * nsteps)()
