@@ -45,11 +45,18 @@ RUNS = [
 ]
 FULL_STATE = {(r[0], r[1]) for r in RUNS}
 
+# second-order branch (ACCUR = 1, DG(P1)): the reference's print_state_DGP1 writes the node-averaged
+# reconstruction (FileIO.cpp:117-217), stored as n<k> (ny, nx, 4) per block
+RUNS_DG = [
+    ("Case_ffstep8", "dgp1_axi_cpg", 1, 1.4, 200),
+    ("Case_rktnoz9", "dgp1_axi_tpg", 1, -1.4, 100),
+]
+
 
 def main():
     if not run_ref.available():
         raise SystemExit("oracle/_ref/MPI2DFV missing: run oracle/build_ref.sh first")
-    for name, variant, iaxi, igam, steps in RUNS:
+    for name, variant, iaxi, igam, steps in (RUNS if "--dg-only" not in sys.argv else []):
         case = Case.load(os.path.join(CASES, name))
         shapes = [case.shape(b) for b in range(case.nblocks)]
         out = run_ref.run(os.path.join(CASES, name), THERM, shapes, steps, iaxi=iaxi, igam=igam)
@@ -60,6 +67,18 @@ def main():
             data[f"sum{b}"] = st.reshape(-1, 4).sum(axis=0)
             if (name, variant) in FULL_STATE:
                 data[f"b{b}"] = st
+        path = os.path.join(HERE, f"golden_{name}_{variant}.npz")
+        np.savez_compressed(path, **data)
+        print(f"{path}: {steps} steps, {os.path.getsize(path) / 1e6:.2f} MB, relres[-1]={out['relres'][-1]:.6e}")
+    for name, variant, iaxi, igam, steps in RUNS_DG:
+        case = Case.load(os.path.join(CASES, name))
+        shapes = [case.shape(b) for b in range(case.nblocks)]
+        out = run_ref.run(os.path.join(CASES, name), THERM, shapes, steps, iaxi=iaxi, igam=igam, accur=1)
+        assert not out["failed"], out["stdout_tail"]
+        assert len(out["relres"]) == steps and len(out["dt"]) == steps
+        data = dict(relres=out["relres"], dt=out["dt"], steps=np.int64(steps), iaxi=np.int64(iaxi), igam=np.float64(igam))
+        for b, nd in enumerate(out["nodal"]):
+            data[f"n{b}"] = nd
         path = os.path.join(HERE, f"golden_{name}_{variant}.npz")
         np.savez_compressed(path, **data)
         print(f"{path}: {steps} steps, {os.path.getsize(path) / 1e6:.2f} MB, relres[-1]={out['relres'][-1]:.6e}")
