@@ -144,6 +144,14 @@ int par2d_get_state(par2d_ctx* ctx, int32_t block, double* unk);
  * = dudt.  Does not advance the state or the iteration counter. */
 int par2d_get_residual(par2d_ctx* ctx, int32_t block, double* res);
 
+/* Second-order branch (cfg.accur == 1): the xi / eta slopes of the DG(P1) representation, reference layout
+ * ux/uy[(j*(nx-1)+i)*4+k] (FV/main.cpp:169-172; zero after create, main.cpp:199-209), and the three
+ * right-hand sides dudt, duxdt, duydt of one calc_dudt evaluation with ACCUR == 1 (test hook,
+ * FV/SpatialDiscretization.cpp:159-1050 + FV/DGP1Tools.cpp). */
+int par2d_set_slopes(par2d_ctx* ctx, int32_t block, const double* ux, const double* uy);
+int par2d_get_slopes(par2d_ctx* ctx, int32_t block, double* ux, double* uy);
+int par2d_get_residual_dg(par2d_ctx* ctx, int32_t block, double* res, double* resx, double* resy);
+
 /* ---- the hot path ------------------------------------------------------- */
 
 /* Advances nsteps explicit-Euler iterations = nsteps passes of the loop body

@@ -180,6 +180,11 @@ struct par2d_ctx {
     int hist_cap = 0;
     double* staging = nullptr;
     long long staging_doubles = 0;
+    // second-order branch (cfg.accur == 1)
+    bool dg = false;
+    std::vector<double*> dg_mem;      // per owned block: ux | uy | uxt | uyt | ghost points
+    double* dg_partials = nullptr;
+    int dg_total_tiles = 0, dg_max_tiles = 0;
 
     int cur = 0;
     long long iter = 0;
@@ -268,6 +273,7 @@ struct par2d_ctx {
         f.ticket = ticket;
         f.dt_used = dt_used + (iter_queued & 1);
         f.blk_norm = blk_norm;
+        f.dg_partials = dg ? dg_partials : nullptr;
         f.tol = cfg.tol;
         f.stop_on_tol = stop_on_tol;
         f.hist_cap = hist_cap;
@@ -362,7 +368,32 @@ void flush_finalize(par2d_ctx* c) {
     c->fin_pending = false;
 }
 
+DgArgs dg_args(const par2d_ctx* c, int update) {
+    DgArgs d;
+    d.partials = c->dg_partials;
+    d.max_tiles = c->dg_max_tiles;
+    d.max_points = 2 * c->max_faces;
+    d.res_out = nullptr;
+    d.res_block = -1;
+    d.update = update;
+    return d;
+}
+
+// second-order branch: ghost points -> cell kernel (means into the other buffer, damped slopes) -> limiter ->
+// bookkeeping (dg.cuh)
+void queue_step_dg(par2d_ctx* c, int stop_on_tol) {
+    StepArgs a = c->step_args(1);
+    const DgArgs d = dg_args(c, 1);
+    c->kt->dg_ghost(c->stream, a, c->gas, d);
+    c->kt->dg_cell(c->stream, a, c->gas, d, c->tpg, c->axi);
+    c->kt->dg_limit(c->stream, a, d);
+    launch_finalize(c->stream, c->finalize_args(stop_on_tol));
+    c->iter_queued++;
+    c->cur ^= 1;
+}
+
 void queue_step(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
+    if (c->dg) { queue_step_dg(c, stop_on_tol); return; }
     StepArgs a = c->step_args(1);
     c->kt->ghost(c->stream, a, c->gas, with_ghost_dt ? 1 : 0, c->fin_pending ? &c->fin_args : nullptr);
     c->fin_pending = false;
@@ -461,6 +492,8 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
     if (!cfg || !blocks || !out || nblocks < 1) return fail(PAR2D_ERR_ARG, "create: null argument");
     if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(PAR2D_ERR_ARG, "create: bad rank %d of %d", cfg->rank, cfg->nranks);
     if (cfg->mode != PAR2D_MODE_FAST && cfg->mode != PAR2D_MODE_FAITHFUL) return fail(PAR2D_ERR_ARG, "create: unknown mode %d", cfg->mode);
+    if (cfg->accur != 0 && cfg->accur != 1) return fail(PAR2D_ERR_ARG, "create: accur must be 0 or 1 (SpatialDiscretization.cpp:204)");
+    if (cfg->accur == 1 && cfg->nranks != 1) return fail(PAR2D_ERR_ARG, "create: the second-order branch (accur = 1) runs on one rank in this version");
     int rc = validate_table(nblocks, blocks, cfg->nranks);
     if (rc) return rc;
 
@@ -481,6 +514,7 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
     c->tpg = !(cfg->igam > 0);
     c->axi = cfg->iaxi == 1;
     c->kt = cfg->mode == PAR2D_MODE_FAITHFUL ? kernels_faithful() : kernels_fast();
+    c->dg = cfg->accur == 1;
     c->device = dev;
     {
         // Rows per warp strip.  A strip is marched by ONE warp, row after row (~1 us per row), so small meshes
@@ -569,6 +603,26 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
         CU_TRY(cudaMalloc(&c->block_ibound[k], sizeof(int) * nfaces));
         CU_TRY(cudaMemcpyAsync(c->block_ibound[k], d.ibound, sizeof(int) * nfaces, cudaMemcpyHostToDevice, c->stream));
         b.ibound = c->block_ibound[k];
+        b.ux = b.uy = b.uxt = b.uyt = nullptr;
+        for (int s = 0; s < 4; s++) b.ghost2[s] = nullptr;
+        b.dg_tile0 = b.dg_ntiles = 0;
+        if (c->dg) {
+            const size_t nc4 = 4 * (size_t)b.ncx * b.ncy, ng = 8 * (size_t)(2 * b.ncx + 2 * b.ncy);
+            double* m = nullptr;
+            CU_TRY(cudaMalloc(&m, sizeof(double) * (4 * nc4 + ng)));
+            CU_TRY(cudaMemsetAsync(m, 0, sizeof(double) * (4 * nc4 + ng), c->stream));   // slopes start at zero, main.cpp:199-209
+            c->dg_mem.push_back(m);
+            b.ux = m; b.uy = m + nc4; b.uxt = m + 2 * nc4; b.uyt = m + 3 * nc4;
+            double* gp = m + 4 * nc4;
+            b.ghost2[SIDE_BOTTOM] = gp; gp += 8 * (size_t)b.ncx;
+            b.ghost2[SIDE_RIGHT] = gp; gp += 8 * (size_t)b.ncy;
+            b.ghost2[SIDE_TOP] = gp; gp += 8 * (size_t)b.ncx;
+            b.ghost2[SIDE_LEFT] = gp;
+            b.dg_ntiles = (int)(((long long)b.ncx * b.ncy + DG_THREADS - 1) / DG_THREADS);
+            b.dg_tile0 = c->dg_total_tiles;
+            c->dg_total_tiles += b.dg_ntiles;
+            c->dg_max_tiles = std::max(c->dg_max_tiles, b.dg_ntiles);
+        }
         b.tiles_x = (b.ncx + MCELLS - 1) / MCELLS;
         b.tiles_y = (b.ncy + c->march_rows - 1) / c->march_rows;
         b.tile0 = c->total_tiles;
@@ -677,6 +731,7 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
         CU_TRY(cudaMemsetAsync(c->dt_table, 0, sizeof(double) * nblocks, c->stream));
     }
     CU_TRY(cudaMalloc(&c->partials, sizeof(double) * 4 * (size_t)c->total_tiles));
+    if (c->dg) CU_TRY(cudaMalloc(&c->dg_partials, sizeof(double) * 12 * (size_t)c->dg_total_tiles));
     CU_TRY(cudaMalloc(&c->flags, sizeof(unsigned)));
     CU_TRY(cudaMalloc(&c->stop, sizeof(int)));
     CU_TRY(cudaMalloc(&c->d_iter, sizeof(long long)));
@@ -710,6 +765,8 @@ int par2d_destroy(par2d_ctx* c) {
     for (Peer& p : c->peers) cudaFree(p.d_send);
     if (c->arena) cudaFree(c->arena); else cudaFree(c->dt_table);
     cudaFree(c->put_ticket); cudaFree(c->dlines_peer); cudaFree(c->d_dt_dst); cudaFree(c->d_flag_dst);
+    for (double* m : c->dg_mem) cudaFree(m);
+    cudaFree(c->dg_partials);
     cudaFree(c->dblk); cudaFree(c->dtmaps); cudaFree(c->partials); cudaFree(c->flags);
     cudaFree(c->stop); cudaFree(c->d_iter); cudaFree(c->hist_pos); cudaFree(c->ticket); cudaFree(c->res0);
     cudaFree(c->blk_norm); cudaFree(c->dt_used); cudaFree(c->blk_hist); cudaFree(c->step_hist); cudaFree(c->staging); cudaFree(c->dlines);
@@ -767,6 +824,56 @@ int par2d_get_residual(par2d_ctx* c, int32_t block, double* res) {
     const size_t bytes = sizeof(double) * 4 * (size_t)b.ncx * b.ncy;
     CU_TRY(cudaMemcpyAsync(res, c->staging, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int par2d_set_slopes(par2d_ctx* c, int32_t block, const double* ux, const double* uy) {
+    const int k = owned_k(c, block, "set_slopes");
+    if (k < 0 || !ux || !uy) return PAR2D_ERR_ARG;
+    if (!c->dg) return fail(PAR2D_ERR_ARG, "set_slopes: the ctx was created with accur = 0");
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    const BlockDev& b = c->hblk[k];
+    const size_t bytes = sizeof(double) * 4 * (size_t)b.ncx * b.ncy;
+    CU_TRY(cudaMemcpyAsync(b.ux, ux, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(b.uy, uy, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int par2d_get_slopes(par2d_ctx* c, int32_t block, double* ux, double* uy) {
+    const int k = owned_k(c, block, "get_slopes");
+    if (k < 0 || !ux || !uy) return PAR2D_ERR_ARG;
+    if (!c->dg) return fail(PAR2D_ERR_ARG, "get_slopes: the ctx was created with accur = 0");
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    const BlockDev& b = c->hblk[k];
+    const size_t bytes = sizeof(double) * 4 * (size_t)b.ncx * b.ncy;
+    CU_TRY(cudaMemcpyAsync(ux, b.ux, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(uy, b.uy, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int par2d_get_residual_dg(par2d_ctx* c, int32_t block, double* res, double* resx, double* resy) {
+    const int k = owned_k(c, block, "get_residual_dg");
+    if (k < 0 || !res || !resx || !resy) return PAR2D_ERR_ARG;
+    if (!c->dg) return fail(PAR2D_ERR_ARG, "get_residual_dg: the ctx was created with accur = 0");
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    const BlockDev& b = c->hblk[k];
+    const size_t n4 = 4 * (size_t)b.ncx * b.ncy;
+    double* out = nullptr;
+    CU_TRY(cudaMalloc(&out, sizeof(double) * 3 * n4));
+    StepArgs a = c->step_args(0);
+    DgArgs d = dg_args(c, 0);
+    d.res_out = out;
+    d.res_block = k;
+    c->kt->dg_ghost(c->stream, a, c->gas, d);
+    c->kt->dg_cell(c->stream, a, c->gas, d, c->tpg, c->axi);
+    CU_TRY(cudaMemcpyAsync(res, out, sizeof(double) * n4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(resx, out + n4, sizeof(double) * n4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(resy, out + 2 * n4, sizeof(double) * n4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(out);
     CU_TRY(cudaGetLastError());
     return 0;
 }

@@ -46,6 +46,11 @@ struct BlockDev {
     int tiles_x, tiles_y; // work decomposition: 30-column strips x row chunks (marching kernel)
     int tile0;          // first tile/strip of this block in the partial-sum array
     double min_face;    // static part of find_dt (main.cpp:26-32)
+    // second-order branch (cfg.accur == 1, dg.cuh); null / 0 otherwise
+    double *ux, *uy;    // xi / eta slopes, AoS [(j*ncx+i)*4+k] (main.cpp:169-172)
+    double *uxt, *uyt;  // damped, not yet limited slopes of the step in flight
+    double* ghost2[4];  // two Gauss-point ghost states per boundary face, [(2n+pt)*4+k]
+    int dg_tile0, dg_ntiles;  // this block's CTAs of the cell kernel in the [.][12] partial-sum array
 };
 
 // one edge line to pack for an off-rank neighbour (SpatialDiscretization.cpp:236-257)
@@ -120,6 +125,7 @@ struct FinalizeArgs {
     double tol;
     int stop_on_tol;
     int hist_cap;
+    const double* dg_partials;  // second-order branch: [dg tiles][12] sums of squares of dudt, duxdt, duydt (else null)
 };
 
 __host__ __device__ inline int edge_cells(int ncx, int ncy, int side) {

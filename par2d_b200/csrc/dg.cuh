@@ -1,0 +1,462 @@
+// dg.cuh -- the second-order branch of the path (cfg.accur == 1): the reference's DG(P1) discretisation
+// (FV/DGP1Tools.cpp, the ACCUR == 1 paths of FV/SpatialDiscretization.cpp:159-1050 and FV/main.cpp:300-463).
+//
+// Unknowns per cell: the mean (rho,u,v,T) in the padded state planes (common.cuh) plus xi / eta slopes in
+// AoS arrays ux/uy[(j*ncx+i)*4+k]; two Gauss points per face with LDFSS at each; the slopes' right-hand
+// sides carry the xi/eta moments of the face fluxes plus a volume integral; the slopes are damped (0.9) and
+// limited against the neighbouring means after every update.
+//
+// Three kernels per step, written in GATHER form (a cell evaluates the Gauss-point fluxes of its own four
+// faces and accumulates them in the reference's order, so in PAR2D_MODE_FAITHFUL every cell's right-hand
+// sides are bit-identical to the reference's scatter loops):
+//   dg_ghost_kernel : two ghost states per boundary face (DGP1_ghost_cell_generator, blended normals),
+//                     or the same-GPU neighbour's reconstruction at its Gauss points (the reference's halo)
+//   dg_cell_kernel  : face + boundary + volume integrals, /vol, norms, three solves with one Jacobian,
+//                     mean update into the other state buffer, damped slopes into the temporary arrays
+//   dg_limit_kernel : the reference's in-place, sequential slope limiter restated per cell: it reads the OLD
+//                     mean of the cells after it in memory order and the NEW mean of the cells before it
+//                     (both state buffers are at hand), including the row wrap of its flat-index tests
+// This first version favours exactness over speed: every interior face flux is evaluated by both adjacent
+// cells, with the reference's divisions.  Both arithmetic modes share the formulation; MODE_FAST only adds
+// FMA contraction.  Single rank (nranks == 1); any number of blocks per GPU.
+#pragma once
+#include "common.cuh"
+#include "physics.cuh"
+
+namespace par2d {
+
+constexpr double DG_DAMP = 0.9;       // main.cpp:92
+constexpr double DG_DUSCALE = 0.5;    // main.cpp:93
+constexpr int DG_THREADS = 128;
+
+struct DgArgs {
+    double* partials;    // [dg tiles][12]: sum of squares of dudt, duxdt, duydt per CTA
+    int max_tiles;       // CTAs of the largest owned block (grid.x of the cell and limiter kernels)
+    int max_points;      // 2 x longest perimeter (grid.x of the ghost kernel, in threads)
+    double* res_out;     // optional dump of dudt | duxdt | duydt (3 x ncell x 4) of block res_block
+    int res_block;
+    int update;
+};
+
+struct DgCell {
+    double u[4], ux[4], uy[4], p;
+};
+
+__device__ __forceinline__ double dg_gauss() { return 1.0 / sqrt(3.0); }   // folded at compile time, as 1.0/sqrt(3.0) is in the reference
+
+// mean + slopes + pressure of cell (i,j) (State::p of ElemVar, StateVariables.h:49-50)
+__device__ __forceinline__ void dg_load_cell(const Gas& g, const BlockDev& b, int buf, int i, int j, DgCell& c) {
+    const double* S = b.state[buf];
+    const long long o = (long long)(j + 1) * b.pitch + COL0 + i;
+    const long long e = 4 * ((long long)j * b.ncx + i);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { c.u[k] = S[k * b.plane + o]; c.ux[k] = b.ux[e + k]; c.uy[k] = b.uy[e + k]; }
+    c.p = fmax(c.u[0] * g.Rs * c.u[3], 1.0);
+}
+
+// get_u_val, DGP1Tools.cpp:10-37: the density is extrapolated through the pressure
+__device__ __forceinline__ void dg_u_val(const Gas& g, const DgCell& c, double xsi, double eta, double out[4]) {
+    const double dpdxsi = c.ux[0] * g.Rs * c.u[3] + c.u[0] * g.Rs * c.ux[3];
+    const double dpdeta = c.uy[0] * g.Rs * c.u[3] + c.u[0] * g.Rs * c.uy[3];
+    const double pout = c.p + (xsi * dpdxsi) + (eta * dpdeta);
+    out[0] = pout / (g.Rs * (c.u[3] + (xsi * c.ux[3]) + (eta * c.uy[3])));
+#pragma unroll
+    for (int k = 1; k < 4; k++) out[k] = c.u[k] + (xsi * c.ux[k]) + (eta * c.uy[k]);
+}
+
+// the reconstructed state at a Gauss point, UpdateState'd (T clamp, StateVariables.h:38-68)
+template <bool TPG>
+__device__ __forceinline__ FaceState dg_point_state(const Gas& g, const DgCell& c, double xsi, double eta, unsigned& flags) {
+    double u[4];
+    dg_u_val(g, c, xsi, eta, u);
+    u[3] = fmax(u[3], 201.0);
+    return face_state<true, TPG>(g, u[0], u[1], u[2], u[3], flags);
+}
+
+struct DgAcc {
+    double r[4], rx[4], ry[4];
+};
+
+// the accumulation statements of DGP1Tools.cpp:168-184 (and twins) for ONE of the two cells of a face
+template <bool AXI>
+__device__ __forceinline__ void dg_accumulate(DgAcc& a, const Flux& F, double yc, bool subtract, double xsi, double eta) {
+    const double weight = 0.5;
+    double f[4] = {F.f0, F.f1, F.f2, F.f3};
+    if constexpr (AXI) f[2] = (F.f2 + (yc * F.parr));
+    else f[2] = (F.f2 + (0.0 * F.parr));
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (subtract) {
+            a.r[k] -= weight * f[k];
+            a.rx[k] -= weight * f[k] * xsi;
+            a.ry[k] -= weight * f[k] * eta;
+        } else {
+            a.r[k] += weight * f[k];
+            a.rx[k] += weight * f[k] * xsi;
+            a.ry[k] += weight * f[k] * eta;
+        }
+    }
+}
+
+// DGP1_xsi_face_integral (dir 0) / DGP1_eta_face_integral (dir 1), the part that lands in one cell
+template <bool TPG, bool AXI>
+__device__ __forceinline__ void dg_face(const Gas& g, const FaceGeom& fg, const DgCell& L, const DgCell& R, int dir, bool mine_is_left,
+                                        double yc, DgAcc& a, unsigned& flags) {
+    const double G = dg_gauss();
+#pragma unroll
+    for (int pt = 0; pt < 2; pt++) {
+        const double s = pt == 0 ? G : -G;
+        double xsiL, etaL, xsiR, etaR;
+        if (dir == 0) { xsiL = 1.0; xsiR = -1.0; etaL = etaR = s; }
+        else { etaL = -1.0; etaR = 1.0; xsiL = xsiR = s; }
+        const FaceState sl = dg_point_state<TPG>(g, L, xsiL, etaL, flags);
+        const FaceState sr = dg_point_state<TPG>(g, R, xsiR, etaR, flags);
+        const Flux F = ldfss<true, AXI>(fg, sl, sr);
+        if (isnan(F.f0 + F.f1 + F.f2 + F.f3)) flags |= FLAG_NAN;
+        if (mine_is_left) dg_accumulate<AXI>(a, F, yc, true, xsiL, etaL);
+        else dg_accumulate<AXI>(a, F, yc, false, xsiR, etaR);
+    }
+}
+
+// unit normal + length + mid-point radius of the face node (i0,j0) -> (i1,j1) (MeshModule.cpp:52-85)
+__device__ __forceinline__ FaceGeom dg_geom(const BlockDev& b, int i0, int j0, int i1, int j1) {
+    const double* X = b.nodes;
+    const double* Y = b.nodes + b.plane;
+    const long long p0 = (long long)(j0 + 1) * b.pitch + COL0 + i0, p1 = (long long)(j1 + 1) * b.pitch + COL0 + i1;
+    return face_geom<true>(X[p0], Y[p0], X[p1], Y[p1]);
+}
+
+// DGP1_boundary_face_integral, DGP1Tools.cpp:317-531: type 1 bottom, 2 right, 3 top, 4 left
+template <bool TPG, bool AXI>
+__device__ __forceinline__ void dg_boundary_face(const Gas& g, const BlockDev& b, int type, int side, int n, const DgCell& in, const FaceGeom& fg,
+                                                 double nLx, double nLy, double nRx, double nRy, double yc, DgAcc& a, unsigned& flags) {
+    const double G = dg_gauss();
+    const double* gh = b.ghost2[side];
+#pragma unroll
+    for (int pt = 0; pt < 2; pt++) {
+        const double s = pt == 0 ? G : -G;
+        double xsi, eta;
+        if (type == 1) { xsi = s; eta = -1.0; }
+        else if (type == 2) { xsi = 1.0; eta = s; }
+        else if (type == 3) { xsi = s; eta = 1.0; }
+        else { xsi = -1.0; eta = s; }
+        const double temp = fabs(s);
+        FaceGeom f2 = fg;
+        f2.nx = (1.0 - 0.5 * temp) * fg.nx + 0.5 * temp * (pt == 0 ? nRx : nLx);
+        f2.ny = (1.0 - 0.5 * temp) * fg.ny + 0.5 * temp * (pt == 0 ? nRy : nLy);
+        const double* e = gh + 4 * (2 * (long long)n + pt);
+        const FaceState ex = face_state<true, TPG>(g, e[0], e[1], e[2], e[3], flags);   // ghosts are stored clamped
+        const FaceState si = dg_point_state<TPG>(g, in, xsi, eta, flags);
+        Flux F;
+        if (type == 1 || type == 2) F = ldfss<true, AXI>(f2, si, ex);
+        else F = ldfss<true, AXI>(f2, ex, si);
+        if (isnan(F.f0 + F.f1 + F.f2 + F.f3)) flags |= FLAG_NAN;
+        // rhs += sideMult * weight * f: sideMult = -1 on the bottom and right faces
+        const double weight = 0.5, sm = (type == 1 || type == 2) ? -1.0 : 1.0;
+        double f[4] = {F.f0, F.f1, F.f2, F.f3};
+        if constexpr (AXI) f[2] = (F.f2 + (yc * F.parr));
+        else f[2] = (F.f2 + (0.0 * F.parr));
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            a.r[k] += sm * weight * f[k];
+            a.rx[k] += sm * weight * f[k] * xsi;
+            a.ry[k] += sm * weight * f[k] * eta;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ ghost points
+template <bool FAITHFUL>
+__global__ void __launch_bounds__(256) dg_ghost_kernel(StepArgs a, Gas g, DgArgs d, int tpg) {
+    if (*a.stop) return;
+    const BlockDev& b = a.blocks[blockIdx.y];
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ncx = b.ncx, ncy = b.ncy;
+    if (t == 0) {   // find_dt of this block from cell (0,0), main.cpp:19-37
+        const double* S = b.state[a.cur];
+        const long long o = (long long)b.pitch + COL0;
+        const double u = S[b.plane + o], v = S[2 * b.plane + o], T = S[3 * b.plane + o];
+        const double vmax = sqrt(u * u + v * v) + sqrt(g.gamRs * T);
+        const double dt = g.cfl * b.min_face / vmax;
+        if (isnan(dt)) atomicOr(a.flags, FLAG_NAN);
+        a.dt_table[b.gid] = dt;
+    }
+    if (t >= 4 * (ncx + ncy)) return;
+    const int pt = t & 1;
+    int n = t >> 1, side;
+    if (n < ncx) side = SIDE_BOTTOM;
+    else if ((n -= ncx) < ncy) side = SIDE_RIGHT;
+    else if ((n -= ncy) < ncx) side = SIDE_TOP;
+    else { n -= ncx; side = SIDE_LEFT; }
+    const double G = dg_gauss();
+    const double s = pt == 0 ? G : -G;
+    double* out = b.ghost2[side] + 4 * (2 * (long long)n + pt);
+    unsigned fl = 0;
+    if (b.nb_kind[side] == NB_LOCAL) {
+        // halo of the second-order branch (SpatialDiscretization.cpp:243-256 and twins): the neighbour's
+        // reconstruction at the Gauss points of ITS edge face
+        const BlockDev& o = a.blocks[b.nb_block[side]];
+        const int os = b.nb_side[side];
+        int i, j;
+        double xsi, eta;
+        if (os == SIDE_LEFT) { i = 0; j = n; xsi = -1.0; eta = s; }
+        else if (os == SIDE_RIGHT) { i = o.ncx - 1; j = n; xsi = 1.0; eta = s; }
+        else if (os == SIDE_BOTTOM) { i = n; j = 0; xsi = s; eta = -1.0; }
+        else { i = n; j = o.ncy - 1; xsi = s; eta = 1.0; }
+        DgCell c;
+        dg_load_cell(g, o, a.cur, i, j, c);
+        double u[4];
+        dg_u_val(g, c, xsi, eta, u);
+        out[0] = u[0]; out[1] = u[1]; out[2] = u[2]; out[3] = fmax(u[3], 201.0);
+        return;
+    }
+    // DGP1_ghost_cell_generator, DGP1Tools.cpp:548-784
+    int i, j, code, i0, j0, i1, j1, ir0, jr0, ir1, jr1, il0, jl0, il1, jl1;
+    double sg, xsi, eta;
+    const int last = (side == SIDE_BOTTOM || side == SIDE_TOP) ? ncx - 1 : ncy - 1;
+    const int nr = n != last ? n + 1 : n, nl = n != 0 ? n - 1 : n;
+    if (side == SIDE_BOTTOM) {
+        i = n; j = 0; code = b.ibound[n]; sg = 1.0; xsi = s; eta = -1.0;
+        i0 = n; j0 = 0; i1 = n + 1; j1 = 0; ir0 = nr; jr0 = 0; ir1 = nr + 1; jr1 = 0; il0 = nl; jl0 = 0; il1 = nl + 1; jl1 = 0;
+    } else if (side == SIDE_RIGHT) {   // column nx-1 here (the first-order generator reads column 0)
+        i = ncx - 1; j = n; code = b.ibound[ncx + n]; sg = 1.0; xsi = 1.0; eta = s;
+        i0 = ncx; j0 = n; i1 = ncx; j1 = n + 1; ir0 = ncx; jr0 = nr; ir1 = ncx; jr1 = nr + 1; il0 = ncx; jl0 = nl; il1 = ncx; jl1 = nl + 1;
+    } else if (side == SIDE_TOP) {
+        i = n; j = ncy - 1; code = b.ibound[2 * ncx + ncy - 1 - n]; sg = -1.0; xsi = s; eta = 1.0;
+        i0 = n; j0 = ncy; i1 = n + 1; j1 = ncy; ir0 = nr; jr0 = ncy; ir1 = nr + 1; jr1 = ncy; il0 = nl; jl0 = ncy; il1 = nl + 1; jl1 = ncy;
+    } else {
+        i = 0; j = n; code = b.ibound[2 * ncx + 2 * ncy - 1 - n]; sg = -1.0; xsi = -1.0; eta = s;
+        i0 = 0; j0 = n; i1 = 0; j1 = n + 1; ir0 = 0; jr0 = nr; ir1 = 0; jr1 = nr + 1; il0 = 0; jl0 = nl; il1 = 0; jl1 = nl + 1;
+    }
+    const FaceGeom f0 = dg_geom(b, i0, j0, i1, j1);
+    const FaceGeom fo = pt == 0 ? dg_geom(b, ir0, jr0, ir1, jr1) : dg_geom(b, il0, jl0, il1, jl1);
+    double normx = sg < 0 ? -f0.nx : f0.nx, normy = sg < 0 ? -f0.ny : f0.ny;
+    const double ox = sg < 0 ? -fo.nx : fo.nx, oy = sg < 0 ? -fo.ny : fo.ny;
+    if (pt == 0) {
+        normx = normx * (1.0 - 0.5 * s) + 0.5 * s * ox;
+        normy = normy * (1.0 - 0.5 * s) + 0.5 * s * oy;
+    } else {
+        normx = normx * (1.0 + 0.5 * s) - 0.5 * s * ox;
+        normy = normy * (1.0 + 0.5 * s) - 0.5 * s * oy;
+    }
+    // get_boundary_point, DGP1Tools.cpp:533-546
+    DgCell c;
+    dg_load_cell(g, b, a.cur, i, j, c);
+    double u[4];
+    dg_u_val(g, c, xsi, eta, u);
+    u[3] = fmax(u[3], 201.0);
+    const double v2 = u[1] * u[1] + u[2] * u[2];
+    const double p = fmax(u[0] * g.Rs * u[3], 1.0);
+    const double aint = sqrt(g.gamRs * u[3]);
+    double gh[4] = {out[0], out[1], out[2], out[3]};   // stays as is when the BC leaves it unwritten
+    boundary_state(g, code, normx, normy, u, aint, p, v2, gh);
+    out[0] = gh[0]; out[1] = gh[1]; out[2] = gh[2]; out[3] = gh[3];
+    (void)fl; (void)tpg;
+}
+
+// ------------------------------------------------------------------ residual + solve + update of the means
+template <bool FAITHFUL, bool TPG, bool AXI>
+__global__ void __launch_bounds__(DG_THREADS) dg_cell_kernel(StepArgs a, Gas g, DgArgs d) {
+    __shared__ double red[DG_THREADS / 32][12];
+    if (*a.stop) return;
+    const int k = blockIdx.y;
+    const BlockDev& b = a.blocks[k];
+    const int ncx = b.ncx, ncy = b.ncy;
+    const long long ncell = (long long)ncx * ncy;
+    const int ntiles = (int)((ncell + DG_THREADS - 1) / DG_THREADS);
+    if ((int)blockIdx.x >= ntiles) return;
+    const long long e = (long long)blockIdx.x * DG_THREADS + threadIdx.x;
+    const bool live = e < ncell;
+    unsigned flags = 0;
+    double sq[12];
+#pragma unroll
+    for (int q = 0; q < 12; q++) sq[q] = 0.0;
+
+    // global dt = max over blocks (main.cpp:270-292)
+    double dt = 0.0;
+    for (int t = 0; t < a.nblocks_global; t++) dt = fmax(dt, a.dt_table[t]);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.dt_used = dt;
+
+    if (live) {
+        const int i = (int)(e % ncx), j = (int)(e / ncx);
+        DgCell me;
+        dg_load_cell(g, b, a.cur, i, j, me);
+        const double* X = b.nodes;
+        const double* Y = b.nodes + b.plane;
+        const long long n00 = (long long)(j + 1) * b.pitch + COL0 + i;
+        const double xa = X[n00], ya = Y[n00], xb = X[n00 + 1], yb = Y[n00 + 1];
+        const double xd = X[n00 + b.pitch], yd = Y[n00 + b.pitch], xc = X[n00 + b.pitch + 1], yc_ = Y[n00 + b.pitch + 1];
+        const double ycc = 0.25 * (ya + yb + yc_ + yd);           // geoel[2], MeshModule.cpp:40
+        const double vol = cell_volume(xa, ya, xb, yb, xc, yc_, xd, yd);
+        const double ycs = AXI ? ycc : 0.0;
+        DgAcc acc;
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc.r[q] = acc.rx[q] = acc.ry[q] = 0.0;
+        DgCell nb;
+        // interior xi faces (SpatialDiscretization.cpp:481-552): face i (this cell is the right one), face i+1 (left)
+        if (i >= 1) {
+            dg_load_cell(g, b, a.cur, i - 1, j, nb);
+            dg_face<TPG, AXI>(g, face_geom<true>(xa, ya, xd, yd), nb, me, 0, false, ycs, acc, flags);
+        }
+        if (i <= ncx - 2) {
+            dg_load_cell(g, b, a.cur, i + 1, j, nb);
+            dg_face<TPG, AXI>(g, face_geom<true>(xb, yb, xc, yc_), me, nb, 0, true, ycs, acc, flags);
+        }
+        // interior eta faces (:556-625): face j (this cell is the left = upper one), face j+1 (right = lower)
+        if (j >= 1) {
+            dg_load_cell(g, b, a.cur, i, j - 1, nb);
+            dg_face<TPG, AXI>(g, face_geom<true>(xa, ya, xb, yb), me, nb, 1, true, ycs, acc, flags);
+        }
+        if (j <= ncy - 2) {
+            dg_load_cell(g, b, a.cur, i, j + 1, nb);
+            dg_face<TPG, AXI>(g, face_geom<true>(xd, yd, xc, yc_), nb, me, 1, false, ycs, acc, flags);
+        }
+        // boundary faces (:643-977).  fNormalL / fNormalR are declared once per row (column) and shared by the
+        // left and right (bottom and top) face of it: at the ends of the right (top) side they still hold the
+        // left (bottom) side's values
+        if (i == 0) {
+            const FaceGeom f = face_geom<true>(xa, ya, xd, yd);
+            const FaceGeom fL = j != 0 ? dg_geom(b, 0, j - 1, 0, j) : f, fR = j != ncy - 1 ? dg_geom(b, 0, j + 1, 0, j + 2) : f;
+            dg_boundary_face<TPG, AXI>(g, b, 4, SIDE_LEFT, j, me, f, fL.nx, fL.ny, fR.nx, fR.ny, ycs, acc, flags);
+        }
+        if (i == ncx - 1) {
+            const FaceGeom f = face_geom<true>(xb, yb, xc, yc_);
+            const FaceGeom fL = j != 0 ? dg_geom(b, ncx, j - 1, ncx, j) : dg_geom(b, 0, j, 0, j + 1);
+            const FaceGeom fR = j != ncy - 1 ? dg_geom(b, ncx, j + 1, ncx, j + 2) : dg_geom(b, 0, j, 0, j + 1);
+            dg_boundary_face<TPG, AXI>(g, b, 2, SIDE_RIGHT, j, me, f, fL.nx, fL.ny, fR.nx, fR.ny, ycs, acc, flags);
+        }
+        if (j == 0) {
+            const FaceGeom f = face_geom<true>(xa, ya, xb, yb);
+            const FaceGeom fL = i != 0 ? dg_geom(b, i - 1, 0, i, 0) : f, fR = i != ncx - 1 ? dg_geom(b, i + 1, 0, i + 2, 0) : f;
+            dg_boundary_face<TPG, AXI>(g, b, 1, SIDE_BOTTOM, i, me, f, fL.nx, fL.ny, fR.nx, fR.ny, ycs, acc, flags);
+        }
+        if (j == ncy - 1) {
+            const FaceGeom f = face_geom<true>(xd, yd, xc, yc_);
+            const FaceGeom fL = i != 0 ? dg_geom(b, i - 1, ncy, i, ncy) : dg_geom(b, i, 0, i + 1, 0);
+            const FaceGeom fR = i != ncx - 1 ? dg_geom(b, i + 1, ncy, i + 2, ncy) : dg_geom(b, i, 0, i + 1, 0);
+            dg_boundary_face<TPG, AXI>(g, b, 3, SIDE_TOP, i, me, f, fL.nx, fL.ny, fR.nx, fR.ny, ycs, acc, flags);
+        }
+        // :980-1011 division by the volume, then the volume integral of the slopes' equations (DGP1Tools.cpp:52-124)
+        double r[4], rx[4], ry[4];
+        unsigned fl2 = 0;
+        const FaceState sme = face_state<true, TPG>(g, me.u[0], me.u[1], me.u[2], me.u[3], fl2);
+        {
+            const double ycv = AXI ? ycc : 1.0;
+            const double rho = me.u[0];
+            double Fx[4], Fy[4];
+            Fx[0] = ycv * rho * me.u[1];
+            Fx[1] = ycv * (rho * me.u[1] * me.u[1] + sme.p);
+            Fx[2] = ycv * rho * me.u[1] * me.u[2];
+            Fx[3] = ycv * rho * me.u[1] * sme.h0;
+            Fy[0] = ycv * rho * me.u[2];
+            Fy[1] = ycv * rho * me.u[1] * me.u[2];
+            Fy[2] = ycv * (rho * me.u[2] * me.u[2] + sme.p);
+            Fy[3] = ycv * rho * me.u[2] * sme.h0;
+            const double xL = 0.5 * (xd + xa), xR = 0.5 * (xc + xb), xD = 0.5 * (xb + xa), xU = 0.5 * (xc + xd);
+            const double yL = 0.5 * (yd + ya), yR = 0.5 * (yc_ + yb), yD = 0.5 * (yb + ya), yU = 0.5 * (yc_ + yd);
+            const double nxs0 = -0.5 * (yU - yD), nxs1 = 0.5 * (xU - xD);
+            const double nxs2 = -0.25 * ((xU - xD) * (yL - yR) - (yU - yD) * (xL - xR));
+            const double db1dx = nxs0 / nxs2, db1dy = nxs1 / nxs2;
+            const double net0 = -0.5 * (yL - yR), net1 = 0.5 * (xL - xR);
+            const double net2 = -0.25 * ((xL - xR) * (yD - yU) - (yL - yR) * (xD - xU));
+            const double db2dx = net0 / net2, db2dy = net1 / net2;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                r[q] = acc.r[q] / vol;
+                rx[q] = 3.0 * acc.rx[q] / vol;
+                ry[q] = 3.0 * acc.ry[q] / vol;
+                rx[q] += 3.0 * (Fx[q] * db1dx + Fy[q] * db1dy);
+                ry[q] += 3.0 * (Fx[q] * db2dx + Fy[q] * db2dy);
+            }
+        }
+        if (isnan(r[0])) flags |= FLAG_NAN;
+#pragma unroll
+        for (int q = 0; q < 4; q++) { sq[q] = r[q] * r[q]; sq[4 + q] = rx[q] * rx[q]; sq[8 + q] = ry[q] * ry[q]; }
+        if (d.res_out != nullptr && d.res_block == k) {
+            double* o = d.res_out + 4 * e;
+#pragma unroll
+            for (int q = 0; q < 4; q++) { o[q] = r[q]; o[4 * ncell + q] = rx[q]; o[8 * ncell + q] = ry[q]; }
+        }
+        if (d.update) {
+            // main.cpp:307-351: one Jacobian, three right-hand sides; :394-425 update of the mean, damped slopes
+            const double v2 = me.u[1] * me.u[1] + me.u[2] * me.u[2];
+            const double e0 = enthalpy<TPG>(g, me.u[3], fl2) - g.Rs * me.u[3] + 0.5 * v2;
+            const double Cv = heat_capacity<TPG>(g, me.u[3], fl2) - g.Rs;
+            double dv[4], dvx[4], dvy[4];
+            solve_cell<true, AXI>(dt, ycc, me.u[0], me.u[1], me.u[2], e0, Cv, 0.0, r, dv, flags);
+            solve_cell<true, AXI>(dt, ycc, me.u[0], me.u[1], me.u[2], e0, Cv, 0.0, rx, dvx, flags);
+            solve_cell<true, AXI>(dt, ycc, me.u[0], me.u[1], me.u[2], e0, Cv, 0.0, ry, dvy, flags);
+            double* So = b.state[a.cur ^ 1];
+            const long long o = (long long)(j + 1) * b.pitch + COL0 + i;
+            double nu[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) nu[q] = me.u[q] + dv[q];
+            if (!(nu[0] > 0.0)) flags |= FLAG_DENSITY;
+            nu[3] = fmax(nu[3], 201.0);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                So[q * b.plane + o] = nu[q];
+                b.uxt[4 * e + q] = (me.ux[q] + dvx[q]) * DG_DAMP;
+                b.uyt[4 * e + q] = (me.uy[q] + dvy[q]) * DG_DAMP;
+            }
+        }
+        flags |= fl2;
+    }
+    // sums of squares of this CTA in a fixed order: lanes (xor tree), then warps
+#pragma unroll
+    for (int q = 0; q < 12; q++) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) sq[q] += __shfl_xor_sync(0xffffffffu, sq[q], s);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 12; q++) red[warp][q] = sq[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        double s = 0.0;
+        for (int w = 0; w < DG_THREADS / 32; w++) s += red[w][threadIdx.x];
+        if (isnan(s)) flags |= FLAG_NAN;
+        d.partials[12 * (long long)(b.dg_tile0 + blockIdx.x) + threadIdx.x] = s;
+    }
+    if (flags) atomicOr(a.flags, flags);
+}
+
+// ------------------------------------------------------------------ slope limiter (main.cpp:427-461)
+__device__ __forceinline__ double dg_sign(double x) { return signbit(x) ? -1.0 : 1.0; }   // Indexing.h:22
+
+template <bool FAITHFUL>
+__global__ void __launch_bounds__(DG_THREADS) dg_limit_kernel(StepArgs a, DgArgs d) {
+    if (*a.stop) return;
+    const BlockDev& b = a.blocks[blockIdx.y];
+    const int ncx = b.ncx;
+    const long long ncell = (long long)ncx * b.ncy;
+    const long long e = (long long)blockIdx.x * DG_THREADS + threadIdx.x;
+    if (e >= ncell) return;
+    // a.cur was the buffer read by the step: OLD means there, NEW means in the other one.  The reference updates
+    // cell after cell in memory order, so a cell sees new means behind it (e-1, e-ncx) and old ones ahead
+    const double* Sold = b.state[a.cur];
+    const double* Snew = b.state[a.cur ^ 1];
+    auto off = [&](long long c) { return (long long)(c / ncx + 1) * b.pitch + COL0 + (c % ncx); };
+    const long long om = off(e);
+    const bool has_ip = e + 1 < ncell, has_im = e - 1 >= 0, has_jp = e + ncx < ncell, has_jm = e - ncx >= 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const double me = Snew[q * b.plane + om];
+        double ux = b.uxt[4 * e + q], uy = b.uyt[4 * e + q];
+        double du;
+        if (has_ip && has_im) du = DG_DUSCALE * ((Sold[q * b.plane + off(e + 1)] - Snew[q * b.plane + off(e - 1)]) / 2.0);
+        else if (!has_im) du = DG_DUSCALE * ((Sold[q * b.plane + off(e + 1)] - me) / 1.0);
+        else du = DG_DUSCALE * ((me - Snew[q * b.plane + off(e - 1)]) / 1.0);
+        ux = dg_sign(ux) * fmin(fabs(ux), fabs(du));
+        if (has_jp && has_jm) du = DG_DUSCALE * ((Sold[q * b.plane + off(e + ncx)] - Snew[q * b.plane + off(e - ncx)]) / 2.0);
+        else if (!has_jm) du = DG_DUSCALE * ((Sold[q * b.plane + off(e + ncx)] - me) / 1.0);
+        else du = DG_DUSCALE * ((me - Snew[q * b.plane + off(e - ncx)]) / 1.0);
+        uy = dg_sign(uy) * fmin(fabs(uy), fabs(du));
+        b.ux[4 * e + q] = ux;
+        b.uy[4 * e + q] = uy;
+    }
+}
+
+}  // namespace par2d

@@ -18,6 +18,7 @@
 #include "physics.cuh"
 #include "march.cuh"
 #include "kernels_common.cuh"
+#include "dg.cuh"
 
 namespace par2d {
 
@@ -296,6 +297,9 @@ struct KernelTable {
     void (*ghost)(cudaStream_t, const StepArgs&, const Gas&, int write_dt, const FinalizeArgs* pending);
     void (*pack)(cudaStream_t, const StepArgs&, const Gas&, const SendLine*, int nlines, int max_n, const PutArgs&);
     void (*march)(cudaStream_t, const StepArgs&, const Gas&, bool tpg, bool axi);
+    void (*dg_ghost)(cudaStream_t, const StepArgs&, const Gas&, const DgArgs&);
+    void (*dg_cell)(cudaStream_t, const StepArgs&, const Gas&, const DgArgs&, bool tpg, bool axi);
+    void (*dg_limit)(cudaStream_t, const StepArgs&, const DgArgs&);
     void (*test_ldfss)(cudaStream_t, const Gas&, bool tpg, bool axi, long long n, const double*, const double*, const double*, double*, double*);
     void (*test_boundary)(cudaStream_t, const Gas&, long long n, const int*, const double*, const double*, double*);
     void (*test_update_state)(cudaStream_t, const Gas&, bool tpg, long long n, double*, double*);
@@ -326,6 +330,18 @@ struct Launch {
         dim3 grid((unsigned)((max_n + 255) / 256 > 0 ? (max_n + 255) / 256 : 1), (unsigned)(nlines > 0 ? nlines : 1));
         pack_kernel<FAITHFUL><<<grid, 256, 0, s>>>(a, g, lines, nlines, put);
     }
+    // second-order branch (dg.cuh)
+    static void dg_ghost(cudaStream_t s, const StepArgs& a, const Gas& g, const DgArgs& d) {
+        dg_ghost_kernel<FAITHFUL><<<dim3((d.max_points + 255) / 256, a.nowned), 256, 0, s>>>(a, g, d, 0);
+    }
+    static void dg_cell(cudaStream_t s, const StepArgs& a, const Gas& g, const DgArgs& d, bool tpg, bool axi) {
+        const dim3 grid(d.max_tiles, a.nowned);
+        if (tpg) { if (axi) dg_cell_kernel<FAITHFUL, true, true><<<grid, DG_THREADS, 0, s>>>(a, g, d); else dg_cell_kernel<FAITHFUL, true, false><<<grid, DG_THREADS, 0, s>>>(a, g, d); }
+        else { if (axi) dg_cell_kernel<FAITHFUL, false, true><<<grid, DG_THREADS, 0, s>>>(a, g, d); else dg_cell_kernel<FAITHFUL, false, false><<<grid, DG_THREADS, 0, s>>>(a, g, d); }
+    }
+    static void dg_limit(cudaStream_t s, const StepArgs& a, const DgArgs& d) {
+        dg_limit_kernel<FAITHFUL><<<dim3(d.max_tiles, a.nowned), DG_THREADS, 0, s>>>(a, d);
+    }
     static void test_ldfss(cudaStream_t s, const Gas& g, bool tpg, bool axi, long long n, const double* face, const double* uL, const double* uR, double* flux, double* parr) {
         const int grid = (int)((n + 127) / 128);
         if (tpg) { if (axi) test_ldfss_kernel<FAITHFUL, true, true><<<grid, 128, 0, s>>>(g, n, face, uL, uR, flux, parr); else test_ldfss_kernel<FAITHFUL, true, false><<<grid, 128, 0, s>>>(g, n, face, uL, uR, flux, parr); }
@@ -345,7 +361,7 @@ struct Launch {
         else { if (axi) test_solve_kernel<FAITHFUL, false, true><<<grid, 128, 0, s>>>(g, n, dy, unk, res, dv); else test_solve_kernel<FAITHFUL, false, false><<<grid, 128, 0, s>>>(g, n, dy, unk, res, dv); }
     }
     static const KernelTable* table() {
-        static const KernelTable t = {&ghost, &pack, &march, &test_ldfss, &test_boundary, &test_update_state, &test_solve};
+        static const KernelTable t = {&ghost, &pack, &march, &dg_ghost, &dg_cell, &dg_limit, &test_ldfss, &test_boundary, &test_update_state, &test_solve};
         return &t;
     }
 };

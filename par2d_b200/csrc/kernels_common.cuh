@@ -15,22 +15,39 @@ namespace par2d {
 __device__ __forceinline__ void finalize_block(const FinalizeArgs& a, int k, double (*red)[4], bool* last) {
     const int tid = threadIdx.x;
     const BlockDev& b = a.blocks[k];
-    const int ntiles = b.tiles_x * b.tiles_y;
-    double s[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int t = tid; t < ntiles; t += 256) {
-        const double2* p = reinterpret_cast<const double2*>(a.partials + 4 * (long long)(b.tile0 + t));
-        const double2 p0 = __ldcg(p), p1 = __ldcg(p + 1);
-        s[0] += p0.x; s[1] += p0.y; s[2] += p1.x; s[3] += p1.y;
-    }
-    for (int v = 0; v < 4; v++) red[tid][v] = s[v];
-    __syncthreads();
-    for (int w = 128; w > 0; w >>= 1) {
-        if (tid < w)
-            for (int v = 0; v < 4; v++) red[tid][v] += red[tid + w][v];
+    double norm[4] = {0.0, 0.0, 0.0, 0.0};   // thread 0: the block's norms
+    // first order: one group of 4 sums; second-order branch: three groups (dudt, duxdt, duydt) whose square roots
+    // are added as main.cpp:360-364 does, ressum + (ressumx + ressumy)
+    const int ngroups = a.dg_partials ? 3 : 1;
+    double parked[4] = {0.0, 0.0, 0.0, 0.0};   // thread 0: ressumx while ressumy is being reduced
+    for (int grp = 0; grp < ngroups; grp++) {
+        const int ntiles = a.dg_partials ? b.dg_ntiles : b.tiles_x * b.tiles_y;
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int t = tid; t < ntiles; t += 256) {
+            const double2* p = a.dg_partials ? reinterpret_cast<const double2*>(a.dg_partials + 12 * (long long)(b.dg_tile0 + t) + 4 * grp)
+                                             : reinterpret_cast<const double2*>(a.partials + 4 * (long long)(b.tile0 + t));
+            const double2 p0 = __ldcg(p), p1 = __ldcg(p + 1);
+            s[0] += p0.x; s[1] += p0.y; s[2] += p1.x; s[3] += p1.y;
+        }
         __syncthreads();
+        for (int v = 0; v < 4; v++) red[tid][v] = s[v];
+        __syncthreads();
+        for (int w = 128; w > 0; w >>= 1) {
+            if (tid < w)
+                for (int v = 0; v < 4; v++) red[tid][v] += red[tid + w][v];
+            __syncthreads();
+        }
+        if (tid == 0) {
+            for (int v = 0; v < 4; v++) {
+                const double rt = sqrt(red[0][v]);
+                if (grp == 0) norm[v] = rt;
+                else if (grp == 1) parked[v] = rt;
+                else norm[v] = norm[v] + (parked[v] + rt);
+            }
+        }
     }
     if (tid == 0) {
-        for (int v = 0; v < 4; v++) a.blk_norm[4 * k + v] = sqrt(red[0][v]);
+        for (int v = 0; v < 4; v++) a.blk_norm[4 * k + v] = norm[v];
         __threadfence();
         *last = atomicAdd(a.ticket, 1u) == (unsigned)(a.nowned - 1);
     }
