@@ -67,6 +67,13 @@ int par2d_thermo_load(const char* path, par2d_config* cfg);
 int par2d_write_solution(const char* path, const char* title, const par2d_config* cfg,
                          int32_t nx, int32_t ny, const double* x, const double* y, const double* unk);
 
+/* Output of the second-order branch, byte format of print_state_DGP1 (FV/FileIO.cpp:117-217; the reference names
+ * the file ../Outputs/time/solution.b%03d.it%05d.tec): rho,u,v,T of the DG(P1) representation averaged at the
+ * nx x ny NODES, then p, c, M of that state. */
+int par2d_write_solution_dgp1(const char* path, const char* title, const par2d_config* cfg, int32_t nx, int32_t ny,
+                              const double* x, const double* y, const double* unk, const double* ux, const double* uy,
+                              int32_t iter, double time);
+
 /* Restart reader for the same file format (the reference writes these files, FV/FileIO.cpp:78-116,
  * but cannot read them back): fills unk[(j*(nx-1)+i)*4+k] = rho,u,v,T and, when non-null,
  * the cell centroids xc/yc[(j*(nx-1)+i)].  The zone header must match nx-1 x ny-1 cells. */

@@ -129,6 +129,7 @@ HOST_API = {
     "par2d_case_free": (None, [C.c_void_p]),
     "par2d_thermo_load": (C.c_int, [C.c_char_p, _CFGP]),
     "par2d_write_solution": (C.c_int, [C.c_char_p, C.c_char_p, _CFGP, C.c_int32, C.c_int32, _DP, _DP, _DP]),
+    "par2d_write_solution_dgp1": (C.c_int, [C.c_char_p, C.c_char_p, _CFGP, C.c_int32, C.c_int32, _DP, _DP, _DP, _DP, _DP, C.c_int32, C.c_double]),
     "par2d_read_solution": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, _DP, _DP, _DP]),
     "par2d_host_last_error": (C.c_char_p, []),
 }

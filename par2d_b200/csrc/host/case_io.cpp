@@ -404,6 +404,46 @@ int par2d_write_solution(const char* path, const char* title, const par2d_config
     return 0;
 }
 
+// print_state_DGP1 (FV/FileIO.cpp:117-217): node values of the DG(P1) representation - every node takes the mean
+// of the standard reconstruction unk + xsi*ux + eta*uy of its 1, 2 or 4 adjacent cells at the corner facing it.
+int par2d_write_solution_dgp1(const char* path, const char* title, const par2d_config* cfg, int32_t nx, int32_t ny,
+                              const double* x, const double* y, const double* unk, const double* ux, const double* uy,
+                              int32_t iter, double time) {
+    if (!path || !cfg || !x || !y || !unk || !ux || !uy) return host_fail(PAR2D_ERR_ARG, "write_solution_dgp1: null argument");
+    FILE* f = fopen(path, "w");
+    if (!f) return host_fail(PAR2D_ERR_ARG, "cannot write %s", path);
+    fprintf(f, "TITLE = \"%s\"\n", title ? title : "");
+    fprintf(f, "VARIABLES = \"X\", \"Y\", \"rho\", \"u\", \"v\", \"T\", \"p\", \"c\", \"M\"\n");
+    fprintf(f, "ZONE I=%d, J=%d, DATAPACKING=POINT, STRANDID=%d, SOLUTIONTIME=%lf\n", nx, ny, iter, time);
+    const double gam = fabs(cfg->igam);
+    const int ncx = nx - 1, ncy = ny - 1;
+    auto recon = [&](int ci, int cj, double xsi, double eta, double* out) {
+        const size_t e = 4 * ((size_t)cj * ncx + ci);
+        for (int k = 0; k < 4; k++) out[k] = unk[e + k] + (xsi * ux[e + k]) + (eta * uy[e + k]);
+    };
+    for (int j = 0; j < ny; j++)
+        for (int i = 0; i < nx; i++) {
+            // adjacent cells in the reference's order: pp (i,j), pm (i,j-1), mp (i-1,j), mm (i-1,j-1)
+            const int ci[4] = {i, i, i - 1, i - 1}, cj[4] = {j, j - 1, j, j - 1};
+            const double xs[4] = {-1.0, -1.0, 1.0, 1.0}, et[4] = {-1.0, 1.0, -1.0, 1.0};
+            double t[4][4], u[4];
+            int n = 0;
+            for (int q = 0; q < 4; q++)
+                if (ci[q] >= 0 && ci[q] < ncx && cj[q] >= 0 && cj[q] < ncy) recon(ci[q], cj[q], xs[q], et[q], t[n++]);
+            for (int k = 0; k < 4; k++)
+                u[k] = n == 1 ? t[0][k] : n == 2 ? 0.5 * (t[0][k] + t[1][k]) : 0.25 * (t[0][k] + t[1][k] + t[2][k] + t[3][k]);
+            u[3] = fmax(u[3], 201.0);
+            const double p = fmax(u[0] * cfg->Rs * u[3], 1.0);
+            const double a = sqrt(gam * cfg->Rs * u[3]);
+            const double M = sqrt(u[1] * u[1] + u[2] * u[2]) / a;
+            const size_t nd = (size_t)j * nx + i;
+            fprintf(f, "%.16e,\t %.16e,\t %.16e,\t %.16e,\t %.16e,\t %.16e,\t %.16e,\t %.16e,\t %.16e \n", x[nd], y[nd], u[0], u[1], u[2],
+                    u[3], p, a, M);
+        }
+    fclose(f);
+    return 0;
+}
+
 // Restart reader (the reference has none): parses a solution.b<N>.tec written by print_state
 // (FV/FileIO.cpp:84-115) or by par2d_write_solution back into the state layout unk[(j*(nx-1)+i)*4+k].
 // The zone header must match the block's cell counts; %.16e round-trips every double exactly.

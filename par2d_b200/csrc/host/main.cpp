@@ -23,7 +23,8 @@
 static void usage() {
     printf("usage: par2d_fv --case DIR [--out DIR] [--therm FILE] [--niter N] [--iaxi 0|1] [--igam G]\n"
            "                [--cfl C] [--tol T] [--printiter N] [--saveiter N] [--batch N] [--faithful]\n"
-           "                [--restart DIR]   start from DIR/solution.b<b+1>.tec instead of the uniform state\n");
+           "                [--restart DIR]   start from DIR/solution.b<b+1>.tec instead of the uniform state\n"
+           "                [--accur 0|1]     1: the DG(P1) second-order branch (ACCUR, FV/Indexing.h:17)\n");
 }
 
 int main(int argc, char** argv) {
@@ -48,6 +49,7 @@ int main(int argc, char** argv) {
         else if (a == "--batch") batch = atoi(next());
         else if (a == "--faithful") cfg.mode = PAR2D_MODE_FAITHFUL;
         else if (a == "--restart") restart_dir = next();
+        else if (a == "--accur") cfg.accur = atoi(next());
         else { usage(); return 2; }
     }
     if (batch < 1) batch = 1;
@@ -77,10 +79,22 @@ int main(int argc, char** argv) {
         printf("restarted from %s\n", restart_dir.c_str());
     }
 
+    double sim_time = 0.0;   // time += dt, main.cpp:293
+    long iter = 0;
     auto save = [&](const char* title) {
         for (int b = 0; b < nb; b++) {
             std::vector<double> unk((size_t)4 * (blocks[b].nx - 1) * (blocks[b].ny - 1));
             if (par2d_get_state(ctx, b, unk.data())) { printf("get_state: %s\n", par2d_last_error()); exit(1); }
+            if (cfg.accur == 1) {   // print_state_DGP1, main.cpp:215-217,486-487,541-542
+                std::vector<double> ux(unk.size()), uy(unk.size());
+                if (par2d_get_slopes(ctx, b, ux.data(), uy.data())) { printf("get_slopes: %s\n", par2d_last_error()); exit(1); }
+                char name[64];
+                snprintf(name, sizeof name, "/solution.b%03d.it%05ld.tec", b + 1, iter);
+                if (par2d_write_solution_dgp1((out_dir + name).c_str(), title, &cfg, blocks[b].nx, blocks[b].ny, blocks[b].x, blocks[b].y,
+                                              unk.data(), ux.data(), uy.data(), (int)iter, sim_time))
+                    printf("%s\n", par2d_host_last_error());
+                continue;
+            }
             const std::string path = out_dir + "/solution.b" + std::to_string(b + 1) + ".tec";  // bnum+1, FileIO.cpp:84
             if (par2d_write_solution(path.c_str(), title, &cfg, blocks[b].nx, blocks[b].ny, blocks[b].x, blocks[b].y, unk.data()))
                 printf("%s\n", par2d_host_last_error());
@@ -95,7 +109,6 @@ int main(int argc, char** argv) {
 
     printf("==================== Starting Solver ====================\n");
     std::vector<par2d_step_info> info(batch);
-    long iter = 0;
     bool converged = false;
     int rc = 0;
     while (iter < niter && !converged) {
@@ -113,6 +126,7 @@ int main(int argc, char** argv) {
             if (info[s].iter % printiter == 0)
                 printf("Iter:%7d\tdt:%7.4e \t\t RelativeTotalResisual:  %8.5e \n", (int)info[s].iter, info[s].dt, info[s].relres);
             iter = info[s].iter + 1;
+            sim_time += info[s].dt;
             if (nb > 1 && info[s].relres < cfg.tol) { converged = true; break; }
         }
         if (rc) { printf("Failed Assert on the device: %s\n", par2d_last_error()); break; }

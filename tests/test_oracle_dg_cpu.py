@@ -95,3 +95,28 @@ def _single_block_case(directory, x, y, ibound):
         for c in ibound:
             f.write("%d\n" % c)
     return Case.load(str(directory))
+
+
+def test_dgp1_writer_reproduces_the_references_nodal_file(oracle, tmp_path):
+    """par2d_write_solution_dgp1 (print_state_DGP1, FileIO.cpp:117-217): the values it writes for the state the
+    port reaches after the golden's N steps are the reference file's, digit for digit (%.16e)."""
+    import ctypes as C
+    from par2d_b200 import _capi
+    g, case, s, info = dg.run_golden(oracle, "Case_rktnoz9", "dgp1_axi_tpg")
+    host = _capi.load_host()
+    dp = C.POINTER(C.c_double)
+    for b in (0, 4, 8):
+        nx, ny = case.shape(b)
+        x, y = case.nodes(b)
+        unk = s.get_state(b)
+        ux, uy = s.get_slopes(b)
+        path = str(tmp_path / ("solution.b%03d.it%05d.tec" % (b + 1, len(info))))
+        host.check(host.par2d_write_solution_dgp1(path.encode(), b"Final State", C.byref(s.cfg), nx, ny, x.ctypes.data_as(dp),
+                                                  y.ctypes.data_as(dp), unk.ctypes.data_as(dp), ux.ctypes.data_as(dp),
+                                                  uy.ctypes.data_as(dp), len(info), sum(i.dt for i in info)), "write_solution_dgp1")
+        with open(path) as f:
+            head = [next(f) for _ in range(3)]
+            data = np.loadtxt(f, delimiter=",")
+        assert head[2].startswith("ZONE I=%d, J=%d, DATAPACKING=POINT, STRANDID=%d, SOLUTIONTIME=" % (nx, ny, len(info)))
+        assert np.array_equal(data[:, 2:6].reshape(ny, nx, 4), g[f"n{b}"])
+        assert np.array_equal(data[:, 0].reshape(ny, nx), x) and np.array_equal(data[:, 1].reshape(ny, nx), y)
