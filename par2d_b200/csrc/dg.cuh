@@ -17,8 +17,9 @@
 //                     mean of the cells after it in memory order and the NEW mean of the cells before it
 //                     (both state buffers are at hand), including the row wrap of its flat-index tests
 // This first version favours exactness over speed: every interior face flux is evaluated by both adjacent
-// cells, with the reference's divisions.  Both arithmetic modes share the formulation; MODE_FAST only adds
-// FMA contraction.  Single rank (nranks == 1); any number of blocks per GPU.
+// cells.  PAR2D_MODE_FAITHFUL keeps the reference's operation order and divisions; PAR2D_MODE_FAST uses the lean
+// LDFSS / state / solve of physics.cuh on interior faces (boundary faces, whose blended normals are not unit
+// vectors, keep the general form).  Single rank (nranks == 1); any number of blocks per GPU.
 #pragma once
 #include "common.cuh"
 #include "physics.cuh"
@@ -55,22 +56,26 @@ __device__ __forceinline__ void dg_load_cell(const Gas& g, const BlockDev& b, in
 }
 
 // get_u_val, DGP1Tools.cpp:10-37: the density is extrapolated through the pressure
+template <bool FAITHFUL = true>
 __device__ __forceinline__ void dg_u_val(const Gas& g, const DgCell& c, double xsi, double eta, double out[4]) {
     const double dpdxsi = c.ux[0] * g.Rs * c.u[3] + c.u[0] * g.Rs * c.ux[3];
     const double dpdeta = c.uy[0] * g.Rs * c.u[3] + c.u[0] * g.Rs * c.uy[3];
     const double pout = c.p + (xsi * dpdxsi) + (eta * dpdeta);
-    out[0] = pout / (g.Rs * (c.u[3] + (xsi * c.ux[3]) + (eta * c.uy[3])));
+    if constexpr (FAITHFUL) out[0] = pout / (g.Rs * (c.u[3] + (xsi * c.ux[3]) + (eta * c.uy[3])));
+    else out[0] = pout * fast_rcp(g.Rs * (c.u[3] + (xsi * c.ux[3]) + (eta * c.uy[3])));
 #pragma unroll
     for (int k = 1; k < 4; k++) out[k] = c.u[k] + (xsi * c.ux[k]) + (eta * c.uy[k]);
 }
 
 // the reconstructed state at a Gauss point, UpdateState'd (T clamp, StateVariables.h:38-68)
-template <bool TPG>
+// FAITHFUL = false: the lean state of physics.cuh (a/2 carried, series sqrt), for the lean LDFSS of interior faces
+template <bool FAITHFUL, bool TPG>
 __device__ __forceinline__ FaceState dg_point_state(const Gas& g, const DgCell& c, double xsi, double eta, unsigned& flags) {
     double u[4];
-    dg_u_val(g, c, xsi, eta, u);
-    u[3] = fmax(u[3], 201.0);
-    return face_state<true, TPG>(g, u[0], u[1], u[2], u[3], flags);
+    dg_u_val<FAITHFUL>(g, c, xsi, eta, u);
+    if constexpr (FAITHFUL) u[3] = fmax(u[3], 201.0);
+    else u[3] = max_sel(u[3], 201.0);
+    return face_state<FAITHFUL, TPG>(g, u[0], u[1], u[2], u[3], flags);
 }
 
 struct DgAcc {
@@ -99,7 +104,7 @@ __device__ __forceinline__ void dg_accumulate(DgAcc& a, const Flux& F, double yc
 }
 
 // DGP1_xsi_face_integral (dir 0) / DGP1_eta_face_integral (dir 1), the part that lands in one cell
-template <bool TPG, bool AXI>
+template <bool FAITHFUL, bool TPG, bool AXI>
 __device__ __forceinline__ void dg_face(const Gas& g, const FaceGeom& fg, const DgCell& L, const DgCell& R, int dir, bool mine_is_left,
                                         double yc, DgAcc& a, unsigned& flags) {
     const double G = dg_gauss();
@@ -109,9 +114,9 @@ __device__ __forceinline__ void dg_face(const Gas& g, const FaceGeom& fg, const 
         double xsiL, etaL, xsiR, etaR;
         if (dir == 0) { xsiL = 1.0; xsiR = -1.0; etaL = etaR = s; }
         else { etaL = -1.0; etaR = 1.0; xsiL = xsiR = s; }
-        const FaceState sl = dg_point_state<TPG>(g, L, xsiL, etaL, flags);
-        const FaceState sr = dg_point_state<TPG>(g, R, xsiR, etaR, flags);
-        const Flux F = ldfss<true, AXI>(fg, sl, sr);
+        const FaceState sl = dg_point_state<FAITHFUL, TPG>(g, L, xsiL, etaL, flags);
+        const FaceState sr = dg_point_state<FAITHFUL, TPG>(g, R, xsiR, etaR, flags);
+        const Flux F = ldfss<FAITHFUL, AXI>(fg, sl, sr);
         if (isnan(F.f0 + F.f1 + F.f2 + F.f3)) flags |= FLAG_NAN;
         if (mine_is_left) dg_accumulate<AXI>(a, F, yc, true, xsiL, etaL);
         else dg_accumulate<AXI>(a, F, yc, false, xsiR, etaR);
@@ -146,7 +151,7 @@ __device__ __forceinline__ void dg_boundary_face(const Gas& g, const BlockDev& b
         f2.ny = (1.0 - 0.5 * temp) * fg.ny + 0.5 * temp * (pt == 0 ? nRy : nLy);
         const double* e = gh + 4 * (2 * (long long)n + pt);
         const FaceState ex = face_state<true, TPG>(g, e[0], e[1], e[2], e[3], flags);   // ghosts are stored clamped
-        const FaceState si = dg_point_state<TPG>(g, in, xsi, eta, flags);
+        const FaceState si = dg_point_state<true, TPG>(g, in, xsi, eta, flags);   // blended, non-unit normals: the general form in both modes
         Flux F;
         if (type == 1 || type == 2) F = ldfss<true, AXI>(f2, si, ex);
         else F = ldfss<true, AXI>(f2, ex, si);
@@ -296,20 +301,20 @@ __global__ void __launch_bounds__(DG_THREADS) dg_cell_kernel(StepArgs a, Gas g, 
         // interior xi faces (SpatialDiscretization.cpp:481-552): face i (this cell is the right one), face i+1 (left)
         if (i >= 1) {
             dg_load_cell(g, b, a.cur, i - 1, j, nb);
-            dg_face<TPG, AXI>(g, face_geom<true>(xa, ya, xd, yd), nb, me, 0, false, ycs, acc, flags);
+            dg_face<FAITHFUL, TPG, AXI>(g, face_geom<FAITHFUL>(xa, ya, xd, yd), nb, me, 0, false, ycs, acc, flags);
         }
         if (i <= ncx - 2) {
             dg_load_cell(g, b, a.cur, i + 1, j, nb);
-            dg_face<TPG, AXI>(g, face_geom<true>(xb, yb, xc, yc_), me, nb, 0, true, ycs, acc, flags);
+            dg_face<FAITHFUL, TPG, AXI>(g, face_geom<FAITHFUL>(xb, yb, xc, yc_), me, nb, 0, true, ycs, acc, flags);
         }
         // interior eta faces (:556-625): face j (this cell is the left = upper one), face j+1 (right = lower)
         if (j >= 1) {
             dg_load_cell(g, b, a.cur, i, j - 1, nb);
-            dg_face<TPG, AXI>(g, face_geom<true>(xa, ya, xb, yb), me, nb, 1, true, ycs, acc, flags);
+            dg_face<FAITHFUL, TPG, AXI>(g, face_geom<FAITHFUL>(xa, ya, xb, yb), me, nb, 1, true, ycs, acc, flags);
         }
         if (j <= ncy - 2) {
             dg_load_cell(g, b, a.cur, i, j + 1, nb);
-            dg_face<TPG, AXI>(g, face_geom<true>(xd, yd, xc, yc_), nb, me, 1, false, ycs, acc, flags);
+            dg_face<FAITHFUL, TPG, AXI>(g, face_geom<FAITHFUL>(xd, yd, xc, yc_), nb, me, 1, false, ycs, acc, flags);
         }
         // boundary faces (:643-977).  fNormalL / fNormalR are declared once per row (column) and shared by the
         // left and right (bottom and top) face of it: at the ends of the right (top) side they still hold the
@@ -356,15 +361,24 @@ __global__ void __launch_bounds__(DG_THREADS) dg_cell_kernel(StepArgs a, Gas g, 
             const double yL = 0.5 * (yd + ya), yR = 0.5 * (yc_ + yb), yD = 0.5 * (yb + ya), yU = 0.5 * (yc_ + yd);
             const double nxs0 = -0.5 * (yU - yD), nxs1 = 0.5 * (xU - xD);
             const double nxs2 = -0.25 * ((xU - xD) * (yL - yR) - (yU - yD) * (xL - xR));
-            const double db1dx = nxs0 / nxs2, db1dy = nxs1 / nxs2;
+            double db1dx, db1dy, db2dx, db2dy, ivol = 0.0;
+            if constexpr (FAITHFUL) { db1dx = nxs0 / nxs2; db1dy = nxs1 / nxs2; }
+            else { const double q2 = fast_rcp(nxs2); db1dx = nxs0 * q2; db1dy = nxs1 * q2; ivol = fast_rcp(vol); }
             const double net0 = -0.5 * (yL - yR), net1 = 0.5 * (xL - xR);
             const double net2 = -0.25 * ((xL - xR) * (yD - yU) - (yL - yR) * (xD - xU));
-            const double db2dx = net0 / net2, db2dy = net1 / net2;
+            if constexpr (FAITHFUL) { db2dx = net0 / net2; db2dy = net1 / net2; }
+            else { const double q2 = fast_rcp(net2); db2dx = net0 * q2; db2dy = net1 * q2; }
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                r[q] = acc.r[q] / vol;
-                rx[q] = 3.0 * acc.rx[q] / vol;
-                ry[q] = 3.0 * acc.ry[q] / vol;
+                if constexpr (FAITHFUL) {
+                    r[q] = acc.r[q] / vol;
+                    rx[q] = 3.0 * acc.rx[q] / vol;
+                    ry[q] = 3.0 * acc.ry[q] / vol;
+                } else {
+                    r[q] = acc.r[q] * ivol;
+                    rx[q] = 3.0 * acc.rx[q] * ivol;
+                    ry[q] = 3.0 * acc.ry[q] * ivol;
+                }
                 rx[q] += 3.0 * (Fx[q] * db1dx + Fy[q] * db1dy);
                 ry[q] += 3.0 * (Fx[q] * db2dx + Fy[q] * db2dy);
             }
@@ -383,9 +397,18 @@ __global__ void __launch_bounds__(DG_THREADS) dg_cell_kernel(StepArgs a, Gas g, 
             const double e0 = enthalpy<TPG>(g, me.u[3], fl2) - g.Rs * me.u[3] + 0.5 * v2;
             const double Cv = heat_capacity<TPG>(g, me.u[3], fl2) - g.Rs;
             double dv[4], dvx[4], dvy[4];
-            solve_cell<true, AXI>(dt, ycc, me.u[0], me.u[1], me.u[2], e0, Cv, 0.0, r, dv, flags);
-            solve_cell<true, AXI>(dt, ycc, me.u[0], me.u[1], me.u[2], e0, Cv, 0.0, rx, dvx, flags);
-            solve_cell<true, AXI>(dt, ycc, me.u[0], me.u[1], me.u[2], e0, Cv, 0.0, ry, dvy, flags);
+            if constexpr (FAITHFUL) {
+                solve_cell<true, AXI>(dt, ycc, me.u[0], me.u[1], me.u[2], e0, Cv, 0.0, r, dv, flags);
+                solve_cell<true, AXI>(dt, ycc, me.u[0], me.u[1], me.u[2], e0, Cv, 0.0, rx, dvx, flags);
+                solve_cell<true, AXI>(dt, ycc, me.u[0], me.u[1], me.u[2], e0, Cv, 0.0, ry, dvy, flags);
+            } else {
+                // D is lower triangular: closed-form forward substitution, one reciprocal of rho for the three systems
+                const double sc = AXI ? dt * fast_rcp(ycc) : dt;
+                const double inv_cv = fast_rcp(Cv);
+                solve_lean(sc, me.u[0], me.u[1], me.u[2], e0, inv_cv, r, dv);
+                solve_lean(sc, me.u[0], me.u[1], me.u[2], e0, inv_cv, rx, dvx);
+                solve_lean(sc, me.u[0], me.u[1], me.u[2], e0, inv_cv, ry, dvy);
+            }
             double* So = b.state[a.cur ^ 1];
             const long long o = (long long)(j + 1) * b.pitch + COL0 + i;
             double nu[4];
