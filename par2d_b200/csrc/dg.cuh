@@ -29,6 +29,9 @@ namespace par2d {
 constexpr double DG_DAMP = 0.9;       // main.cpp:92
 constexpr double DG_DUSCALE = 0.5;    // main.cpp:93
 constexpr int DG_THREADS = 128;
+#ifndef DG_MINB
+#define DG_MINB 3      // CTAs per SM the cell kernel is compiled for (register budget 65536 / (128 * DG_MINB))
+#endif
 
 struct DgArgs {
     double* partials;    // [dg tiles][12]: sum of squares of dudt, duxdt, duydt per CTA
@@ -103,23 +106,33 @@ __device__ __forceinline__ void dg_accumulate(DgAcc& a, const Flux& F, double yc
     }
 }
 
-// DGP1_xsi_face_integral (dir 0) / DGP1_eta_face_integral (dir 1), the part that lands in one cell
+// DGP1_xsi_face_integral (dir 0) / DGP1_eta_face_integral (dir 1), the part that lands in one cell: `me` is the
+// face's left cell when mine_is_left, `nb` the cell across.  One body for the four faces of a cell (the caller
+// loops over them without unrolling: the kernel is instruction-cache and register bound otherwise).
 template <bool FAITHFUL, bool TPG, bool AXI>
-__device__ __forceinline__ void dg_face(const Gas& g, const FaceGeom& fg, const DgCell& L, const DgCell& R, int dir, bool mine_is_left,
+__device__ __forceinline__ void dg_face(const Gas& g, const FaceGeom& fg, const DgCell& me, const DgCell& nb, int dir, bool mine_is_left,
                                         double yc, DgAcc& a, unsigned& flags) {
     const double G = dg_gauss();
-#pragma unroll
+#pragma unroll 1
     for (int pt = 0; pt < 2; pt++) {
         const double s = pt == 0 ? G : -G;
         double xsiL, etaL, xsiR, etaR;
         if (dir == 0) { xsiL = 1.0; xsiR = -1.0; etaL = etaR = s; }
         else { etaL = -1.0; etaR = 1.0; xsiL = xsiR = s; }
-        const FaceState sl = dg_point_state<FAITHFUL, TPG>(g, L, xsiL, etaL, flags);
-        const FaceState sr = dg_point_state<FAITHFUL, TPG>(g, R, xsiR, etaR, flags);
+        const double xm = mine_is_left ? xsiL : xsiR, em = mine_is_left ? etaL : etaR;
+        const double xo = mine_is_left ? xsiR : xsiL, eo = mine_is_left ? etaR : etaL;
+        const FaceState sm = dg_point_state<FAITHFUL, TPG>(g, me, xm, em, flags);
+        const FaceState so = dg_point_state<FAITHFUL, TPG>(g, nb, xo, eo, flags);
+        FaceState sl, sr;
+        sl.rho = mine_is_left ? sm.rho : so.rho; sr.rho = mine_is_left ? so.rho : sm.rho;
+        sl.u = mine_is_left ? sm.u : so.u;       sr.u = mine_is_left ? so.u : sm.u;
+        sl.v = mine_is_left ? sm.v : so.v;       sr.v = mine_is_left ? so.v : sm.v;
+        sl.p = mine_is_left ? sm.p : so.p;       sr.p = mine_is_left ? so.p : sm.p;
+        sl.a = mine_is_left ? sm.a : so.a;       sr.a = mine_is_left ? so.a : sm.a;
+        sl.h0 = mine_is_left ? sm.h0 : so.h0;    sr.h0 = mine_is_left ? so.h0 : sm.h0;
         const Flux F = ldfss<FAITHFUL, AXI>(fg, sl, sr);
         if (isnan(F.f0 + F.f1 + F.f2 + F.f3)) flags |= FLAG_NAN;
-        if (mine_is_left) dg_accumulate<AXI>(a, F, yc, true, xsiL, etaL);
-        else dg_accumulate<AXI>(a, F, yc, false, xsiR, etaR);
+        dg_accumulate<AXI>(a, F, yc, mine_is_left, xm, em);
     }
 }
 
@@ -137,7 +150,7 @@ __device__ __forceinline__ void dg_boundary_face(const Gas& g, const BlockDev& b
                                                  double nLx, double nLy, double nRx, double nRy, double yc, DgAcc& a, unsigned& flags) {
     const double G = dg_gauss();
     const double* gh = b.ghost2[side];
-#pragma unroll
+#pragma unroll 1
     for (int pt = 0; pt < 2; pt++) {
         const double s = pt == 0 ? G : -G;
         double xsi, eta;
@@ -261,7 +274,7 @@ __global__ void __launch_bounds__(256) dg_ghost_kernel(StepArgs a, Gas g, DgArgs
 
 // ------------------------------------------------------------------ residual + solve + update of the means
 template <bool FAITHFUL, bool TPG, bool AXI>
-__global__ void __launch_bounds__(DG_THREADS) dg_cell_kernel(StepArgs a, Gas g, DgArgs d) {
+__global__ void __launch_bounds__(DG_THREADS, DG_MINB) dg_cell_kernel(StepArgs a, Gas g, DgArgs d) {
     __shared__ double red[DG_THREADS / 32][12];
     if (*a.stop) return;
     const int k = blockIdx.y;
@@ -297,49 +310,58 @@ __global__ void __launch_bounds__(DG_THREADS) dg_cell_kernel(StepArgs a, Gas g, 
         DgAcc acc;
 #pragma unroll
         for (int q = 0; q < 4; q++) acc.r[q] = acc.rx[q] = acc.ry[q] = 0.0;
-        DgCell nb;
-        // interior xi faces (SpatialDiscretization.cpp:481-552): face i (this cell is the right one), face i+1 (left)
-        if (i >= 1) {
-            dg_load_cell(g, b, a.cur, i - 1, j, nb);
-            dg_face<FAITHFUL, TPG, AXI>(g, face_geom<FAITHFUL>(xa, ya, xd, yd), nb, me, 0, false, ycs, acc, flags);
+        // interior faces in the reference's accumulation order: xi face i (this cell is the right one) and i+1 (left)
+        // (SpatialDiscretization.cpp:481-552), eta face j (this cell is the left = upper one) and j+1 (:556-625)
+#pragma unroll 1
+        for (int f = 0; f < 4; f++) {
+            int ni, nj, dir;
+            bool exists, mine_left;
+            double x0, y0, x1, y1;
+            if (f == 0) { exists = i >= 1; ni = i - 1; nj = j; dir = 0; mine_left = false; x0 = xa; y0 = ya; x1 = xd; y1 = yd; }
+            else if (f == 1) { exists = i <= ncx - 2; ni = i + 1; nj = j; dir = 0; mine_left = true; x0 = xb; y0 = yb; x1 = xc; y1 = yc_; }
+            else if (f == 2) { exists = j >= 1; ni = i; nj = j - 1; dir = 1; mine_left = true; x0 = xa; y0 = ya; x1 = xb; y1 = yb; }
+            else { exists = j <= ncy - 2; ni = i; nj = j + 1; dir = 1; mine_left = false; x0 = xd; y0 = yd; x1 = xc; y1 = yc_; }
+            if (!exists) continue;
+            DgCell nb;
+            dg_load_cell(g, b, a.cur, ni, nj, nb);
+            dg_face<FAITHFUL, TPG, AXI>(g, face_geom<FAITHFUL>(x0, y0, x1, y1), me, nb, dir, mine_left, ycs, acc, flags);
         }
-        if (i <= ncx - 2) {
-            dg_load_cell(g, b, a.cur, i + 1, j, nb);
-            dg_face<FAITHFUL, TPG, AXI>(g, face_geom<FAITHFUL>(xb, yb, xc, yc_), me, nb, 0, true, ycs, acc, flags);
-        }
-        // interior eta faces (:556-625): face j (this cell is the left = upper one), face j+1 (right = lower)
-        if (j >= 1) {
-            dg_load_cell(g, b, a.cur, i, j - 1, nb);
-            dg_face<FAITHFUL, TPG, AXI>(g, face_geom<FAITHFUL>(xa, ya, xb, yb), me, nb, 1, true, ycs, acc, flags);
-        }
-        if (j <= ncy - 2) {
-            dg_load_cell(g, b, a.cur, i, j + 1, nb);
-            dg_face<FAITHFUL, TPG, AXI>(g, face_geom<FAITHFUL>(xd, yd, xc, yc_), nb, me, 1, false, ycs, acc, flags);
-        }
-        // boundary faces (:643-977).  fNormalL / fNormalR are declared once per row (column) and shared by the
-        // left and right (bottom and top) face of it: at the ends of the right (top) side they still hold the
-        // left (bottom) side's values
-        if (i == 0) {
-            const FaceGeom f = face_geom<true>(xa, ya, xd, yd);
-            const FaceGeom fL = j != 0 ? dg_geom(b, 0, j - 1, 0, j) : f, fR = j != ncy - 1 ? dg_geom(b, 0, j + 1, 0, j + 2) : f;
-            dg_boundary_face<TPG, AXI>(g, b, 4, SIDE_LEFT, j, me, f, fL.nx, fL.ny, fR.nx, fR.ny, ycs, acc, flags);
-        }
-        if (i == ncx - 1) {
-            const FaceGeom f = face_geom<true>(xb, yb, xc, yc_);
-            const FaceGeom fL = j != 0 ? dg_geom(b, ncx, j - 1, ncx, j) : dg_geom(b, 0, j, 0, j + 1);
-            const FaceGeom fR = j != ncy - 1 ? dg_geom(b, ncx, j + 1, ncx, j + 2) : dg_geom(b, 0, j, 0, j + 1);
-            dg_boundary_face<TPG, AXI>(g, b, 2, SIDE_RIGHT, j, me, f, fL.nx, fL.ny, fR.nx, fR.ny, ycs, acc, flags);
-        }
-        if (j == 0) {
-            const FaceGeom f = face_geom<true>(xa, ya, xb, yb);
-            const FaceGeom fL = i != 0 ? dg_geom(b, i - 1, 0, i, 0) : f, fR = i != ncx - 1 ? dg_geom(b, i + 1, 0, i + 2, 0) : f;
-            dg_boundary_face<TPG, AXI>(g, b, 1, SIDE_BOTTOM, i, me, f, fL.nx, fL.ny, fR.nx, fR.ny, ycs, acc, flags);
-        }
-        if (j == ncy - 1) {
-            const FaceGeom f = face_geom<true>(xd, yd, xc, yc_);
-            const FaceGeom fL = i != 0 ? dg_geom(b, i - 1, ncy, i, ncy) : dg_geom(b, i, 0, i + 1, 0);
-            const FaceGeom fR = i != ncx - 1 ? dg_geom(b, i + 1, ncy, i + 2, ncy) : dg_geom(b, i, 0, i + 1, 0);
-            dg_boundary_face<TPG, AXI>(g, b, 3, SIDE_TOP, i, me, f, fL.nx, fL.ny, fR.nx, fR.ny, ycs, acc, flags);
+        // boundary faces (:643-977), left, right, bottom, top.  fNormalL / fNormalR are declared once per row
+        // (column) and shared by the left and right (bottom and top) face of it: at the ends of the right (top)
+        // side they still hold the left (bottom) side's values
+        if (i == 0 || i == ncx - 1 || j == 0 || j == ncy - 1) {
+#pragma unroll 1
+            for (int sd = 0; sd < 4; sd++) {
+                int type, side, n;
+                bool exists;
+                FaceGeom f, fL, fR;
+                if (sd == 0) {
+                    exists = i == 0; type = 4; side = SIDE_LEFT; n = j;
+                    if (!exists) continue;
+                    f = face_geom<true>(xa, ya, xd, yd);
+                    fL = j != 0 ? dg_geom(b, 0, j - 1, 0, j) : f;
+                    fR = j != ncy - 1 ? dg_geom(b, 0, j + 1, 0, j + 2) : f;
+                } else if (sd == 1) {
+                    exists = i == ncx - 1; type = 2; side = SIDE_RIGHT; n = j;
+                    if (!exists) continue;
+                    f = face_geom<true>(xb, yb, xc, yc_);
+                    fL = j != 0 ? dg_geom(b, ncx, j - 1, ncx, j) : dg_geom(b, 0, j, 0, j + 1);
+                    fR = j != ncy - 1 ? dg_geom(b, ncx, j + 1, ncx, j + 2) : dg_geom(b, 0, j, 0, j + 1);
+                } else if (sd == 2) {
+                    exists = j == 0; type = 1; side = SIDE_BOTTOM; n = i;
+                    if (!exists) continue;
+                    f = face_geom<true>(xa, ya, xb, yb);
+                    fL = i != 0 ? dg_geom(b, i - 1, 0, i, 0) : f;
+                    fR = i != ncx - 1 ? dg_geom(b, i + 1, 0, i + 2, 0) : f;
+                } else {
+                    exists = j == ncy - 1; type = 3; side = SIDE_TOP; n = i;
+                    if (!exists) continue;
+                    f = face_geom<true>(xd, yd, xc, yc_);
+                    fL = i != 0 ? dg_geom(b, i - 1, ncy, i, ncy) : dg_geom(b, i, 0, i + 1, 0);
+                    fR = i != ncx - 1 ? dg_geom(b, i + 1, ncy, i + 2, ncy) : dg_geom(b, i, 0, i + 1, 0);
+                }
+                dg_boundary_face<TPG, AXI>(g, b, type, side, n, me, f, fL.nx, fL.ny, fR.nx, fR.ny, ycs, acc, flags);
+            }
         }
         // :980-1011 division by the volume, then the volume integral of the slopes' equations (DGP1Tools.cpp:52-124)
         double r[4], rx[4], ry[4];
