@@ -30,7 +30,7 @@ constexpr double DG_DAMP = 0.9;       // main.cpp:92
 constexpr double DG_DUSCALE = 0.5;    // main.cpp:93
 constexpr int DG_THREADS = 128;
 #ifndef DG_MINB
-#define DG_MINB 3      // CTAs per SM the cell kernel is compiled for (register budget 65536 / (128 * DG_MINB))
+#define DG_MINB 4      // CTAs per SM the cell kernel is compiled for (register budget 65536 / (128 * DG_MINB))
 #endif
 
 struct DgArgs {
