@@ -208,6 +208,14 @@ struct par2d_ctx {
     unsigned long long** d_flag_dst = nullptr;
     unsigned* put_ticket = nullptr;
     unsigned long long seq = 0;      // exchange events produced so far (identical on every rank)
+    // overlap of the exchange with interior work (peer-mapped mode): strips that touch an off-rank face run first on
+    // a side stream, followed by the put of the NEW state's edge lines; the interior strips run beside them
+    int2* d_edge_tiles = nullptr;
+    int2* d_inner_tiles = nullptr;
+    int n_edge_tiles = 0, n_inner_tiles = 0;
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_ghost = nullptr, ev_edge = nullptr;
+    bool overlap = true;             // PAR2D_NO_OVERLAP=1 keeps put -> ghost -> march in one stream (A/B runs)
     long long timeout_ns = 20000000000ll;
 
     // history of the last batch, host copies
@@ -243,6 +251,9 @@ struct par2d_ctx {
         a.res_block = -1;
         a.update = update;
         a.march_rows = march_rows;
+        a.tile_list = nullptr;
+        a.tile_count = 0;
+        a.dt_ready = 0;
         a.wait_flags = nullptr;
         a.wait_seq = 0;
         a.recv_off = 0;
@@ -342,7 +353,8 @@ int build_tensor_maps(par2d_ctx* c) {
 void launch_step(par2d_ctx* c, const StepArgs& a) { c->kt->march(c->stream, a, c->gas, c->tpg, c->axi); }
 
 // peer-mapped mode: produce the next exchange event from the current state
-void queue_put(par2d_ctx* c) {
+void queue_put(par2d_ctx* c, cudaStream_t stream = nullptr) {
+    if (!stream) stream = c->stream;
     c->seq++;
     PutArgs put;
     memset(&put, 0, sizeof put);
@@ -357,7 +369,7 @@ void queue_put(par2d_ctx* c) {
     put.nranks = c->cfg.nranks;
     put.rank = c->cfg.rank;
     put.timeout_ns = c->timeout_ns;
-    c->kt->pack(c->stream, c->step_args(1), c->gas, c->dlines_peer, c->nlines, c->max_line, put);
+    c->kt->pack(stream, c->step_args(1), c->gas, c->dlines_peer, c->nlines, c->max_line, put);
 }
 
 // The bookkeeping of a step (finalize) is deferred into the NEXT step's ghost launch, where it overlaps
@@ -392,9 +404,46 @@ void queue_step_dg(par2d_ctx* c, int stop_on_tol) {
     c->cur ^= 1;
 }
 
+// peer-mapped mode with overlap: the exchange event of the state being read was produced before this call.
+//   main stream : ghost (waits for the peers' flags) ........ march(interior strips) ... wait(edge) ->
+//   side stream :           wait(ghost) -> march(edge strips) -> put(new state's edge lines + dt, flag)
+// so the NVLink stores, the flag latency and the skew between GPUs hide behind the interior strips.
+void queue_step_overlapped(par2d_ctx* c) {
+    StepArgs a = c->step_args(1);
+    a.dt_ready = 1;
+    c->kt->ghost(c->stream, a, c->gas, 0, c->fin_pending ? &c->fin_args : nullptr);
+    c->fin_pending = false;
+    cudaEventRecord(c->ev_ghost, c->stream);
+    cudaStreamWaitEvent(c->side_stream, c->ev_ghost, 0);
+    if (c->timing) {
+        if ((int)c->ev.size() < 2 * (c->ev_used + 1)) {
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            c->ev.push_back(e0);
+            c->ev.push_back(e1);
+        }
+        cudaEventRecord(c->ev[2 * c->ev_used], c->stream);
+    }
+    StepArgs ae = a, ai = a;
+    ae.tile_list = c->d_edge_tiles; ae.tile_count = c->n_edge_tiles;
+    ai.tile_list = c->d_inner_tiles; ai.tile_count = c->n_inner_tiles;
+    c->kt->march(c->side_stream, ae, c->gas, c->tpg, c->axi);
+    c->kt->march(c->stream, ai, c->gas, c->tpg, c->axi);
+    c->fin_args = c->finalize_args(0);
+    c->fin_pending = true;
+    c->iter_queued++;
+    c->cur ^= 1;
+    queue_put(c, c->side_stream);      // reads the NEW state's edge cells (all in edge strips) and cell (0,0) of every block
+    cudaEventRecord(c->ev_edge, c->side_stream);
+    cudaStreamWaitEvent(c->stream, c->ev_edge, 0);
+    if (c->timing) cudaEventRecord(c->ev[2 * c->ev_used++ + 1], c->stream);
+}
+
 void queue_step(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
     if (c->dg) { queue_step_dg(c, stop_on_tol); return; }
     StepArgs a = c->step_args(1);
+    a.dt_ready = with_ghost_dt ? 0 : 1;
     c->kt->ghost(c->stream, a, c->gas, with_ghost_dt ? 1 : 0, c->fin_pending ? &c->fin_args : nullptr);
     c->fin_pending = false;
     if (c->timing) {
@@ -893,11 +942,16 @@ int par2d_step(par2d_ctx* c, int32_t nsteps, int32_t stop_on_tol, par2d_step_inf
         // collective batch, no host transport: every step is  put (edge lines + dt_b into the neighbours'
         // arenas, flag) -> ghost (waits for the flags) -> march -> finalize.  The trailing put leaves the
         // final state's lines in the arenas for par2d_get_residual.
-        for (int s = 0; s < nsteps; s++) {
+        if (c->overlap && c->d_edge_tiles) {
+            queue_put(c);              // the first state's lines; every step then produces the next state's
+            for (int s = 0; s < nsteps; s++) queue_step_overlapped(c);
+        } else {
+            for (int s = 0; s < nsteps; s++) {
+                queue_put(c);
+                queue_step(c, 0, false);
+            }
             queue_put(c);
-            queue_step(c, 0, false);
         }
-        queue_put(c);
     } else {
         for (int s = 0; s < nsteps; s++) queue_step(c, stop_on_tol, true);
     }
@@ -1036,6 +1090,35 @@ int par2d_peer_connect(par2d_ctx* c, const void* all_handles) {
         CU_TRY(cudaMemcpy(c->dlines_peer, lines.data(), sizeof(SendLine) * lines.size(), cudaMemcpyHostToDevice));
     }
     c->seq = 0;
+    // strips for the overlapped step: everything that touches an off-rank face (its cells are what the put sends)
+    // plus strip 0 of every block (cell (0,0) feeds the block's dt) goes first, on the side stream
+    {
+        const char* no = getenv("PAR2D_NO_OVERLAP");
+        c->overlap = !(no && atoi(no) != 0);
+        std::vector<int2> edge, inner;
+        for (int k = 0; k < c->nowned; k++) {
+            const BlockDev& b = c->hblk[k];
+            for (int s = 0; s < b.tiles_x * b.tiles_y; s++) {
+                const int tx = s % b.tiles_x, ty = s / b.tiles_x;
+                const bool e = s == 0 || (tx == 0 && b.nb_kind[SIDE_LEFT] == NB_REMOTE) || (tx == b.tiles_x - 1 && b.nb_kind[SIDE_RIGHT] == NB_REMOTE) ||
+                               (ty == 0 && b.nb_kind[SIDE_BOTTOM] == NB_REMOTE) || (ty == b.tiles_y - 1 && b.nb_kind[SIDE_TOP] == NB_REMOTE);
+                (e ? edge : inner).push_back(make_int2(k, s));
+            }
+        }
+        c->n_edge_tiles = (int)edge.size();
+        c->n_inner_tiles = (int)inner.size();
+        CU_TRY(cudaMalloc(&c->d_edge_tiles, sizeof(int2) * std::max<size_t>(edge.size(), 1)));
+        CU_TRY(cudaMalloc(&c->d_inner_tiles, sizeof(int2) * std::max<size_t>(inner.size(), 1)));
+        CU_TRY(cudaMemcpy(c->d_edge_tiles, edge.data(), sizeof(int2) * edge.size(), cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(c->d_inner_tiles, inner.data(), sizeof(int2) * inner.size(), cudaMemcpyHostToDevice));
+        if (!c->side_stream) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            CU_TRY(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, hi));   // edge strips + put ahead of interior strips
+            CU_TRY(cudaEventCreateWithFlags(&c->ev_ghost, cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming));
+        }
+    }
     c->peer_connected = true;
     return 0;
 }
@@ -1048,6 +1131,11 @@ int par2d_peer_disconnect(par2d_ctx* c) {
         if ((int)p != c->cfg.rank && c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
     c->peer_base.clear();
     c->peer_connected = false;
+    if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); c->side_stream = nullptr; }
+    if (c->ev_ghost) { cudaEventDestroy(c->ev_ghost); c->ev_ghost = nullptr; }
+    if (c->ev_edge) { cudaEventDestroy(c->ev_edge); c->ev_edge = nullptr; }
+    cudaFree(c->d_edge_tiles); cudaFree(c->d_inner_tiles);
+    c->d_edge_tiles = c->d_inner_tiles = nullptr;
     return 0;
 }
 

@@ -93,7 +93,11 @@ struct StepArgs {
     int max_faces;           // longest block perimeter (grid.x of the ghost kernel)
     const void* tmaps;       // CUtensorMap[nowned] over each block's 11 planes; boxes of 32 columns x 2 rows x 7 planes
     double* dt_table;        // nblocks_global
-    double* dt_used;         // the global dt this step advanced with (written by the march kernel, read by finalize)
+    double* dt_used;         // the global dt this step advances with (read by finalize; written by the march kernel, or by
+                             // the ghost kernel when dt_ready)
+    int dt_ready;            // the dt table is complete BEFORE the ghost launch (multi-rank modes): the ghost kernel reduces
+                             // it into *dt_used and the march kernel reads that one value - the table may already be
+                             // receiving the next event's entries while interior strips still run
     double* partials;        // [total_tiles][4] sum of res_k^2
     unsigned* flags;         // device error bits
     const int* stop;         // non-zero -> batch already converged, kernels return at once
@@ -101,6 +105,8 @@ struct StepArgs {
     int res_block;           // owned index whose residual is dumped, or -1
     int update;              // 0: residual only (test hook), 1: advance the state
     int march_rows;          // cell rows per strip of the marching kernel
+    const int2* tile_list;   // optional subset launch of the march kernel: (owned block, strip) per CTA, grid.x = tile_count;
+    int tile_count;          // null: grid = (max_tiles, nowned), every strip of every block
     // peer-mapped mode: the ghost kernel consumes exchange event wait_seq from this rank's arena
     const unsigned long long* wait_flags;  // null: nothing to wait for
     unsigned long long wait_seq;

@@ -109,6 +109,12 @@ __global__ void __launch_bounds__(256) ghost_kernel(StepArgs a, Gas g, int write
         }
         __syncthreads();
     }
+    if (a.dt_ready && blockIdx.x == 0 && (int)blockIdx.y == nfin && threadIdx.x == 0) {
+        // global dt = max over blocks (main.cpp:270-292) of the table the exchange completed before this launch
+        double dt = 0.0;
+        for (int t = 0; t < a.nblocks_global; t++) dt = fmax(dt, __ldcg(a.dt_table + t));
+        *a.dt_used = dt;
+    }
     const BlockDev b = a.blocks[blockIdx.y - nfin];   // grid.y = [pending finalize rows +] owned blocks, grid.x covers the longest perimeter
     int n = blockIdx.x * blockDim.x + threadIdx.x, side;
     if (n >= 2 * (b.ncx + b.ncy)) return;
@@ -310,7 +316,8 @@ template <bool FAITHFUL>
 struct Launch {
     template <bool HOOKS>
     static void march_h(cudaStream_t s, const StepArgs& a, const Gas& g, bool tpg, bool axi) {
-        const dim3 grid(a.max_tiles, a.nowned);   // one warp strip per CTA
+        const dim3 grid = a.tile_list ? dim3(a.tile_count, 1) : dim3(a.max_tiles, a.nowned);   // one warp strip per CTA
+        if (a.tile_list && a.tile_count == 0) return;
         if (tpg) { if (axi) march_kernel<FAITHFUL, true, true, HOOKS><<<grid, MARCH_THREADS, 0, s>>>(a, g); else march_kernel<FAITHFUL, true, false, HOOKS><<<grid, MARCH_THREADS, 0, s>>>(a, g); }
         else { if (axi) march_kernel<FAITHFUL, false, true, HOOKS><<<grid, MARCH_THREADS, 0, s>>>(a, g); else march_kernel<FAITHFUL, false, false, HOOKS><<<grid, MARCH_THREADS, 0, s>>>(a, g); }
     }

@@ -334,9 +334,16 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
     __shared__ __align__(128) MarchSmem sm;
     if (*a.stop) return;
     const int lane = threadIdx.x;
-    const int k = blockIdx.y;                      // grid.y = owned blocks, grid.x covers the block with most strips
+    int k, strip;
+    if (a.tile_list != nullptr) {                  // subset launch (edge strips first, interior strips beside the exchange)
+        if ((int)blockIdx.x >= a.tile_count) return;
+        const int2 t = __ldg(a.tile_list + blockIdx.x);
+        k = t.x; strip = t.y;
+    } else {
+        k = blockIdx.y;                            // grid.y = owned blocks, grid.x covers the block with most strips
+        strip = blockIdx.x;
+    }
     const BlockDev& b = a.blocks[k];
-    const int strip = blockIdx.x;
     if (strip >= b.tiles_x * b.tiles_y) return;    // CTA-uniform
     MarchCtx m;
     m.k = k; m.ncx = b.ncx; m.ncy = b.ncy; m.pitch = b.pitch; m.plane = b.plane; m.lane = lane;
@@ -380,11 +387,15 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
 
     // global dt = max over blocks (main.cpp:270-292); the table was written by the ghost kernel
     double dt = 0.0;
-    for (int t = lane; t < a.nblocks_global; t += 32) dt = fmax(dt, __ldcg(a.dt_table + t));   // peer-mapped mode: written by other GPUs
+    if (a.dt_ready) {
+        dt = __ldcg(a.dt_used);                    // reduced by the ghost kernel
+    } else {
+        for (int t = lane; t < a.nblocks_global; t += 32) dt = fmax(dt, __ldcg(a.dt_table + t));
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) dt = fmax(dt, __shfl_xor_sync(0xffffffffu, dt, s));
+        for (int s = 16; s > 0; s >>= 1) dt = fmax(dt, __shfl_xor_sync(0xffffffffu, dt, s));
+        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) *a.dt_used = dt;   // for the step's history record
+    }
     m.dt = dt;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) *a.dt_used = dt;   // for the step's history record
 
     unsigned flags = 0;
     bool ok = true;
