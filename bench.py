@@ -333,12 +333,13 @@ def run_gpu_arm(args):
         "config": {"workload": f"synthetic 10deg ramp, {nbx * nby} blocks of {blk}x{blk} cells (8 per GPU), "
                                f"{total_cells} cells, IAXI=1, CPG, CFL=0.01 (shipped macros)",
                    "global_cells": total_cells, "parallelism": f"blocks sharded over {args.gpus} GPU(s), 1 process per GPU",
-                   "halo_exchange": (f"{transport} (" + ("kernel stores into NVLink peer-mapped arenas + sequence flags, no host transport"
+                   "halo_exchange": (f"{transport} (" + ("kernel stores into NVLink peer-mapped arenas + sequence flags, no host transport; edge strips + put on a side stream beside the interior strips"
                                      if transport == "peer" else "NCCL send/recv + all-reduce(MAX) per step") + ")") if multi else "none (single GPU)",
                    "l2": "state per GPU 1.07 GB read + 1.07 GB written per step >> 126 MB L2; no flush needed",
                    "arith_mode": "PAR2D_MODE_FAST"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-        "gpu_launches": (LAUNCHES_PER_STEP + (1 if multi else 0)) * args.steps + 1 + (1 if transport == "peer" else 0),
+        # peer transport: ghost + edge strips + interior strips + put per step; external: ghost + march + pack
+        "gpu_launches": (LAUNCHES_PER_STEP + (2 if transport == "peer" else 1 if multi else 0)) * args.steps + 1 + (1 if transport == "peer" else 0),
         "relres_last": info[-1].relres if not multi else None, "dt": info[-1].dt,
     }
     print(json.dumps(line), flush=True)
