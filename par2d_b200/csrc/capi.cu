@@ -67,24 +67,25 @@ struct ArenaLayout {
     long long dt_stride = 0;     // doubles
     long long lines_stride = 0;  // doubles = everything rank r receives per event
 };
-long long recv_count(const par2d_block_desc* t, int nblocks, int r, int src) {  // doubles rank r receives from rank src
+// lw = doubles per edge cell of a line: 4 (first order: the cell mean) or 8 (second-order branch: two Gauss points)
+long long recv_count(const par2d_block_desc* t, int nblocks, int r, int src, int lw) {  // doubles rank r receives from rank src
     long long n = 0;
     for (int g = 0; g < nblocks; g++) {
         if (t[g].owner != r) continue;
         for (int s = 0; s < 4; s++) {
             const int nb = t[g].bid[s];
-            if (nb >= 0 && t[nb].owner == src) n += 4ll * desc_edge(t[g], s);
+            if (nb >= 0 && t[nb].owner == src) n += (long long)lw * desc_edge(t[g], s);
         }
     }
     return n;
 }
-long long recv_segment_off(const par2d_block_desc* t, int nblocks, int r, int src) {  // where src's segment starts in r's lines
+long long recv_segment_off(const par2d_block_desc* t, int nblocks, int r, int src, int lw) {  // where src's segment starts in r's lines
     long long off = 0;
     for (int p = 0; p < src; p++)
-        if (p != r) off += recv_count(t, nblocks, r, p);
+        if (p != r) off += recv_count(t, nblocks, r, p, lw);
     return off;
 }
-ArenaLayout arena_layout(const par2d_block_desc* t, int nblocks, int nranks, int r) {
+ArenaLayout arena_layout(const par2d_block_desc* t, int nblocks, int nranks, int r, int lw) {
     ArenaLayout L;
     auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
     L.flags_off = 0;
@@ -92,7 +93,7 @@ ArenaLayout arena_layout(const par2d_block_desc* t, int nblocks, int nranks, int
     L.dt_stride = (long long)((nblocks + 31) / 32 * 32);
     L.lines_off = up(L.dt_off + sizeof(double) * 2 * (size_t)L.dt_stride);
     for (int p = 0; p < nranks; p++)
-        if (p != r) L.lines_stride += recv_count(t, nblocks, r, p);
+        if (p != r) L.lines_stride += recv_count(t, nblocks, r, p, lw);
     L.bytes = up(L.lines_off + sizeof(double) * 2 * (size_t)std::max<long long>(L.lines_stride, 1));
     return L;
 }
@@ -369,6 +370,7 @@ void queue_put(par2d_ctx* c, cudaStream_t stream = nullptr) {
     put.nranks = c->cfg.nranks;
     put.rank = c->cfg.rank;
     put.timeout_ns = c->timeout_ns;
+    put.dg = c->dg ? 1 : 0;
     c->kt->pack(stream, c->step_args(1), c->gas, c->dlines_peer, c->nlines, c->max_line, put);
 }
 
@@ -393,10 +395,10 @@ DgArgs dg_args(const par2d_ctx* c, int update) {
 
 // second-order branch: ghost points -> cell kernel (means into the other buffer, damped slopes) -> limiter ->
 // bookkeeping (dg.cuh)
-void queue_step_dg(par2d_ctx* c, int stop_on_tol) {
+void queue_step_dg(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
     StepArgs a = c->step_args(1);
     const DgArgs d = dg_args(c, 1);
-    c->kt->dg_ghost(c->stream, a, c->gas, d);
+    c->kt->dg_ghost(c->stream, a, c->gas, d, with_ghost_dt ? 1 : 0);
     c->kt->dg_cell(c->stream, a, c->gas, d, c->tpg, c->axi);
     c->kt->dg_limit(c->stream, a, d);
     launch_finalize(c->stream, c->finalize_args(stop_on_tol));
@@ -441,7 +443,7 @@ void queue_step_overlapped(par2d_ctx* c) {
 }
 
 void queue_step(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
-    if (c->dg) { queue_step_dg(c, stop_on_tol); return; }
+    if (c->dg) { queue_step_dg(c, stop_on_tol, with_ghost_dt); return; }
     StepArgs a = c->step_args(1);
     a.dt_ready = with_ghost_dt ? 0 : 1;
     c->kt->ghost(c->stream, a, c->gas, with_ghost_dt ? 1 : 0, c->fin_pending ? &c->fin_args : nullptr);
@@ -542,7 +544,6 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
     if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(PAR2D_ERR_ARG, "create: bad rank %d of %d", cfg->rank, cfg->nranks);
     if (cfg->mode != PAR2D_MODE_FAST && cfg->mode != PAR2D_MODE_FAITHFUL) return fail(PAR2D_ERR_ARG, "create: unknown mode %d", cfg->mode);
     if (cfg->accur != 0 && cfg->accur != 1) return fail(PAR2D_ERR_ARG, "create: accur must be 0 or 1 (SpatialDiscretization.cpp:204)");
-    if (cfg->accur == 1 && cfg->nranks != 1) return fail(PAR2D_ERR_ARG, "create: the second-order branch (accur = 1) runs on one rank in this version");
     int rc = validate_table(nblocks, blocks, cfg->nranks);
     if (rc) return rc;
 
@@ -600,6 +601,7 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
     if (c->nowned == 0) return fail(PAR2D_ERR_ARG, "rank %d owns no block", cfg->rank);
 
     // peer buffers: lines ordered by (receiving block id, receiving side)
+    const int lw = c->dg ? 8 : 4;   // doubles per edge cell (SpatialDiscretization.cpp:231: ntrans *= (ACCUR + 1))
     c->peers.resize(cfg->nranks);
     for (int p = 0; p < cfg->nranks; p++) {
         if (p == cfg->rank) continue;
@@ -607,20 +609,20 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
             for (int s = 0; s < 4; s++) {
                 const int nb = blocks[g].bid[s];
                 if (nb < 0) continue;
-                if (blocks[g].owner == cfg->rank && blocks[nb].owner == p) c->peers[p].n_recv += 4ll * desc_edge(blocks[g], s);
-                if (blocks[g].owner == p && blocks[nb].owner == cfg->rank) c->peers[p].n_send += 4ll * desc_edge(blocks[g], s);
+                if (blocks[g].owner == cfg->rank && blocks[nb].owner == p) c->peers[p].n_recv += (long long)lw * desc_edge(blocks[g], s);
+                if (blocks[g].owner == p && blocks[nb].owner == cfg->rank) c->peers[p].n_send += (long long)lw * desc_edge(blocks[g], s);
             }
         if (c->peers[p].n_send) { CU_TRY(cudaMalloc(&c->peers[p].d_send, sizeof(double) * c->peers[p].n_send)); CU_TRY(cudaMemset(c->peers[p].d_send, 0, sizeof(double) * c->peers[p].n_send)); }
     }
     if (cfg->nranks > 1) {
         // the receive side lives in one exportable allocation (the arena); with the external transport
         // only parity 0 of it is used
-        c->lay = arena_layout(blocks, nblocks, cfg->nranks, cfg->rank);
+        c->lay = arena_layout(blocks, nblocks, cfg->nranks, cfg->rank, lw);
         CU_TRY(cudaMalloc(&c->arena, c->lay.bytes));
         CU_TRY(cudaMemset(c->arena, 0, c->lay.bytes));
         double* lines0 = reinterpret_cast<double*>(c->arena + c->lay.lines_off);
         for (int p = 0; p < cfg->nranks; p++)
-            if (p != cfg->rank && c->peers[p].n_recv) c->peers[p].d_recv = lines0 + recv_segment_off(blocks, nblocks, cfg->rank, p);
+            if (p != cfg->rank && c->peers[p].n_recv) c->peers[p].d_recv = lines0 + recv_segment_off(blocks, nblocks, cfg->rank, p, lw);
         CU_TRY(cudaMalloc(&c->put_ticket, sizeof(unsigned)));
         CU_TRY(cudaMemset(c->put_ticket, 0, sizeof(unsigned)));
         const char* tmo = getenv("PAR2D_PEER_TIMEOUT_MS");
@@ -704,7 +706,7 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
                         const int n2 = blocks[gg].bid[ss];
                         if (n2 < 0 || blocks[n2].owner != p) continue;
                         if (gg == g && ss == s) { found = true; break; }
-                        off += 4ll * desc_edge(blocks[gg], ss);
+                        off += (long long)lw * desc_edge(blocks[gg], ss);
                     }
                 }
                 b.recv[s] = c->peers[p].d_recv + off;
@@ -760,7 +762,7 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
                 ln.parity_stride = 0;
                 c->hline_peer.push_back(p);
                 c->hline_off.push_back(off);
-                off += 4ll * ln.n;
+                off += (long long)lw * ln.n;
                 lines.push_back(ln);
                 c->max_line = std::max(c->max_line, ln.n);
             }
@@ -916,7 +918,7 @@ int par2d_get_residual_dg(par2d_ctx* c, int32_t block, double* res, double* resx
     DgArgs d = dg_args(c, 0);
     d.res_out = out;
     d.res_block = k;
-    c->kt->dg_ghost(c->stream, a, c->gas, d);
+    c->kt->dg_ghost(c->stream, a, c->gas, d, c->peer_connected ? 0 : 1);
     c->kt->dg_cell(c->stream, a, c->gas, d, c->tpg, c->axi);
     CU_TRY(cudaMemcpyAsync(res, out, sizeof(double) * n4, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaMemcpyAsync(resx, out + n4, sizeof(double) * n4, cudaMemcpyDeviceToHost, c->stream));
@@ -942,7 +944,7 @@ int par2d_step(par2d_ctx* c, int32_t nsteps, int32_t stop_on_tol, par2d_step_inf
         // collective batch, no host transport: every step is  put (edge lines + dt_b into the neighbours'
         // arenas, flag) -> ghost (waits for the flags) -> march -> finalize.  The trailing put leaves the
         // final state's lines in the arenas for par2d_get_residual.
-        if (c->overlap && c->d_edge_tiles) {
+        if (c->overlap && c->d_edge_tiles && !c->dg) {
             queue_put(c);              // the first state's lines; every step then produces the next state's
             for (int s = 0; s < nsteps; s++) queue_step_overlapped(c);
         } else {
@@ -1004,6 +1006,7 @@ int par2d_step_begin(par2d_ctx* c) {
     CU_TRY(cudaMemsetAsync(c->dt_table, 0, sizeof(double) * c->nblocks, c->stream));
     PutArgs put;
     memset(&put, 0, sizeof put);
+    put.dg = c->dg ? 1 : 0;
     c->kt->pack(c->stream, c->step_args(1), c->gas, c->dlines, c->nlines, c->max_line, put);
     return 0;
 }
@@ -1071,14 +1074,14 @@ int par2d_peer_connect(par2d_ctx* c, const void* all_handles) {
     std::vector<unsigned long long*> flag_dst(nr);
     std::vector<ArenaLayout> lay(nr);
     for (int p = 0; p < nr; p++) {
-        lay[p] = arena_layout(c->table.data(), c->nblocks, nr, p);
+        lay[p] = arena_layout(c->table.data(), c->nblocks, nr, p, c->dg ? 8 : 4);
         dt_dst[p] = reinterpret_cast<double*>(c->peer_base[p] + lay[p].dt_off);
         flag_dst[p] = reinterpret_cast<unsigned long long*>(c->peer_base[p] + lay[p].flags_off) + 16 * me;
     }
     std::vector<SendLine> lines = c->hlines;
     for (size_t l = 0; l < lines.size(); l++) {
         const int p = c->hline_peer[l];
-        lines[l].dst = reinterpret_cast<double*>(c->peer_base[p] + lay[p].lines_off) + recv_segment_off(c->table.data(), c->nblocks, p, me) + c->hline_off[l];
+        lines[l].dst = reinterpret_cast<double*>(c->peer_base[p] + lay[p].lines_off) + recv_segment_off(c->table.data(), c->nblocks, p, me, c->dg ? 8 : 4) + c->hline_off[l];
         lines[l].parity_stride = lay[p].lines_stride;
     }
     CU_TRY(cudaMalloc(&c->d_dt_dst, sizeof(double*) * nr));

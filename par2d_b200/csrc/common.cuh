@@ -81,6 +81,8 @@ struct PutArgs {
     const unsigned long long* local_flags; // this rank's own flag array (for the pre-wait)
     int nranks, rank;
     long long timeout_ns;
+    int dg;                              // second-order branch: a line carries the reconstruction at the two Gauss points
+                                         // of every edge face, 8 doubles per edge cell (SpatialDiscretization.cpp:243-256)
 };
 
 struct StepArgs {

@@ -19,7 +19,8 @@
 // This first version favours exactness over speed: every interior face flux is evaluated by both adjacent
 // cells.  PAR2D_MODE_FAITHFUL keeps the reference's operation order and divisions; PAR2D_MODE_FAST uses the lean
 // LDFSS / state / solve of physics.cuh on interior faces (boundary faces, whose blended normals are not unit
-// vectors, keep the general form).  Single rank (nranks == 1); any number of blocks per GPU.
+// vectors, keep the general form).  Off-rank neighbours: pack_kernel (kernels.cuh) sends the reconstruction at the two
+// Gauss points of every edge face, 8 doubles per edge cell.
 #pragma once
 #include "common.cuh"
 #include "physics.cuh"
@@ -183,14 +184,41 @@ __device__ __forceinline__ void dg_boundary_face(const Gas& g, const BlockDev& b
     }
 }
 
+// bounded wait for the peers' sequence flags (same protocol as kernels.cuh::wait_peers, which is defined after this header)
+__device__ __forceinline__ bool dg_wait_peers(const unsigned long long* flags, int nranks, int rank, unsigned long long need, long long timeout_ns) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int r = 0; r < nranks; r++) {
+        if (r == rank) continue;
+        for (;;) {
+            unsigned long long v, now;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + 16 * r) : "memory");
+            if (v >= need) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if ((long long)(now - t0) > timeout_ns) return false;
+            __nanosleep(200);
+        }
+    }
+    return true;
+}
+
 // ------------------------------------------------------------------ ghost points
 template <bool FAITHFUL>
-__global__ void __launch_bounds__(256) dg_ghost_kernel(StepArgs a, Gas g, DgArgs d, int tpg) {
+__global__ void __launch_bounds__(256) dg_ghost_kernel(StepArgs a, Gas g, DgArgs d, int write_dt) {
     if (*a.stop) return;
+    if (a.wait_flags != nullptr) {
+        // peer-mapped mode: wait for the neighbours' lines and dts of this state (see ghost_kernel)
+        __shared__ int arrived;
+        if (threadIdx.x == 0) {
+            arrived = dg_wait_peers(a.wait_flags, a.nranks, a.rank, a.wait_seq, a.timeout_ns) ? 1 : 0;
+            if (!arrived) atomicOr(a.flags, FLAG_COMM);
+        }
+        __syncthreads();
+    }
     const BlockDev& b = a.blocks[blockIdx.y];
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int ncx = b.ncx, ncy = b.ncy;
-    if (t == 0) {   // find_dt of this block from cell (0,0), main.cpp:19-37
+    if (t == 0 && write_dt) {   // find_dt of this block from cell (0,0), main.cpp:19-37 (multi-rank: the pack kernel's job)
         const double* S = b.state[a.cur];
         const long long o = (long long)b.pitch + COL0;
         const double u = S[b.plane + o], v = S[2 * b.plane + o], T = S[3 * b.plane + o];
@@ -210,6 +238,12 @@ __global__ void __launch_bounds__(256) dg_ghost_kernel(StepArgs a, Gas g, DgArgs
     const double s = pt == 0 ? G : -G;
     double* out = b.ghost2[side] + 4 * (2 * (long long)n + pt);
     unsigned fl = 0;
+    if (b.nb_kind[side] == NB_REMOTE) {
+        // the line an off-rank neighbour packed (pack_kernel): 8 doubles per edge cell, point 1 then point 2
+        const double* line = b.recv[side] + a.recv_off + 8 * (long long)n + 4 * pt;
+        out[0] = __ldcg(line); out[1] = __ldcg(line + 1); out[2] = __ldcg(line + 2); out[3] = fmax(__ldcg(line + 3), 201.0);
+        return;
+    }
     if (b.nb_kind[side] == NB_LOCAL) {
         // halo of the second-order branch (SpatialDiscretization.cpp:243-256 and twins): the neighbour's
         // reconstruction at the Gauss points of ITS edge face
@@ -269,7 +303,7 @@ __global__ void __launch_bounds__(256) dg_ghost_kernel(StepArgs a, Gas g, DgArgs
     double gh[4] = {out[0], out[1], out[2], out[3]};   // stays as is when the BC leaves it unwritten
     boundary_state(g, code, normx, normy, u, aint, p, v2, gh);
     out[0] = gh[0]; out[1] = gh[1]; out[2] = gh[2]; out[3] = gh[3];
-    (void)fl; (void)tpg;
+    (void)fl;
 }
 
 // ------------------------------------------------------------------ residual + solve + update of the means

@@ -209,6 +209,27 @@ __global__ void __launch_bounds__(256) pack_kernel(StepArgs a, Gas g, const Send
             int c, r;
             edge_cell_pos(b.ncx, b.ncy, ln.side, n, c, r);
             const long long o = (long long)r * b.pitch + c;
+            if (put.dg) {
+                // second-order branch: the reconstruction at the two Gauss points of this rank's edge face,
+                // usend[k + 2*NVAR*j] = point 1, usend[k + NVAR + 2*NVAR*j] = point 2 (SpatialDiscretization.cpp:243-256)
+                DgCell cell;
+                dg_load_cell(g, b, a.cur, c - COL0, r - 1, cell);
+                const double G = dg_gauss();
+                double2* d2 = reinterpret_cast<double2*>(dst + 8 * (long long)n);
+#pragma unroll
+                for (int pt = 0; pt < 2; pt++) {
+                    const double sgp = pt == 0 ? G : -G;
+                    double xsi, eta, u[4];
+                    if (ln.side == SIDE_LEFT) { xsi = -1.0; eta = sgp; }
+                    else if (ln.side == SIDE_RIGHT) { xsi = 1.0; eta = sgp; }
+                    else if (ln.side == SIDE_BOTTOM) { xsi = sgp; eta = -1.0; }
+                    else { xsi = sgp; eta = 1.0; }
+                    dg_u_val(g, cell, xsi, eta, u);
+                    d2[2 * pt] = make_double2(u[0], u[1]);
+                    d2[2 * pt + 1] = make_double2(u[2], u[3]);
+                }
+                continue;
+            }
             // one 32-byte AoS record per edge cell (usend[k + NVAR*j], SpatialDiscretization.cpp:241)
             double2* d2 = reinterpret_cast<double2*>(dst + 4 * (long long)n);
             d2[0] = make_double2(S[o], S[b.plane + o]);
@@ -303,7 +324,7 @@ struct KernelTable {
     void (*ghost)(cudaStream_t, const StepArgs&, const Gas&, int write_dt, const FinalizeArgs* pending);
     void (*pack)(cudaStream_t, const StepArgs&, const Gas&, const SendLine*, int nlines, int max_n, const PutArgs&);
     void (*march)(cudaStream_t, const StepArgs&, const Gas&, bool tpg, bool axi);
-    void (*dg_ghost)(cudaStream_t, const StepArgs&, const Gas&, const DgArgs&);
+    void (*dg_ghost)(cudaStream_t, const StepArgs&, const Gas&, const DgArgs&, int write_dt);
     void (*dg_cell)(cudaStream_t, const StepArgs&, const Gas&, const DgArgs&, bool tpg, bool axi);
     void (*dg_limit)(cudaStream_t, const StepArgs&, const DgArgs&);
     void (*test_ldfss)(cudaStream_t, const Gas&, bool tpg, bool axi, long long n, const double*, const double*, const double*, double*, double*);
@@ -338,8 +359,8 @@ struct Launch {
         pack_kernel<FAITHFUL><<<grid, 256, 0, s>>>(a, g, lines, nlines, put);
     }
     // second-order branch (dg.cuh)
-    static void dg_ghost(cudaStream_t s, const StepArgs& a, const Gas& g, const DgArgs& d) {
-        dg_ghost_kernel<FAITHFUL><<<dim3((d.max_points + 255) / 256, a.nowned), 256, 0, s>>>(a, g, d, 0);
+    static void dg_ghost(cudaStream_t s, const StepArgs& a, const Gas& g, const DgArgs& d, int write_dt) {
+        dg_ghost_kernel<FAITHFUL><<<dim3((d.max_points + 255) / 256, a.nowned), 256, 0, s>>>(a, g, d, write_dt);
     }
     static void dg_cell(cudaStream_t s, const StepArgs& a, const Gas& g, const DgArgs& d, bool tpg, bool axi) {
         const dim3 grid(d.max_tiles, a.nowned);

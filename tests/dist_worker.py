@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--tol", type=float, default=0.0)
     ap.add_argument("--transport", default="auto")
     ap.add_argument("--batches", type=int, default=1)   # the steps are taken in this many par2d_step batches
+    ap.add_argument("--accur", type=int, default=0)     # 1: the second-order branch (lines carry two Gauss points per face)
     a = ap.parse_args()
     if a.backend == "nccl":
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
@@ -49,6 +50,7 @@ def main():
         return Case.load(os.path.join(REPO, "tests", "golden", "cases", a.case))
 
     cfg = default_config(lib)
+    cfg.accur = a.accur
     if a.impl == "gpu":
         cfg.device = torch.cuda.current_device()
     ds = DistSolver(make_case(), cfg, lib=lib, transport=a.transport)
@@ -59,7 +61,9 @@ def main():
     dt = np.concatenate([p[0] for p in parts])
     relres = np.concatenate([p[1] for p in parts])
 
-    single = Solver(make_case(), default_config(orc), lib=orc)
+    ocfg = default_config(orc)
+    ocfg.accur = a.accur
+    single = Solver(make_case(), ocfg, lib=orc)
     info = single.step(a.steps)
     ref_rel = np.array([i.relres for i in info])
     ref_dt = np.array([i.dt for i in info])
@@ -82,8 +86,15 @@ def main():
         oinfo = one.step(a.steps)
         for b in ds.owned:
             assert np.array_equal(ds.get_state(b), one.get_state(b)), f"rank {rank}: block {b} differs from the single-GPU run"
+            if a.accur == 1:
+                for x, y in zip(ds.solver.get_slopes(b), one.get_slopes(b)):
+                    assert np.array_equal(x, y), f"rank {rank}: slopes of block {b} differ from the single-GPU run"
             if ds.transport == "peer":   # the arenas hold the final state's halos (trailing put of par2d_step)
-                assert np.array_equal(ds.solver.get_residual(b), one.get_residual(b)), f"rank {rank}: residual of block {b} differs"
+                if a.accur == 1:
+                    for x, y in zip(ds.solver.get_residual_dg(b), one.get_residual_dg(b)):
+                        assert np.array_equal(x, y), f"rank {rank}: right-hand sides of block {b} differ"
+                else:
+                    assert np.array_equal(ds.solver.get_residual(b), one.get_residual(b)), f"rank {rank}: residual of block {b} differs"
         assert np.array_equal(dt, np.array([i.dt for i in oinfo]))
         assert np.array_equal(relres, np.array([i.relres for i in oinfo])), (relres, [i.relres for i in oinfo])
         one.close()

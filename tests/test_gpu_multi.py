@@ -48,6 +48,22 @@ def test_two_gpus_match_oracle_and_single_gpu_bitwise(transport, extra):
     assert f"transport={transport}" in p.stdout
 
 
+@pytest.mark.parametrize("transport", ["peer", "external"])
+@pytest.mark.parametrize("extra", [
+    ["--case", "Case_spikefine24", "--steps", "10", "--batches", "2"],
+    ["--case", "Case_rktnoz9", "--steps", "8"],
+])
+def test_two_gpus_second_order_branch(transport, extra):
+    """cfg.accur = 1 across ranks: the halo lines carry the reconstruction at two Gauss points per edge face
+    (8 doubles per edge cell, SpatialDiscretization.cpp:243-256); means, slopes, right-hand sides and the residual
+    history must equal the single-GPU run bit for bit and the oracle within tolerance."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    p = _launch(2, extra + ["--transport", transport, "--accur", "1"])
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert "RANK0 OK" in p.stdout and "RANK1 OK" in p.stdout
+
+
 def test_all_gpus_peer_mapped():
     n = _ngpus()
     if n < 3:
