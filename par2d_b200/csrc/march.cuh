@@ -28,9 +28,9 @@
 // parked flux: the kernel is bound by warps x ILP under the register file; both take live values out
 // of registers (ncu history in DESIGN.md).
 //
-// Compared with the TMA-staged 32x8 tile kernel (kernels.cuh::step_kernel, kept as the A/B baseline,
-// PAR2D_KERNEL=tile): no block-wide barriers, ~1/6 of the shared-memory traffic, a fifth of the index
-// arithmetic.
+// Compared with the first version of this step (a TMA-staged 32x8 tile kernel with block barriers, retired:
+// profiles/r01_step_v1_tile_kernel_ncu_summary.txt): no block-wide barriers, ~1/6 of the shared-memory traffic,
+// a fifth of the index arithmetic.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>

@@ -1,5 +1,5 @@
 """Diagnostic: a few steps of a shipped case through the C ABI, printing the state error vs the oracle.
-Usage: python tools/diag_step.py [case] [steps] [mode] [verbose]  (PAR2D_NO_TMA=1 uses the plain staging path)"""
+Usage: python tools/diag_step.py [case] [steps] [mode] [verbose]"""
 import os, sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
@@ -43,5 +43,5 @@ for b in range(case.nblocks):
         if verbose and w > 1e-11:
             j, i = np.unravel_index(np.argmax(e), e.shape)
             print(f"  state block {b} var {k} rel={w:.3e} at j={j} i={i} dev={s[j,i,k]:.9e} orc={r[j,i,k]:.9e} nbad={(e > 1e-9 * np.abs(r[..., k]).max()).sum()}")
-print(f"{name} steps={steps} mode={mode} tma={'off' if os.environ.get('PAR2D_NO_TMA') else 'on'} "
+print(f"{name} steps={steps} mode={mode} tma=on "
       f"worst={worst:.3e} relres={info[-1].relres:.9e} ref={ref[-1].relres:.9e} dt={info[-1].dt:.6e}")
