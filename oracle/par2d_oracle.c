@@ -590,6 +590,7 @@ static void refresh_derived(orc_ctx* c, orc_block* b) {
 }
 
 /* ------------------------------------------------ second-order branch */
+static int64_t peer_slot_offset(const orc_ctx* c, int peer, int recv_block, int recv_side, int sending);
 #include "par2d_oracle_dg.inc"
 
 /* ------------------------------------------------------------ exchange */
@@ -598,6 +599,10 @@ static void refresh_derived(orc_ctx* c, orc_block* b) {
  * read directly, off-rank ones from the peer receive buffer (filled by the
  * host transport between step_begin and step_end).  The received line is
  * copied verbatim and UpdateState'd, SpatialDiscretization.cpp:263-269. */
+/* doubles per edge cell of a halo line: NVAR, or 2*NVAR in the second-order branch
+ * (SpatialDiscretization.cpp:231 ntrans *= (ACCUR + 1)) */
+static int line_width(const par2d_config* cfg) { return cfg->accur == 1 ? 2 * NV : NV; }
+
 static int64_t peer_slot_offset(const orc_ctx* c, int peer, int recv_block, int recv_side, int sending) {
     /* lines are ordered by (receiving block id, receiving side); when `sending`
      * the receiver is the peer's block, otherwise ours */
@@ -611,7 +616,7 @@ static int64_t peer_slot_offset(const orc_ctx* c, int peer, int recv_block, int 
             int nb = d->bid[s];
             if (nb < 0 || c->table[nb].owner != send_owner) continue;
             if (g == recv_block && s == recv_side) return off;
-            off += (int64_t)NV * desc_edge_len(d, s);
+            off += (int64_t)line_width(&c->cfg) * desc_edge_len(d, s);
         }
     }
     return -1;
@@ -631,9 +636,11 @@ static void pack_sends(orc_ctx* c) {
                 orc_block* mine = &c->blk[c->owned_index[nb]];
                 int ms = facing_side(&c->table[nb], g, s);
                 int n = desc_edge_len(d, s);
-                for (int q = 0; q < n; q++)
-                    memcpy(c->peers[p].send + off + NV * q, mine->unk + NV * edge_cell(mine, ms, q), sizeof(double) * NV);
-                off += (int64_t)NV * n;
+                if (c->cfg.accur == 1) dg_pack_line(c, mine, ms, n, c->peers[p].send + off);
+                else
+                    for (int q = 0; q < n; q++)
+                        memcpy(c->peers[p].send + off + NV * q, mine->unk + NV * edge_cell(mine, ms, q), sizeof(double) * NV);
+                off += (int64_t)line_width(&c->cfg) * n;
             }
         }
     }
@@ -680,7 +687,6 @@ int orc_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_desc*
     if (!cfg || !blocks || !out || nblocks < 1) return fail(PAR2D_ERR_ARG, "null argument");
     if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail(PAR2D_ERR_ARG, "bad rank");
     if (cfg->accur != 0 && cfg->accur != 1) return fail(PAR2D_ERR_ARG, "accur must be 0 or 1 (SpatialDiscretization.cpp:204)");
-    if (cfg->accur == 1 && cfg->nranks != 1) return fail(PAR2D_ERR_ARG, "the second-order branch of the oracle is single-rank");
     int rc = validate_table(nblocks, blocks, cfg->nranks);
     if (rc) return rc;
     orc_ctx* c = (orc_ctx*)calloc(1, sizeof *c);
@@ -741,8 +747,8 @@ int orc_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_desc*
             for (int s = 0; s < 4; s++) {
                 int nb = blocks[g].bid[s];
                 if (nb < 0) continue;
-                if (blocks[g].owner == cfg->rank && blocks[nb].owner == p) c->peers[p].n_recv += (int64_t)NV * desc_edge_len(&blocks[g], s);
-                if (blocks[g].owner == p && blocks[nb].owner == cfg->rank) c->peers[p].n_send += (int64_t)NV * desc_edge_len(&blocks[g], s);
+                if (blocks[g].owner == cfg->rank && blocks[nb].owner == p) c->peers[p].n_recv += (int64_t)line_width(cfg) * desc_edge_len(&blocks[g], s);
+                if (blocks[g].owner == p && blocks[nb].owner == cfg->rank) c->peers[p].n_send += (int64_t)line_width(cfg) * desc_edge_len(&blocks[g], s);
             }
         c->peers[p].send = (double*)calloc(c->peers[p].n_send ? c->peers[p].n_send : 1, sizeof(double));
         c->peers[p].recv = (double*)calloc(c->peers[p].n_recv ? c->peers[p].n_recv : 1, sizeof(double));

@@ -40,3 +40,15 @@ def test_three_ranks_uneven(tmp_path):
     p = _launch(3, ["--case", "Case_ffstep8", "--steps", "5"])
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert all(f"RANK{r} OK" in p.stdout for r in range(3))
+
+
+@pytest.mark.parametrize("extra", [
+    ["--case", "Case_spikefine24", "--steps", "8", "--accur", "1"],
+    ["--case", "Case_ffstep8", "--steps", "10", "--accur", "1"],
+])
+def test_two_ranks_second_order_branch_bitwise(extra):
+    """cfg.accur = 1: the exchange buffers carry two Gauss points per edge face (8 doubles per edge cell); the
+    sharded run must still reproduce the single-process means and residual history bit for bit."""
+    p = _launch(2, extra)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert "RANK0 OK" in p.stdout and "RANK1 OK" in p.stdout
