@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(DG_THREADS, DG_MINB) dg_cell_kernel(StepArgs a
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.dt_used = dt;
 
     if (live) {
-        const int i = (int)(e % ncx), j = (int)(e / ncx);
+        const int i = (int)e % ncx, j = (int)e / ncx;   // blocks stay below 2^31 cells
         DgCell me;
         dg_load_cell(g, b, a.cur, i, j, me);
         const double* X = b.nodes;
@@ -517,21 +517,26 @@ __global__ void __launch_bounds__(DG_THREADS) dg_limit_kernel(StepArgs a, DgArgs
     // cell after cell in memory order, so a cell sees new means behind it (e-1, e-ncx) and old ones ahead
     const double* Sold = b.state[a.cur];
     const double* Snew = b.state[a.cur ^ 1];
-    auto off = [&](long long c) { return (long long)(c / ncx + 1) * b.pitch + COL0 + (c % ncx); };
-    const long long om = off(e);
+    // flat neighbours e-1, e+1 (they wrap across rows at the ends of a row, as the reference's flat index does) and
+    // e-ncx, e+ncx as offsets in the padded planes - 32-bit index arithmetic, one division per thread
+    const int ei = (int)e, i = ei % ncx, j = ei / ncx;
+    const long long om = (long long)(j + 1) * b.pitch + COL0 + i;
+    const long long o_im = i > 0 ? om - 1 : om - b.pitch + (ncx - 1);
+    const long long o_ip = i < ncx - 1 ? om + 1 : om + b.pitch - (ncx - 1);
+    const long long o_jm = om - b.pitch, o_jp = om + b.pitch;
     const bool has_ip = e + 1 < ncell, has_im = e - 1 >= 0, has_jp = e + ncx < ncell, has_jm = e - ncx >= 0;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const double me = Snew[q * b.plane + om];
         double ux = b.uxt[4 * e + q], uy = b.uyt[4 * e + q];
         double du;
-        if (has_ip && has_im) du = DG_DUSCALE * ((Sold[q * b.plane + off(e + 1)] - Snew[q * b.plane + off(e - 1)]) / 2.0);
-        else if (!has_im) du = DG_DUSCALE * ((Sold[q * b.plane + off(e + 1)] - me) / 1.0);
-        else du = DG_DUSCALE * ((me - Snew[q * b.plane + off(e - 1)]) / 1.0);
+        if (has_ip && has_im) du = DG_DUSCALE * ((Sold[q * b.plane + o_ip] - Snew[q * b.plane + o_im]) / 2.0);
+        else if (!has_im) du = DG_DUSCALE * ((Sold[q * b.plane + o_ip] - me) / 1.0);
+        else du = DG_DUSCALE * ((me - Snew[q * b.plane + o_im]) / 1.0);
         ux = dg_sign(ux) * fmin(fabs(ux), fabs(du));
-        if (has_jp && has_jm) du = DG_DUSCALE * ((Sold[q * b.plane + off(e + ncx)] - Snew[q * b.plane + off(e - ncx)]) / 2.0);
-        else if (!has_jm) du = DG_DUSCALE * ((Sold[q * b.plane + off(e + ncx)] - me) / 1.0);
-        else du = DG_DUSCALE * ((me - Snew[q * b.plane + off(e - ncx)]) / 1.0);
+        if (has_jp && has_jm) du = DG_DUSCALE * ((Sold[q * b.plane + o_jp] - Snew[q * b.plane + o_jm]) / 2.0);
+        else if (!has_jm) du = DG_DUSCALE * ((Sold[q * b.plane + o_jp] - me) / 1.0);
+        else du = DG_DUSCALE * ((me - Snew[q * b.plane + o_jm]) / 1.0);
         uy = dg_sign(uy) * fmin(fabs(uy), fabs(du));
         b.ux[4 * e + q] = ux;
         b.uy[4 * e + q] = uy;
