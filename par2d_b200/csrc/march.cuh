@@ -48,6 +48,9 @@ namespace par2d {
 #ifndef MARCH_NODE_LDS
 #define MARCH_NODE_LDS 0
 #endif
+#ifndef MARCH_WRITER_PRED
+#define MARCH_WRITER_PRED 0
+#endif
 #ifndef MARCH_STAGES
 #define MARCH_STAGES 3    // ring stages of two rows each
 #endif
@@ -151,7 +154,7 @@ template <bool FAITHFUL, bool TPG, bool AXI, bool HOOKS>
 __device__ __forceinline__ void cell_update(const StepArgs& a, const Gas& g, const MarchCtx& m, int c, int j, const FaceState& cur, double T, double im,
                                             double xa, double ya, double xb, double yb, double xc, double yc_, double xd, double yd,
                                             const Flux& Fl, const Flux& Fr, const Flux& Gb, const Flux& Gt,
-                                            double out[4], double& sq0, double& sq1, double& sq2, double& sq3, unsigned& flags) {
+                                            double out[4], double& sq0, double& sq1, double& sq2, double& sq3, unsigned& flags, bool live = true) {
     const bool update = HOOKS ? a.update != 0 : true;   // HOOKS = false: the production step (no residual dump, always advancing)
     const double ycc = 0.25 * (ya + yb + yc_ + yd);
     double r[4];        // residual = calc_dudt's dudt
@@ -213,7 +216,7 @@ __device__ __forceinline__ void cell_update(const StepArgs& a, const Gas& g, con
             solve_lean(sc, cur.rho, cur.u, cur.v, e0, inv_cv, R, dv);
         }
     }
-    sq0 = fma(r[0], r[0], sq0); sq1 = fma(r[1], r[1], sq1); sq2 = fma(r[2], r[2], sq2); sq3 = fma(r[3], r[3], sq3);
+    if (live) { sq0 = fma(r[0], r[0], sq0); sq1 = fma(r[1], r[1], sq1); sq2 = fma(r[2], r[2], sq2); sq3 = fma(r[3], r[3], sq3); }
     if constexpr (HOOKS) {
         if (a.res_out != nullptr && a.res_block == m.k) {
             double* o = a.res_out + 4 * ((long long)j * m.ncx + c);
@@ -225,10 +228,12 @@ __device__ __forceinline__ void cell_update(const StepArgs& a, const Gas& g, con
         out[0] = cur.rho + dv[0]; out[1] = cur.u + dv[1]; out[2] = cur.v + dv[2];
         if constexpr (FAITHFUL) out[3] = fmax(T + dv[3], 201.0);
         else out[3] = max_sel(T + dv[3], 201.0);
-        if (!(out[0] > 0.0)) flags |= FLAG_DENSITY;
+        if (live && !(out[0] > 0.0)) flags |= FLAG_DENSITY;
         if constexpr (CPL == 1) {
-            double* o = m.Sout + ((long long)(j + 1) * m.pitch + COL0 + c);
-            __stcg(o, out[0]); __stcg(o + m.plane, out[1]); __stcg(o + 2 * m.plane, out[2]); __stcg(o + 3 * m.plane, out[3]);
+            if (live) {
+                double* o = m.Sout + ((long long)(j + 1) * m.pitch + COL0 + c);
+                __stcg(o, out[0]); __stcg(o + m.plane, out[1]); __stcg(o + 2 * m.plane, out[2]); __stcg(o + 3 * m.plane, out[3]);
+            }
         }
     }
 }
@@ -305,6 +310,15 @@ __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const
     double out[CPL][4];
 #pragma unroll
     for (int e = 0; e < CPL; e++) {
+#if MARCH_WRITER_PRED
+        if constexpr (!FAITHFUL && !HOOKS && CPL == 1) {
+            // the two halo lanes run the cell update as well (their sums, flags and stores are switched off): no
+            // branch between the fluxes and the update, one larger block for the instruction scheduler
+            if (m.writer[e]) flags |= flu[e];
+            cell_update<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, m.c + e, j, lo.s[e], lo.T[e], lo.im[e], lo.x[e], lo.y[e], lo.x[e + 1], lo.y[e + 1],
+                                            hi.x[e + 1], hi.y[e + 1], hi.x[e], hi.y[e], F[e], F[e + 1], Gb[e], Gt[e], out[e], sq0, sq1, sq2, sq3, flags, m.writer[e]);
+        } else
+#endif
         if (m.writer[e]) {
             flags |= flu[e];   // state checks of the cell above: a real cell or a filled ghost
             cell_update<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, m.c + e, j, lo.s[e], lo.T[e], lo.im[e], lo.x[e], lo.y[e], lo.x[e + 1], lo.y[e + 1],
