@@ -260,6 +260,12 @@ PAR2D_FN double sgn_bit(double x) { return signbit(x) ? -1.0 : 1.0; }  // Indexi
 #ifndef LDFSS_UPWIND_VOTE
 #define LDFSS_UPWIND_VOTE 1
 #endif
+#ifndef LDFSS_VOTE_MIRROR
+#define LDFSS_VOTE_MIRROR 0   // 1: a second vote for 'every face supersonic from the right', 2: one vote for both
+                              // directions with the upwind side picked by selects.  Measured on B200 (march kernel,
+                              // +x flow): 0 -> 0.5195 ms, 1 -> 0.5276 ms, 2 -> 0.5341 ms: every extra vote/branch on the
+                              // general path costs more than the shortcut saves, so only the left-upwind case is voted
+#endif
 template <bool FAITHFUL, bool AXI, bool WARP_VOTE = false>
 PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) {
     Flux o;
@@ -315,6 +321,31 @@ PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) 
         const double xmr = fma(R.u, fg.dy, -R.v * fg.dx) * q;
 #if defined(__CUDA_ARCH__) && LDFSS_UPWIND_VOTE
         if constexpr (WARP_VOTE) {
+#if LDFSS_VOTE_MIRROR == 2
+            // ONE vote for both directions: every face of the warp supersonic, each from its own upwind side
+            // (all/alr = 1/0 or 0/1, btl = btr = 0); the upwind state is picked by selects
+            const bool fromL = xml >= 1.0 && xmr >= 1.0, fromR = xml <= -1.0 && xmr <= -1.0;
+            if (__all_sync(0xffffffffu, fromL || fromR)) {
+                const double rho = fromL ? L.rho : R.rho, uu = fromL ? L.u : R.u, vv = fromL ? L.v : R.v;
+                const double pp = fromL ? L.p : R.p, hh = fromL ? L.h0 : R.h0, mm = fromL ? xml : xmr;
+                if constexpr (AXI) {
+                    const double fm = ((la * fg.yf) * rho) * mm;
+                    o.parr = -pp * fg.dx;
+                    o.f0 = fm;
+                    o.f1 = fma(fm, uu, (pp * fg.yf) * fg.dy);
+                    o.f2 = fm * vv;
+                    o.f3 = fm * hh;
+                } else {
+                    const double fm = (la * rho) * mm;
+                    o.parr = 0.0;
+                    o.f0 = fm;
+                    o.f1 = fma(fm, uu, pp * fg.dy);
+                    o.f2 = fma(fm, vv, -pp * fg.dx);
+                    o.f3 = fm * hh;
+                }
+                return o;
+            }
+#else
             if (__all_sync(0xffffffffu, xml >= 1.0 && xmr >= 1.0)) {          // all/alr = 1/0, btl = btr = 0
                 if constexpr (AXI) {
                     const double fml = ((la * fg.yf) * L.rho) * xml;
@@ -333,7 +364,7 @@ PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) 
                 }
                 return o;
             }
-            if (__all_sync(0xffffffffu, xml <= -1.0 && xmr <= -1.0)) {        // all/alr = 0/1
+            if (LDFSS_VOTE_MIRROR && __all_sync(0xffffffffu, xml <= -1.0 && xmr <= -1.0)) {        // all/alr = 0/1
                 if constexpr (AXI) {
                     const double fmr = ((la * fg.yf) * R.rho) * xmr;
                     o.parr = -R.p * fg.dx;
@@ -351,6 +382,7 @@ PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) 
                 }
                 return o;
             }
+#endif
         }
 #endif
         const bool subL = fabs(xml) < 1.0, subR = fabs(xmr) < 1.0;
