@@ -48,6 +48,12 @@ namespace par2d {
 #ifndef MARCH_NODE_LDS
 #define MARCH_NODE_LDS 0
 #endif
+#ifndef MARCH_SPLIT_PRE
+#define MARCH_SPLIT_PRE 0
+#endif
+#ifndef MARCH_VOTE_J
+#define MARCH_VOTE_J 1       // the fully-upwind warp vote also on j-faces (0: i-faces only, A/B runs)
+#endif
 #ifndef MARCH_WRITER_PRED
 #define MARCH_WRITER_PRED 0
 #endif
@@ -282,16 +288,32 @@ __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const
     // i-faces of row j: face e between cell (c+e-1, j) [left state] and (c+e, j): node (c+e, j) -> (c+e, j+1);
     // the left state of face 0 is the last cell of lane-1, the flux of face CPL is face 0 of lane+1
     Flux F[CPL + 1];
+    Flux Gt[CPL], Gb[CPL];
+#if MARCH_SPLIT_PRE
+    if constexpr (!FAITHFUL && CPL == 1) {
+        // lean path: the Mach-number parts (one rsqrt chain each) of the i-face and of the j-face are evaluated side
+        // by side BEFORE either flux reaches its warp vote - two independent dependency chains in one block
+        const FaceGeom gi = face_geom<false>(lo.x[0], lo.y[0], hi.x[0], hi.y[0]);
+        const FaceGeom gj = face_geom<false>(hi.x[0], hi.y[0], hi.x[1], hi.y[1]);
+        const FaceState left = shfl_up1(lo.s[0]);
+        const LdfssPre pi = ldfss_lean_pre(gi, left, lo.s[0]);
+        const LdfssPre pj = ldfss_lean_pre(gj, hi.s[0], lo.s[0]);
+        F[0] = ldfss_lean_post<AXI, true>(gi, left, lo.s[0], pi);
+        Gt[0] = ldfss_lean_post<AXI, MARCH_VOTE_J != 0>(gj, hi.s[0], lo.s[0], pj);
+        F[1] = shfl_down1(F[0]);
+    } else
+#endif
+    {
     F[0] = ldfss<FAITHFUL, AXI, !FAITHFUL>(face_geom<FAITHFUL>(lo.x[0], lo.y[0], hi.x[0], hi.y[0]), shfl_up1(lo.s[CPL - 1]), lo.s[0]);
 #pragma unroll
     for (int e = 1; e < CPL; e++)
         F[e] = ldfss<FAITHFUL, AXI, !FAITHFUL>(face_geom<FAITHFUL>(lo.x[e], lo.y[e], hi.x[e], hi.y[e]), lo.s[e - 1], lo.s[e]);
     F[CPL] = shfl_down1(F[0]);
     // j-faces: between cell (c+e, j+1) [left state = upper cell] and (c+e, j): node (c+e, j+1) -> (c+e+1, j+1)
-    Flux Gt[CPL], Gb[CPL];
 #pragma unroll
     for (int e = 0; e < CPL; e++)
-        Gt[e] = ldfss<FAITHFUL, AXI, !FAITHFUL>(face_geom<FAITHFUL>(hi.x[e], hi.y[e], hi.x[e + 1], hi.y[e + 1]), hi.s[e], lo.s[e]);
+        Gt[e] = ldfss<FAITHFUL, AXI, !FAITHFUL && MARCH_VOTE_J>(face_geom<FAITHFUL>(hi.x[e], hi.y[e], hi.x[e + 1], hi.y[e + 1]), hi.s[e], lo.s[e]);
+    }
     // swap the parked bottom fluxes with the new top fluxes
     if constexpr (CPL == 2) {
         double2* G2 = reinterpret_cast<double2*>(&sm.G[0][q]);
@@ -434,7 +456,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
         for (int e = 0; e < CPL; e++) {
             const FaceState lo = face_state<FAITHFUL, TPG>(g, rs[e], rs[PLANE_D + e], rs[2 * PLANE_D + e], rs[3 * PLANE_D + e], fl0[e]);
             // j-face: left state = upper cell, right state = lower cell (SpatialDiscretization.cpp:556-625)
-            const Flux G0 = ldfss<FAITHFUL, AXI, !FAITHFUL>(face_geom<FAITHFUL>(A.x[e], A.y[e], A.x[e + 1], A.y[e + 1]), A.s[e], lo);
+            const Flux G0 = ldfss<FAITHFUL, AXI, !FAITHFUL && MARCH_VOTE_J>(face_geom<FAITHFUL>(A.x[e], A.y[e], A.x[e + 1], A.y[e + 1]), A.s[e], lo);
             sm.G[0][q + e] = G0.f0; sm.G[1][q + e] = G0.f1; sm.G[2][q + e] = G0.f2; sm.G[3][q + e] = G0.f3; sm.G[4][q + e] = G0.parr;
             if (m.writer[e]) flags |= fl0[e];
         }

@@ -37,6 +37,15 @@ inline double __dsub_rn(double a, double b) { volatile double r = a - b; return 
 #ifndef LDFSS_SQRT
 #define LDFSS_SQRT 0
 #endif
+#ifndef LDFSS_UPWIND_VOTE
+#define LDFSS_UPWIND_VOTE 1
+#endif
+#ifndef LDFSS_VOTE_MIRROR
+#define LDFSS_VOTE_MIRROR 0   // 1: a second vote for 'every face supersonic from the right', 2: one vote for both
+                              // directions with the upwind side picked by selects.  Measured on B200 (march kernel,
+                              // +x flow): 0 -> 0.5195 ms, 1 -> 0.5276 ms, 2 -> 0.5341 ms: every extra vote/branch on the
+                              // general path costs more than the shortcut saves, so only the left-upwind case is voted
+#endif
 #ifndef LDFSS_BRANCHFREE
 #define LDFSS_BRANCHFREE 1    // the subsonic diffusion term is evaluated without a branch and switched off by a select: measured
                               // +1.3% on B200 together with the warp vote (fully supersonic warps skip it anyway; fewer basic
@@ -253,19 +262,193 @@ struct Flux {
 
 PAR2D_FN double sgn_bit(double x) { return signbit(x) ? -1.0 : 1.0; }  // Indexing.h:22
 
+// The lean LDFSS in two parts, so that a caller can evaluate the Mach-number parts of several faces in one block
+// before any of them reaches the warp vote (march.cuh): ldfss_lean_pre = len*ahalf and the two face Mach numbers
+// from ONE rsqrt; ldfss_lean_post = the splitting and the flux.
+struct LdfssPre {
+    double la, xml, xmr;
+};
+PAR2D_FN LdfssPre ldfss_lean_pre(const FaceGeom& fg, const FaceState& L, const FaceState& R) {
+    LdfssPre p;
+    const double ahalf = L.a + R.a;          // the lean FaceState carries a/2
+    const double w = fma(fg.dx, fg.dx, fg.dy * fg.dy) * (ahalf * ahalf);
+    const double q = fast_rsqrt(w);          // 1 / (len * ahalf)
+    p.la = w * q;                            // len * ahalf
+    p.xml = fma(L.u, fg.dy, -L.v * fg.dx) * q;
+    p.xmr = fma(R.u, fg.dy, -R.v * fg.dx) * q;
+    return p;
+}
+template <bool AXI, bool WARP_VOTE>
+PAR2D_FN Flux ldfss_lean_post(const FaceGeom& fg, const FaceState& L, const FaceState& R, const LdfssPre& pre) {
+    Flux o;
+    // lean evaluation: one rsqrt of (|d| ahalf)^2 yields both len*ahalf and its reciprocal, and
+    // the pressure-weighted diffusion term (with its three divisions) is
+    // evaluated only where both sides are subsonic (it is multiplied by btl*btr = 0 otherwise).
+    const double la = pre.la, xml = pre.xml, xmr = pre.xmr;
+#if defined(__CUDA_ARCH__) && LDFSS_UPWIND_VOTE
+    if constexpr (WARP_VOTE) {
+#if LDFSS_VOTE_MIRROR == 2
+        // ONE vote for both directions: every face of the warp supersonic, each from its own upwind side
+        // (all/alr = 1/0 or 0/1, btl = btr = 0); the upwind state is picked by selects
+        const bool fromL = xml >= 1.0 && xmr >= 1.0, fromR = xml <= -1.0 && xmr <= -1.0;
+        if (__all_sync(0xffffffffu, fromL || fromR)) {
+            const double rho = fromL ? L.rho : R.rho, uu = fromL ? L.u : R.u, vv = fromL ? L.v : R.v;
+            const double pp = fromL ? L.p : R.p, hh = fromL ? L.h0 : R.h0, mm = fromL ? xml : xmr;
+            if constexpr (AXI) {
+                const double fm = ((la * fg.yf) * rho) * mm;
+                o.parr = -pp * fg.dx;
+                o.f0 = fm;
+                o.f1 = fma(fm, uu, (pp * fg.yf) * fg.dy);
+                o.f2 = fm * vv;
+                o.f3 = fm * hh;
+            } else {
+                const double fm = (la * rho) * mm;
+                o.parr = 0.0;
+                o.f0 = fm;
+                o.f1 = fma(fm, uu, pp * fg.dy);
+                o.f2 = fma(fm, vv, -pp * fg.dx);
+                o.f3 = fm * hh;
+            }
+            return o;
+        }
+#else
+        if (__all_sync(0xffffffffu, xml >= 1.0 && xmr >= 1.0)) {          // all/alr = 1/0, btl = btr = 0
+            if constexpr (AXI) {
+                const double fml = ((la * fg.yf) * L.rho) * xml;
+                o.parr = -L.p * fg.dx;
+                o.f0 = fml;
+                o.f1 = fma(fml, L.u, (L.p * fg.yf) * fg.dy);
+                o.f2 = fml * L.v;
+                o.f3 = fml * L.h0;
+            } else {
+                const double fml = (la * L.rho) * xml;
+                o.parr = 0.0;
+                o.f0 = fml;
+                o.f1 = fma(fml, L.u, L.p * fg.dy);
+                o.f2 = fma(fml, L.v, -L.p * fg.dx);
+                o.f3 = fml * L.h0;
+            }
+            return o;
+        }
+        if (LDFSS_VOTE_MIRROR && __all_sync(0xffffffffu, xml <= -1.0 && xmr <= -1.0)) {        // all/alr = 0/1
+            if constexpr (AXI) {
+                const double fmr = ((la * fg.yf) * R.rho) * xmr;
+                o.parr = -R.p * fg.dx;
+                o.f0 = fmr;
+                o.f1 = fma(fmr, R.u, (R.p * fg.yf) * fg.dy);
+                o.f2 = fmr * R.v;
+                o.f3 = fmr * R.h0;
+            } else {
+                const double fmr = (la * R.rho) * xmr;
+                o.parr = 0.0;
+                o.f0 = fmr;
+                o.f1 = fma(fmr, R.u, R.p * fg.dy);
+                o.f2 = fma(fmr, R.v, -R.p * fg.dx);
+                o.f3 = fmr * R.h0;
+            }
+            return o;
+        }
+#endif
+    }
+#endif
+    const bool subL = fabs(xml) < 1.0, subR = fabs(xmr) < 1.0;
+    // split Mach numbers and pressure weights (EulerFlux.cpp:146-175 with all/alr in {0,1} and
+    // btl/btr in {-1,0} substituted).  Selects, not branches: skipping the polynomials on
+    // supersonic faces was measured 1.6% SLOWER on B200 (the kernel is issue-bound, a branch
+    // costs more slots than the eight operations it skips).
+    const double hl = fma(0.5, xml, 0.5), hr = fma(0.5, xmr, -0.5);
+    const double xmml = hl * hl, xmmr = -(hr * hr);
+    double cep = subL ? xmml : (signbit(xml) ? 0.0 : xml);
+    double cem = subR ? xmmr : (signbit(xmr) ? xmr : 0.0);
+    const double wl = subL ? xmml * (2.0 - xml) : (signbit(xml) ? 0.0 : 1.0);
+    const double wr = subR ? -xmmr * (2.0 + xmr) : (signbit(xmr) ? 1.0 : 0.0);
+#if LDFSS_BRANCHFREE
+    {   // A/B: the subsonic diffusion term evaluated on every face and switched off by a select (one basic block)
+        const double t = 0.25 * fma(xml, xml, fma(xmr, xmr, 1e-199));
+        const double xs = t * fast_rsqrt(t);
+        const double d = xs - 0.70710678118654752440;
+        const double delp = L.p - R.p, psum = L.p + R.p;
+        const double plr = L.p * R.p;
+        const double w3 = fast_rcp(plr * psum);
+        const double N = max_sel(fma(-fabs(delp), psum, plr), 0.0);
+        const double k = (subL && subR) ? ((d * d) * w3) * N : 0.0;
+        cep = fma(-k, R.p, cep);
+        cem = fma(k, L.p, cem);
+    }
+    if (false) {
+#else
+    if (subL && subR) {
+#endif
+#if LDFSS_PRESSURE_V1
+        const double t = 0.5 * fma(xml, xml, xmr * xmr);
+        // rsqrt.approx flushes subnormals: below 1e-200 sqrt(t) is 0 to 100 digits of (xmhalf-1)
+#if LDFSS_SQRT
+        const double xmhalf = t > 1e-200 ? fast_sqrt(t) : 0.0;
+#else
+        const double xmhalf = t > 1e-200 ? t * fast_rsqrt(t) : 0.0;
+#endif
+        const double d1 = xmhalf - 1.0;
+        const double xmc = 0.25 * d1 * d1;
+        // delp/psum, 2|delp|/pL, 2|delp|/pR (EulerFlux.cpp:157-160) from ONE reciprocal,
+        // w = 1/(pL pR psum):  1/psum = pL pR w,  1/pL = pR psum w,  1/pR = pL psum w
+        const double delp = L.p - R.p, psum = L.p + R.p;
+        const double plr = L.p * R.p;
+        const double w3 = fast_rcp(plr * psum);
+        const double tw = psum * w3;
+        const double dps = delp * (plr * w3);
+        const double ad2 = 2.0 * fabs(delp);
+        cep -= xmc * max_sel(1.0 - fma(ad2, R.p * tw, dps), 0.0);
+        cem += xmc * max_sel(1.0 + fma(-ad2, L.p * tw, dps), 0.0);
+#else
+        // xmc = (xmhalf-1)^2/4 with xmhalf = sqrt((xml^2+xmr^2)/2) (EulerFlux.cpp:152-154).  Here
+        // xs = xmhalf/sqrt(2) and d = xs - 1/sqrt(2), so d*d = 2 xmc.  The 1e-199 keeps the argument of
+        // rsqrt.approx (which flushes subnormals) normal: it vanishes in the sum unless both Mach
+        // numbers are below 1e-92, where xs is 0 to 90 digits of d either way.  No branch, no compare.
+        const double t = 0.25 * fma(xml, xml, fma(xmr, xmr, 1e-199));
+        const double xs = t * fast_rsqrt(t);
+        const double d = xs - 0.70710678118654752440;
+        // pressure switches (EulerFlux.cpp:157-160) over their common denominator: with delp = pL - pR,
+        // psum = pL + pR and N = pL pR - |delp| psum,
+        //   1 - (delp/psum + 2|delp|/pL) = 2 N / (pL psum),   1 + (delp/psum - 2|delp|/pR) = 2 N / (pR psum)
+        // (psum -+ delp = 2 pR, 2 pL), so ONE reciprocal w3 = 1/(pL pR psum) and ONE max(.,0) serve both:
+        //   xmcp = xmc max(0, 2 N pR w3) = (2 xmc) max(0,N) w3 pR,   xmcm = (2 xmc) max(0,N) w3 pL
+        const double delp = L.p - R.p, psum = L.p + R.p;
+        const double plr = L.p * R.p;
+        const double w3 = fast_rcp(plr * psum);
+        const double N = max_sel(fma(-fabs(delp), psum, plr), 0.0);
+        const double k = ((d * d) * w3) * N;
+        cep = fma(-k, R.p, cep);
+        cem = fma(k, L.p, cem);
+#endif
+    }
+    const double pnet = fma(wl, L.p, wr * R.p);
+    if constexpr (AXI) {
+        // every flux component carries yface (EulerFlux.cpp:178-186): fold it into len*ahalf and pnet
+        const double lay = la * fg.yf;
+        const double fml = lay * L.rho * cep;
+        const double fmr = lay * R.rho * cem;
+        const double px = (pnet * fg.yf) * fg.dy;   // yface*len*pnet*normx
+        o.parr = -pnet * fg.dx;                     // len*pnet*normy, without yface (:181)
+        o.f0 = fml + fmr;
+        o.f1 = fma(fml, L.u, fma(fmr, R.u, px));
+        o.f2 = fma(fml, L.v, fmr * R.v);
+        o.f3 = fma(fml, L.h0, fmr * R.h0);
+    } else {
+        const double fml = la * L.rho * cep;
+        const double fmr = la * R.rho * cem;
+        o.parr = 0.0;
+        o.f0 = fml + fmr;
+        o.f1 = fma(fml, L.u, fma(fmr, R.u, pnet * fg.dy));
+        o.f2 = fma(fml, L.v, fma(fmr, R.v, -pnet * fg.dx));
+        o.f3 = fma(fml, L.h0, fmr * R.h0);
+    }
+    return o;
+}
+
 // WARP_VOTE (device, lean path, all 32 lanes of the warp calling together): when EVERY face of the warp is
 // supersonic in the same direction the flux is fully upwind - cep = xml, cem = 0, pnet = pL (or the mirror
 // image) - and the split polynomials, their selects and the dead side's terms are skipped.  The result is
 // bit-identical to the general path (the skipped terms are exact zeros there).
-#ifndef LDFSS_UPWIND_VOTE
-#define LDFSS_UPWIND_VOTE 1
-#endif
-#ifndef LDFSS_VOTE_MIRROR
-#define LDFSS_VOTE_MIRROR 0   // 1: a second vote for 'every face supersonic from the right', 2: one vote for both
-                              // directions with the upwind side picked by selects.  Measured on B200 (march kernel,
-                              // +x flow): 0 -> 0.5195 ms, 1 -> 0.5276 ms, 2 -> 0.5341 ms: every extra vote/branch on the
-                              // general path costs more than the shortcut saves, so only the left-upwind case is voted
-#endif
 template <bool FAITHFUL, bool AXI, bool WARP_VOTE = false>
 PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) {
     Flux o;
@@ -310,172 +493,7 @@ PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) 
         o.f2 = yface * (fml * L.v + fmr * R.v + py_planar);
         o.f3 = yface * (fml * L.h0 + fmr * (R.h0));
     } else {
-        // lean evaluation: one rsqrt of (|d| ahalf)^2 yields both len*ahalf and its reciprocal, and
-        // the pressure-weighted diffusion term (with its three divisions) is
-        // evaluated only where both sides are subsonic (it is multiplied by btl*btr = 0 otherwise).
-        const double ahalf = L.a + R.a;          // the lean FaceState carries a/2
-        const double w = fma(fg.dx, fg.dx, fg.dy * fg.dy) * (ahalf * ahalf);
-        const double q = fast_rsqrt(w);          // 1 / (len * ahalf)
-        const double la = w * q;                 // len * ahalf
-        const double xml = fma(L.u, fg.dy, -L.v * fg.dx) * q;
-        const double xmr = fma(R.u, fg.dy, -R.v * fg.dx) * q;
-#if defined(__CUDA_ARCH__) && LDFSS_UPWIND_VOTE
-        if constexpr (WARP_VOTE) {
-#if LDFSS_VOTE_MIRROR == 2
-            // ONE vote for both directions: every face of the warp supersonic, each from its own upwind side
-            // (all/alr = 1/0 or 0/1, btl = btr = 0); the upwind state is picked by selects
-            const bool fromL = xml >= 1.0 && xmr >= 1.0, fromR = xml <= -1.0 && xmr <= -1.0;
-            if (__all_sync(0xffffffffu, fromL || fromR)) {
-                const double rho = fromL ? L.rho : R.rho, uu = fromL ? L.u : R.u, vv = fromL ? L.v : R.v;
-                const double pp = fromL ? L.p : R.p, hh = fromL ? L.h0 : R.h0, mm = fromL ? xml : xmr;
-                if constexpr (AXI) {
-                    const double fm = ((la * fg.yf) * rho) * mm;
-                    o.parr = -pp * fg.dx;
-                    o.f0 = fm;
-                    o.f1 = fma(fm, uu, (pp * fg.yf) * fg.dy);
-                    o.f2 = fm * vv;
-                    o.f3 = fm * hh;
-                } else {
-                    const double fm = (la * rho) * mm;
-                    o.parr = 0.0;
-                    o.f0 = fm;
-                    o.f1 = fma(fm, uu, pp * fg.dy);
-                    o.f2 = fma(fm, vv, -pp * fg.dx);
-                    o.f3 = fm * hh;
-                }
-                return o;
-            }
-#else
-            if (__all_sync(0xffffffffu, xml >= 1.0 && xmr >= 1.0)) {          // all/alr = 1/0, btl = btr = 0
-                if constexpr (AXI) {
-                    const double fml = ((la * fg.yf) * L.rho) * xml;
-                    o.parr = -L.p * fg.dx;
-                    o.f0 = fml;
-                    o.f1 = fma(fml, L.u, (L.p * fg.yf) * fg.dy);
-                    o.f2 = fml * L.v;
-                    o.f3 = fml * L.h0;
-                } else {
-                    const double fml = (la * L.rho) * xml;
-                    o.parr = 0.0;
-                    o.f0 = fml;
-                    o.f1 = fma(fml, L.u, L.p * fg.dy);
-                    o.f2 = fma(fml, L.v, -L.p * fg.dx);
-                    o.f3 = fml * L.h0;
-                }
-                return o;
-            }
-            if (LDFSS_VOTE_MIRROR && __all_sync(0xffffffffu, xml <= -1.0 && xmr <= -1.0)) {        // all/alr = 0/1
-                if constexpr (AXI) {
-                    const double fmr = ((la * fg.yf) * R.rho) * xmr;
-                    o.parr = -R.p * fg.dx;
-                    o.f0 = fmr;
-                    o.f1 = fma(fmr, R.u, (R.p * fg.yf) * fg.dy);
-                    o.f2 = fmr * R.v;
-                    o.f3 = fmr * R.h0;
-                } else {
-                    const double fmr = (la * R.rho) * xmr;
-                    o.parr = 0.0;
-                    o.f0 = fmr;
-                    o.f1 = fma(fmr, R.u, R.p * fg.dy);
-                    o.f2 = fma(fmr, R.v, -R.p * fg.dx);
-                    o.f3 = fmr * R.h0;
-                }
-                return o;
-            }
-#endif
-        }
-#endif
-        const bool subL = fabs(xml) < 1.0, subR = fabs(xmr) < 1.0;
-        // split Mach numbers and pressure weights (EulerFlux.cpp:146-175 with all/alr in {0,1} and
-        // btl/btr in {-1,0} substituted).  Selects, not branches: skipping the polynomials on
-        // supersonic faces was measured 1.6% SLOWER on B200 (the kernel is issue-bound, a branch
-        // costs more slots than the eight operations it skips).
-        const double hl = fma(0.5, xml, 0.5), hr = fma(0.5, xmr, -0.5);
-        const double xmml = hl * hl, xmmr = -(hr * hr);
-        double cep = subL ? xmml : (signbit(xml) ? 0.0 : xml);
-        double cem = subR ? xmmr : (signbit(xmr) ? xmr : 0.0);
-        const double wl = subL ? xmml * (2.0 - xml) : (signbit(xml) ? 0.0 : 1.0);
-        const double wr = subR ? -xmmr * (2.0 + xmr) : (signbit(xmr) ? 1.0 : 0.0);
-#if LDFSS_BRANCHFREE
-        {   // A/B: the subsonic diffusion term evaluated on every face and switched off by a select (one basic block)
-            const double t = 0.25 * fma(xml, xml, fma(xmr, xmr, 1e-199));
-            const double xs = t * fast_rsqrt(t);
-            const double d = xs - 0.70710678118654752440;
-            const double delp = L.p - R.p, psum = L.p + R.p;
-            const double plr = L.p * R.p;
-            const double w3 = fast_rcp(plr * psum);
-            const double N = max_sel(fma(-fabs(delp), psum, plr), 0.0);
-            const double k = (subL && subR) ? ((d * d) * w3) * N : 0.0;
-            cep = fma(-k, R.p, cep);
-            cem = fma(k, L.p, cem);
-        }
-        if (false) {
-#else
-        if (subL && subR) {
-#endif
-#if LDFSS_PRESSURE_V1
-            const double t = 0.5 * fma(xml, xml, xmr * xmr);
-            // rsqrt.approx flushes subnormals: below 1e-200 sqrt(t) is 0 to 100 digits of (xmhalf-1)
-#if LDFSS_SQRT
-            const double xmhalf = t > 1e-200 ? fast_sqrt(t) : 0.0;
-#else
-            const double xmhalf = t > 1e-200 ? t * fast_rsqrt(t) : 0.0;
-#endif
-            const double d1 = xmhalf - 1.0;
-            const double xmc = 0.25 * d1 * d1;
-            // delp/psum, 2|delp|/pL, 2|delp|/pR (EulerFlux.cpp:157-160) from ONE reciprocal,
-            // w = 1/(pL pR psum):  1/psum = pL pR w,  1/pL = pR psum w,  1/pR = pL psum w
-            const double delp = L.p - R.p, psum = L.p + R.p;
-            const double plr = L.p * R.p;
-            const double w3 = fast_rcp(plr * psum);
-            const double tw = psum * w3;
-            const double dps = delp * (plr * w3);
-            const double ad2 = 2.0 * fabs(delp);
-            cep -= xmc * max_sel(1.0 - fma(ad2, R.p * tw, dps), 0.0);
-            cem += xmc * max_sel(1.0 + fma(-ad2, L.p * tw, dps), 0.0);
-#else
-            // xmc = (xmhalf-1)^2/4 with xmhalf = sqrt((xml^2+xmr^2)/2) (EulerFlux.cpp:152-154).  Here
-            // xs = xmhalf/sqrt(2) and d = xs - 1/sqrt(2), so d*d = 2 xmc.  The 1e-199 keeps the argument of
-            // rsqrt.approx (which flushes subnormals) normal: it vanishes in the sum unless both Mach
-            // numbers are below 1e-92, where xs is 0 to 90 digits of d either way.  No branch, no compare.
-            const double t = 0.25 * fma(xml, xml, fma(xmr, xmr, 1e-199));
-            const double xs = t * fast_rsqrt(t);
-            const double d = xs - 0.70710678118654752440;
-            // pressure switches (EulerFlux.cpp:157-160) over their common denominator: with delp = pL - pR,
-            // psum = pL + pR and N = pL pR - |delp| psum,
-            //   1 - (delp/psum + 2|delp|/pL) = 2 N / (pL psum),   1 + (delp/psum - 2|delp|/pR) = 2 N / (pR psum)
-            // (psum -+ delp = 2 pR, 2 pL), so ONE reciprocal w3 = 1/(pL pR psum) and ONE max(.,0) serve both:
-            //   xmcp = xmc max(0, 2 N pR w3) = (2 xmc) max(0,N) w3 pR,   xmcm = (2 xmc) max(0,N) w3 pL
-            const double delp = L.p - R.p, psum = L.p + R.p;
-            const double plr = L.p * R.p;
-            const double w3 = fast_rcp(plr * psum);
-            const double N = max_sel(fma(-fabs(delp), psum, plr), 0.0);
-            const double k = ((d * d) * w3) * N;
-            cep = fma(-k, R.p, cep);
-            cem = fma(k, L.p, cem);
-#endif
-        }
-        const double pnet = fma(wl, L.p, wr * R.p);
-        if constexpr (AXI) {
-            // every flux component carries yface (EulerFlux.cpp:178-186): fold it into len*ahalf and pnet
-            const double lay = la * fg.yf;
-            const double fml = lay * L.rho * cep;
-            const double fmr = lay * R.rho * cem;
-            const double px = (pnet * fg.yf) * fg.dy;   // yface*len*pnet*normx
-            o.parr = -pnet * fg.dx;                     // len*pnet*normy, without yface (:181)
-            o.f0 = fml + fmr;
-            o.f1 = fma(fml, L.u, fma(fmr, R.u, px));
-            o.f2 = fma(fml, L.v, fmr * R.v);
-            o.f3 = fma(fml, L.h0, fmr * R.h0);
-        } else {
-            const double fml = la * L.rho * cep;
-            const double fmr = la * R.rho * cem;
-            o.parr = 0.0;
-            o.f0 = fml + fmr;
-            o.f1 = fma(fml, L.u, fma(fmr, R.u, pnet * fg.dy));
-            o.f2 = fma(fml, L.v, fma(fmr, R.v, -pnet * fg.dx));
-            o.f3 = fma(fml, L.h0, fmr * R.h0);
-        }
+        o = ldfss_lean_post<AXI, WARP_VOTE>(fg, L, R, ldfss_lean_pre(fg, L, R));
     }
     return o;
 }
