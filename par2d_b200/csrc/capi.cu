@@ -217,6 +217,12 @@ struct par2d_ctx {
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_ghost = nullptr, ev_edge = nullptr;
     bool overlap = true;             // PAR2D_NO_OVERLAP=1 keeps put -> ghost -> march in one stream (A/B runs)
+    // single rank: the same two-stream scheme hides the ghost fill + bookkeeping of step n+1 behind the interior
+    // strips of step n (par2d_step without stop_on_tol); needs double-buffered dt table and strip partials
+    bool single_overlap = false;
+    cudaEvent_t ev_main = nullptr;
+    long long partials_stride = 0;   // doubles between the two parities of the partial sums (0: single buffer)
+    int dt_parities = 1;
     long long timeout_ns = 20000000000ll;
 
     // history of the last batch, host copies
@@ -243,9 +249,9 @@ struct par2d_ctx {
         a.max_tiles = max_tiles;
         a.max_faces = max_faces;
         a.tmaps = dtmaps;
-        a.dt_table = dt_table;
+        a.dt_table = dt_table + (dt_parities == 2 ? (iter_queued & 1) * (long long)nblocks : 0);
         a.dt_used = dt_used + (iter_queued & 1);
-        a.partials = partials;
+        a.partials = partials + (iter_queued & 1) * partials_stride;
         a.flags = flags;
         a.stop = stop;
         a.res_out = nullptr;
@@ -275,7 +281,7 @@ struct par2d_ctx {
         FinalizeArgs f;
         f.blocks = dblk;
         f.nowned = nowned;
-        f.partials = partials;
+        f.partials = partials + (iter_queued & 1) * partials_stride;
         f.res0 = res0;
         f.blk_hist = blk_hist;
         f.step_hist = step_hist;
@@ -440,6 +446,59 @@ void queue_step_overlapped(par2d_ctx* c) {
     cudaEventRecord(c->ev_edge, c->side_stream);
     cudaStreamWaitEvent(c->stream, c->ev_edge, 0);
     if (c->timing) cudaEventRecord(c->ev[2 * c->ev_used++ + 1], c->stream);
+}
+
+// Single rank, no stop test inside the batch: nsteps steps with the ghost fill (+ dt) of step n+1 and the bookkeeping
+// of step n-1 running on the side stream beside the interior strips of step n.
+//   side : edge strips(n) -> ghost(n+1) [+ finalize(n-1)]          -> (waits for interior(n))  edge strips(n+1) ...
+//   main : interior strips(n)  -> (waits for the side stream)  interior strips(n+1) ...
+// Buffers touched concurrently are double-buffered by step parity: state (ping-pong), per-block dt table, strip
+// partial sums, dt_used.  The bookkeeping lags the state by at most two steps inside the batch and is complete
+// when the batch returns.
+void queue_batch_overlapped(par2d_ctx* c, int nsteps) {
+    std::vector<FinalizeArgs> pending;                // bookkeeping not launched yet, oldest first (at most two)
+    {
+        StepArgs a0 = c->step_args(1);
+        c->kt->ghost(c->stream, a0, c->gas, 1, nullptr);
+        cudaEventRecord(c->ev_main, c->stream);
+        cudaStreamWaitEvent(c->side_stream, c->ev_main, 0);
+    }
+    for (int n = 0; n < nsteps; n++) {
+        StepArgs a = c->step_args(1);
+        if (c->timing) {
+            if ((int)c->ev.size() < 2 * (c->ev_used + 1)) {
+                cudaEvent_t e0, e1;
+                cudaEventCreate(&e0);
+                cudaEventCreate(&e1);
+                c->ev.push_back(e0);
+                c->ev.push_back(e1);
+            }
+            cudaEventRecord(c->ev[2 * c->ev_used], c->stream);
+        }
+        StepArgs ae = a, ai = a;
+        ae.tile_list = c->d_edge_tiles; ae.tile_count = c->n_edge_tiles;
+        ai.tile_list = c->d_inner_tiles; ai.tile_count = c->n_inner_tiles;
+        c->kt->march(c->side_stream, ae, c->gas, c->tpg, c->axi);
+        c->kt->march(c->stream, ai, c->gas, c->tpg, c->axi);
+        pending.push_back(c->finalize_args(0));
+        c->iter_queued++;
+        c->cur ^= 1;
+        if (n + 1 < nsteps) {
+            // ghost fill of the new state from its edge strips; the bookkeeping of step n-1 (complete: the side
+            // stream waited for interior(n-1) before edge(n)) rides along
+            StepArgs an = c->step_args(1);
+            const FinalizeArgs* ride = nullptr;
+            FinalizeArgs f;
+            if (pending.size() == 2) { f = pending.front(); pending.erase(pending.begin()); ride = &f; }
+            c->kt->ghost(c->side_stream, an, c->gas, 1, ride);
+        }
+        cudaEventRecord(c->ev_edge, c->side_stream);
+        cudaEventRecord(c->ev_main, c->stream);
+        cudaStreamWaitEvent(c->stream, c->ev_edge, 0);        // interior(n+1) reads cells of the edge strips; edge(n) read the buffer it writes
+        cudaStreamWaitEvent(c->side_stream, c->ev_main, 0);   // edge(n+1) reads cells of the interior strips
+        if (c->timing) cudaEventRecord(c->ev[2 * c->ev_used++ + 1], c->stream);
+    }
+    for (const FinalizeArgs& f : pending) launch_finalize(c->stream, f);
 }
 
 void queue_step(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
@@ -778,10 +837,43 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
     if (c->arena) {
         c->dt_table = reinterpret_cast<double*>(c->arena + c->lay.dt_off);   // parity 0
     } else {
-        CU_TRY(cudaMalloc(&c->dt_table, sizeof(double) * nblocks));
-        CU_TRY(cudaMemsetAsync(c->dt_table, 0, sizeof(double) * nblocks, c->stream));
+        CU_TRY(cudaMalloc(&c->dt_table, sizeof(double) * 2 * nblocks));
+        CU_TRY(cudaMemsetAsync(c->dt_table, 0, sizeof(double) * 2 * nblocks, c->stream));
     }
-    CU_TRY(cudaMalloc(&c->partials, sizeof(double) * 4 * (size_t)c->total_tiles));
+    {
+        // single rank, first-order path, a mesh large enough that a step is not launch-bound: overlapped batches
+        // OPT-IN (PAR2D_SINGLE_OVERLAP=1): measured on B200 the step time does not move (0.5597 vs 0.5609 ms) - the board
+        // runs at its power cap, where the idle gaps between launches cost nothing and only energy per step counts
+        const char* yes = getenv("PAR2D_SINGLE_OVERLAP");
+        c->single_overlap = cfg->nranks == 1 && !c->dg && yes && atoi(yes) != 0 && c->owned_cells >= (1ll << 21);
+        if (c->single_overlap) {
+            c->dt_parities = 2;
+            c->partials_stride = 4ll * c->total_tiles;
+            std::vector<int2> edge, inner;   // strips on the perimeter of a block feed the ghost fill of the next step
+            for (int k = 0; k < c->nowned; k++) {
+                const BlockDev& b = c->hblk[k];
+                for (int t = 0; t < b.tiles_x * b.tiles_y; t++) {
+                    const int tx = t % b.tiles_x, ty = t / b.tiles_x;
+                    const bool e = tx == 0 || tx == b.tiles_x - 1 || ty == 0 || ty == b.tiles_y - 1;
+                    (e ? edge : inner).push_back(make_int2(k, t));
+                }
+            }
+            c->n_edge_tiles = (int)edge.size();
+            c->n_inner_tiles = (int)inner.size();
+            CU_TRY(cudaMalloc(&c->d_edge_tiles, sizeof(int2) * std::max<size_t>(edge.size(), 1)));
+            CU_TRY(cudaMalloc(&c->d_inner_tiles, sizeof(int2) * std::max<size_t>(inner.size(), 1)));
+            CU_TRY(cudaMemcpyAsync(c->d_edge_tiles, edge.data(), sizeof(int2) * edge.size(), cudaMemcpyHostToDevice, c->stream));
+            CU_TRY(cudaMemcpyAsync(c->d_inner_tiles, inner.data(), sizeof(int2) * inner.size(), cudaMemcpyHostToDevice, c->stream));
+            CU_TRY(cudaStreamSynchronize(c->stream));
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            const char* pr = getenv("PAR2D_SIDE_PRIORITY");   // A/B runs: 0 = same priority as the main stream
+            CU_TRY(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, (pr && atoi(pr) == 0) ? lo : hi));
+            CU_TRY(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming));
+        }
+    }
+    CU_TRY(cudaMalloc(&c->partials, sizeof(double) * 4 * (size_t)c->total_tiles * (c->single_overlap ? 2 : 1)));
     if (c->dg) CU_TRY(cudaMalloc(&c->dg_partials, sizeof(double) * 12 * (size_t)c->dg_total_tiles));
     CU_TRY(cudaMalloc(&c->flags, sizeof(unsigned)));
     CU_TRY(cudaMalloc(&c->stop, sizeof(int)));
@@ -816,6 +908,12 @@ int par2d_destroy(par2d_ctx* c) {
     for (Peer& p : c->peers) cudaFree(p.d_send);
     if (c->arena) cudaFree(c->arena); else cudaFree(c->dt_table);
     cudaFree(c->put_ticket); cudaFree(c->dlines_peer); cudaFree(c->d_dt_dst); cudaFree(c->d_flag_dst);
+    if (c->single_overlap) {
+        if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); c->side_stream = nullptr; }
+        if (c->ev_main) cudaEventDestroy(c->ev_main);
+        if (c->ev_edge) cudaEventDestroy(c->ev_edge);
+        cudaFree(c->d_edge_tiles); cudaFree(c->d_inner_tiles);
+    }
     for (double* m : c->dg_mem) cudaFree(m);
     cudaFree(c->dg_partials);
     cudaFree(c->dblk); cudaFree(c->dtmaps); cudaFree(c->partials); cudaFree(c->flags);
@@ -954,6 +1052,8 @@ int par2d_step(par2d_ctx* c, int32_t nsteps, int32_t stop_on_tol, par2d_step_inf
             }
             queue_put(c);
         }
+    } else if (c->single_overlap && !stop_on_tol && nsteps > 0) {
+        queue_batch_overlapped(c, nsteps);
     } else {
         for (int s = 0; s < nsteps; s++) queue_step(c, stop_on_tol, true);
     }

@@ -316,3 +316,25 @@ def test_full_size_fast_vs_faithful(gpu):
     assert worst <= TOL_STATE, worst
     assert max(abs(a.relres / b.relres - 1) for a, b in zip(fi, si)) <= TOL_HIST
     assert all(a.dt == b.dt for a, b in zip(fi[:1], si[:1]))
+
+
+def test_overlapped_batches_change_nothing(gpu, monkeypatch):
+    """PAR2D_SINGLE_OVERLAP=1: meshes of 2 M cells and more run par2d_step batches with the ghost fill and the
+    bookkeeping on a side stream beside the interior strips (capi.cu::queue_batch_overlapped; opt-in, it buys nothing
+    under the power cap).  State, dt and residual history must equal the serial order bit for bit, over several
+    batches, in both arithmetic modes."""
+    for mode in (MODE_FAST, MODE_FAITHFUL):
+        runs = []
+        for overlap in ("1", "0"):
+            monkeypatch.setenv("PAR2D_SINGLE_OVERLAP", overlap)
+            case = Case.synthetic_ramp(2048, 1056, 2, 2)
+            s = Solver(case, make_cfg(gpu, 1, 1.4, mode), lib=gpu)
+            u = s.get_state(1)
+            u[200:260, 300:380, 0] *= 1.3          # a disturbance, so that the blocks really exchange something
+            s.set_state(1, u)
+            info = s.step(5) + s.step(1) + s.step(4)
+            runs.append(([s.get_state(b) for b in range(4)], [(i.iter, i.dt, i.relres, i.ressumsum) for i in info]))
+            s.close()
+        for a, b in zip(runs[0][0], runs[1][0]):
+            assert np.array_equal(a, b)
+        assert runs[0][1] == runs[1][1] and len(runs[0][1]) == 10
