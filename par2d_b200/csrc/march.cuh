@@ -48,6 +48,9 @@ namespace par2d {
 #ifndef MARCH_NODE_LDS
 #define MARCH_NODE_LDS 0
 #endif
+#ifndef MARCH_YCC_FROM_FACES
+#define MARCH_YCC_FROM_FACES 1
+#endif
 #ifndef MARCH_SPLIT_PRE
 #define MARCH_SPLIT_PRE 0
 #endif
@@ -143,6 +146,7 @@ struct RowState {
     double T[CPL];
     double im[CPL];          // 1/(vol*ycc) (axisymmetric) or 1/vol (planar) of cell (c, j): cell_metric_kernel
     double x[CPL + 1], y[CPL + 1];   // nodes (c, j) .. (c+CPL, j)
+    double yfb[CPL];         // mid-point radius of the cell's bottom face (lean path: ycc = (bottom + top)/2)
 };
 
 struct MarchCtx {
@@ -160,9 +164,12 @@ template <bool FAITHFUL, bool TPG, bool AXI, bool HOOKS>
 __device__ __forceinline__ void cell_update(const StepArgs& a, const Gas& g, const MarchCtx& m, int c, int j, const FaceState& cur, double T, double im,
                                             double xa, double ya, double xb, double yb, double xc, double yc_, double xd, double yd,
                                             const Flux& Fl, const Flux& Fr, const Flux& Gb, const Flux& Gt,
-                                            double out[4], double& sq0, double& sq1, double& sq2, double& sq3, unsigned& flags, bool live = true) {
+                                            double out[4], double& sq0, double& sq1, double& sq2, double& sq3, unsigned& flags, bool live = true,
+                                            double ycc_lean = 0.0) {
     const bool update = HOOKS ? a.update != 0 : true;   // HOOKS = false: the production step (no residual dump, always advancing)
-    const double ycc = 0.25 * (ya + yb + yc_ + yd);
+    // centroid radius (MeshModule.cpp:40).  Lean path: the mean of the bottom and top face mid-points, which the
+    // fluxes computed anyway (same value to an ulp, two operations instead of four, two fewer carried coordinates)
+    const double ycc = (!FAITHFUL && MARCH_YCC_FROM_FACES) ? ycc_lean : 0.25 * (ya + yb + yc_ + yd);
     double r[4];        // residual = calc_dudt's dudt
     double dv[4];
     if constexpr (FAITHFUL) {
@@ -300,6 +307,7 @@ __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const
         const LdfssPre pj = ldfss_lean_pre(gj, hi.s[0], lo.s[0]);
         F[0] = ldfss_lean_post<AXI, true>(gi, left, lo.s[0], pi);
         Gt[0] = ldfss_lean_post<AXI, MARCH_VOTE_J != 0>(gj, hi.s[0], lo.s[0], pj);
+        hi.yfb[0] = gj.yf;
         F[1] = shfl_down1(F[0]);
     } else
 #endif
@@ -311,8 +319,11 @@ __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const
     F[CPL] = shfl_down1(F[0]);
     // j-faces: between cell (c+e, j+1) [left state = upper cell] and (c+e, j): node (c+e, j+1) -> (c+e+1, j+1)
 #pragma unroll
-    for (int e = 0; e < CPL; e++)
-        Gt[e] = ldfss<FAITHFUL, AXI, !FAITHFUL && MARCH_VOTE_J>(face_geom<FAITHFUL>(hi.x[e], hi.y[e], hi.x[e + 1], hi.y[e + 1]), hi.s[e], lo.s[e]);
+    for (int e = 0; e < CPL; e++) {
+        const FaceGeom gj = face_geom<FAITHFUL>(hi.x[e], hi.y[e], hi.x[e + 1], hi.y[e + 1]);
+        hi.yfb[e] = gj.yf;
+        Gt[e] = ldfss<FAITHFUL, AXI, !FAITHFUL && MARCH_VOTE_J>(gj, hi.s[e], lo.s[e]);
+    }
     }
     // swap the parked bottom fluxes with the new top fluxes
     if constexpr (CPL == 2) {
@@ -338,13 +349,15 @@ __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const
             // branch between the fluxes and the update, one larger block for the instruction scheduler
             if (m.writer[e]) flags |= flu[e];
             cell_update<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, m.c + e, j, lo.s[e], lo.T[e], lo.im[e], lo.x[e], lo.y[e], lo.x[e + 1], lo.y[e + 1],
-                                            hi.x[e + 1], hi.y[e + 1], hi.x[e], hi.y[e], F[e], F[e + 1], Gb[e], Gt[e], out[e], sq0, sq1, sq2, sq3, flags, m.writer[e]);
+                                            hi.x[e + 1], hi.y[e + 1], hi.x[e], hi.y[e], F[e], F[e + 1], Gb[e], Gt[e], out[e], sq0, sq1, sq2, sq3, flags, m.writer[e],
+                                            0.5 * (lo.yfb[e] + hi.yfb[e]));
         } else
 #endif
         if (m.writer[e]) {
             flags |= flu[e];   // state checks of the cell above: a real cell or a filled ghost
             cell_update<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, m.c + e, j, lo.s[e], lo.T[e], lo.im[e], lo.x[e], lo.y[e], lo.x[e + 1], lo.y[e + 1],
-                                            hi.x[e + 1], hi.y[e + 1], hi.x[e], hi.y[e], F[e], F[e + 1], Gb[e], Gt[e], out[e], sq0, sq1, sq2, sq3, flags);
+                                            hi.x[e + 1], hi.y[e + 1], hi.x[e], hi.y[e], F[e], F[e + 1], Gb[e], Gt[e], out[e], sq0, sq1, sq2, sq3, flags, true,
+                                            0.5 * (lo.yfb[e] + hi.yfb[e]));
         }
     }
     if constexpr (CPL == 2) {
@@ -456,7 +469,9 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
         for (int e = 0; e < CPL; e++) {
             const FaceState lo = face_state<FAITHFUL, TPG>(g, rs[e], rs[PLANE_D + e], rs[2 * PLANE_D + e], rs[3 * PLANE_D + e], fl0[e]);
             // j-face: left state = upper cell, right state = lower cell (SpatialDiscretization.cpp:556-625)
-            const Flux G0 = ldfss<FAITHFUL, AXI, !FAITHFUL && MARCH_VOTE_J>(face_geom<FAITHFUL>(A.x[e], A.y[e], A.x[e + 1], A.y[e + 1]), A.s[e], lo);
+            const FaceGeom g0 = face_geom<FAITHFUL>(A.x[e], A.y[e], A.x[e + 1], A.y[e + 1]);
+            A.yfb[e] = g0.yf;
+            const Flux G0 = ldfss<FAITHFUL, AXI, !FAITHFUL && MARCH_VOTE_J>(g0, A.s[e], lo);
             sm.G[0][q + e] = G0.f0; sm.G[1][q + e] = G0.f1; sm.G[2][q + e] = G0.f2; sm.G[3][q + e] = G0.f3; sm.G[4][q + e] = G0.parr;
             if (m.writer[e]) flags |= fl0[e];
         }
