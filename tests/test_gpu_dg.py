@@ -80,3 +80,37 @@ def test_dg_needs_its_config(gpu):
     cfg.accur = 2
     with pytest.raises(Par2dError):
         Solver(case, cfg, lib=gpu)
+
+
+@pytest.mark.parametrize("ncx,ncy", [(2, 2), (31, 3), (5, 40), (33, 9)])
+@pytest.mark.parametrize("mode", [MODE_FAST, MODE_FAITHFUL])
+def test_dg_small_block_shapes_vs_oracle(gpu, oracle, tmp_path, ncx, ncy, mode):
+    """The second-order branch on blocks of a few cells (every cell next to a boundary, the limiter's flat-index
+    tests wrapping across the short rows) against the oracle."""
+    import os
+    nx, ny = ncx + 1, ncy + 1
+    x = np.tile(np.linspace(0.0, 0.01 * ncx, nx), (ny, 1))
+    y = np.tile(np.linspace(0.02, 0.02 + 0.008 * ncy, ny)[:, None], (1, nx)) + 0.001 * np.sin(40.0 * x)
+    ib = np.array([4] * ncx + [3] * ncy + [4] * ncx + [1] * ncy, dtype=np.int32)
+    d = tmp_path / f"c{ncx}x{ncy}"
+    os.makedirs(d / "subgrids")
+    with open(d / "grid.conn", "w") as f:
+        f.write("1\n0: (1,-1) (3,-1) (4,-1) (4,-1)\n")
+    with open(d / "subgrids" / "grid.block0.dat", "w") as f:
+        f.write("npart: 1 1\nipart: 0 0\nngrid: %d %d\n" % (nx, ny))
+        for j in range(ny):
+            for i in range(nx):
+                f.write("%.17e %.17e\n" % (x[j, i], y[j, i]))
+        f.write("BC\n" + "".join("%d\n" % c for c in ib))
+    case = Case.load(str(d))
+    sg = Solver(case, dg.dg_cfg(gpu, 1, 1.4, mode), lib=gpu)
+    so = Solver(case, dg.dg_cfg(oracle, 1, 1.4), lib=oracle)
+    for s in (sg, so):
+        dg.perturbed_slopes(s, case, seed=9, amp=0.01)
+    for a, b in zip(sg.get_residual_dg(0), so.get_residual_dg(0)):
+        scale = np.abs(b).reshape(-1, 4).max(axis=0) + 1e-300
+        assert (np.abs(a - b).reshape(-1, 4).max(axis=0) / scale).max() < 1e-11
+    ig, io = sg.step(15), so.step(15)
+    assert [i.status for i in ig] == [i.status for i in io]
+    assert state_err(sg.get_state(0), so.get_state(0)) < 1e-11
+    assert max(abs(a.relres / b.relres - 1.0) for a, b in zip(ig, io)) < 1e-9

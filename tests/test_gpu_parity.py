@@ -338,3 +338,40 @@ def test_overlapped_batches_change_nothing(gpu, monkeypatch):
         for a, b in zip(runs[0][0], runs[1][0]):
             assert np.array_equal(a, b)
         assert runs[0][1] == runs[1][1] and len(runs[0][1]) == 10
+
+
+@pytest.mark.parametrize("ncx,ncy", [(1, 1), (1, 7), (9, 1), (2, 2), (31, 3), (30, 64), (61, 65)])
+@pytest.mark.parametrize("mode", [MODE_FAST, MODE_FAITHFUL])
+def test_degenerate_block_shapes_vs_oracle(gpu, oracle, tmp_path, ncx, ncy, mode):
+    """Blocks of one cell, one column, one row, exactly one strip (30 columns), one strip + 1 ... : the strip/row-chunk
+    decomposition of the march kernel against the oracle (every face of such a block is a boundary face or next to
+    one; BC codes 1, 3, 4 and 2 around the perimeter)."""
+    nx, ny = ncx + 1, ncy + 1
+    x = np.tile(np.linspace(0.0, 0.01 * ncx, nx), (ny, 1))
+    y = np.tile(np.linspace(0.02, 0.02 + 0.008 * ncy, ny)[:, None], (1, nx)) + 0.001 * np.sin(40.0 * x)
+    ib = np.array([4] * ncx + [3] * ncy + [2] * ncx + [1] * ncy, dtype=np.int32)     # bottom, right, top, left (CCW)
+    d = tmp_path / f"c{ncx}x{ncy}"
+    os.makedirs(d / "subgrids")
+    with open(d / "grid.conn", "w") as f:
+        f.write("1\n0: (1,-1) (3,-1) (4,-1) (2,-1)\n")
+    with open(d / "subgrids" / "grid.block0.dat", "w") as f:
+        f.write("npart: 1 1\nipart: 0 0\nngrid: %d %d\n" % (nx, ny))
+        for j in range(ny):
+            for i in range(nx):
+                f.write("%.17e %.17e\n" % (x[j, i], y[j, i]))
+        f.write("BC\n" + "".join("%d\n" % c for c in ib))
+    case = Case.load(str(d))
+    sg = Solver(case, make_cfg(gpu, 1, 1.4, mode), lib=gpu)
+    so = Solver(case, make_cfg(oracle, 1, 1.4), lib=oracle)
+    rng = np.random.default_rng(3)
+    u = so.get_state(0) * (1.0 + 0.05 * rng.uniform(-1, 1, (ncy, ncx, 4)))
+    u[..., 1] *= 0.3                               # a subsonic patch: the far-field BC takes its characteristic branches
+    sg.set_state(0, u)
+    so.set_state(0, u)
+    rg, ro = sg.get_residual(0), so.get_residual(0)
+    scale = np.abs(ro).reshape(-1, 4).max(axis=0) + 1e-300
+    assert (np.abs(rg - ro).reshape(-1, 4).max(axis=0) / scale).max() < (1e-13 if mode == MODE_FAITHFUL else 1e-11)
+    ig, io = sg.step(20), so.step(20)
+    assert [i.status for i in ig] == [i.status for i in io]
+    assert state_err(sg.get_state(0), so.get_state(0)) < TOL_STATE
+    assert max(abs(a.relres / b.relres - 1.0) for a, b in zip(ig, io)) < TOL_HIST
