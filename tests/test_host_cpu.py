@@ -199,3 +199,18 @@ def test_solution_reader_round_trips_the_writer(tmp_path):
     assert np.array_equal(xc, 0.25 * (x[:-1, :-1] + x[:-1, 1:] + x[1:, 1:] + x[1:, :-1]))
     with pytest.raises(Par2dError):
         read_solution(path, nx + 1, ny)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the reference's own CPU implementation on the host cores, bounded sample): one JSON
+    line with the driver's keys.  Needs oracle/_ref (the unmodified reference build) or falls back to the oracle port."""
+    import json
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "cell-updates/s" and line["value"] > 1e5
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 3
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
