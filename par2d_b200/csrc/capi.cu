@@ -185,7 +185,7 @@ struct par2d_ctx {
     bool dg = false;
     std::vector<double*> dg_mem;      // per owned block: ux | uy | uxt | uyt | ghost points
     double* dg_partials = nullptr;
-    int dg_total_tiles = 0, dg_max_tiles = 0;
+    int dg_total_tiles = 0, dg_max_tiles = 0, dg_max_lim_tiles = 0;
 
     int cur = 0;
     long long iter = 0;
@@ -392,6 +392,7 @@ DgArgs dg_args(const par2d_ctx* c, int update) {
     DgArgs d;
     d.partials = c->dg_partials;
     d.max_tiles = c->dg_max_tiles;
+    d.max_lim_tiles = c->dg_max_lim_tiles;
     d.max_points = 2 * c->max_faces;
     d.res_out = nullptr;
     d.res_block = -1;
@@ -728,7 +729,8 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
             b.ghost2[SIDE_RIGHT] = gp; gp += 8 * (size_t)b.ncy;
             b.ghost2[SIDE_TOP] = gp; gp += 8 * (size_t)b.ncx;
             b.ghost2[SIDE_LEFT] = gp;
-            b.dg_ntiles = (int)(((long long)b.ncx * b.ncy + DG_THREADS - 1) / DG_THREADS);
+            b.dg_ntiles = ((b.ncx + DG_SW - 1) / DG_SW) * ((b.ncy + DG_ROWS - 1) / DG_ROWS);   // strips of the cell kernel
+            c->dg_max_lim_tiles = std::max(c->dg_max_lim_tiles, (int)(((long long)b.ncx * b.ncy + DG_THREADS - 1) / DG_THREADS));
             b.dg_tile0 = c->dg_total_tiles;
             c->dg_total_tiles += b.dg_ntiles;
             c->dg_max_tiles = std::max(c->dg_max_tiles, b.dg_ntiles);

@@ -50,7 +50,7 @@ struct BlockDev {
     double *ux, *uy;    // xi / eta slopes, AoS [(j*ncx+i)*4+k] (main.cpp:169-172)
     double *uxt, *uyt;  // damped, not yet limited slopes of the step in flight
     double* ghost2[4];  // two Gauss-point ghost states per boundary face, [(2n+pt)*4+k]
-    int dg_tile0, dg_ntiles;  // this block's CTAs of the cell kernel in the [.][12] partial-sum array
+    int dg_tile0, dg_ntiles;  // this block's strips of the cell kernel (one record each in the [.][12] partial-sum array)
 };
 
 // one edge line to pack for an off-rank neighbour (SpatialDiscretization.cpp:236-257)

@@ -6,18 +6,18 @@
 // sides carry the xi/eta moments of the face fluxes plus a volume integral; the slopes are damped (0.9) and
 // limited against the neighbouring means after every update.
 //
-// Three kernels per step, written in GATHER form (a cell evaluates the Gauss-point fluxes of its own four
-// faces and accumulates them in the reference's order, so in PAR2D_MODE_FAITHFUL every cell's right-hand
-// sides are bit-identical to the reference's scatter loops):
+// Three kernels per step:
 //   dg_ghost_kernel : two ghost states per boundary face (DGP1_ghost_cell_generator, blended normals),
 //                     or the same-GPU neighbour's reconstruction at its Gauss points (the reference's halo)
-//   dg_cell_kernel  : face + boundary + volume integrals, /vol, norms, three solves with one Jacobian,
-//                     mean update into the other state buffer, damped slopes into the temporary arrays
+//   dg_cell_kernel  : marching warp strips - every interior face flux (two Gauss points) evaluated once per strip -
+//                     then per cell the four faces accumulated in the reference's order (so in PAR2D_MODE_FAITHFUL
+//                     every cell's right-hand sides are bit-identical to the reference's scatter loops), boundary
+//                     + volume integrals, /vol, norms, three solves with one Jacobian, mean update into the other
+//                     state buffer, damped slopes into the temporary arrays
 //   dg_limit_kernel : the reference's in-place, sequential slope limiter restated per cell: it reads the OLD
 //                     mean of the cells after it in memory order and the NEW mean of the cells before it
 //                     (both state buffers are at hand), including the row wrap of its flat-index tests
-// This first version favours exactness over speed: every interior face flux is evaluated by both adjacent
-// cells.  PAR2D_MODE_FAITHFUL keeps the reference's operation order and divisions; PAR2D_MODE_FAST uses the lean
+// PAR2D_MODE_FAITHFUL keeps the reference's operation order and divisions; PAR2D_MODE_FAST uses the lean
 // LDFSS / state / solve of physics.cuh on interior faces (boundary faces, whose blended normals are not unit
 // vectors, keep the general form).  Off-rank neighbours: pack_kernel (kernels.cuh) sends the reconstruction at the two
 // Gauss points of every edge face, 8 doubles per edge cell.
@@ -31,12 +31,13 @@ constexpr double DG_DAMP = 0.9;       // main.cpp:92
 constexpr double DG_DUSCALE = 0.5;    // main.cpp:93
 constexpr int DG_THREADS = 128;
 #ifndef DG_MINB
-#define DG_MINB 4      // CTAs per SM the cell kernel is compiled for (register budget 65536 / (128 * DG_MINB))
+#define DG_MINB 4      // CTAs per SM the cell kernel is compiled for (register budget 65536 / (32 * DG_WARPS * DG_MINB))
 #endif
 
 struct DgArgs {
-    double* partials;    // [dg tiles][12]: sum of squares of dudt, duxdt, duydt per CTA
-    int max_tiles;       // CTAs of the largest owned block (grid.x of the cell and limiter kernels)
+    double* partials;    // [dg strips][12]: sum of squares of dudt, duxdt, duydt per strip of the cell kernel
+    int max_tiles;       // strips of the largest owned block (the cell kernel runs DG_WARPS strips per CTA)
+    int max_lim_tiles;   // grid.x of the limiter kernel: ceil(cells of the largest block / DG_THREADS)
     int max_points;      // 2 x longest perimeter (grid.x of the ghost kernel, in threads)
     double* res_out;     // optional dump of dudt | duxdt | duydt (3 x ncell x 4) of block res_block
     int res_block;
@@ -48,6 +49,17 @@ struct DgCell {
 };
 
 __device__ __forceinline__ double dg_gauss() { return 1.0 / sqrt(3.0); }   // folded at compile time, as 1.0/sqrt(3.0) is in the reference
+
+// pull the mean and the slopes of cell (i,j) towards the SM ahead of their use (the strips of the cell kernel run at
+// ~8 warps per SM: nothing else hides the latency of a row's first touch)
+__device__ __forceinline__ void dg_prefetch_cell(const BlockDev& b, int buf, int i, int j) {
+    const double* S = b.state[buf] + (long long)(j + 1) * b.pitch + COL0 + i;
+    const long long e = 4 * ((long long)j * b.ncx + i);
+#pragma unroll
+    for (int k = 0; k < 4; k++) asm volatile("prefetch.global.L1 [%0];" ::"l"(S + k * b.plane));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(b.ux + e));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(b.uy + e));
+}
 
 // mean + slopes + pressure of cell (i,j) (State::p of ElemVar, StateVariables.h:49-50)
 __device__ __forceinline__ void dg_load_cell(const Gas& g, const BlockDev& b, int buf, int i, int j, DgCell& c) {
@@ -307,18 +319,74 @@ __global__ void __launch_bounds__(256) dg_ghost_kernel(StepArgs a, Gas g, DgArgs
 }
 
 // ------------------------------------------------------------------ residual + solve + update of the means
+// One WARP marches a strip of DG_SW = 31 cell columns (lane 31 is a halo lane: it only evaluates the xi face
+// between column 30 of the strip and the next column) upwards over DG_ROWS rows.  Per row a lane evaluates ONE
+// xi face (its left one; the right one is the left face of lane+1, fetched by warp shuffles) and ONE eta face
+// (its top one; the bottom one is the previous row's top face, carried in registers) - every interior face flux
+// once per strip instead of once per adjacent cell - and then accumulates its four faces in the reference's
+// order, so that PAR2D_MODE_FAITHFUL stays bit-identical to the reference's scatter loops.
+constexpr int DG_SW = 31;
+#ifndef DG_PREFETCH
+#define DG_PREFETCH 1
+#endif
+#ifndef DG_ROWS
+#define DG_ROWS 32
+#endif
+#ifndef DG_WARPS
+#define DG_WARPS 2          // independent strips per CTA (no shared memory, no barrier)
+#endif
+
+struct DgFluxPair {
+    Flux F[2];              // the two Gauss points of a face
+};
+
+// the two Gauss-point fluxes of the interior face with left cell L and right cell R (DGP1Tools.cpp:150-222)
 template <bool FAITHFUL, bool TPG, bool AXI>
-__global__ void __launch_bounds__(DG_THREADS, DG_MINB) dg_cell_kernel(StepArgs a, Gas g, DgArgs d) {
-    __shared__ double red[DG_THREADS / 32][12];
+__device__ __forceinline__ void dg_face_flux(const Gas& g, const FaceGeom& fg, const DgCell& L, const DgCell& R, int dir, DgFluxPair& out, unsigned& flags) {
+    const double G = dg_gauss();
+#pragma unroll 1
+    for (int pt = 0; pt < 2; pt++) {
+        const double s = pt == 0 ? G : -G;
+        double xsiL, etaL, xsiR, etaR;
+        if (dir == 0) { xsiL = 1.0; xsiR = -1.0; etaL = etaR = s; }
+        else { etaL = -1.0; etaR = 1.0; xsiL = xsiR = s; }
+        const FaceState sl = dg_point_state<FAITHFUL, TPG>(g, L, xsiL, etaL, flags);
+        const FaceState sr = dg_point_state<FAITHFUL, TPG>(g, R, xsiR, etaR, flags);
+        const Flux F = ldfss<FAITHFUL, AXI>(fg, sl, sr);
+        if (isnan(F.f0 + F.f1 + F.f2 + F.f3)) flags |= FLAG_NAN;
+        if (pt == 0) out.F[0] = F; else out.F[1] = F;
+    }
+}
+
+__device__ __forceinline__ DgFluxPair dg_shfl_down1(const DgFluxPair& p) {
+    DgFluxPair o;
+#pragma unroll
+    for (int pt = 0; pt < 2; pt++) {
+        o.F[pt].f0 = __shfl_down_sync(0xffffffffu, p.F[pt].f0, 1); o.F[pt].f1 = __shfl_down_sync(0xffffffffu, p.F[pt].f1, 1);
+        o.F[pt].f2 = __shfl_down_sync(0xffffffffu, p.F[pt].f2, 1); o.F[pt].f3 = __shfl_down_sync(0xffffffffu, p.F[pt].f3, 1);
+        o.F[pt].parr = __shfl_down_sync(0xffffffffu, p.F[pt].parr, 1);
+    }
+    return o;
+}
+
+template <bool FAITHFUL, bool TPG, bool AXI>
+__global__ void __launch_bounds__(32 * DG_WARPS, DG_MINB) dg_cell_kernel(StepArgs a, Gas g, DgArgs d) {
     if (*a.stop) return;
     const int k = blockIdx.y;
     const BlockDev& b = a.blocks[k];
     const int ncx = b.ncx, ncy = b.ncy;
+    const int lane = threadIdx.x & 31;
+    const int strip = (int)blockIdx.x * DG_WARPS + (threadIdx.x >> 5);
+    if (strip >= b.dg_ntiles) return;              // warp-uniform
+    const int strips_x = (ncx + DG_SW - 1) / DG_SW;
+    const int i = (strip % strips_x) * DG_SW + lane;
+    const int j0 = (strip / strips_x) * DG_ROWS, j1 = min(j0 + DG_ROWS, ncy);
+    const bool has = i < ncx;                      // a real cell column (the halo lane included)
+    const bool cell = has && lane < DG_SW;         // this lane updates the cells of its column
     const long long ncell = (long long)ncx * ncy;
-    const int ntiles = (int)((ncell + DG_THREADS - 1) / DG_THREADS);
-    if ((int)blockIdx.x >= ntiles) return;
-    const long long e = (long long)blockIdx.x * DG_THREADS + threadIdx.x;
-    const bool live = e < ncell;
+    const double* X = b.nodes;
+    const double* Y = b.nodes + b.plane;
+    const double G = dg_gauss();
     unsigned flags = 0;
     double sq[12];
 #pragma unroll
@@ -329,175 +397,194 @@ __global__ void __launch_bounds__(DG_THREADS, DG_MINB) dg_cell_kernel(StepArgs a
     for (int t = 0; t < a.nblocks_global; t++) dt = fmax(dt, a.dt_table[t]);
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.dt_used = dt;
 
-    if (live) {
-        const int i = (int)e % ncx, j = (int)e / ncx;   // blocks stay below 2^31 cells
-        DgCell me;
-        dg_load_cell(g, b, a.cur, i, j, me);
-        const double* X = b.nodes;
-        const double* Y = b.nodes + b.plane;
-        const long long n00 = (long long)(j + 1) * b.pitch + COL0 + i;
-        const double xa = X[n00], ya = Y[n00], xb = X[n00 + 1], yb = Y[n00 + 1];
-        const double xd = X[n00 + b.pitch], yd = Y[n00 + b.pitch], xc = X[n00 + b.pitch + 1], yc_ = Y[n00 + b.pitch + 1];
-        const double ycc = 0.25 * (ya + yb + yc_ + yd);           // geoel[2], MeshModule.cpp:40
-        const double vol = cell_volume(xa, ya, xb, yb, xc, yc_, xd, yd);
-        const double ycs = AXI ? ycc : 0.0;
-        DgAcc acc;
-#pragma unroll
-        for (int q = 0; q < 4; q++) acc.r[q] = acc.rx[q] = acc.ry[q] = 0.0;
-        // interior faces in the reference's accumulation order: xi face i (this cell is the right one) and i+1 (left)
-        // (SpatialDiscretization.cpp:481-552), eta face j (this cell is the left = upper one) and j+1 (:556-625)
-#pragma unroll 1
-        for (int f = 0; f < 4; f++) {
-            int ni, nj, dir;
-            bool exists, mine_left;
-            double x0, y0, x1, y1;
-            if (f == 0) { exists = i >= 1; ni = i - 1; nj = j; dir = 0; mine_left = false; x0 = xa; y0 = ya; x1 = xd; y1 = yd; }
-            else if (f == 1) { exists = i <= ncx - 2; ni = i + 1; nj = j; dir = 0; mine_left = true; x0 = xb; y0 = yb; x1 = xc; y1 = yc_; }
-            else if (f == 2) { exists = j >= 1; ni = i; nj = j - 1; dir = 1; mine_left = true; x0 = xa; y0 = ya; x1 = xb; y1 = yb; }
-            else { exists = j <= ncy - 2; ni = i; nj = j + 1; dir = 1; mine_left = false; x0 = xd; y0 = yd; x1 = xc; y1 = yc_; }
-            if (!exists) continue;
-            DgCell nb;
-            dg_load_cell(g, b, a.cur, ni, nj, nb);
-            dg_face<FAITHFUL, TPG, AXI>(g, face_geom<FAITHFUL>(x0, y0, x1, y1), me, nb, dir, mine_left, ycs, acc, flags);
-        }
-        // boundary faces (:643-977), left, right, bottom, top.  fNormalL / fNormalR are declared once per row
-        // (column) and shared by the left and right (bottom and top) face of it: at the ends of the right (top)
-        // side they still hold the left (bottom) side's values
-        if (i == 0 || i == ncx - 1 || j == 0 || j == ncy - 1) {
-#pragma unroll 1
-            for (int sd = 0; sd < 4; sd++) {
-                int type, side, n;
-                bool exists;
-                FaceGeom f, fL, fR;
-                if (sd == 0) {
-                    exists = i == 0; type = 4; side = SIDE_LEFT; n = j;
-                    if (!exists) continue;
-                    f = face_geom<true>(xa, ya, xd, yd);
-                    fL = j != 0 ? dg_geom(b, 0, j - 1, 0, j) : f;
-                    fR = j != ncy - 1 ? dg_geom(b, 0, j + 1, 0, j + 2) : f;
-                } else if (sd == 1) {
-                    exists = i == ncx - 1; type = 2; side = SIDE_RIGHT; n = j;
-                    if (!exists) continue;
-                    f = face_geom<true>(xb, yb, xc, yc_);
-                    fL = j != 0 ? dg_geom(b, ncx, j - 1, ncx, j) : dg_geom(b, 0, j, 0, j + 1);
-                    fR = j != ncy - 1 ? dg_geom(b, ncx, j + 1, ncx, j + 2) : dg_geom(b, 0, j, 0, j + 1);
-                } else if (sd == 2) {
-                    exists = j == 0; type = 1; side = SIDE_BOTTOM; n = i;
-                    if (!exists) continue;
-                    f = face_geom<true>(xa, ya, xb, yb);
-                    fL = i != 0 ? dg_geom(b, i - 1, 0, i, 0) : f;
-                    fR = i != ncx - 1 ? dg_geom(b, i + 1, 0, i + 2, 0) : f;
-                } else {
-                    exists = j == ncy - 1; type = 3; side = SIDE_TOP; n = i;
-                    if (!exists) continue;
-                    f = face_geom<true>(xd, yd, xc, yc_);
-                    fL = i != 0 ? dg_geom(b, i - 1, ncy, i, ncy) : dg_geom(b, i, 0, i + 1, 0);
-                    fR = i != ncx - 1 ? dg_geom(b, i + 1, ncy, i + 2, ncy) : dg_geom(b, i, 0, i + 1, 0);
-                }
-                dg_boundary_face<TPG, AXI>(g, b, type, side, n, me, f, fL.nx, fL.ny, fR.nx, fR.ny, ycs, acc, flags);
-            }
-        }
-        // :980-1011 division by the volume, then the volume integral of the slopes' equations (DGP1Tools.cpp:52-124)
-        double r[4], rx[4], ry[4];
-        unsigned fl2 = 0;
-        const FaceState sme = face_state<true, TPG>(g, me.u[0], me.u[1], me.u[2], me.u[3], fl2);
-        {
-            const double ycv = AXI ? ycc : 1.0;
-            const double rho = me.u[0];
-            double Fx[4], Fy[4];
-            Fx[0] = ycv * rho * me.u[1];
-            Fx[1] = ycv * (rho * me.u[1] * me.u[1] + sme.p);
-            Fx[2] = ycv * rho * me.u[1] * me.u[2];
-            Fx[3] = ycv * rho * me.u[1] * sme.h0;
-            Fy[0] = ycv * rho * me.u[2];
-            Fy[1] = ycv * rho * me.u[1] * me.u[2];
-            Fy[2] = ycv * (rho * me.u[2] * me.u[2] + sme.p);
-            Fy[3] = ycv * rho * me.u[2] * sme.h0;
-            const double xL = 0.5 * (xd + xa), xR = 0.5 * (xc + xb), xD = 0.5 * (xb + xa), xU = 0.5 * (xc + xd);
-            const double yL = 0.5 * (yd + ya), yR = 0.5 * (yc_ + yb), yD = 0.5 * (yb + ya), yU = 0.5 * (yc_ + yd);
-            const double nxs0 = -0.5 * (yU - yD), nxs1 = 0.5 * (xU - xD);
-            const double nxs2 = -0.25 * ((xU - xD) * (yL - yR) - (yU - yD) * (xL - xR));
-            double db1dx, db1dy, db2dx, db2dy, ivol = 0.0;
-            if constexpr (FAITHFUL) { db1dx = nxs0 / nxs2; db1dy = nxs1 / nxs2; }
-            else { const double q2 = fast_rcp(nxs2); db1dx = nxs0 * q2; db1dy = nxs1 * q2; ivol = fast_rcp(vol); }
-            const double net0 = -0.5 * (yL - yR), net1 = 0.5 * (xL - xR);
-            const double net2 = -0.25 * ((xL - xR) * (yD - yU) - (yL - yR) * (xD - xU));
-            if constexpr (FAITHFUL) { db2dx = net0 / net2; db2dy = net1 / net2; }
-            else { const double q2 = fast_rcp(net2); db2dx = net0 * q2; db2dy = net1 * q2; }
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if constexpr (FAITHFUL) {
-                    r[q] = acc.r[q] / vol;
-                    rx[q] = 3.0 * acc.rx[q] / vol;
-                    ry[q] = 3.0 * acc.ry[q] / vol;
-                } else {
-                    r[q] = acc.r[q] * ivol;
-                    rx[q] = 3.0 * acc.rx[q] * ivol;
-                    ry[q] = 3.0 * acc.ry[q] * ivol;
-                }
-                rx[q] += 3.0 * (Fx[q] * db1dx + Fy[q] * db1dy);
-                ry[q] += 3.0 * (Fx[q] * db2dx + Fy[q] * db2dy);
-            }
-        }
-        if (isnan(r[0])) flags |= FLAG_NAN;
-#pragma unroll
-        for (int q = 0; q < 4; q++) { sq[q] = r[q] * r[q]; sq[4 + q] = rx[q] * rx[q]; sq[8 + q] = ry[q] * ry[q]; }
-        if (d.res_out != nullptr && d.res_block == k) {
-            double* o = d.res_out + 4 * e;
-#pragma unroll
-            for (int q = 0; q < 4; q++) { o[q] = r[q]; o[4 * ncell + q] = rx[q]; o[8 * ncell + q] = ry[q]; }
-        }
-        if (d.update) {
-            // main.cpp:307-351: one Jacobian, three right-hand sides; :394-425 update of the mean, damped slopes
-            const double v2 = me.u[1] * me.u[1] + me.u[2] * me.u[2];
-            const double e0 = enthalpy<TPG>(g, me.u[3], fl2) - g.Rs * me.u[3] + 0.5 * v2;
-            const double Cv = heat_capacity<TPG>(g, me.u[3], fl2) - g.Rs;
-            double dv[4], dvx[4], dvy[4];
-            if constexpr (FAITHFUL) {
-                solve_cell<true, AXI>(dt, ycc, me.u[0], me.u[1], me.u[2], e0, Cv, 0.0, r, dv, flags);
-                solve_cell<true, AXI>(dt, ycc, me.u[0], me.u[1], me.u[2], e0, Cv, 0.0, rx, dvx, flags);
-                solve_cell<true, AXI>(dt, ycc, me.u[0], me.u[1], me.u[2], e0, Cv, 0.0, ry, dvy, flags);
-            } else {
-                // D is lower triangular: closed-form forward substitution, one reciprocal of rho for the three systems
-                const double sc = AXI ? dt * fast_rcp(ycc) : dt;
-                const double inv_cv = fast_rcp(Cv);
-                solve_lean(sc, me.u[0], me.u[1], me.u[2], e0, inv_cv, r, dv);
-                solve_lean(sc, me.u[0], me.u[1], me.u[2], e0, inv_cv, rx, dvx);
-                solve_lean(sc, me.u[0], me.u[1], me.u[2], e0, inv_cv, ry, dvy);
-            }
-            double* So = b.state[a.cur ^ 1];
-            const long long o = (long long)(j + 1) * b.pitch + COL0 + i;
-            double nu[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) nu[q] = me.u[q] + dv[q];
-            if (!(nu[0] > 0.0)) flags |= FLAG_DENSITY;
-            nu[3] = fmax(nu[3], 201.0);
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                So[q * b.plane + o] = nu[q];
-                b.uxt[4 * e + q] = (me.ux[q] + dvx[q]) * DG_DAMP;
-                b.uyt[4 * e + q] = (me.uy[q] + dvy[q]) * DG_DAMP;
-            }
-        }
-        flags |= fl2;
+    // eta face j0 (between row j0, the left = upper cell, and row j0-1): the first row's bottom face
+    DgFluxPair Fb = {};
+    if (cell && j0 >= 1) {
+        DgCell up, lo;
+        dg_load_cell(g, b, a.cur, i, j0, up);
+        dg_load_cell(g, b, a.cur, i, j0 - 1, lo);
+        const long long n00 = (long long)(j0 + 1) * b.pitch + COL0 + i;
+        dg_face_flux<FAITHFUL, TPG, AXI>(g, face_geom<FAITHFUL>(X[n00], Y[n00], X[n00 + 1], Y[n00 + 1]), up, lo, 1, Fb, flags);
     }
-    // sums of squares of this CTA in a fixed order: lanes (xor tree), then warps
+#pragma unroll 1
+    for (int j = j0; j < j1; j++) {
+        DgCell me;
+        DgFluxPair Fl = {}, Fr;
+        const long long n00 = (long long)(j + 1) * b.pitch + COL0 + i;
+        double xa = 0.0, ya = 0.0, xd = 0.0, yd = 0.0;
+        if (has) {
+#if DG_PREFETCH
+            if (j + 2 < ncy) dg_prefetch_cell(b, a.cur, i, j + 2);   // the row after next: its first touch is row j+1's top face
+#endif
+            dg_load_cell(g, b, a.cur, i, j, me);
+            xa = X[n00]; ya = Y[n00]; xd = X[n00 + b.pitch]; yd = Y[n00 + b.pitch];
+            if (i >= 1) {          // xi face i: node (i,j) -> (i,j+1), left cell (i-1,j), right cell (i,j)
+                DgCell le;
+                dg_load_cell(g, b, a.cur, i - 1, j, le);
+                dg_face_flux<FAITHFUL, TPG, AXI>(g, face_geom<FAITHFUL>(xa, ya, xd, yd), le, me, 0, Fl, flags);
+            }
+        }
+        Fr = dg_shfl_down1(Fl);    // xi face i+1 = the left face of the next lane
+        if (!cell) continue;       // the halo lane and lanes past the block only feed the shuffle
+        const double xb = X[n00 + 1], yb = Y[n00 + 1], xc = X[n00 + b.pitch + 1], yc_ = Y[n00 + b.pitch + 1];
+        {
+            const long long e = (long long)j * ncx + i;
+            const double ycc = 0.25 * (ya + yb + yc_ + yd);           // geoel[2], MeshModule.cpp:40
+            const double vol = cell_volume(xa, ya, xb, yb, xc, yc_, xd, yd);
+            const double ycs = AXI ? ycc : 0.0;
+            DgAcc acc;
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc.r[q] = acc.rx[q] = acc.ry[q] = 0.0;
+            // the reference's accumulation order: xi face i (this cell is the right one), xi face i+1 (left)
+            // (SpatialDiscretization.cpp:481-552), eta face j (left = upper), eta face j+1 (right) (:556-625);
+            // per face point 1 then point 2.  Each flux pair is consumed as early as the order allows (registers)
+#pragma unroll
+            for (int pt = 0; pt < 2; pt++) if (i >= 1) dg_accumulate<AXI>(acc, Fl.F[pt], ycs, false, -1.0, pt == 0 ? G : -G);
+#pragma unroll
+            for (int pt = 0; pt < 2; pt++) if (i <= ncx - 2) dg_accumulate<AXI>(acc, Fr.F[pt], ycs, true, 1.0, pt == 0 ? G : -G);
+#pragma unroll
+            for (int pt = 0; pt < 2; pt++) if (j >= 1) dg_accumulate<AXI>(acc, Fb.F[pt], ycs, true, pt == 0 ? G : -G, -1.0);
+            if (j <= ncy - 2) {    // eta face j+1: node (i,j+1) -> (i+1,j+1), left = upper cell (i,j+1), right cell (i,j)
+                DgCell ab;
+                dg_load_cell(g, b, a.cur, i, j + 1, ab);
+                dg_face_flux<FAITHFUL, TPG, AXI>(g, face_geom<FAITHFUL>(xd, yd, xc, yc_), ab, me, 1, Fb, flags);   // next row's bottom face
+#pragma unroll
+                for (int pt = 0; pt < 2; pt++) dg_accumulate<AXI>(acc, Fb.F[pt], ycs, false, pt == 0 ? G : -G, 1.0);
+            }
+            // boundary faces (:643-977), left, right, bottom, top.  fNormalL / fNormalR are declared once per row
+            // (column) and shared by the left and right (bottom and top) face of it: at the ends of the right (top)
+            // side they still hold the left (bottom) side's values
+            if (i == 0 || i == ncx - 1 || j == 0 || j == ncy - 1) {
+    #pragma unroll 1
+                for (int sd = 0; sd < 4; sd++) {
+                    int type, side, n;
+                    bool exists;
+                    FaceGeom f, fL, fR;
+                    if (sd == 0) {
+                        exists = i == 0; type = 4; side = SIDE_LEFT; n = j;
+                        if (!exists) continue;
+                        f = face_geom<true>(xa, ya, xd, yd);
+                        fL = j != 0 ? dg_geom(b, 0, j - 1, 0, j) : f;
+                        fR = j != ncy - 1 ? dg_geom(b, 0, j + 1, 0, j + 2) : f;
+                    } else if (sd == 1) {
+                        exists = i == ncx - 1; type = 2; side = SIDE_RIGHT; n = j;
+                        if (!exists) continue;
+                        f = face_geom<true>(xb, yb, xc, yc_);
+                        fL = j != 0 ? dg_geom(b, ncx, j - 1, ncx, j) : dg_geom(b, 0, j, 0, j + 1);
+                        fR = j != ncy - 1 ? dg_geom(b, ncx, j + 1, ncx, j + 2) : dg_geom(b, 0, j, 0, j + 1);
+                    } else if (sd == 2) {
+                        exists = j == 0; type = 1; side = SIDE_BOTTOM; n = i;
+                        if (!exists) continue;
+                        f = face_geom<true>(xa, ya, xb, yb);
+                        fL = i != 0 ? dg_geom(b, i - 1, 0, i, 0) : f;
+                        fR = i != ncx - 1 ? dg_geom(b, i + 1, 0, i + 2, 0) : f;
+                    } else {
+                        exists = j == ncy - 1; type = 3; side = SIDE_TOP; n = i;
+                        if (!exists) continue;
+                        f = face_geom<true>(xd, yd, xc, yc_);
+                        fL = i != 0 ? dg_geom(b, i - 1, ncy, i, ncy) : dg_geom(b, i, 0, i + 1, 0);
+                        fR = i != ncx - 1 ? dg_geom(b, i + 1, ncy, i + 2, ncy) : dg_geom(b, i, 0, i + 1, 0);
+                    }
+                    dg_boundary_face<TPG, AXI>(g, b, type, side, n, me, f, fL.nx, fL.ny, fR.nx, fR.ny, ycs, acc, flags);
+                }
+            }
+            // :980-1011 division by the volume, then the volume integral of the slopes' equations (DGP1Tools.cpp:52-124)
+            double r[4], rx[4], ry[4];
+            unsigned fl2 = 0;
+            const FaceState sme = face_state<true, TPG>(g, me.u[0], me.u[1], me.u[2], me.u[3], fl2);
+            {
+                const double ycv = AXI ? ycc : 1.0;
+                const double rho = me.u[0];
+                double Fx[4], Fy[4];
+                Fx[0] = ycv * rho * me.u[1];
+                Fx[1] = ycv * (rho * me.u[1] * me.u[1] + sme.p);
+                Fx[2] = ycv * rho * me.u[1] * me.u[2];
+                Fx[3] = ycv * rho * me.u[1] * sme.h0;
+                Fy[0] = ycv * rho * me.u[2];
+                Fy[1] = ycv * rho * me.u[1] * me.u[2];
+                Fy[2] = ycv * (rho * me.u[2] * me.u[2] + sme.p);
+                Fy[3] = ycv * rho * me.u[2] * sme.h0;
+                const double xL = 0.5 * (xd + xa), xR = 0.5 * (xc + xb), xD = 0.5 * (xb + xa), xU = 0.5 * (xc + xd);
+                const double yL = 0.5 * (yd + ya), yR = 0.5 * (yc_ + yb), yD = 0.5 * (yb + ya), yU = 0.5 * (yc_ + yd);
+                const double nxs0 = -0.5 * (yU - yD), nxs1 = 0.5 * (xU - xD);
+                const double nxs2 = -0.25 * ((xU - xD) * (yL - yR) - (yU - yD) * (xL - xR));
+                double db1dx, db1dy, db2dx, db2dy, ivol = 0.0;
+                if constexpr (FAITHFUL) { db1dx = nxs0 / nxs2; db1dy = nxs1 / nxs2; }
+                else { const double q2 = fast_rcp(nxs2); db1dx = nxs0 * q2; db1dy = nxs1 * q2; ivol = fast_rcp(vol); }
+                const double net0 = -0.5 * (yL - yR), net1 = 0.5 * (xL - xR);
+                const double net2 = -0.25 * ((xL - xR) * (yD - yU) - (yL - yR) * (xD - xU));
+                if constexpr (FAITHFUL) { db2dx = net0 / net2; db2dy = net1 / net2; }
+                else { const double q2 = fast_rcp(net2); db2dx = net0 * q2; db2dy = net1 * q2; }
+    #pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if constexpr (FAITHFUL) {
+                        r[q] = acc.r[q] / vol;
+                        rx[q] = 3.0 * acc.rx[q] / vol;
+                        ry[q] = 3.0 * acc.ry[q] / vol;
+                    } else {
+                        r[q] = acc.r[q] * ivol;
+                        rx[q] = 3.0 * acc.rx[q] * ivol;
+                        ry[q] = 3.0 * acc.ry[q] * ivol;
+                    }
+                    rx[q] += 3.0 * (Fx[q] * db1dx + Fy[q] * db1dy);
+                    ry[q] += 3.0 * (Fx[q] * db2dx + Fy[q] * db2dy);
+                }
+            }
+            if (isnan(r[0])) flags |= FLAG_NAN;
+    #pragma unroll
+            for (int q = 0; q < 4; q++) { sq[q] += r[q] * r[q]; sq[4 + q] += rx[q] * rx[q]; sq[8 + q] += ry[q] * ry[q]; }
+            if (d.res_out != nullptr && d.res_block == k) {
+                double* o = d.res_out + 4 * e;
+    #pragma unroll
+                for (int q = 0; q < 4; q++) { o[q] = r[q]; o[4 * ncell + q] = rx[q]; o[8 * ncell + q] = ry[q]; }
+            }
+            if (d.update) {
+                // main.cpp:307-351: one Jacobian, three right-hand sides; :394-425 update of the mean, damped slopes
+                const double v2 = me.u[1] * me.u[1] + me.u[2] * me.u[2];
+                const double e0 = enthalpy<TPG>(g, me.u[3], fl2) - g.Rs * me.u[3] + 0.5 * v2;
+                const double Cv = heat_capacity<TPG>(g, me.u[3], fl2) - g.Rs;
+                double dv[4], dvx[4], dvy[4];
+                if constexpr (FAITHFUL) {
+                    solve_cell<true, AXI>(dt, ycc, me.u[0], me.u[1], me.u[2], e0, Cv, 0.0, r, dv, flags);
+                    solve_cell<true, AXI>(dt, ycc, me.u[0], me.u[1], me.u[2], e0, Cv, 0.0, rx, dvx, flags);
+                    solve_cell<true, AXI>(dt, ycc, me.u[0], me.u[1], me.u[2], e0, Cv, 0.0, ry, dvy, flags);
+                } else {
+                    // D is lower triangular: closed-form forward substitution, one reciprocal of rho for the three systems
+                    const double sc = AXI ? dt * fast_rcp(ycc) : dt;
+                    const double inv_cv = fast_rcp(Cv);
+                    solve_lean(sc, me.u[0], me.u[1], me.u[2], e0, inv_cv, r, dv);
+                    solve_lean(sc, me.u[0], me.u[1], me.u[2], e0, inv_cv, rx, dvx);
+                    solve_lean(sc, me.u[0], me.u[1], me.u[2], e0, inv_cv, ry, dvy);
+                }
+                double* So = b.state[a.cur ^ 1];
+                const long long o = (long long)(j + 1) * b.pitch + COL0 + i;
+                double nu[4];
+    #pragma unroll
+                for (int q = 0; q < 4; q++) nu[q] = me.u[q] + dv[q];
+                if (!(nu[0] > 0.0)) flags |= FLAG_DENSITY;
+                nu[3] = fmax(nu[3], 201.0);
+    #pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    So[q * b.plane + o] = nu[q];
+                    b.uxt[4 * e + q] = (me.ux[q] + dvx[q]) * DG_DAMP;
+                    b.uyt[4 * e + q] = (me.uy[q] + dvy[q]) * DG_DAMP;
+                }
+            }
+            flags |= fl2;
+        }
+    }
+    // sums of squares of the strip: lanes (xor tree), one record per strip
 #pragma unroll
     for (int q = 0; q < 12; q++) {
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) sq[q] += __shfl_xor_sync(0xffffffffu, sq[q], s);
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) {
+    if (lane < 12) {
+        double s = sq[0];
 #pragma unroll
-        for (int q = 0; q < 12; q++) red[warp][q] = sq[q];
-    }
-    __syncthreads();
-    if (threadIdx.x < 12) {
-        double s = 0.0;
-        for (int w = 0; w < DG_THREADS / 32; w++) s += red[w][threadIdx.x];
+        for (int q = 1; q < 12; q++) s = lane == q ? sq[q] : s;
         if (isnan(s)) flags |= FLAG_NAN;
-        d.partials[12 * (long long)(b.dg_tile0 + blockIdx.x) + threadIdx.x] = s;
+        d.partials[12 * (long long)(b.dg_tile0 + strip) + lane] = s;
     }
     if (flags) atomicOr(a.flags, flags);
 }

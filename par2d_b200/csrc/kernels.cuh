@@ -363,12 +363,12 @@ struct Launch {
         dg_ghost_kernel<FAITHFUL><<<dim3((d.max_points + 255) / 256, a.nowned), 256, 0, s>>>(a, g, d, write_dt);
     }
     static void dg_cell(cudaStream_t s, const StepArgs& a, const Gas& g, const DgArgs& d, bool tpg, bool axi) {
-        const dim3 grid(d.max_tiles, a.nowned);
-        if (tpg) { if (axi) dg_cell_kernel<FAITHFUL, true, true><<<grid, DG_THREADS, 0, s>>>(a, g, d); else dg_cell_kernel<FAITHFUL, true, false><<<grid, DG_THREADS, 0, s>>>(a, g, d); }
-        else { if (axi) dg_cell_kernel<FAITHFUL, false, true><<<grid, DG_THREADS, 0, s>>>(a, g, d); else dg_cell_kernel<FAITHFUL, false, false><<<grid, DG_THREADS, 0, s>>>(a, g, d); }
+        const dim3 grid((d.max_tiles + DG_WARPS - 1) / DG_WARPS, a.nowned);   // DG_WARPS strips per CTA
+        if (tpg) { if (axi) dg_cell_kernel<FAITHFUL, true, true><<<grid, 32 * DG_WARPS, 0, s>>>(a, g, d); else dg_cell_kernel<FAITHFUL, true, false><<<grid, 32 * DG_WARPS, 0, s>>>(a, g, d); }
+        else { if (axi) dg_cell_kernel<FAITHFUL, false, true><<<grid, 32 * DG_WARPS, 0, s>>>(a, g, d); else dg_cell_kernel<FAITHFUL, false, false><<<grid, 32 * DG_WARPS, 0, s>>>(a, g, d); }
     }
     static void dg_limit(cudaStream_t s, const StepArgs& a, const DgArgs& d) {
-        dg_limit_kernel<FAITHFUL><<<dim3(d.max_tiles, a.nowned), DG_THREADS, 0, s>>>(a, d);
+        dg_limit_kernel<FAITHFUL><<<dim3(d.max_lim_tiles, a.nowned), DG_THREADS, 0, s>>>(a, d);
     }
     static void test_ldfss(cudaStream_t s, const Gas& g, bool tpg, bool axi, long long n, const double* face, const double* uL, const double* uR, double* flux, double* parr) {
         const int grid = (int)((n + 127) / 128);
