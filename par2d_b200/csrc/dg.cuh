@@ -31,7 +31,7 @@ constexpr double DG_DAMP = 0.9;       // main.cpp:92
 constexpr double DG_DUSCALE = 0.5;    // main.cpp:93
 constexpr int DG_THREADS = 128;
 #ifndef DG_MINB
-#define DG_MINB 4      // CTAs per SM the cell kernel is compiled for (register budget 65536 / (32 * DG_WARPS * DG_MINB))
+#define DG_MINB 6      // CTAs per SM the cell kernel is compiled for (register budget 65536 / (32 * DG_WARPS * DG_MINB))
 #endif
 
 struct DgArgs {
@@ -326,6 +326,9 @@ __global__ void __launch_bounds__(256) dg_ghost_kernel(StepArgs a, Gas g, DgArgs
 // once per strip instead of once per adjacent cell - and then accumulates its four faces in the reference's
 // order, so that PAR2D_MODE_FAITHFUL stays bit-identical to the reference's scatter loops.
 constexpr int DG_SW = 31;
+#ifndef DG_PARK
+#define DG_PARK 1
+#endif
 #ifndef DG_PREFETCH
 #define DG_PREFETCH 1
 #endif
@@ -388,9 +391,18 @@ __global__ void __launch_bounds__(32 * DG_WARPS, DG_MINB) dg_cell_kernel(StepArg
     const double* Y = b.nodes + b.plane;
     const double G = dg_gauss();
     unsigned flags = 0;
+#if DG_PARK
+    // the 12 running sums of squares and the carried bottom-face flux pair live in shared memory between rows:
+    // 22 doubles per lane that would otherwise sit in registers through the whole row
+    __shared__ double park[DG_WARPS][22][32];
+    double (*pk)[32] = park[threadIdx.x >> 5];
+#pragma unroll
+    for (int q = 0; q < 12; q++) pk[q][lane] = 0.0;
+#else
     double sq[12];
 #pragma unroll
     for (int q = 0; q < 12; q++) sq[q] = 0.0;
+#endif
 
     // global dt = max over blocks (main.cpp:270-292)
     double dt = 0.0;
@@ -406,6 +418,11 @@ __global__ void __launch_bounds__(32 * DG_WARPS, DG_MINB) dg_cell_kernel(StepArg
         const long long n00 = (long long)(j0 + 1) * b.pitch + COL0 + i;
         dg_face_flux<FAITHFUL, TPG, AXI>(g, face_geom<FAITHFUL>(X[n00], Y[n00], X[n00 + 1], Y[n00 + 1]), up, lo, 1, Fb, flags);
     }
+#if DG_PARK
+#define DG_PARK_PUT(P) { _Pragma("unroll") for (int pt = 0; pt < 2; pt++) { pk[12 + 5 * pt][lane] = (P).F[pt].f0; pk[13 + 5 * pt][lane] = (P).F[pt].f1; pk[14 + 5 * pt][lane] = (P).F[pt].f2; pk[15 + 5 * pt][lane] = (P).F[pt].f3; pk[16 + 5 * pt][lane] = (P).F[pt].parr; } }
+#define DG_PARK_GET(P) { _Pragma("unroll") for (int pt = 0; pt < 2; pt++) { (P).F[pt].f0 = pk[12 + 5 * pt][lane]; (P).F[pt].f1 = pk[13 + 5 * pt][lane]; (P).F[pt].f2 = pk[14 + 5 * pt][lane]; (P).F[pt].f3 = pk[15 + 5 * pt][lane]; (P).F[pt].parr = pk[16 + 5 * pt][lane]; } }
+    DG_PARK_PUT(Fb)
+#endif
 #pragma unroll 1
     for (int j = j0; j < j1; j++) {
         DgCell me;
@@ -442,6 +459,10 @@ __global__ void __launch_bounds__(32 * DG_WARPS, DG_MINB) dg_cell_kernel(StepArg
             for (int pt = 0; pt < 2; pt++) if (i >= 1) dg_accumulate<AXI>(acc, Fl.F[pt], ycs, false, -1.0, pt == 0 ? G : -G);
 #pragma unroll
             for (int pt = 0; pt < 2; pt++) if (i <= ncx - 2) dg_accumulate<AXI>(acc, Fr.F[pt], ycs, true, 1.0, pt == 0 ? G : -G);
+#if DG_PARK
+            DgFluxPair Fb;
+            DG_PARK_GET(Fb)
+#endif
 #pragma unroll
             for (int pt = 0; pt < 2; pt++) if (j >= 1) dg_accumulate<AXI>(acc, Fb.F[pt], ycs, true, pt == 0 ? G : -G, -1.0);
             if (j <= ncy - 2) {    // eta face j+1: node (i,j+1) -> (i+1,j+1), left = upper cell (i,j+1), right cell (i,j)
@@ -450,6 +471,9 @@ __global__ void __launch_bounds__(32 * DG_WARPS, DG_MINB) dg_cell_kernel(StepArg
                 dg_face_flux<FAITHFUL, TPG, AXI>(g, face_geom<FAITHFUL>(xd, yd, xc, yc_), ab, me, 1, Fb, flags);   // next row's bottom face
 #pragma unroll
                 for (int pt = 0; pt < 2; pt++) dg_accumulate<AXI>(acc, Fb.F[pt], ycs, false, pt == 0 ? G : -G, 1.0);
+#if DG_PARK
+                DG_PARK_PUT(Fb)
+#endif
             }
             // boundary faces (:643-977), left, right, bottom, top.  fNormalL / fNormalR are declared once per row
             // (column) and shared by the left and right (bottom and top) face of it: at the ends of the right (top)
@@ -532,7 +556,11 @@ __global__ void __launch_bounds__(32 * DG_WARPS, DG_MINB) dg_cell_kernel(StepArg
             }
             if (isnan(r[0])) flags |= FLAG_NAN;
     #pragma unroll
+#if DG_PARK
+            for (int q = 0; q < 4; q++) { pk[q][lane] += r[q] * r[q]; pk[4 + q][lane] += rx[q] * rx[q]; pk[8 + q][lane] += ry[q] * ry[q]; }
+#else
             for (int q = 0; q < 4; q++) { sq[q] += r[q] * r[q]; sq[4 + q] += rx[q] * rx[q]; sq[8 + q] += ry[q] * ry[q]; }
+#endif
             if (d.res_out != nullptr && d.res_block == k) {
                 double* o = d.res_out + 4 * e;
     #pragma unroll
@@ -574,6 +602,11 @@ __global__ void __launch_bounds__(32 * DG_WARPS, DG_MINB) dg_cell_kernel(StepArg
         }
     }
     // sums of squares of the strip: lanes (xor tree), one record per strip
+#if DG_PARK
+    double sq[12];
+#pragma unroll
+    for (int q = 0; q < 12; q++) sq[q] = pk[q][lane];
+#endif
 #pragma unroll
     for (int q = 0; q < 12; q++) {
 #pragma unroll
