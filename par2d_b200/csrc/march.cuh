@@ -45,20 +45,11 @@ namespace par2d {
 #ifndef MARCH_MINB
 #define MARCH_MINB (MARCH_CPL == 2 ? 8 : 16)
 #endif
-#ifndef MARCH_NODE_LDS
-#define MARCH_NODE_LDS 0
-#endif
 #ifndef MARCH_YCC_FROM_FACES
 #define MARCH_YCC_FROM_FACES 1
 #endif
-#ifndef MARCH_SPLIT_PRE
-#define MARCH_SPLIT_PRE 0
-#endif
 #ifndef MARCH_VOTE_J
 #define MARCH_VOTE_J 1       // the fully-upwind warp vote also on j-faces (0: i-faces only, A/B runs)
-#endif
-#ifndef MARCH_WRITER_PRED
-#define MARCH_WRITER_PRED 0
 #endif
 #ifndef MARCH_STAGES
 #define MARCH_STAGES 3    // ring stages of two rows each
@@ -286,31 +277,12 @@ __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const
         hi.im[e] = raw[6][e];
     }
     // node right of this lane's last column = first node of lane+1 (for lane 31 it is never used)
-#if MARCH_NODE_LDS
-    hi.x[CPL] = nrow[CPL]; hi.y[CPL] = nrow[PLANE_D + CPL];   // lane 31 reads one slot past its row: unused
-#else
     hi.x[CPL] = shfl_down1(hi.x[0]); hi.y[CPL] = shfl_down1(hi.y[0]);
-#endif
 
     // i-faces of row j: face e between cell (c+e-1, j) [left state] and (c+e, j): node (c+e, j) -> (c+e, j+1);
     // the left state of face 0 is the last cell of lane-1, the flux of face CPL is face 0 of lane+1
     Flux F[CPL + 1];
     Flux Gt[CPL], Gb[CPL];
-#if MARCH_SPLIT_PRE
-    if constexpr (!FAITHFUL && CPL == 1) {
-        // lean path: the Mach-number parts (one rsqrt chain each) of the i-face and of the j-face are evaluated side
-        // by side BEFORE either flux reaches its warp vote - two independent dependency chains in one block
-        const FaceGeom gi = face_geom<false>(lo.x[0], lo.y[0], hi.x[0], hi.y[0]);
-        const FaceGeom gj = face_geom<false>(hi.x[0], hi.y[0], hi.x[1], hi.y[1]);
-        const FaceState left = shfl_up1(lo.s[0]);
-        const LdfssPre pi = ldfss_lean_pre(gi, left, lo.s[0]);
-        const LdfssPre pj = ldfss_lean_pre(gj, hi.s[0], lo.s[0]);
-        F[0] = ldfss_lean_post<AXI, true>(gi, left, lo.s[0], pi);
-        Gt[0] = ldfss_lean_post<AXI, MARCH_VOTE_J != 0>(gj, hi.s[0], lo.s[0], pj);
-        hi.yfb[0] = gj.yf;
-        F[1] = shfl_down1(F[0]);
-    } else
-#endif
     {
     F[0] = ldfss<FAITHFUL, AXI, !FAITHFUL>(face_geom<FAITHFUL>(lo.x[0], lo.y[0], hi.x[0], hi.y[0]), shfl_up1(lo.s[CPL - 1]), lo.s[0]);
 #pragma unroll
@@ -343,16 +315,6 @@ __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const
     double out[CPL][4];
 #pragma unroll
     for (int e = 0; e < CPL; e++) {
-#if MARCH_WRITER_PRED
-        if constexpr (!FAITHFUL && !HOOKS && CPL == 1) {
-            // the two halo lanes run the cell update as well (their sums, flags and stores are switched off): no
-            // branch between the fluxes and the update, one larger block for the instruction scheduler
-            if (m.writer[e]) flags |= flu[e];
-            cell_update<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, m.c + e, j, lo.s[e], lo.T[e], lo.im[e], lo.x[e], lo.y[e], lo.x[e + 1], lo.y[e + 1],
-                                            hi.x[e + 1], hi.y[e + 1], hi.x[e], hi.y[e], F[e], F[e + 1], Gb[e], Gt[e], out[e], sq0, sq1, sq2, sq3, flags, m.writer[e],
-                                            0.5 * (lo.yfb[e] + hi.yfb[e]));
-        } else
-#endif
         if (m.writer[e]) {
             flags |= flu[e];   // state checks of the cell above: a real cell or a filled ghost
             cell_update<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, m.c + e, j, lo.s[e], lo.T[e], lo.im[e], lo.x[e], lo.y[e], lo.x[e + 1], lo.y[e + 1],

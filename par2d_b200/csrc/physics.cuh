@@ -34,9 +34,6 @@ inline double __dsub_rn(double a, double b) { volatile double r = a - b; return 
 }  // namespace par2d
 #endif
 
-#ifndef LDFSS_SQRT
-#define LDFSS_SQRT 0
-#endif
 #ifndef LDFSS_UPWIND_VOTE
 #define LDFSS_UPWIND_VOTE 1
 #endif
@@ -50,9 +47,6 @@ inline double __dsub_rn(double a, double b) { volatile double r = a - b; return 
 #define LDFSS_BRANCHFREE 1    // the subsonic diffusion term is evaluated without a branch and switched off by a select: measured
                               // +1.3% on B200 together with the warp vote (fully supersonic warps skip it anyway; fewer basic
                               // blocks for the scheduler elsewhere); 0: branch around it (A/B runs)
-#endif
-#ifndef LDFSS_PRESSURE_V1
-#define LDFSS_PRESSURE_V1 0   // 1: the earlier evaluation of the subsonic diffusion term (A/B runs)
 #endif
 
 namespace par2d {
@@ -362,64 +356,34 @@ PAR2D_FN Flux ldfss_lean_post(const FaceGeom& fg, const FaceState& L, const Face
     double cem = subR ? xmmr : (signbit(xmr) ? xmr : 0.0);
     const double wl = subL ? xmml * (2.0 - xml) : (signbit(xml) ? 0.0 : 1.0);
     const double wr = subR ? -xmmr * (2.0 + xmr) : (signbit(xmr) ? 1.0 : 0.0);
-#if LDFSS_BRANCHFREE
-    {   // A/B: the subsonic diffusion term evaluated on every face and switched off by a select (one basic block)
-        const double t = 0.25 * fma(xml, xml, fma(xmr, xmr, 1e-199));
-        const double xs = t * fast_rsqrt(t);
-        const double d = xs - 0.70710678118654752440;
-        const double delp = L.p - R.p, psum = L.p + R.p;
-        const double plr = L.p * R.p;
-        const double w3 = fast_rcp(plr * psum);
-        const double N = max_sel(fma(-fabs(delp), psum, plr), 0.0);
-        const double k = (subL && subR) ? ((d * d) * w3) * N : 0.0;
-        cep = fma(-k, R.p, cep);
-        cem = fma(k, L.p, cem);
-    }
-    if (false) {
-#else
-    if (subL && subR) {
-#endif
-#if LDFSS_PRESSURE_V1
-        const double t = 0.5 * fma(xml, xml, xmr * xmr);
-        // rsqrt.approx flushes subnormals: below 1e-200 sqrt(t) is 0 to 100 digits of (xmhalf-1)
-#if LDFSS_SQRT
-        const double xmhalf = t > 1e-200 ? fast_sqrt(t) : 0.0;
-#else
-        const double xmhalf = t > 1e-200 ? t * fast_rsqrt(t) : 0.0;
-#endif
-        const double d1 = xmhalf - 1.0;
-        const double xmc = 0.25 * d1 * d1;
-        // delp/psum, 2|delp|/pL, 2|delp|/pR (EulerFlux.cpp:157-160) from ONE reciprocal,
-        // w = 1/(pL pR psum):  1/psum = pL pR w,  1/pL = pR psum w,  1/pR = pL psum w
-        const double delp = L.p - R.p, psum = L.p + R.p;
-        const double plr = L.p * R.p;
-        const double w3 = fast_rcp(plr * psum);
-        const double tw = psum * w3;
-        const double dps = delp * (plr * w3);
-        const double ad2 = 2.0 * fabs(delp);
-        cep -= xmc * max_sel(1.0 - fma(ad2, R.p * tw, dps), 0.0);
-        cem += xmc * max_sel(1.0 + fma(-ad2, L.p * tw, dps), 0.0);
-#else
-        // xmc = (xmhalf-1)^2/4 with xmhalf = sqrt((xml^2+xmr^2)/2) (EulerFlux.cpp:152-154).  Here
-        // xs = xmhalf/sqrt(2) and d = xs - 1/sqrt(2), so d*d = 2 xmc.  The 1e-199 keeps the argument of
-        // rsqrt.approx (which flushes subnormals) normal: it vanishes in the sum unless both Mach
-        // numbers are below 1e-92, where xs is 0 to 90 digits of d either way.  No branch, no compare.
-        const double t = 0.25 * fma(xml, xml, fma(xmr, xmr, 1e-199));
-        const double xs = t * fast_rsqrt(t);
-        const double d = xs - 0.70710678118654752440;
-        // pressure switches (EulerFlux.cpp:157-160) over their common denominator: with delp = pL - pR,
-        // psum = pL + pR and N = pL pR - |delp| psum,
+    {
+        // subsonic diffusion term, EulerFlux.cpp:152-163.
+        // xmc = (xmhalf-1)^2/4 with xmhalf = sqrt((xml^2+xmr^2)/2) (:152-154).  Here xs = xmhalf/sqrt(2) and
+        // d = xs - 1/sqrt(2), so d*d = 2 xmc.  The 1e-199 keeps the argument of rsqrt.approx (which flushes
+        // subnormals) normal: it vanishes in the sum unless both Mach numbers are below 1e-92, where xs is 0 to 90
+        // digits of d either way.  No compare, no branch.
+        // Pressure switches (:157-160) over their common denominator: with delp = pL - pR, psum = pL + pR and
+        // N = pL pR - |delp| psum,
         //   1 - (delp/psum + 2|delp|/pL) = 2 N / (pL psum),   1 + (delp/psum - 2|delp|/pR) = 2 N / (pR psum)
         // (psum -+ delp = 2 pR, 2 pL), so ONE reciprocal w3 = 1/(pL pR psum) and ONE max(.,0) serve both:
         //   xmcp = xmc max(0, 2 N pR w3) = (2 xmc) max(0,N) w3 pR,   xmcm = (2 xmc) max(0,N) w3 pL
-        const double delp = L.p - R.p, psum = L.p + R.p;
-        const double plr = L.p * R.p;
-        const double w3 = fast_rcp(plr * psum);
-        const double N = max_sel(fma(-fabs(delp), psum, plr), 0.0);
-        const double k = ((d * d) * w3) * N;
-        cep = fma(-k, R.p, cep);
-        cem = fma(k, L.p, cem);
+#if LDFSS_BRANCHFREE
+        const bool both = true;        // evaluated on every face, switched off by the select below (one basic block)
+#else
+        const bool both = subL && subR;
 #endif
+        if (both) {
+            const double t = 0.25 * fma(xml, xml, fma(xmr, xmr, 1e-199));
+            const double xs = t * fast_rsqrt(t);
+            const double d = xs - 0.70710678118654752440;
+            const double delp = L.p - R.p, psum = L.p + R.p;
+            const double plr = L.p * R.p;
+            const double w3 = fast_rcp(plr * psum);
+            const double N = max_sel(fma(-fabs(delp), psum, plr), 0.0);
+            const double k = (subL && subR) ? ((d * d) * w3) * N : 0.0;
+            cep = fma(-k, R.p, cep);
+            cem = fma(k, L.p, cem);
+        }
     }
     const double pnet = fma(wl, L.p, wr * R.p);
     if constexpr (AXI) {
