@@ -203,6 +203,8 @@ def run_gpu_arm(args):
     total_cells = case.ncells
     cfg = default_config(gpu)
     cfg.device = local
+    if args.faithful:
+        cfg.mode = 1     # PAR2D_MODE_FAITHFUL: the reference's operation order, bit-identical results (not the headline)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -341,7 +343,7 @@ def run_gpu_arm(args):
                    "halo_exchange": (f"{transport} (" + ("kernel stores into NVLink peer-mapped arenas + sequence flags, no host transport; edge strips + put on a side stream beside the interior strips"
                                      if transport == "peer" else "NCCL send/recv + all-reduce(MAX) per step") + ")") if multi else "none (single GPU)",
                    "l2": "state per GPU 1.07 GB read + 1.07 GB written per step >> 126 MB L2; no flush needed",
-                   "arith_mode": "PAR2D_MODE_FAST"},
+                   "arith_mode": "PAR2D_MODE_FAITHFUL" if args.faithful else "PAR2D_MODE_FAST"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
         # peer transport: ghost + edge strips + interior strips + put per step; external: ghost + march + pack
         "gpu_launches": (LAUNCHES_PER_STEP + (2 if transport == "peer" else 1 if multi else 0)) * args.steps + 1 + (1 if transport == "peer" else 0),
@@ -360,6 +362,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--block", type=int, default=BLOCK, help="cells per block side (default: the benchmark's 2048)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--faithful", action="store_true", help="time the bit-faithful arithmetic mode instead of the default fast one")
     ap.add_argument("--strong", action="store_true", help="strong scaling: the full 16k x 16k / 64-block mesh on N GPUs (default: weak, 8 blocks per GPU)")
     ap.add_argument("--transport", default="auto", choices=["auto", "peer", "external"],
                     help="multi-GPU halo exchange: NVLink peer-mapped arenas (default) or NCCL send/recv per step")
