@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) ghost_kernel(StepArgs a, Gas g, int write
         for (int t = 0; t < a.nblocks_global; t++) dt = fmax(dt, __ldcg(a.dt_table + t));
         *a.dt_used = dt;
     }
-    const BlockDev b = a.blocks[blockIdx.y - nfin];   // grid.y = [pending finalize rows +] owned blocks, grid.x covers the longest perimeter
+    const BlockDev& b = a.blocks[blockIdx.y - nfin];   // grid.y = [pending finalize rows +] owned blocks, grid.x covers the longest perimeter
     int n = blockIdx.x * blockDim.x + threadIdx.x, side;
     if (n >= 2 * (b.ncx + b.ncy)) return;
     if (n < b.ncx) side = SIDE_BOTTOM;
