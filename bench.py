@@ -329,7 +329,7 @@ def run_gpu_arm(args):
                 "cell_updates_per_s_per_gpu": owned_cells / (k_ms * 1e-3)}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and args.gpus == 1:      # the CPU baseline is reported at N = 1 only
         res = cpu_reference_run(iters=500, warm=25)
         cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
