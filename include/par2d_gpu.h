@@ -138,6 +138,11 @@ int par2d_destroy(par2d_ctx* ctx);
  * reference's unk array (main.cpp:163,193-197,394-404). */
 int par2d_set_state(par2d_ctx* ctx, int32_t block, const double* unk);
 int par2d_get_state(par2d_ctx* ctx, int32_t block, double* unk);
+/* The same for n owned blocks in one call: the host<->device copy of one block overlaps the AoS<->plane transpose
+ * of the previous one (two staging buffers, a copy stream); give pinned host buffers for the copies to be
+ * asynchronous.  blocks[i] = global block id, unk[i] = that block's array. */
+int par2d_set_states(par2d_ctx* ctx, int32_t n, const int32_t* blocks, const double* const* unk);
+int par2d_get_states(par2d_ctx* ctx, int32_t n, const int32_t* blocks, double* const* unk);
 
 /* Test hook = one calc_dudt() evaluation (SpatialDiscretization.h:10) on the
  * current state, ghost fill and halo exchange included: res[(j*(nx-1)+i)*4+k]
@@ -164,6 +169,12 @@ int par2d_get_residual_dg(par2d_ctx* ctx, int32_t block, double* res, double* re
  * stop_on_tol != 0 and nranks == 1, like main.cpp:506-511 does for multi-block
  * runs; the state is then the one after the converged iteration. */
 int par2d_step(par2d_ctx* ctx, int32_t nsteps, int32_t stop_on_tol, par2d_step_info* info);
+/* par2d_step in two halves: _async queues the whole batch on the ctx stream and returns, _wait blocks until it has
+ * completed and fills info[nsteps of the _async call].  One host thread can so drive the contexts of several GPUs
+ * (par2d_peer_connect_local): _async on every ctx, then _wait on every ctx - the batches of peer-mapped contexts
+ * depend on each other's progress. */
+int par2d_step_async(par2d_ctx* ctx, int32_t nsteps, int32_t stop_on_tol);
+int par2d_step_wait(par2d_ctx* ctx, par2d_step_info* info);
 
 /* Per-owned-block residual sums of the last `nsteps` steps, in owned-block
  * order: out[(s*nowned + b)*2 + {0: sum_k||res_k||, 1: sum_k res0_k}]
@@ -221,6 +232,13 @@ int par2d_step_collect(par2d_ctx* ctx, int32_t nsteps, par2d_step_info* info);
 int par2d_peer_export(par2d_ctx* ctx, void* handle_out);
 int par2d_peer_connect(par2d_ctx* ctx, const void* all_handles /* nranks*64 bytes */);
 int par2d_peer_disconnect(par2d_ctx* ctx);
+/* After every rank has returned from par2d_peer_connect (host barrier): verifies that all ranks cut their blocks
+ * into the same strips, i.e. add the residual norms in the same order. */
+int par2d_peer_check(par2d_ctx* ctx);
+/* The same connection for n contexts of ONE process (ctxs[r] = rank r of n, one per GPU; replaces the rank setup of
+ * FV/main.cpp:68-74,125-142 for a single-process multi-GPU host): enables peer access between the devices and
+ * hands every context the others' arenas directly - no handle exchange, no second process. */
+int par2d_peer_connect_local(par2d_ctx** ctxs, int32_t n);
 
 /* All device work of this ctx is issued on one CUDA stream.  stream is a
  * cudaStream_t passed as an integer (0 = a private non-blocking stream). */
@@ -250,6 +268,9 @@ int par2d_test_solve(const par2d_config* cfg, int64_t n, const double* dt_ycc /*
  * their durations and the launch count.  bench.py derives roofline.achieved from it. */
 int par2d_kernel_timing(par2d_ctx* ctx, int32_t enable);
 int par2d_kernel_time(par2d_ctx* ctx, double* total_ms, int64_t* launches);
+
+/* Number of CUDA devices this process sees (the reference asks MPI_Comm_size, FV/main.cpp:70-71). */
+int par2d_device_count(int32_t* n);
 
 /* Measured fp64 FMA throughput of the device in TFLOP/s (2 flops per FMA);
  * used by bench.py to report the secondary (fp64-pipe) bound. */

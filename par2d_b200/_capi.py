@@ -102,9 +102,16 @@ GPU_ONLY_API = {
     "peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "peer_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "peer_disconnect": (C.c_int, [C.c_void_p]),
+    "peer_check": (C.c_int, [C.c_void_p]),
+    "peer_connect_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32]),
+    "step_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "step_wait": (C.c_int, [C.c_void_p, C.POINTER(StepInfo)]),
+    "set_states": (C.c_int, [C.c_void_p, C.c_int32, _IP, C.POINTER(_DP)]),
+    "get_states": (C.c_int, [C.c_void_p, C.c_int32, _IP, C.POINTER(_DP)]),
     "set_stream": (C.c_int, [C.c_void_p, C.c_uint64]),
     "synchronize": (C.c_int, [C.c_void_p]),
     "probe_fp64": (C.c_int, [C.c_int32, _DP]),
+    "device_count": (C.c_int, [_IP]),
     "kernel_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "kernel_time": (C.c_int, [C.c_void_p, _DP, C.POINTER(C.c_int64)]),
 }

@@ -63,7 +63,7 @@ int facing_side(const par2d_block_desc& nb, int me, int my_side) {
 // Arena layout of rank r, a pure function of the global block table (so every rank can address every
 // other rank's arena without asking): see common.cuh PutArgs.
 struct ArenaLayout {
-    size_t flags_off = 0, dt_off = 0, lines_off = 0, bytes = 0;
+    size_t flags_off = 0, dt_off = 0, res_off = 0, lines_off = 0, bytes = 0;
     long long dt_stride = 0;     // doubles
     long long lines_stride = 0;  // doubles = everything rank r receives per event
 };
@@ -91,7 +91,8 @@ ArenaLayout arena_layout(const par2d_block_desc* t, int nblocks, int nranks, int
     L.flags_off = 0;
     L.dt_off = up(sizeof(unsigned long long) * 16 * (size_t)nranks);
     L.dt_stride = (long long)((nblocks + 31) / 32 * 32);
-    L.lines_off = up(L.dt_off + sizeof(double) * 2 * (size_t)L.dt_stride);
+    L.res_off = up(L.dt_off + sizeof(double) * 2 * (size_t)L.dt_stride);     // [4 slots][nblocks][2] per-block residual sums (stop test)
+    L.lines_off = up(L.res_off + sizeof(double) * 8 * (size_t)nblocks);
     for (int p = 0; p < nranks; p++)
         if (p != r) L.lines_stride += recv_count(t, nblocks, r, p, lw);
     L.bytes = up(L.lines_off + sizeof(double) * 2 * (size_t)std::max<long long>(L.lines_stride, 1));
@@ -164,7 +165,8 @@ struct par2d_ctx {
     BlockDev* dblk = nullptr;
     void* dtmaps = nullptr;
 
-    double* dt_table = nullptr;
+    Gas* gas_dev = nullptr;          // the Gas constants in global memory (non-inlined boundary-condition code)
+    double* dt_table = nullptr;      // single rank: [2][nblocks], the parity of a step is iter_queued & 1
     double* dt_used = nullptr;       // [2]: the dt of the step in flight / of the step whose bookkeeping is pending
     bool fin_pending = false;        // the last queued step's bookkeeping has not been launched yet
     FinalizeArgs fin_args;
@@ -176,10 +178,16 @@ struct par2d_ctx {
     unsigned* ticket = nullptr;
     double* res0 = nullptr;
     double* blk_norm = nullptr;
+    double* blk_sum = nullptr;
+    unsigned* flag_hist = nullptr;
+    std::vector<unsigned> h_flag_hist;
     double* blk_hist = nullptr;
     double* step_hist = nullptr;
     int hist_cap = 0;
     double* staging = nullptr;
+    double* staging2 = nullptr;      // second staging buffer + copy stream of the batched state transfers (created on first use)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     long long staging_doubles = 0;
     // second-order branch (cfg.accur == 1)
     bool dg = false;
@@ -204,25 +212,32 @@ struct par2d_ctx {
     char* arena = nullptr;
     ArenaLayout lay;
     bool peer_connected = false;
+    bool peer_ipc = false;           // the peers' arenas are cudaIpc mappings (separate processes), not same-process pointers
     std::vector<char*> peer_base;    // mapped arena of every rank (own: arena)
     double** d_dt_dst = nullptr;
     unsigned long long** d_flag_dst = nullptr;
     unsigned* put_ticket = nullptr;
     unsigned long long seq = 0;      // exchange events produced so far (identical on every rank)
-    // overlap of the exchange with interior work (peer-mapped mode): strips that touch an off-rank face run first on
-    // a side stream, followed by the put of the NEW state's edge lines; the interior strips run beside them
-    int2* d_edge_tiles = nullptr;
-    int2* d_inner_tiles = nullptr;
-    int n_edge_tiles = 0, n_inner_tiles = 0;
-    cudaStream_t side_stream = nullptr;
-    cudaEvent_t ev_ghost = nullptr, ev_edge = nullptr;
-    bool overlap = true;             // PAR2D_NO_OVERLAP=1 keeps put -> ghost -> march in one stream (A/B runs)
-    // single rank: the same two-stream scheme hides the ghost fill + bookkeeping of step n+1 behind the interior
-    // strips of step n (par2d_step without stop_on_tol); needs double-buffered dt table and strip partials
-    bool single_overlap = false;
-    cudaEvent_t ev_main = nullptr;
-    long long partials_stride = 0;   // doubles between the two parities of the partial sums (0: single buffer)
-    int dt_parities = 1;
+    double** d_res_dst = nullptr;    // stop test across ranks: residual table of every arena / this rank's residual flag there
+    unsigned long long** d_rflag_dst = nullptr;
+    int* go = nullptr;               // [0]: launch whose stop decision is made; stop_iter follows
+    long long* stop_iter = nullptr;
+    // fused step (march.cuh, PUSH): one launch per step.  Across ranks the strips run in tile-list order, those that
+    // border another rank (their puts travel while the interior strips run) and strip 0 of every block (its dt) first
+    int2* d_push_tiles = nullptr;
+    int n_push_tiles = 0;
+    unsigned n_put_tiles = 0;        // strips of a launch that put something into a peer's arena
+    bool fused = true;               // PAR2D_NO_OVERLAP=1: put -> ghost -> march as separate launches (A/B runs)
+    // persistent launch: a whole batch of a small mesh in one cooperative kernel
+    int2* d_all_tiles = nullptr;
+    unsigned* grid_bar = nullptr;
+    int coop_capacity = 0;
+    bool persist = true;             // PAR2D_NO_PERSIST=1: one launch per step (A/B runs)
+    long long partials_stride = 0;   // doubles between the two parities of the strip sums
+    // asynchronous batch (par2d_step_async / par2d_step_wait)
+    bool batch_open = false;
+    int batch_steps = 0, batch_cur0 = 0, batch_stop = 0;
+    unsigned long long batch_seq0 = 0;
     long long timeout_ns = 20000000000ll;
 
     // history of the last batch, host copies
@@ -242,6 +257,7 @@ struct par2d_ctx {
     StepArgs step_args(int update) const {
         StepArgs a;
         a.blocks = dblk;
+        a.gas_dev = gas_dev;
         a.nowned = nowned;
         a.nblocks_global = nblocks;
         a.cur = cur;
@@ -249,7 +265,12 @@ struct par2d_ctx {
         a.max_tiles = max_tiles;
         a.max_faces = max_faces;
         a.tmaps = dtmaps;
-        a.dt_table = dt_table + (dt_parities == 2 ? (iter_queued & 1) * (long long)nblocks : 0);
+        a.dt_table = dt_table + (arena ? 0 : (iter_queued & 1) * (long long)nblocks);
+        a.dt_next = arena ? nullptr : dt_table + ((iter_queued + 1) & 1) * (long long)nblocks;
+        a.nfin = 0;
+        a.launch_no = 0;
+        a.coop_steps = 1;
+        a.grid_bar = grid_bar;
         a.dt_used = dt_used + (iter_queued & 1);
         a.partials = partials + (iter_queued & 1) * partials_stride;
         a.flags = flags;
@@ -291,6 +312,10 @@ struct par2d_ctx {
         f.ticket = ticket;
         f.dt_used = dt_used + (iter_queued & 1);
         f.blk_norm = blk_norm;
+        f.blk_sum = blk_sum;
+        f.flag_hist = flag_hist;
+        f.flags = flags;
+        memset(&f.stop_x, 0, sizeof f.stop_x);
         f.dg_partials = dg ? dg_partials : nullptr;
         f.tol = cfg.tol;
         f.stop_on_tol = stop_on_tol;
@@ -311,7 +336,10 @@ int ensure_hist(par2d_ctx* c, int nsteps) {
     const int cap = std::max(nsteps, 64);
     if (c->blk_hist) cudaFree(c->blk_hist);
     if (c->step_hist) cudaFree(c->step_hist);
+    if (c->flag_hist) cudaFree(c->flag_hist);
     c->blk_hist = c->step_hist = nullptr;
+    c->flag_hist = nullptr;
+    CU_TRY(cudaMalloc(&c->flag_hist, sizeof(unsigned) * (size_t)cap));
     CU_TRY(cudaMalloc(&c->blk_hist, sizeof(double) * 2 * (size_t)cap * c->nowned));
     CU_TRY(cudaMalloc(&c->step_hist, sizeof(double) * 4 * (size_t)cap));
     c->hist_cap = cap;
@@ -359,25 +387,13 @@ int build_tensor_maps(par2d_ctx* c) {
 
 void launch_step(par2d_ctx* c, const StepArgs& a) { c->kt->march(c->stream, a, c->gas, c->tpg, c->axi); }
 
-// peer-mapped mode: produce the next exchange event from the current state
-void queue_put(par2d_ctx* c, cudaStream_t stream = nullptr) {
-    if (!stream) stream = c->stream;
+PutArgs put_args(const par2d_ctx* c);
+
+// peer-mapped mode: produce the next exchange event from the current state with a launch of its own (start of a
+// batch; every step of the second-order branch and of the serial A/B order)
+void queue_put(par2d_ctx* c) {
     c->seq++;
-    PutArgs put;
-    memset(&put, 0, sizeof put);
-    put.peer_mode = 1;
-    put.parity = (int)(c->seq & 1);
-    put.seq = c->seq;
-    put.dt_dst = c->d_dt_dst;
-    put.dt_stride = c->lay.dt_stride;
-    put.flag_dst = c->d_flag_dst;
-    put.ticket = c->put_ticket;
-    put.local_flags = reinterpret_cast<const unsigned long long*>(c->arena + c->lay.flags_off);
-    put.nranks = c->cfg.nranks;
-    put.rank = c->cfg.rank;
-    put.timeout_ns = c->timeout_ns;
-    put.dg = c->dg ? 1 : 0;
-    c->kt->pack(stream, c->step_args(1), c->gas, c->dlines_peer, c->nlines, c->max_line, put);
+    c->kt->pack(c->stream, c->step_args(1), c->gas, c->dlines_peer, c->nlines, c->max_line, put_args(c));
 }
 
 // The bookkeeping of a step (finalize) is deferred into the NEXT step's ghost launch, where it overlaps
@@ -413,93 +429,114 @@ void queue_step_dg(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
     c->cur ^= 1;
 }
 
-// peer-mapped mode with overlap: the exchange event of the state being read was produced before this call.
-//   main stream : ghost (waits for the peers' flags) ........ march(interior strips) ... wait(edge) ->
-//   side stream :           wait(ghost) -> march(edge strips) -> put(new state's edge lines + dt, flag)
-// so the NVLink stores, the flag latency and the skew between GPUs hide behind the interior strips.
-void queue_step_overlapped(par2d_ctx* c) {
-    StepArgs a = c->step_args(1);
-    a.dt_ready = 1;
-    c->kt->ghost(c->stream, a, c->gas, 0, c->fin_pending ? &c->fin_args : nullptr);
-    c->fin_pending = false;
-    cudaEventRecord(c->ev_ghost, c->stream);
-    cudaStreamWaitEvent(c->side_stream, c->ev_ghost, 0);
-    if (c->timing) {
-        if ((int)c->ev.size() < 2 * (c->ev_used + 1)) {
-            cudaEvent_t e0, e1;
-            cudaEventCreate(&e0);
-            cudaEventCreate(&e1);
-            c->ev.push_back(e0);
-            c->ev.push_back(e1);
-        }
-        cudaEventRecord(c->ev[2 * c->ev_used], c->stream);
+void time_begin(par2d_ctx* c) {
+    if (!c->timing) return;
+    if ((int)c->ev.size() < 2 * (c->ev_used + 1)) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        c->ev.push_back(e0);
+        c->ev.push_back(e1);
     }
-    StepArgs ae = a, ai = a;
-    ae.tile_list = c->d_edge_tiles; ae.tile_count = c->n_edge_tiles;
-    ai.tile_list = c->d_inner_tiles; ai.tile_count = c->n_inner_tiles;
-    c->kt->march(c->side_stream, ae, c->gas, c->tpg, c->axi);
-    c->kt->march(c->stream, ai, c->gas, c->tpg, c->axi);
-    c->fin_args = c->finalize_args(0);
-    c->fin_pending = true;
-    c->iter_queued++;
-    c->cur ^= 1;
-    queue_put(c, c->side_stream);      // reads the NEW state's edge cells (all in edge strips) and cell (0,0) of every block
-    cudaEventRecord(c->ev_edge, c->side_stream);
-    cudaStreamWaitEvent(c->stream, c->ev_edge, 0);
+    cudaEventRecord(c->ev[2 * c->ev_used], c->stream);
+}
+void time_end(par2d_ctx* c) {
     if (c->timing) cudaEventRecord(c->ev[2 * c->ev_used++ + 1], c->stream);
 }
 
-// Single rank, no stop test inside the batch: nsteps steps with the ghost fill (+ dt) of step n+1 and the bookkeeping
-// of step n-1 running on the side stream beside the interior strips of step n.
-//   side : edge strips(n) -> ghost(n+1) [+ finalize(n-1)]          -> (waits for interior(n))  edge strips(n+1) ...
-//   main : interior strips(n)  -> (waits for the side stream)  interior strips(n+1) ...
-// Buffers touched concurrently are double-buffered by step parity: state (ping-pong), per-block dt table, strip
-// partial sums, dt_used.  The bookkeeping lags the state by at most two steps inside the batch and is complete
-// when the batch returns.
-void queue_batch_overlapped(par2d_ctx* c, int nsteps) {
-    std::vector<FinalizeArgs> pending;                // bookkeeping not launched yet, oldest first (at most two)
-    {
-        StepArgs a0 = c->step_args(1);
-        c->kt->ghost(c->stream, a0, c->gas, 1, nullptr);
-        cudaEventRecord(c->ev_main, c->stream);
-        cudaStreamWaitEvent(c->side_stream, c->ev_main, 0);
+// stop test across ranks (StopArgs, common.cuh) for the batch that starts at iteration c->iter
+StopArgs stop_args(const par2d_ctx* c) {
+    StopArgs sx;
+    memset(&sx, 0, sizeof sx);
+    sx.enabled = 1;
+    sx.nranks = c->cfg.nranks;
+    sx.rank = c->cfg.rank;
+    sx.res_dst = c->d_res_dst;
+    sx.rflag_dst = c->d_rflag_dst;
+    sx.res_table = reinterpret_cast<const double*>(c->arena + c->lay.res_off);
+    sx.local_flags = reinterpret_cast<const unsigned long long*>(c->arena + c->lay.flags_off);
+    sx.nblocks_global = c->nblocks;
+    sx.go = c->go;
+    sx.stop_iter = c->stop_iter;
+    sx.iter0 = c->iter;
+    sx.tol = c->cfg.tol;
+    sx.timeout_ns = c->timeout_ns;
+    return sx;
+}
+
+PutArgs put_args(const par2d_ctx* c) {
+    PutArgs put;
+    memset(&put, 0, sizeof put);
+    if (!c->peer_connected) return put;
+    put.peer_mode = 1;
+    put.parity = (int)(c->seq & 1);
+    put.seq = c->seq;
+    put.dt_dst = c->d_dt_dst;
+    put.dt_stride = c->lay.dt_stride;
+    put.flag_dst = c->d_flag_dst;
+    put.ticket = c->put_ticket;
+    put.local_flags = reinterpret_cast<const unsigned long long*>(c->arena + c->lay.flags_off);
+    put.nranks = c->cfg.nranks;
+    put.rank = c->cfg.rank;
+    put.timeout_ns = c->timeout_ns;
+    put.expected = c->n_put_tiles;
+    put.dg = c->dg ? 1 : 0;
+    return put;
+}
+
+// The fused step (first-order path): ONE launch = the bookkeeping of the previous step (leading CTAs) + every strip;
+// the strips on a block's perimeter push the new state's ghost ring, the edge lines of off-rank faces (straight into
+// the neighbours' arenas over NVLink, flag raised by the last of them) and the block's dt.  Across ranks the strips
+// that border another rank run first, so their puts, the flag latency and the skew between GPUs hide behind the
+// interior strips; only those strips wait for a peer's lines, the others only for its dt.
+void queue_step_fused(par2d_ctx* c, int launch_no, int stop_on_tol) {
+    StepArgs a = c->step_args(1);       // across ranks: consumes exchange event c->seq
+    a.dt_ready = 0;
+    a.launch_no = launch_no;
+    a.nfin = c->fin_pending ? c->nowned : 0;
+    FinalizeArgs fin;
+    memset(&fin, 0, sizeof fin);
+    if (c->fin_pending) fin = c->fin_args;
+    const bool across = c->peer_connected && stop_on_tol;
+    if (across && !c->fin_pending) fin.stop_x = stop_args(c);   // the stop test of a launch that carries no bookkeeping
+    if (c->peer_connected) {
+        a.tile_list = c->d_push_tiles;
+        a.tile_count = c->n_push_tiles;
+        c->seq++;                       // ... and produces the next one
+    } else {
+        a.tile_list = nullptr;
+        a.tile_count = 0;
     }
-    for (int n = 0; n < nsteps; n++) {
-        StepArgs a = c->step_args(1);
-        if (c->timing) {
-            if ((int)c->ev.size() < 2 * (c->ev_used + 1)) {
-                cudaEvent_t e0, e1;
-                cudaEventCreate(&e0);
-                cudaEventCreate(&e1);
-                c->ev.push_back(e0);
-                c->ev.push_back(e1);
-            }
-            cudaEventRecord(c->ev[2 * c->ev_used], c->stream);
-        }
-        StepArgs ae = a, ai = a;
-        ae.tile_list = c->d_edge_tiles; ae.tile_count = c->n_edge_tiles;
-        ai.tile_list = c->d_inner_tiles; ai.tile_count = c->n_inner_tiles;
-        c->kt->march(c->side_stream, ae, c->gas, c->tpg, c->axi);
-        c->kt->march(c->stream, ai, c->gas, c->tpg, c->axi);
-        pending.push_back(c->finalize_args(0));
-        c->iter_queued++;
-        c->cur ^= 1;
-        if (n + 1 < nsteps) {
-            // ghost fill of the new state from its edge strips; the bookkeeping of step n-1 (complete: the side
-            // stream waited for interior(n-1) before edge(n)) rides along
-            StepArgs an = c->step_args(1);
-            const FinalizeArgs* ride = nullptr;
-            FinalizeArgs f;
-            if (pending.size() == 2) { f = pending.front(); pending.erase(pending.begin()); ride = &f; }
-            c->kt->ghost(c->side_stream, an, c->gas, 1, ride);
-        }
-        cudaEventRecord(c->ev_edge, c->side_stream);
-        cudaEventRecord(c->ev_main, c->stream);
-        cudaStreamWaitEvent(c->stream, c->ev_edge, 0);        // interior(n+1) reads cells of the edge strips; edge(n) read the buffer it writes
-        cudaStreamWaitEvent(c->side_stream, c->ev_main, 0);   // edge(n+1) reads cells of the interior strips
-        if (c->timing) cudaEventRecord(c->ev[2 * c->ev_used++ + 1], c->stream);
-    }
-    for (const FinalizeArgs& f : pending) launch_finalize(c->stream, f);
+    const PutArgs put = put_args(c);
+    time_begin(c);
+    c->kt->march_push(c->stream, a, c->gas, put, fin, c->tpg, c->axi);
+    time_end(c);
+    c->fin_args = c->finalize_args(stop_on_tol);
+    if (across) c->fin_args.stop_x = stop_args(c);
+    c->fin_pending = true;
+    c->iter_queued++;
+    c->cur ^= 1;
+}
+
+// Single rank, small mesh: the whole batch in one cooperative launch (march_persist_kernel).  Returns false when the
+// launch was refused (the caller then falls back to one launch per step - still the CUDA path).
+bool queue_batch_persistent(par2d_ctx* c, int nsteps, int stop_on_tol) {
+    StepArgs a = c->step_args(1);
+    a.dt_ready = 0;
+    a.coop_steps = nsteps;
+    a.tile_list = c->d_all_tiles;
+    a.tile_count = c->total_tiles;
+    const FinalizeArgs fin = c->finalize_args(stop_on_tol);
+    double* dt_used_alt = c->dt_used + ((c->iter_queued + 1) & 1);
+    double* partials_alt = c->partials + ((c->iter_queued + 1) & 1) * c->partials_stride;
+    if (cudaMemsetAsync(c->grid_bar, 0, sizeof(unsigned), c->stream) != cudaSuccess) return false;
+    time_begin(c);
+    const cudaError_t e = c->kt->march_coop(c->stream, a, c->gas, fin, dt_used_alt, partials_alt, c->tpg, c->axi);
+    time_end(c);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    c->iter_queued += nsteps;
+    c->cur ^= (nsteps & 1);
+    return true;
 }
 
 void queue_step(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
@@ -508,18 +545,9 @@ void queue_step(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
     a.dt_ready = with_ghost_dt ? 0 : 1;
     c->kt->ghost(c->stream, a, c->gas, with_ghost_dt ? 1 : 0, c->fin_pending ? &c->fin_args : nullptr);
     c->fin_pending = false;
-    if (c->timing) {
-        if ((int)c->ev.size() < 2 * (c->ev_used + 1)) {
-            cudaEvent_t e0, e1;
-            cudaEventCreate(&e0);
-            cudaEventCreate(&e1);
-            c->ev.push_back(e0);
-            c->ev.push_back(e1);
-        }
-        cudaEventRecord(c->ev[2 * c->ev_used], c->stream);
-    }
+    time_begin(c);
     launch_step(c, a);
-    if (c->timing) cudaEventRecord(c->ev[2 * c->ev_used++ + 1], c->stream);
+    time_end(c);
     c->fin_args = c->finalize_args(stop_on_tol);
     c->fin_pending = true;
     c->iter_queued++;
@@ -527,7 +555,7 @@ void queue_step(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
 }
 
 // after a synchronise: pull the history of `queued` steps, fix up cur/iter if the batch stopped early
-int harvest(par2d_ctx* c, int queued, int cur0, par2d_step_info* info, int ninfo) {
+int harvest(par2d_ctx* c, int queued, int cur0, par2d_step_info* info, int ninfo, bool stop_across = false, unsigned long long seq0 = 0) {
     int done = 0;
     unsigned fl = 0;
     long long it = 0;
@@ -535,6 +563,21 @@ int harvest(par2d_ctx* c, int queued, int cur0, par2d_step_info* info, int ninfo
     CU_TRY(cudaMemcpy(&fl, c->flags, sizeof fl, cudaMemcpyDeviceToHost));
     CU_TRY(cudaMemcpy(&it, c->d_iter, sizeof it, cudaMemcpyDeviceToHost));
     if (done > queued) done = queued;
+    if (stop_across) {
+        // the stop decision was made on the device from the sums of all ranks (stop_test): every rank stops after
+        // the same iteration.  One more step may have run and been recorded: drop it
+        int stopped = 0;
+        long long sit = -1;
+        CU_TRY(cudaMemcpy(&stopped, c->stop, sizeof stopped, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(&sit, c->stop_iter, sizeof sit, cudaMemcpyDeviceToHost));
+        if (stopped && sit >= c->iter) {
+            done = std::min<long long>(done, sit + 1 - c->iter);
+            it = c->iter + done;
+            CU_TRY(cudaMemcpy(c->d_iter, &it, sizeof it, cudaMemcpyHostToDevice));
+            // exchange events really produced: the batch-start put + one per launch that ran
+            c->seq = seq0 + 1 + (unsigned long long)std::min(queued, done + 1);
+        }
+    }
     for (int q = 0; q < c->ev_used; q++) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->ev[2 * q], c->ev[2 * q + 1]) == cudaSuccess) { c->kernel_ms += ms; c->kernel_launches++; }
@@ -546,9 +589,11 @@ int harvest(par2d_ctx* c, int queued, int cur0, par2d_step_info* info, int ninfo
     c->last_steps = done;
     c->h_step_hist.resize((size_t)4 * std::max(done, 1));
     c->h_blk_hist.resize((size_t)2 * std::max(done, 1) * c->nowned);
+    c->h_flag_hist.assign((size_t)std::max(done, 1), 0u);
     if (done > 0) {
         CU_TRY(cudaMemcpy(c->h_step_hist.data(), c->step_hist, sizeof(double) * 4 * done, cudaMemcpyDeviceToHost));
         CU_TRY(cudaMemcpy(c->h_blk_hist.data(), c->blk_hist, sizeof(double) * 2 * (size_t)done * c->nowned, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(c->h_flag_hist.data(), c->flag_hist, sizeof(unsigned) * done, cudaMemcpyDeviceToHost));
     }
     const int code = flags_to_code(fl);
     if (info) {
@@ -559,7 +604,9 @@ int harvest(par2d_ctx* c, int queued, int cur0, par2d_step_info* info, int ninfo
                 const double* h = &c->h_step_hist[4 * (size_t)s];
                 r.iter = c->last_iter0 + s;
                 r.dt = h[0]; r.ressumsum = h[1]; r.res0sum = h[2]; r.relres = h[3];
-                r.status = code;
+                // error bits as of this step's bookkeeping: the first record with a non-zero status is the
+                // iteration that raised it (the last record also carries whatever was raised after its bookkeeping)
+                r.status = flags_to_code(s + 1 == done ? fl : c->h_flag_hist[(size_t)s]);
             } else {
                 r.iter = -1;
             }
@@ -635,7 +682,8 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
         // blocks are spread over ranks (relres stays bit-identical for any number of GPUs).
         long long global_cells = 0;
         for (int g = 0; g < nblocks; g++) global_cells += (long long)(blocks[g].nx - 1) * (blocks[g].ny - 1);
-        const long long want_strips = (long long)prop.multiProcessorCount * 16;   // one full residency of 16 warps per SM
+        const long long want_strips = 148ll * 16;   // one full residency of 16 warps per SM of a B200; a constant, so that every rank of a
+                                                    // multi-GPU job derives the same strips (and with them the same summation order)
         long long rows = global_cells / (MCELLS * want_strips);
         rows -= rows & 1;
         c->march_rows = (int)std::min<long long>(64, std::max<long long>(4, rows));
@@ -705,6 +753,7 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
         b.ncy = d.ny - 1;
         b.pitch = ((b.ncx + COL0 + 1 + 15) / 16) * 16;
         b.plane = (long long)b.pitch * (b.ncy + 2);
+        if (b.plane >= (1ll << 31)) return fail(PAR2D_ERR_ARG, "block %d: %lld doubles per plane; the kernels index a plane with 32 bits", g, b.plane);
         CU_TRY(cudaMalloc(&c->block_mem[k], sizeof(double) * 11 * b.plane));
         CU_TRY(cudaMemsetAsync(c->block_mem[k], 0, sizeof(double) * 11 * b.plane, c->stream));
         b.state[0] = c->block_mem[k];                  // planes 0..3
@@ -843,39 +892,29 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
         CU_TRY(cudaMemsetAsync(c->dt_table, 0, sizeof(double) * 2 * nblocks, c->stream));
     }
     {
-        // single rank, first-order path, a mesh large enough that a step is not launch-bound: overlapped batches
-        // OPT-IN (PAR2D_SINGLE_OVERLAP=1): measured on B200 the step time does not move (0.5597 vs 0.5609 ms) - the board
-        // runs at its power cap, where the idle gaps between launches cost nothing and only energy per step counts
-        const char* yes = getenv("PAR2D_SINGLE_OVERLAP");
-        c->single_overlap = cfg->nranks == 1 && !c->dg && yes && atoi(yes) != 0 && c->owned_cells >= (1ll << 21);
-        if (c->single_overlap) {
-            c->dt_parities = 2;
-            c->partials_stride = 4ll * c->total_tiles;
-            std::vector<int2> edge, inner;   // strips on the perimeter of a block feed the ghost fill of the next step
-            for (int k = 0; k < c->nowned; k++) {
-                const BlockDev& b = c->hblk[k];
-                for (int t = 0; t < b.tiles_x * b.tiles_y; t++) {
-                    const int tx = t % b.tiles_x, ty = t / b.tiles_x;
-                    const bool e = tx == 0 || tx == b.tiles_x - 1 || ty == 0 || ty == b.tiles_y - 1;
-                    (e ? edge : inner).push_back(make_int2(k, t));
-                }
-            }
-            c->n_edge_tiles = (int)edge.size();
-            c->n_inner_tiles = (int)inner.size();
-            CU_TRY(cudaMalloc(&c->d_edge_tiles, sizeof(int2) * std::max<size_t>(edge.size(), 1)));
-            CU_TRY(cudaMalloc(&c->d_inner_tiles, sizeof(int2) * std::max<size_t>(inner.size(), 1)));
-            CU_TRY(cudaMemcpyAsync(c->d_edge_tiles, edge.data(), sizeof(int2) * edge.size(), cudaMemcpyHostToDevice, c->stream));
-            CU_TRY(cudaMemcpyAsync(c->d_inner_tiles, inner.data(), sizeof(int2) * inner.size(), cudaMemcpyHostToDevice, c->stream));
-            CU_TRY(cudaStreamSynchronize(c->stream));
-            int lo = 0, hi = 0;
-            cudaDeviceGetStreamPriorityRange(&lo, &hi);
-            const char* pr = getenv("PAR2D_SIDE_PRIORITY");   // A/B runs: 0 = same priority as the main stream
-            CU_TRY(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, (pr && atoi(pr) == 0) ? lo : hi));
-            CU_TRY(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
-            CU_TRY(cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming));
-        }
+        // every strip of every owned block, for the persistent launch (any order)
+        std::vector<int2> all;
+        for (int k = 0; k < c->nowned; k++)
+            for (int t = 0; t < c->hblk[k].tiles_x * c->hblk[k].tiles_y; t++) all.push_back(make_int2(k, t));
+        CU_TRY(cudaMalloc(&c->d_all_tiles, sizeof(int2) * all.size()));
+        CU_TRY(cudaMemcpyAsync(c->d_all_tiles, all.data(), sizeof(int2) * all.size(), cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        const char* no = getenv("PAR2D_NO_OVERLAP");
+        c->fused = !(no && atoi(no) != 0);
+        const char* np = getenv("PAR2D_NO_PERSIST");
+        c->persist = !(np && atoi(np) != 0);
+        c->coop_capacity = (cfg->nranks == 1 && !c->dg) ? c->kt->coop_capacity(c->tpg, c->axi) : 0;
     }
-    CU_TRY(cudaMalloc(&c->partials, sizeof(double) * 4 * (size_t)c->total_tiles * (c->single_overlap ? 2 : 1)));
+    c->partials_stride = 4ll * c->total_tiles;
+    CU_TRY(cudaMalloc(&c->gas_dev, sizeof(Gas)));
+    CU_TRY(cudaMemcpyAsync(c->gas_dev, &c->gas, sizeof(Gas), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMalloc(&c->blk_sum, sizeof(double) * 2 * c->nowned));
+    CU_TRY(cudaMalloc(&c->grid_bar, sizeof(unsigned)));
+    CU_TRY(cudaMalloc(&c->go, sizeof(int)));
+    CU_TRY(cudaMalloc(&c->stop_iter, sizeof(long long)));
+    CU_TRY(cudaMemsetAsync(c->go, 0, sizeof(int), c->stream));
+    CU_TRY(cudaMemsetAsync(c->stop_iter, 0xff, sizeof(long long), c->stream));
+    CU_TRY(cudaMalloc(&c->partials, sizeof(double) * 2 * (size_t)c->partials_stride));
     if (c->dg) CU_TRY(cudaMalloc(&c->dg_partials, sizeof(double) * 12 * (size_t)c->dg_total_tiles));
     CU_TRY(cudaMalloc(&c->flags, sizeof(unsigned)));
     CU_TRY(cudaMalloc(&c->stop, sizeof(int)));
@@ -909,13 +948,11 @@ int par2d_destroy(par2d_ctx* c) {
     par2d_peer_disconnect(c);
     for (Peer& p : c->peers) cudaFree(p.d_send);
     if (c->arena) cudaFree(c->arena); else cudaFree(c->dt_table);
-    cudaFree(c->put_ticket); cudaFree(c->dlines_peer); cudaFree(c->d_dt_dst); cudaFree(c->d_flag_dst);
-    if (c->single_overlap) {
-        if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); c->side_stream = nullptr; }
-        if (c->ev_main) cudaEventDestroy(c->ev_main);
-        if (c->ev_edge) cudaEventDestroy(c->ev_edge);
-        cudaFree(c->d_edge_tiles); cudaFree(c->d_inner_tiles);
-    }
+    cudaFree(c->put_ticket);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (int q = 0; q < 2; q++) { if (c->ev_ready[q]) cudaEventDestroy(c->ev_ready[q]); if (c->ev_free[q]) cudaEventDestroy(c->ev_free[q]); }
+    cudaFree(c->staging2);
+    cudaFree(c->d_all_tiles); cudaFree(c->gas_dev); cudaFree(c->blk_sum); cudaFree(c->grid_bar); cudaFree(c->go); cudaFree(c->stop_iter); cudaFree(c->flag_hist);
     for (double* m : c->dg_mem) cudaFree(m);
     cudaFree(c->dg_partials);
     cudaFree(c->dblk); cudaFree(c->dtmaps); cudaFree(c->partials); cudaFree(c->flags);
@@ -954,6 +991,68 @@ int par2d_get_state(par2d_ctx* c, int32_t block, double* unk) {
     launch_planes_to_aos(c->stream, b, c->cur, c->staging);
     CU_TRY(cudaMemcpyAsync(unk, c->staging, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// Batched state transfer: the host<->device copy of block i+1 (copy stream) overlaps the AoS<->plane transpose of
+// block i (ctx stream) through two staging buffers.
+static int ensure_copy_pipeline(par2d_ctx* c) {
+    if (c->copy_stream) return 0;
+    CU_TRY(cudaMalloc(&c->staging2, sizeof(double) * c->staging_doubles));
+    CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int q = 0; q < 2; q++) {
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_ready[q], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_free[q], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+int par2d_set_states(par2d_ctx* c, int32_t n, const int32_t* blocks, const double* const* unk) {
+    if (!c || n < 0 || (n > 0 && (!blocks || !unk))) return fail(PAR2D_ERR_ARG, "set_states: bad argument");
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    int rc = ensure_copy_pipeline(c);
+    if (rc) return rc;
+    double* stg[2] = {c->staging, c->staging2};
+    CU_TRY(cudaStreamSynchronize(c->stream));       // the staging buffers are free
+    for (int i = 0; i < n; i++) {
+        const int k = owned_k(c, blocks[i], "set_states");
+        if (k < 0 || !unk[i]) return PAR2D_ERR_ARG;
+        const BlockDev& b = c->hblk[k];
+        const int q = i & 1;
+        if (i >= 2) CU_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_free[q], 0));
+        CU_TRY(cudaMemcpyAsync(stg[q], unk[i], sizeof(double) * 4 * (size_t)b.ncx * b.ncy, cudaMemcpyHostToDevice, c->copy_stream));
+        CU_TRY(cudaEventRecord(c->ev_ready[q], c->copy_stream));
+        CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_ready[q], 0));
+        launch_aos_to_planes(c->stream, b, c->cur, stg[q]);
+        CU_TRY(cudaEventRecord(c->ev_free[q], c->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int par2d_get_states(par2d_ctx* c, int32_t n, const int32_t* blocks, double* const* unk) {
+    if (!c || n < 0 || (n > 0 && (!blocks || !unk))) return fail(PAR2D_ERR_ARG, "get_states: bad argument");
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    int rc = ensure_copy_pipeline(c);
+    if (rc) return rc;
+    double* stg[2] = {c->staging, c->staging2};
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; i++) {
+        const int k = owned_k(c, blocks[i], "get_states");
+        if (k < 0 || !unk[i]) return PAR2D_ERR_ARG;
+        const BlockDev& b = c->hblk[k];
+        const int q = i & 1;
+        if (i >= 2) CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_free[q], 0));
+        launch_planes_to_aos(c->stream, b, c->cur, stg[q]);
+        CU_TRY(cudaEventRecord(c->ev_ready[q], c->stream));
+        CU_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_ready[q], 0));
+        CU_TRY(cudaMemcpyAsync(unk[i], stg[q], sizeof(double) * 4 * (size_t)b.ncx * b.ncy, cudaMemcpyDeviceToHost, c->copy_stream));
+        CU_TRY(cudaEventRecord(c->ev_free[q], c->copy_stream));
+    }
+    CU_TRY(cudaStreamSynchronize(c->copy_stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(cudaGetLastError());
     return 0;
 }
 
@@ -1029,40 +1128,76 @@ int par2d_get_residual_dg(par2d_ctx* c, int32_t block, double* res, double* resx
     return 0;
 }
 
-int par2d_step(par2d_ctx* c, int32_t nsteps, int32_t stop_on_tol, par2d_step_info* info) {
+int par2d_step_async(par2d_ctx* c, int32_t nsteps, int32_t stop_on_tol) {
     if (!c || nsteps < 0) return fail(PAR2D_ERR_ARG, "step: bad argument");
     if (c->cfg.nranks != 1 && !c->peer_connected)
         return fail(PAR2D_ERR_COMM, "step: nranks > 1 needs step_begin/step_end (external transport) or par2d_peer_connect");
     if (c->pending_steps) return fail(PAR2D_ERR_COMM, "step: %d begin/end steps are waiting for step_collect", c->pending_steps);
+    if (c->batch_open) return fail(PAR2D_ERR_COMM, "step: the previous par2d_step_async has not been waited for");
+    if (stop_on_tol && c->peer_connected && (c->dg || !c->fused))
+        return fail(PAR2D_ERR_ARG, "step: the stop test across ranks needs the fused first-order step (accur = 0, PAR2D_NO_OVERLAP unset)");
     if (use_device(c)) return PAR2D_ERR_CUDA;
     int rc = ensure_hist(c, nsteps);
     if (rc) return rc;
     CU_TRY(cudaMemsetAsync(c->hist_pos, 0, sizeof(int), c->stream));
     CU_TRY(cudaMemsetAsync(c->stop, 0, sizeof(int), c->stream));
-    const int cur0 = c->cur;
+    c->batch_cur0 = c->cur;
+    c->batch_steps = nsteps;
+    c->batch_seq0 = c->seq;
+    c->batch_stop = stop_on_tol && c->peer_connected;
     if (c->peer_connected) {
-        // collective batch, no host transport: every step is  put (edge lines + dt_b into the neighbours'
-        // arenas, flag) -> ghost (waits for the flags) -> march -> finalize.  The trailing put leaves the
-        // final state's lines in the arenas for par2d_get_residual.
-        if (c->overlap && c->d_edge_tiles && !c->dg) {
-            queue_put(c);              // the first state's lines; every step then produces the next state's
-            for (int s = 0; s < nsteps; s++) queue_step_overlapped(c);
+        // collective batch, no host transport
+        if (c->fused && !c->dg) {
+            // the current state's lines + dt (a launch of its own: the state may come from par2d_set_state), the ghost
+            // ring by the pull kernel, then one launch per step; the last step leaves the final state's lines in the arenas
+            if (c->batch_stop) CU_TRY(cudaMemsetAsync(c->go, 0, sizeof(int), c->stream));
+            queue_put(c);
+            StepArgs a0 = c->step_args(1);
+            c->kt->ghost(c->stream, a0, c->gas, 0, nullptr);
+            for (int s = 0; s < nsteps; s++) queue_step_fused(c, s + 1, stop_on_tol);
         } else {
+            // every step is  put (edge lines + dt_b into the neighbours' arenas, flag) -> ghost (waits for the
+            // flags) -> march [-> limiter]; the trailing put leaves the final state's lines for par2d_get_residual
             for (int s = 0; s < nsteps; s++) {
                 queue_put(c);
                 queue_step(c, 0, false);
             }
             queue_put(c);
         }
-    } else if (c->single_overlap && !stop_on_tol && nsteps > 0) {
-        queue_batch_overlapped(c, nsteps);
-    } else {
+    } else if (c->dg || !c->fused) {
         for (int s = 0; s < nsteps; s++) queue_step(c, stop_on_tol, true);
+    } else if (nsteps > 0) {
+        // ghost ring + per-block dt of the current state by the pull kernel (it may come from par2d_set_state); every
+        // step after that pushes them for the next one
+        StepArgs a0 = c->step_args(1);
+        c->kt->ghost(c->stream, a0, c->gas, 1, nullptr);
+        const bool small = c->persist && c->coop_capacity >= c->total_tiles + c->nowned;
+        if (!(small && queue_batch_persistent(c, nsteps, stop_on_tol)))
+            for (int s = 0; s < nsteps; s++) queue_step_fused(c, s + 1, stop_on_tol);
     }
     flush_finalize(c);
+    if (c->batch_stop && nsteps > 0) {
+        const long long first = std::max<long long>(c->iter, c->iter + nsteps - 2);
+        c->kt->stop_tail(c->stream, stop_args(c), c->stop, c->flags, first, c->iter + nsteps - 1);
+    }
+    c->batch_open = true;
+    return 0;
+}
+
+int par2d_step_wait(par2d_ctx* c, par2d_step_info* info) {
+    if (!c) return fail(PAR2D_ERR_ARG, "step_wait: null ctx");
+    if (!c->batch_open) return fail(PAR2D_ERR_COMM, "step_wait: no par2d_step_async is in flight");
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    c->batch_open = false;
     CU_TRY(cudaStreamSynchronize(c->stream));
     CU_TRY(cudaGetLastError());
-    return harvest(c, nsteps, cur0, info, nsteps);
+    return harvest(c, c->batch_steps, c->batch_cur0, info, c->batch_steps, c->batch_stop != 0, c->batch_seq0);
+}
+
+int par2d_step(par2d_ctx* c, int32_t nsteps, int32_t stop_on_tol, par2d_step_info* info) {
+    const int rc = par2d_step_async(c, nsteps, stop_on_tol);
+    if (rc) return rc;
+    return par2d_step_wait(c, info);
 }
 
 int par2d_get_block_history(par2d_ctx* c, int32_t nsteps, double* out) {
@@ -1149,6 +1284,91 @@ int par2d_peer_export(par2d_ctx* c, void* handle_out) {
     return 0;
 }
 
+// Everything that follows from knowing where every rank's arena is mapped (c->peer_base): put destinations of the
+// launch-of-its-own put (SendLine) and of the fused step (BlockDev::put_dst), dt / residual tables and flag slots in
+// every arena, the tile order of the fused step.
+static int finish_connect(par2d_ctx* c) {
+    const int nr = c->cfg.nranks, me = c->cfg.rank;
+    const int lw = c->dg ? 8 : 4;
+    // every rank must cut its blocks into the same strips (the summation order of the residual norms): slot 15 of a
+    // rank's own flag group holds its march_rows
+    {
+        unsigned long long mine = (unsigned long long)c->march_rows;
+        unsigned long long* slot = reinterpret_cast<unsigned long long*>(c->arena + c->lay.flags_off) + 16 * me + 15;
+        CU_TRY(cudaMemcpy(slot, &mine, sizeof mine, cudaMemcpyHostToDevice));
+    }
+    std::vector<double*> dt_dst(nr), res_dst(nr);
+    std::vector<unsigned long long*> flag_dst(nr), rflag_dst(nr);
+    std::vector<ArenaLayout> lay(nr);
+    for (int p = 0; p < nr; p++) {
+        lay[p] = arena_layout(c->table.data(), c->nblocks, nr, p, lw);
+        dt_dst[p] = reinterpret_cast<double*>(c->peer_base[p] + lay[p].dt_off);
+        res_dst[p] = reinterpret_cast<double*>(c->peer_base[p] + lay[p].res_off);
+        flag_dst[p] = reinterpret_cast<unsigned long long*>(c->peer_base[p] + lay[p].flags_off) + 16 * me;
+        rflag_dst[p] = flag_dst[p] + 1;
+    }
+    std::vector<SendLine> lines = c->hlines;
+    for (int k = 0; k < c->nowned; k++)
+        for (int sd = 0; sd < 4; sd++) { c->hblk[k].put_dst[sd] = nullptr; c->hblk[k].put_stride[sd] = 0; }
+    for (size_t l = 0; l < lines.size(); l++) {
+        const int p = c->hline_peer[l];
+        lines[l].dst = reinterpret_cast<double*>(c->peer_base[p] + lay[p].lines_off) + recv_segment_off(c->table.data(), c->nblocks, p, me, lw) + c->hline_off[l];
+        lines[l].parity_stride = lay[p].lines_stride;
+        c->hblk[lines[l].block].put_dst[lines[l].side] = lines[l].dst;
+        c->hblk[lines[l].block].put_stride[lines[l].side] = lines[l].parity_stride;
+    }
+    CU_TRY(cudaMemcpy(c->dblk, c->hblk.data(), sizeof(BlockDev) * c->nowned, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMalloc(&c->d_dt_dst, sizeof(double*) * nr));
+    CU_TRY(cudaMalloc(&c->d_res_dst, sizeof(double*) * nr));
+    CU_TRY(cudaMalloc(&c->d_flag_dst, sizeof(unsigned long long*) * nr));
+    CU_TRY(cudaMalloc(&c->d_rflag_dst, sizeof(unsigned long long*) * nr));
+    CU_TRY(cudaMemcpy(c->d_dt_dst, dt_dst.data(), sizeof(double*) * nr, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(c->d_res_dst, res_dst.data(), sizeof(double*) * nr, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(c->d_flag_dst, flag_dst.data(), sizeof(unsigned long long*) * nr, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(c->d_rflag_dst, rflag_dst.data(), sizeof(unsigned long long*) * nr, cudaMemcpyHostToDevice));
+    if (!lines.empty()) {
+        CU_TRY(cudaMalloc(&c->dlines_peer, sizeof(SendLine) * lines.size()));
+        CU_TRY(cudaMemcpy(c->dlines_peer, lines.data(), sizeof(SendLine) * lines.size(), cudaMemcpyHostToDevice));
+    }
+    // tile order of the fused step: the strips that put something (they border another rank, or hold cell (0,0) of a
+    // block, whose dt every rank needs) first
+    {
+        std::vector<int2> first, rest;
+        for (int k = 0; k < c->nowned; k++) {
+            const BlockDev& b = c->hblk[k];
+            for (int t = 0; t < b.tiles_x * b.tiles_y; t++) {
+                const int tx = t % b.tiles_x, ty = t / b.tiles_x;
+                const bool e = t == 0 || (tx == 0 && b.nb_kind[SIDE_LEFT] == NB_REMOTE) || (tx == b.tiles_x - 1 && b.nb_kind[SIDE_RIGHT] == NB_REMOTE) ||
+                               (ty == 0 && b.nb_kind[SIDE_BOTTOM] == NB_REMOTE) || (ty == b.tiles_y - 1 && b.nb_kind[SIDE_TOP] == NB_REMOTE);
+                (e ? first : rest).push_back(make_int2(k, t));
+            }
+        }
+        c->n_put_tiles = (unsigned)first.size();
+        first.insert(first.end(), rest.begin(), rest.end());
+        c->n_push_tiles = (int)first.size();
+        CU_TRY(cudaMalloc(&c->d_push_tiles, sizeof(int2) * first.size()));
+        CU_TRY(cudaMemcpy(c->d_push_tiles, first.data(), sizeof(int2) * first.size(), cudaMemcpyHostToDevice));
+    }
+    c->peer_connected = true;
+    return 0;
+}
+
+// second half of a connect, after EVERY rank has finished the first (the host synchronises in between): the strip
+// decomposition must be the same everywhere
+static int check_peers(par2d_ctx* c) {
+    const int nr = c->cfg.nranks, me = c->cfg.rank;
+    for (int p = 0; p < nr; p++) {
+        if (p == me) continue;
+        unsigned long long theirs = 0;
+        const unsigned long long* slot = reinterpret_cast<const unsigned long long*>(c->peer_base[p]) + 16 * p + 15;   // flags_off == 0
+        CU_TRY(cudaMemcpy(&theirs, slot, sizeof theirs, cudaMemcpyDeviceToHost));
+        if (theirs != 0 && theirs != (unsigned long long)c->march_rows)
+            return fail(PAR2D_ERR_COMM, "rank %d marches strips of %llu rows, rank %d of %d: the residual norms would be summed in different orders (PAR2D_MARCH_ROWS set on one rank only?)",
+                        p, theirs, me, c->march_rows);
+    }
+    return 0;
+}
+
 int par2d_peer_connect(par2d_ctx* c, const void* all_handles) {
     if (!c || !all_handles) return fail(PAR2D_ERR_ARG, "peer_connect: null argument");
     if (!c->arena) return fail(PAR2D_ERR_COMM, "peer_connect: this ctx was created with nranks == 1");
@@ -1158,6 +1378,7 @@ int par2d_peer_connect(par2d_ctx* c, const void* all_handles) {
     const int nr = c->cfg.nranks, me = c->cfg.rank;
     c->peer_base.assign(nr, nullptr);
     c->peer_base[me] = c->arena;
+    c->peer_ipc = true;
     for (int p = 0; p < nr; p++) {
         if (p == me) continue;
         cudaIpcMemHandle_t h;
@@ -1171,60 +1392,49 @@ int par2d_peer_connect(par2d_ctx* c, const void* all_handles) {
         }
         c->peer_base[p] = static_cast<char*>(ptr);
     }
-    // destinations: dt tables and flag slots in every arena, edge lines in the neighbours' arenas
-    std::vector<double*> dt_dst(nr);
-    std::vector<unsigned long long*> flag_dst(nr);
-    std::vector<ArenaLayout> lay(nr);
-    for (int p = 0; p < nr; p++) {
-        lay[p] = arena_layout(c->table.data(), c->nblocks, nr, p, c->dg ? 8 : 4);
-        dt_dst[p] = reinterpret_cast<double*>(c->peer_base[p] + lay[p].dt_off);
-        flag_dst[p] = reinterpret_cast<unsigned long long*>(c->peer_base[p] + lay[p].flags_off) + 16 * me;
+    // The sequence counter is NOT reset: the flag slots of the arenas keep the events of earlier connections, and
+    // every rank has counted the same number of them.
+    int rc = finish_connect(c);
+    if (rc) return rc;
+    return check_peers(c);
+}
+
+int par2d_peer_check(par2d_ctx* c) {
+    if (!c || !c->peer_connected) return fail(PAR2D_ERR_COMM, "peer_check: not connected");
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    return check_peers(c);
+}
+
+int par2d_peer_connect_local(par2d_ctx** ctxs, int32_t n) {
+    if (!ctxs || n < 2) return fail(PAR2D_ERR_ARG, "peer_connect_local: need at least two contexts");
+    for (int r = 0; r < n; r++) {
+        par2d_ctx* c = ctxs[r];
+        if (!c || !c->arena || c->cfg.nranks != n || c->cfg.rank != r) return fail(PAR2D_ERR_ARG, "peer_connect_local: ctxs[%d] must be rank %d of %d", r, r, n);
+        if (c->peer_connected || c->pending_steps) return fail(PAR2D_ERR_COMM, "peer_connect_local: ctxs[%d] is already connected or has steps pending", r);
     }
-    std::vector<SendLine> lines = c->hlines;
-    for (size_t l = 0; l < lines.size(); l++) {
-        const int p = c->hline_peer[l];
-        lines[l].dst = reinterpret_cast<double*>(c->peer_base[p] + lay[p].lines_off) + recv_segment_off(c->table.data(), c->nblocks, p, me, c->dg ? 8 : 4) + c->hline_off[l];
-        lines[l].parity_stride = lay[p].lines_stride;
-    }
-    CU_TRY(cudaMalloc(&c->d_dt_dst, sizeof(double*) * nr));
-    CU_TRY(cudaMalloc(&c->d_flag_dst, sizeof(unsigned long long*) * nr));
-    CU_TRY(cudaMemcpy(c->d_dt_dst, dt_dst.data(), sizeof(double*) * nr, cudaMemcpyHostToDevice));
-    CU_TRY(cudaMemcpy(c->d_flag_dst, flag_dst.data(), sizeof(unsigned long long*) * nr, cudaMemcpyHostToDevice));
-    if (!lines.empty()) {
-        CU_TRY(cudaMalloc(&c->dlines_peer, sizeof(SendLine) * lines.size()));
-        CU_TRY(cudaMemcpy(c->dlines_peer, lines.data(), sizeof(SendLine) * lines.size(), cudaMemcpyHostToDevice));
-    }
-    c->seq = 0;
-    // strips for the overlapped step: everything that touches an off-rank face (its cells are what the put sends)
-    // plus strip 0 of every block (cell (0,0) feeds the block's dt) goes first, on the side stream
-    {
-        const char* no = getenv("PAR2D_NO_OVERLAP");
-        c->overlap = !(no && atoi(no) != 0);
-        std::vector<int2> edge, inner;
-        for (int k = 0; k < c->nowned; k++) {
-            const BlockDev& b = c->hblk[k];
-            for (int s = 0; s < b.tiles_x * b.tiles_y; s++) {
-                const int tx = s % b.tiles_x, ty = s / b.tiles_x;
-                const bool e = s == 0 || (tx == 0 && b.nb_kind[SIDE_LEFT] == NB_REMOTE) || (tx == b.tiles_x - 1 && b.nb_kind[SIDE_RIGHT] == NB_REMOTE) ||
-                               (ty == 0 && b.nb_kind[SIDE_BOTTOM] == NB_REMOTE) || (ty == b.tiles_y - 1 && b.nb_kind[SIDE_TOP] == NB_REMOTE);
-                (e ? edge : inner).push_back(make_int2(k, s));
-            }
+    for (int r = 0; r < n; r++) {
+        par2d_ctx* c = ctxs[r];
+        CU_TRY(cudaSetDevice(c->device));
+        c->peer_base.assign(n, nullptr);
+        c->peer_ipc = false;
+        for (int p = 0; p < n; p++) {
+            c->peer_base[p] = ctxs[p]->arena;
+            if (p == r || ctxs[p]->device == c->device) continue;
+            int can = 0;
+            CU_TRY(cudaDeviceCanAccessPeer(&can, c->device, ctxs[p]->device));
+            if (!can) return fail(PAR2D_ERR_COMM, "peer_connect_local: device %d cannot access device %d", c->device, ctxs[p]->device);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[p]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(PAR2D_ERR_COMM, "cudaDeviceEnablePeerAccess(%d -> %d): %s", c->device, ctxs[p]->device, cudaGetErrorString(e));
+            cudaGetLastError();
         }
-        c->n_edge_tiles = (int)edge.size();
-        c->n_inner_tiles = (int)inner.size();
-        CU_TRY(cudaMalloc(&c->d_edge_tiles, sizeof(int2) * std::max<size_t>(edge.size(), 1)));
-        CU_TRY(cudaMalloc(&c->d_inner_tiles, sizeof(int2) * std::max<size_t>(inner.size(), 1)));
-        CU_TRY(cudaMemcpy(c->d_edge_tiles, edge.data(), sizeof(int2) * edge.size(), cudaMemcpyHostToDevice));
-        CU_TRY(cudaMemcpy(c->d_inner_tiles, inner.data(), sizeof(int2) * inner.size(), cudaMemcpyHostToDevice));
-        if (!c->side_stream) {
-            int lo = 0, hi = 0;
-            cudaDeviceGetStreamPriorityRange(&lo, &hi);
-            CU_TRY(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, hi));   // edge strips + put ahead of interior strips
-            CU_TRY(cudaEventCreateWithFlags(&c->ev_ghost, cudaEventDisableTiming));
-            CU_TRY(cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming));
-        }
+        const int rc = finish_connect(c);
+        if (rc) return rc;
     }
-    c->peer_connected = true;
+    for (int r = 0; r < n; r++) {
+        CU_TRY(cudaSetDevice(ctxs[r]->device));
+        const int rc = check_peers(ctxs[r]);
+        if (rc) return rc;
+    }
     return 0;
 }
 
@@ -1232,15 +1442,13 @@ int par2d_peer_disconnect(par2d_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (size_t p = 0; p < c->peer_base.size(); p++)
-        if ((int)p != c->cfg.rank && c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
+    if (c->peer_ipc)
+        for (size_t p = 0; p < c->peer_base.size(); p++)
+            if ((int)p != c->cfg.rank && c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
     c->peer_base.clear();
     c->peer_connected = false;
-    if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); c->side_stream = nullptr; }
-    if (c->ev_ghost) { cudaEventDestroy(c->ev_ghost); c->ev_ghost = nullptr; }
-    if (c->ev_edge) { cudaEventDestroy(c->ev_edge); c->ev_edge = nullptr; }
-    cudaFree(c->d_edge_tiles); cudaFree(c->d_inner_tiles);
-    c->d_edge_tiles = c->d_inner_tiles = nullptr;
+    cudaFree(c->d_push_tiles); cudaFree(c->dlines_peer); cudaFree(c->d_dt_dst); cudaFree(c->d_flag_dst); cudaFree(c->d_res_dst); cudaFree(c->d_rflag_dst);
+    c->d_push_tiles = nullptr; c->dlines_peer = nullptr; c->d_dt_dst = nullptr; c->d_flag_dst = nullptr; c->d_res_dst = nullptr; c->d_rflag_dst = nullptr;
     return 0;
 }
 
@@ -1360,6 +1568,14 @@ int par2d_test_solve(const par2d_config* cfg, int64_t n, const double* dt_ycc, c
     kt->test_solve(0, g, !(cfg->igam > 0), cfg->iaxi == 1, n, (double*)dy.p, (double*)du.p, (double*)dr.p, (double*)dd.p);
     CU_TRY(cudaDeviceSynchronize());
     CU_TRY(cudaMemcpy(dv, dd.p, 32 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int par2d_device_count(int32_t* n) {
+    if (!n) return fail(PAR2D_ERR_ARG, "device_count: null output");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(PAR2D_ERR_CUDA, "no CUDA device available; par2d_b200 has no CPU fallback");
+    *n = ndev;
     return 0;
 }
 

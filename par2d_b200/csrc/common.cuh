@@ -43,6 +43,8 @@ struct BlockDev {
     int nb_block[4];    // owned-block index of a same-rank neighbour
     int nb_side[4];     // the neighbour's side that faces us
     double* recv[4];    // AoS line [n*4+k] received from an off-rank neighbour (parity 0 of this rank's arena)
+    double* put_dst[4]; // peer-mapped mode: where this block's edge line of a side goes in the off-rank neighbour's arena
+    long long put_stride[4];  //   (parity 0) and the doubles between the two parities there; null / 0 otherwise
     int tiles_x, tiles_y; // work decomposition: 30-column strips x row chunks (marching kernel)
     int tile0;          // first tile/strip of this block in the partial-sum array
     double min_face;    // static part of find_dt (main.cpp:26-32)
@@ -81,12 +83,33 @@ struct PutArgs {
     const unsigned long long* local_flags; // this rank's own flag array (for the pre-wait)
     int nranks, rank;
     long long timeout_ns;
+    unsigned expected;                   // fused step: CTAs of the launch that put something (the last one raises the flags)
     int dg;                              // second-order branch: a line carries the reconstruction at the two Gauss points
                                          // of every edge face, 8 doubles per edge cell (SpatialDiscretization.cpp:243-256)
 };
 
+// Stop test across ranks (main.cpp:506-531 breaks on the GLOBAL relres): every rank's bookkeeping publishes its
+// per-block sums of iteration `it` into slot (it+1)&3 of every arena's residual table and raises its residual flag
+// (slot src*16+1 of the flag array) to it+1; the first CTA of launch m adds the blocks of iteration m-2 in global
+// block order - identical bits on every rank - and sets the stop word before any strip of that launch runs.
+struct StopArgs {
+    int enabled;                          // 0: no test between the steps of this batch
+    int nranks, rank;
+    double* const* res_dst;               // [nranks] residual table (slot 0) of every arena, own included
+    unsigned long long* const* rflag_dst; // [nranks] this rank's residual-flag slot in every arena
+    const double* res_table;              // this rank's own table: [4 slots][nblocks_global][2]
+    const unsigned long long* local_flags;// this rank's flag array
+    int nblocks_global;
+    int* go;                              // launch number whose stop decision has been made (strips wait for it)
+    long long* stop_iter;                 // iteration whose relres fell below the tolerance
+    long long iter0;                      // iteration advanced by launch 1 of this batch
+    double tol;
+    long long timeout_ns;
+};
+
 struct StepArgs {
     const BlockDev* blocks;
+    const Gas* gas_dev;      // the Gas constants in global memory (for the non-inlined boundary-condition code)
     int nowned;
     int nblocks_global;
     int cur;                 // state buffer read this step
@@ -115,6 +138,14 @@ struct StepArgs {
     long long recv_off;      // doubles added to BlockDev::recv[] (parity of the consumed event)
     int nranks, rank;
     long long timeout_ns;
+    // fused step (march.cuh, PUSH instantiation): the strips on a block's perimeter write the NEW state's ghost ring
+    // (boundary-condition faces, same-rank neighbours) and put the edge lines of off-rank faces + the block's dt
+    // straight into the peers' arenas, so a step is ONE launch
+    double* dt_next;         // per-block dt table of the NEXT step (single rank: the other parity of dt_table)
+    int nfin;                // leading CTAs of the launch that run the previous step's bookkeeping (0: none pending)
+    int launch_no;           // 1-based launch number within the batch (stop test across ranks)
+    int coop_steps;          // persistent launch: steps advanced inside the kernel (else 1)
+    unsigned* grid_bar;      // persistent launch: grid barrier counter
 };
 
 struct FinalizeArgs {
@@ -130,10 +161,14 @@ struct FinalizeArgs {
     unsigned* ticket;        // last-block-done counter
     const double* dt_used;   // StepArgs::dt_used of the step being finalised
     double* blk_norm;        // [nowned][4] per-block residual norms (scratch between the block CTAs and the last one)
+    double* blk_sum;         // [nowned][2] per-block sums of the step being finalised (scratch of the last CTA)
     double tol;
     int stop_on_tol;
     int hist_cap;
     const double* dg_partials;  // second-order branch: [dg tiles][12] sums of squares of dudt, duxdt, duydt (else null)
+    unsigned* flag_hist;     // [hist_cap] device error bits as of each step's bookkeeping (per-step status)
+    const unsigned* flags;
+    StopArgs stop_x;         // stop test across ranks (peer-mapped mode); enabled = 0 otherwise
 };
 
 __host__ __device__ inline int edge_cells(int ncx, int ncy, int side) {

@@ -1,0 +1,129 @@
+// halo.cuh -- what surrounds a block: ghost-cell positions, boundary-condition ghost states, the per-block time
+// step, and the flag protocol of the peer-mapped (NVLink) exchange.  Shared by the ghost kernel (pull model: a
+// launch of its own at the start of a batch and for the test hooks) and by the perimeter strips of the fused step
+// kernel (push model, march.cuh), which must produce the same bits: the two arithmetic pieces
+// (bc_ghost_fill, block_dt_value) are therefore NOT inlined - both kernels call the same machine code.
+#pragma once
+#include <cuda_runtime.h>
+#include "common.cuh"
+#include "physics.cuh"
+
+namespace par2d {
+
+// (col,row) in the padded arrays of the n-th cell along a side of a block
+__device__ __forceinline__ void edge_cell_pos(int ncx, int ncy, int side, int n, int& col, int& row) {
+    switch (side) {
+        case SIDE_BOTTOM: col = COL0 + n; row = 1; break;
+        case SIDE_RIGHT: col = COL0 + ncx - 1; row = n + 1; break;
+        case SIDE_TOP: col = COL0 + n; row = ncy; break;
+        default: col = COL0; row = n + 1; break;
+    }
+}
+__device__ __forceinline__ void ghost_cell_pos(int ncx, int ncy, int side, int n, int& col, int& row) {
+    switch (side) {
+        case SIDE_BOTTOM: col = COL0 + n; row = 0; break;
+        case SIDE_RIGHT: col = COL0 + ncx; row = n + 1; break;
+        case SIDE_TOP: col = COL0 + n; row = ncy + 1; break;
+        default: col = COL0 - 1; row = n + 1; break;
+    }
+}
+
+// ------------------------------------------------------------------ peer-mapped exchange: flags
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// generic-proxy writes to global memory (ghost cells, other CTAs' new state) before the TMA (async proxy) reads them
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// Waits until every other rank's flag (slot `slot` of its 16-word group) has reached `need`.  Bounded: a
+// peer that never arrives surfaces as FLAG_COMM (PAR2D_ERR_COMM), never as a hung GPU.  One thread.
+static __device__ __noinline__ bool wait_peers(const unsigned long long* flags, int nranks, int rank, unsigned long long need, long long timeout_ns, int slot = 0) {
+    if (need == 0) return true;
+    const unsigned long long t0 = global_ns();
+    for (int r = 0; r < nranks; r++) {
+        if (r == rank) continue;
+        while (ld_acquire_sys(flags + 16 * r + slot) < need) {
+            if ((long long)(global_ns() - t0) > timeout_ns) return false;
+            __nanosleep(200);
+        }
+    }
+    return true;
+}
+// The same wait by a whole warp, one peer per lane (the perimeter / every strip of the fused step).
+static __device__ __forceinline__ bool wait_peers_warp(const unsigned long long* flags, int nranks, int rank, unsigned long long need, long long timeout_ns) {
+    bool ok = true;
+    const int lane = threadIdx.x & 31;
+    for (int r = lane; r < nranks; r += 32) {
+        if (r == rank) continue;
+        if (ld_acquire_sys(flags + 16 * r) >= need) continue;
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(flags + 16 * r) < need) {
+            if ((long long)(global_ns() - t0) > timeout_ns) { ok = false; break; }
+            __nanosleep(100);
+        }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    __syncwarp();
+    return ok;
+}
+
+// per-block time step from cell (0,0) of state S: find_dt, main.cpp:19-37 (the static min over the face
+// lengths is BlockDev::min_face)
+static __device__ __noinline__ double block_dt_value(const double* S, long long plane, int pitch, double min_face, double gamRs, double cfl) {
+    const long long o = (long long)pitch + COL0;
+    const double u = __ldcg(S + plane + o), v = __ldcg(S + 2 * plane + o), T = __ldcg(S + 3 * plane + o);
+    const double v2 = u * u + v * v;
+    const double vmax = sqrt(v2) + sqrt(gamRs * T);
+    return cfl * min_face / vmax;
+}
+
+// Ghost cell of boundary face n of side `side` of block b, computed from and written into the state buffer S
+// (generate_ghost_cells, SpatialDiscretization.cpp:17-99): outward normal (:33-34,51-52,71-72,91-92; the right
+// side reads the normal of column 0, as the reference does), boundary_state, the ghost's T clamp.  The ghost
+// keeps its present value if the boundary condition leaves it unwritten.  Arguments are pointers to GLOBAL
+// memory (a by-reference kernel parameter would be copied to the stack by every CTA).
+static __device__ __noinline__ void bc_ghost_fill(const Gas* gp, const BlockDev* bp, double* S, int side, int n) {
+    const Gas& g = *gp;
+    const BlockDev& b = *bp;
+    const double* X = b.nodes;
+    const double* Y = b.nodes + b.plane;
+    long long p0, p1;
+    double sgn;
+    int code;
+    if (side == SIDE_BOTTOM) { p0 = (long long)b.pitch + COL0 + n; p1 = p0 + 1; sgn = 1.0; code = b.ibound[n]; }
+    else if (side == SIDE_RIGHT) { p0 = (long long)(n + 1) * b.pitch + COL0; p1 = p0 + b.pitch; sgn = 1.0; code = b.ibound[b.ncx + n]; }
+    else if (side == SIDE_TOP) { p0 = (long long)(b.ncy + 1) * b.pitch + COL0 + n; p1 = p0 + 1; sgn = -1.0; code = b.ibound[2 * b.ncx + b.ncy - 1 - n]; }
+    else { p0 = (long long)(n + 1) * b.pitch + COL0; p1 = p0 + b.pitch; sgn = -1.0; code = b.ibound[2 * b.ncx + 2 * b.ncy - 1 - n]; }
+    const FaceGeom fg = face_geom<true>(X[p0], Y[p0], X[p1], Y[p1]);   // O(perimeter): unit normal as MeshModule.cpp:52-81
+    int c, r;
+    edge_cell_pos(b.ncx, b.ncy, side, n, c, r);
+    const long long io = (long long)r * b.pitch + c;
+    ghost_cell_pos(b.ncx, b.ncy, side, n, c, r);
+    const long long go = (long long)r * b.pitch + c;
+    double ui[4], gh[4];
+#pragma unroll
+    for (int v = 0; v < 4; v++) { ui[v] = __ldcg(S + v * b.plane + io); gh[v] = __ldcg(S + v * b.plane + go); }
+    const double v2 = ui[1] * ui[1] + ui[2] * ui[2];
+    const double p = fmax(ui[0] * g.Rs * ui[3], 1.0);
+    const double aint = sqrt(g.gamRs * ui[3]);
+    boundary_state(g, code, sgn * fg.nx, sgn * fg.ny, ui, aint, p, v2, gh);
+#pragma unroll
+    for (int v = 0; v < 4; v++) __stcg(S + v * b.plane + go, gh[v]);
+}
+
+}  // namespace par2d

@@ -16,75 +16,18 @@
 #include <cuda_runtime.h>
 #include "common.cuh"
 #include "physics.cuh"
+#include "halo.cuh"
 #include "march.cuh"
 #include "kernels_common.cuh"
 #include "dg.cuh"
 
 namespace par2d {
 
-// ------------------------------------------------------------------ small helpers
-// (col,row) in the padded arrays of the n-th cell along a side of a block
-__device__ __forceinline__ void edge_cell_pos(int ncx, int ncy, int side, int n, int& col, int& row) {
-    switch (side) {
-        case SIDE_BOTTOM: col = COL0 + n; row = 1; break;
-        case SIDE_RIGHT: col = COL0 + ncx - 1; row = n + 1; break;
-        case SIDE_TOP: col = COL0 + n; row = ncy; break;
-        default: col = COL0; row = n + 1; break;
-    }
-}
-__device__ __forceinline__ void ghost_cell_pos(int ncx, int ncy, int side, int n, int& col, int& row) {
-    switch (side) {
-        case SIDE_BOTTOM: col = COL0 + n; row = 0; break;
-        case SIDE_RIGHT: col = COL0 + ncx; row = n + 1; break;
-        case SIDE_TOP: col = COL0 + n; row = ncy + 1; break;
-        default: col = COL0 - 1; row = n + 1; break;
-    }
-}
-
-// ------------------------------------------------------------------ peer-mapped exchange: flags
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// Waits until every other rank has completed exchange event `need` into this rank's arena.  Bounded: a
-// peer that never arrives surfaces as FLAG_COMM (PAR2D_ERR_COMM), never as a hung GPU.
-static __device__ __noinline__ bool wait_peers(const unsigned long long* flags, int nranks, int rank, unsigned long long need, long long timeout_ns) {
-    if (need == 0) return true;
-    const unsigned long long t0 = global_ns();
-    for (int r = 0; r < nranks; r++) {
-        if (r == rank) continue;
-        while (ld_acquire_sys(flags + 16 * r) < need) {
-            if ((long long)(global_ns() - t0) > timeout_ns) return false;
-            __nanosleep(200);
-        }
-    }
-    return true;
-}
-
-// per-block time step from cell (0,0): find_dt, main.cpp:19-37
 template <bool FAITHFUL>
-__device__ __forceinline__ double block_dt_value(const StepArgs& a, const Gas& g, const BlockDev& b) {
-    const double* S = b.state[a.cur];
-    const long long o = (long long)b.pitch + COL0;
-    const double u = S[b.plane + o], v = S[2 * b.plane + o], T = S[3 * b.plane + o];
-    const double v2 = u * u + v * v;
-    const double vmax = sqrt(v2) + sqrt(g.gamRs * T);
-    const double dt = g.cfl * b.min_face / vmax;
+__device__ __forceinline__ double block_dt_of(const StepArgs& a, const Gas& g, const BlockDev& b, const double* S) {
+    const double dt = block_dt_value(S, b.plane, b.pitch, b.min_face, g.gamRs, g.cfl);
     if (isnan(dt)) atomicOr(a.flags, FLAG_NAN);
     return dt;
-}
-template <bool FAITHFUL>
-__device__ __forceinline__ void block_dt(const StepArgs& a, const Gas& g, const BlockDev& b) {
-    a.dt_table[b.gid] = block_dt_value<FAITHFUL>(a, g, b);
 }
 
 // ------------------------------------------------------------------ ghost fill
@@ -128,8 +71,12 @@ __global__ void __launch_bounds__(256) ghost_kernel(StepArgs a, Gas g, int write
     ghost_cell_pos(b.ncx, b.ncy, side, n, gc, gr);
     const long long go = (long long)gr * b.pitch + gc;
 
-    if (write_dt && side == SIDE_BOTTOM && n == 0) block_dt<FAITHFUL>(a, g, b);
+    if (write_dt && side == SIDE_BOTTOM && n == 0) a.dt_table[b.gid] = block_dt_of<FAITHFUL>(a, g, b, S);
 
+    if (b.nb_kind[side] == NB_NONE) {
+        bc_ghost_fill(a.gas_dev, a.blocks + (blockIdx.y - nfin), S, side, n);
+        return;
+    }
     double gh[4];
     if (b.nb_kind[side] == NB_LOCAL) {
         // the neighbour's edge line, copied verbatim (SpatialDiscretization.cpp:263-266)
@@ -141,36 +88,11 @@ __global__ void __launch_bounds__(256) ghost_kernel(StepArgs a, Gas g, int write
 #pragma unroll
         for (int v = 0; v < 4; v++) gh[v] = So[v * o.plane + oo];
         gh[3] = fmax(gh[3], 201.0);
-    } else if (b.nb_kind[side] == NB_REMOTE) {
+    } else {
         const double* line = b.recv[side] + a.recv_off + 4 * (long long)n;
 #pragma unroll
         for (int v = 0; v < 4; v++) gh[v] = __ldcg(line + v);   // written by another GPU: read at L2
         gh[3] = fmax(gh[3], 201.0);
-    } else {
-        // outward normal of the boundary face (SpatialDiscretization.cpp:33-34,51-52,71-72,91-92);
-        // the right side reads the normal of column 0, as the reference does
-        const double* X = b.nodes;
-        const double* Y = b.nodes + b.plane;
-        long long p0, p1;
-        double sgn;
-        int code;
-        if (side == SIDE_BOTTOM) { p0 = (long long)b.pitch + COL0 + n; p1 = p0 + 1; sgn = 1.0; code = b.ibound[n]; }
-        else if (side == SIDE_RIGHT) { p0 = (long long)(n + 1) * b.pitch + COL0; p1 = p0 + b.pitch; sgn = 1.0; code = b.ibound[b.ncx + n]; }
-        else if (side == SIDE_TOP) { p0 = (long long)(b.ncy + 1) * b.pitch + COL0 + n; p1 = p0 + 1; sgn = -1.0; code = b.ibound[2 * b.ncx + b.ncy - 1 - n]; }
-        else { p0 = (long long)(n + 1) * b.pitch + COL0; p1 = p0 + b.pitch; sgn = -1.0; code = b.ibound[2 * b.ncx + 2 * b.ncy - 1 - n]; }
-        const FaceGeom fg = face_geom<true>(X[p0], Y[p0], X[p1], Y[p1]);   // O(perimeter): unit normal as MeshModule.cpp:52-81
-        int c, r;
-        edge_cell_pos(b.ncx, b.ncy, side, n, c, r);
-        const long long io = (long long)r * b.pitch + c;
-        double ui[4];
-#pragma unroll
-        for (int v = 0; v < 4; v++) ui[v] = S[v * b.plane + io];
-        const double v2 = ui[1] * ui[1] + ui[2] * ui[2];
-        const double p = fmax(ui[0] * g.Rs * ui[3], 1.0);
-        const double aint = sqrt(g.gamRs * ui[3]);
-#pragma unroll
-        for (int v = 0; v < 4; v++) gh[v] = S[v * b.plane + go];  // stays as is if the BC leaves it unwritten
-        boundary_state(g, code, sgn * fg.nx, sgn * fg.ny, ui, aint, p, v2, gh);
     }
 #pragma unroll
     for (int v = 0; v < 4; v++) S[v * b.plane + go] = gh[v];
@@ -192,7 +114,7 @@ __global__ void __launch_bounds__(256) pack_kernel(StepArgs a, Gas g, const Send
     if (blockIdx.x == 0 && blockIdx.y == 0) {
         for (int k = threadIdx.x; k < a.nowned; k += blockDim.x) {
             const BlockDev& b = a.blocks[k];
-            const double dt = block_dt_value<FAITHFUL>(a, g, b);
+            const double dt = block_dt_of<FAITHFUL>(a, g, b, b.state[a.cur]);
             if (put.peer_mode) {
                 for (int r = 0; r < put.nranks; r++) put.dt_dst[r][put.parity * put.dt_stride + b.gid] = dt;
             } else {
@@ -251,6 +173,14 @@ __global__ void __launch_bounds__(256) pack_kernel(StepArgs a, Gas g, const Send
             }
         }
     }
+}
+
+// ------------------------------------------------------------------ stop test across ranks, end of a batch
+// The launches of a batch test iterations up to the last but two (march.cuh, stop_test); the last two are tested
+// here, in order, once every rank's bookkeeping of them has been published.
+template <bool FAITHFUL>
+__global__ void stop_tail_kernel(StopArgs sx, int* stop, unsigned* flags, long long it_first, long long it_last) {
+    for (long long it = it_first; it <= it_last; it++) stop_test(sx, it, stop, flags, 0x7fffffff);
 }
 
 // ------------------------------------------------------------------ point-wise test kernels
@@ -324,6 +254,10 @@ struct KernelTable {
     void (*ghost)(cudaStream_t, const StepArgs&, const Gas&, int write_dt, const FinalizeArgs* pending);
     void (*pack)(cudaStream_t, const StepArgs&, const Gas&, const SendLine*, int nlines, int max_n, const PutArgs&);
     void (*march)(cudaStream_t, const StepArgs&, const Gas&, bool tpg, bool axi);
+    void (*march_push)(cudaStream_t, const StepArgs&, const Gas&, const PutArgs&, const FinalizeArgs&, bool tpg, bool axi);
+    int (*coop_capacity)(bool tpg, bool axi);   // CTAs of the persistent kernel that are resident at once on the current device
+    cudaError_t (*march_coop)(cudaStream_t, const StepArgs&, const Gas&, const FinalizeArgs&, double* dt_used_alt, double* partials_alt, bool tpg, bool axi);
+    void (*stop_tail)(cudaStream_t, const StopArgs&, int* stop, unsigned* flags, long long it_first, long long it_last);
     void (*dg_ghost)(cudaStream_t, const StepArgs&, const Gas&, const DgArgs&, int write_dt);
     void (*dg_cell)(cudaStream_t, const StepArgs&, const Gas&, const DgArgs&, bool tpg, bool axi);
     void (*dg_limit)(cudaStream_t, const StepArgs&, const DgArgs&);
@@ -339,13 +273,43 @@ struct Launch {
     static void march_h(cudaStream_t s, const StepArgs& a, const Gas& g, bool tpg, bool axi) {
         const dim3 grid = a.tile_list ? dim3(a.tile_count, 1) : dim3(a.max_tiles, a.nowned);   // one warp strip per CTA
         if (a.tile_list && a.tile_count == 0) return;
-        if (tpg) { if (axi) march_kernel<FAITHFUL, true, true, HOOKS><<<grid, MARCH_THREADS, 0, s>>>(a, g); else march_kernel<FAITHFUL, true, false, HOOKS><<<grid, MARCH_THREADS, 0, s>>>(a, g); }
-        else { if (axi) march_kernel<FAITHFUL, false, true, HOOKS><<<grid, MARCH_THREADS, 0, s>>>(a, g); else march_kernel<FAITHFUL, false, false, HOOKS><<<grid, MARCH_THREADS, 0, s>>>(a, g); }
+        PutArgs put;
+        FinalizeArgs fin;
+        memset(&put, 0, sizeof put);
+        memset(&fin, 0, sizeof fin);
+        if (tpg) { if (axi) march_kernel<FAITHFUL, true, true, HOOKS, false><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); else march_kernel<FAITHFUL, true, false, HOOKS, false><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); }
+        else { if (axi) march_kernel<FAITHFUL, false, true, HOOKS, false><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); else march_kernel<FAITHFUL, false, false, HOOKS, false><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); }
     }
     // the production step (advancing, no residual dump) runs the instantiation without the test hooks
     static void march(cudaStream_t s, const StepArgs& a, const Gas& g, bool tpg, bool axi) {
         if (a.update && a.res_out == nullptr) march_h<false>(s, a, g, tpg, axi);
         else march_h<true>(s, a, g, tpg, axi);
+    }
+    // the fused step: bookkeeping of the previous step + all strips, perimeter strips pushing ghosts / edge lines / dt
+    static void march_push(cudaStream_t s, const StepArgs& a, const Gas& g, const PutArgs& put, const FinalizeArgs& fin, bool tpg, bool axi) {
+        // across ranks: tile-list order; single rank: (strips of the largest block, [bookkeeping row +] owned blocks)
+        const dim3 grid = a.tile_list ? dim3(a.nfin + a.tile_count, 1) : dim3(a.max_tiles > a.nfin ? a.max_tiles : a.nfin, a.nowned + (a.nfin ? 1 : 0));
+        if (tpg) { if (axi) march_kernel<FAITHFUL, true, true, false, true><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); else march_kernel<FAITHFUL, true, false, false, true><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); }
+        else { if (axi) march_kernel<FAITHFUL, false, true, false, true><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); else march_kernel<FAITHFUL, false, false, false, true><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); }
+    }
+    static const void* coop_fn(bool tpg, bool axi) {
+        if (tpg) return axi ? (const void*)march_persist_kernel<FAITHFUL, true, true> : (const void*)march_persist_kernel<FAITHFUL, true, false>;
+        return axi ? (const void*)march_persist_kernel<FAITHFUL, false, true> : (const void*)march_persist_kernel<FAITHFUL, false, false>;
+    }
+    static int coop_capacity(bool tpg, bool axi) {
+        int dev = 0, sms = 0, per_sm = 0, coop = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_fn(tpg, axi), MARCH_THREADS, 0) != cudaSuccess) return 0;
+        return per_sm * sms;
+    }
+    static cudaError_t march_coop(cudaStream_t s, const StepArgs& a, const Gas& g, const FinalizeArgs& fin, double* dt_used_alt, double* partials_alt, bool tpg, bool axi) {
+        void* args[] = {(void*)&a, (void*)&g, (void*)&fin, (void*)&dt_used_alt, (void*)&partials_alt};
+        return cudaLaunchCooperativeKernel(coop_fn(tpg, axi), dim3(a.nowned + a.tile_count), dim3(MARCH_THREADS), args, 0, s);
+    }
+    static void stop_tail(cudaStream_t s, const StopArgs& sx, int* stop, unsigned* flags, long long it_first, long long it_last) {
+        stop_tail_kernel<FAITHFUL><<<1, 1, 0, s>>>(sx, stop, flags, it_first, it_last);
     }
     static void ghost(cudaStream_t s, const StepArgs& a, const Gas& g, int write_dt, const FinalizeArgs* pending) {
         FinalizeArgs fin;
@@ -389,7 +353,7 @@ struct Launch {
         else { if (axi) test_solve_kernel<FAITHFUL, false, true><<<grid, 128, 0, s>>>(g, n, dy, unk, res, dv); else test_solve_kernel<FAITHFUL, false, false><<<grid, 128, 0, s>>>(g, n, dy, unk, res, dv); }
     }
     static const KernelTable* table() {
-        static const KernelTable t = {&ghost, &pack, &march, &dg_ghost, &dg_cell, &dg_limit, &test_ldfss, &test_boundary, &test_update_state, &test_solve};
+        static const KernelTable t = {&ghost, &pack, &march, &march_push, &coop_capacity, &march_coop, &stop_tail, &dg_ghost, &dg_cell, &dg_limit, &test_ldfss, &test_boundary, &test_update_state, &test_solve};
         return &t;
     }
 };

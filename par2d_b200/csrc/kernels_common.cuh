@@ -4,16 +4,26 @@
 #include "common.cuh"
 namespace par2d {
 
-// Residual bookkeeping of one step (main.cpp:39-57,365-392,494).  Called by one CTA of 256 threads per
-// owned block k: sums the block's strip partials in a fixed order (thread-strided, then a shared-memory
-// tree) and takes the square roots (main.cpp:53-56); the last CTA to finish adds the blocks in block
-// order and appends dt, sum ||res||, sum res0 and relres to the device history.  No multiply-add is
-// involved, so the result does not depend on the contraction mode of the including TU.
-// Runs either as its own launch (finalize_kernel, end of a batch) or inside the NEXT step's ghost
-// kernel (kernels.cuh): the bookkeeping of step n overlaps the ghost fill of step n+1.
+// Residual bookkeeping of one step (main.cpp:39-57,365-392,494).  Called by one CTA per owned block k (any
+// CTA size that divides 256: the stand-alone finalize_kernel uses 256 threads, the finalize role inside the
+// fused step kernel one warp): sums the block's strip partials in a FIXED order - 256 virtual threads take
+// the strips thread-strided, then a binary tree over the 256 sums, exactly the order of a 256-thread
+// shared-memory reduction whatever the real CTA size - and takes the square roots (main.cpp:53-56); the
+// last CTA to finish adds the blocks in block order and appends dt, sum ||res||, sum res0 and relres to the
+// device history.  No multiply-add is involved, so the result does not depend on the contraction mode of
+// the including TU.
 #ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long fin_ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fin_st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 __device__ __forceinline__ void finalize_block(const FinalizeArgs& a, int k, double (*red)[4], bool* last) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
     const BlockDev& b = a.blocks[k];
     double norm[4] = {0.0, 0.0, 0.0, 0.0};   // thread 0: the block's norms
     // first order: one group of 4 sums; second-order branch: three groups (dudt, duxdt, duydt) whose square roots
@@ -22,19 +32,21 @@ __device__ __forceinline__ void finalize_block(const FinalizeArgs& a, int k, dou
     double parked[4] = {0.0, 0.0, 0.0, 0.0};   // thread 0: ressumx while ressumy is being reduced
     for (int grp = 0; grp < ngroups; grp++) {
         const int ntiles = a.dg_partials ? b.dg_ntiles : b.tiles_x * b.tiles_y;
-        double s[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int t = tid; t < ntiles; t += 256) {
-            const double2* p = a.dg_partials ? reinterpret_cast<const double2*>(a.dg_partials + 12 * (long long)(b.dg_tile0 + t) + 4 * grp)
-                                             : reinterpret_cast<const double2*>(a.partials + 4 * (long long)(b.tile0 + t));
-            const double2 p0 = __ldcg(p), p1 = __ldcg(p + 1);
-            s[0] += p0.x; s[1] += p0.y; s[2] += p1.x; s[3] += p1.y;
+        __syncthreads();
+        for (int vt = tid; vt < 256; vt += nt) {
+            double s[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int t = vt; t < ntiles; t += 256) {
+                const double2* p = a.dg_partials ? reinterpret_cast<const double2*>(a.dg_partials + 12 * (long long)(b.dg_tile0 + t) + 4 * grp)
+                                                 : reinterpret_cast<const double2*>(a.partials + 4 * (long long)(b.tile0 + t));
+                const double2 p0 = __ldcg(p), p1 = __ldcg(p + 1);
+                s[0] += p0.x; s[1] += p0.y; s[2] += p1.x; s[3] += p1.y;
+            }
+            for (int v = 0; v < 4; v++) red[vt][v] = s[v];
         }
         __syncthreads();
-        for (int v = 0; v < 4; v++) red[tid][v] = s[v];
-        __syncthreads();
         for (int w = 128; w > 0; w >>= 1) {
-            if (tid < w)
-                for (int v = 0; v < 4; v++) red[tid][v] += red[tid + w][v];
+            for (int vt = tid; vt < w; vt += nt)
+                for (int v = 0; v < 4; v++) red[vt][v] += red[vt + w][v];
             __syncthreads();
         }
         if (tid == 0) {
@@ -58,44 +70,51 @@ __device__ __forceinline__ void finalize_block(const FinalizeArgs& a, int k, dou
     // blocks in block order (main.cpp:379-392 gathers in rank order)
     const long long it = *a.iter;
     const int pos = *a.hist_pos;
-    double tot = 0.0, tot0 = 0.0;
-    for (int q0 = 0; q0 < a.nowned; q0 += 256) {
-        const int q = q0 + tid;
-        if (q < a.nowned) {
-            double sum = 0.0, sum0 = 0.0;
-            for (int v = 0; v < 4; v++) {
-                const double rs = __ldcg(a.blk_norm + 4 * q + v);
-                double r0 = a.res0[4 * q + v];
-                if (it == 0) r0 = rs;
-                if (r0 < 1e-16) r0 = fmax(rs, 1e-16);
-                a.res0[4 * q + v] = r0;
-                sum += rs;
-                sum0 += r0;
-            }
-            if (pos < a.hist_cap) {
-                a.blk_hist[2 * ((long long)pos * a.nowned + q) + 0] = sum;
-                a.blk_hist[2 * ((long long)pos * a.nowned + q) + 1] = sum0;
-            }
-            red[tid][0] = sum;
-            red[tid][1] = sum0;
+    const StopArgs& sx = a.stop_x;
+    const int slot = (int)((it + 1) & 3);
+    for (int q = tid; q < a.nowned; q += nt) {
+        double sum = 0.0, sum0 = 0.0;
+        for (int v = 0; v < 4; v++) {
+            const double rs = __ldcg(a.blk_norm + 4 * q + v);
+            double r0 = a.res0[4 * q + v];
+            if (it == 0) r0 = rs;
+            if (r0 < 1e-16) r0 = fmax(rs, 1e-16);
+            a.res0[4 * q + v] = r0;
+            sum += rs;
+            sum0 += r0;
         }
-        __syncthreads();
-        if (tid == 0) {
-            const int n = min(256, a.nowned - q0);
-            for (int r = 0; r < n; r++) { tot += red[r][0]; tot0 += red[r][1]; }
+        if (pos < a.hist_cap) {
+            a.blk_hist[2 * ((long long)pos * a.nowned + q) + 0] = sum;
+            a.blk_hist[2 * ((long long)pos * a.nowned + q) + 1] = sum0;
         }
-        __syncthreads();
+        a.blk_sum[2 * q] = sum;
+        a.blk_sum[2 * q + 1] = sum0;
+        if (sx.enabled) {
+            // this block's sums into every rank's residual table (the gather of main.cpp:379-392, one-sided)
+            const long long o = 2 * ((long long)slot * sx.nblocks_global + a.blocks[q].gid);
+            for (int r = 0; r < sx.nranks; r++) { sx.res_dst[r][o] = sum; sx.res_dst[r][o + 1] = sum0; }
+        }
     }
+    if (sx.enabled) __threadfence_system();
+    __syncthreads();
     if (tid != 0) return;
+    if (sx.enabled) {
+        for (int r = 0; r < sx.nranks; r++) fin_st_release_sys(sx.rflag_dst[r], (unsigned long long)(it + 1));
+    }
+    double tot = 0.0, tot0 = 0.0;
+    for (int q = 0; q < a.nowned; q++) { tot += a.blk_sum[2 * q]; tot0 += a.blk_sum[2 * q + 1]; }
     const double relres = tot / tot0;
     if (pos < a.hist_cap) {
         double* h = a.step_hist + 4 * (long long)pos;
         h[0] = __ldcg(a.dt_used); h[1] = tot; h[2] = tot0; h[3] = relres;
+        a.flag_hist[pos] = __ldcg(a.flags);
     }
     *a.iter = it + 1;
     *a.hist_pos = pos + 1;
     *a.ticket = 0u;
-    if (a.stop_on_tol && relres < a.tol) *a.stop = 1;
+    // single rank: the local sums are the global ones (main.cpp:506-511); across ranks the test is made on the
+    // published sums by the first CTA of a later launch (stop_test, march.cuh)
+    if (a.stop_on_tol && !sx.enabled && relres < a.tol) *a.stop = 1;
 }
 #endif
 

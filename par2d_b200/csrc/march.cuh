@@ -36,6 +36,8 @@
 #include <cuda_runtime.h>
 #include "common.cuh"
 #include "physics.cuh"
+#include "halo.cuh"
+#include "kernels_common.cuh"
 
 namespace par2d {
 
@@ -142,7 +144,7 @@ struct RowState {
 
 struct MarchCtx {
     int k, c, ncx, ncy, pitch, lane;   // c = first cell column of this lane
-    long long plane;
+    int plane;                         // doubles per plane (< 2^31: par2d_create checks); 32 bits keep the store addressing to one IMAD.WIDE per plane
     bool writer[CPL];
     double dt;
     double* Sout;
@@ -340,26 +342,98 @@ __device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const
     }
 }
 
-template <bool FAITHFUL, bool TPG, bool AXI, bool HOOKS>
-__global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) march_kernel(const StepArgs a, const Gas g) {
-    __shared__ __align__(128) MarchSmem sm;
-    if (*a.stop) return;
-    const int lane = threadIdx.x;
-    int k, strip;
-    if (a.tile_list != nullptr) {                  // subset launch (edge strips first, interior strips beside the exchange)
-        if ((int)blockIdx.x >= a.tile_count) return;
-        const int2 t = __ldg(a.tile_list + blockIdx.x);
-        k = t.x; strip = t.y;
-    } else {
-        k = blockIdx.y;                            // grid.y = owned blocks, grid.x covers the block with most strips
-        strip = blockIdx.x;
+// What changes from one step to the next inside a batch (the persistent launch advances these in the kernel).
+struct StepVar {
+    int cur;                 // state buffer read
+    const double* dt_table;  // per-block dt of the state being read
+    double* dt_next;         // per-block dt of the state being written (fused step only)
+    double* dt_used;         // the global dt of this step, for the history record
+    double* partials;        // this step's strip sums
+    int parity;              // peer-mapped mode: parity of the exchange event this step produces
+    unsigned long long seq;  //   ... and its number (the step consumes event StepArgs::wait_seq = seq-1)
+};
+
+// ------------------------------------------------------------------ fused step: the perimeter of a block
+// One side of a perimeter strip after its rows are done (the strip's new cells sit in Sout, visible to the whole
+// warp): per edge cell n of [n0, n1)
+//   boundary-condition face : the ghost state of the NEW state -> ghost ring of Sout       (generate_ghost_cells)
+//   same-rank neighbour     : the new cell -> the neighbour block's ghost ring              (halo exchange, :263-269)
+//   off-rank neighbour      : the new cell -> the neighbour rank's arena over NVLink        (halo exchange, :236-259)
+// so that the next step finds its ghost ring complete without a ghost launch.
+template <bool FAITHFUL>
+__device__ __forceinline__ void push_side(const StepArgs& a, const Gas& g, const PutArgs& put, const StepVar& sv, const BlockDev& b, int side, int n0, int n1) {
+    const int kind = b.nb_kind[side];
+    double* Sout = b.state[sv.cur ^ 1];
+    for (int n = n0 + (int)threadIdx.x; n < n1; n += 32) {
+        int c, r;
+        if (kind == NB_NONE) {
+            bc_ghost_fill(a.gas_dev, &b, Sout, side, n);
+            continue;
+        }
+        edge_cell_pos(b.ncx, b.ncy, side, n, c, r);
+        const long long io = (long long)r * b.pitch + c;
+        double u[4];
+#pragma unroll
+        for (int v = 0; v < 4; v++) u[v] = __ldcg(Sout + v * b.plane + io);
+        if (kind == NB_LOCAL) {
+            const BlockDev& o = a.blocks[b.nb_block[side]];
+            ghost_cell_pos(o.ncx, o.ncy, b.nb_side[side], n, c, r);
+            double* So = o.state[sv.cur ^ 1];
+            const long long go = (long long)r * o.pitch + c;
+            u[3] = fmax(u[3], 201.0);
+#pragma unroll
+            for (int v = 0; v < 4; v++) __stcg(So + v * o.plane + go, u[v]);
+        } else if (b.put_dst[side] != nullptr) {
+            // one 32-byte AoS record per edge cell (usend[k + NVAR*j], SpatialDiscretization.cpp:241)
+            double2* d2 = reinterpret_cast<double2*>(b.put_dst[side] + sv.parity * b.put_stride[side] + 4 * (long long)n);
+            d2[0] = make_double2(u[0], u[1]);
+            d2[1] = make_double2(u[2], u[3]);
+        }
     }
+}
+
+// Multi-rank step: the off-rank faces of this strip.  The neighbours' edge lines were put into this rank's arena
+// (event a.wait_seq); copy them into the ghost ring of the state being read, ahead of the TMA copies that stage it.
+__device__ __forceinline__ void pull_remote_side(const StepArgs& a, const StepVar& sv, const BlockDev& b, int side, int n0, int n1) {
+    double* S = b.state[sv.cur];
+    const double* line0 = b.recv[side] + a.recv_off;   // parity of the consumed event
+    for (int n = n0 + (int)threadIdx.x; n < n1; n += 32) {
+        int c, r;
+        ghost_cell_pos(b.ncx, b.ncy, side, n, c, r);
+        const long long go = (long long)r * b.pitch + c;
+        const double* line = line0 + 4 * (long long)n;
+        const double2 lo = __ldcg(reinterpret_cast<const double2*>(line)), hi = __ldcg(reinterpret_cast<const double2*>(line) + 1);
+        __stcg(S + go, lo.x); __stcg(S + b.plane + go, lo.y); __stcg(S + 2 * b.plane + go, hi.x); __stcg(S + 3 * b.plane + go, fmax(hi.y, 201.0));
+    }
+}
+
+// Stop test across ranks, first CTA of launch `launch_no` (see StopArgs): the launch would overwrite the state left
+// by iteration it-1 - it may only run if that iteration's global relres stayed above the tolerance.
+__device__ __forceinline__ void stop_test(const StopArgs& sx, long long it_checked, int* stop, unsigned* flags, int launch_no) {
+    if (it_checked >= 0 && !*stop) {
+        if (!wait_peers(sx.local_flags, sx.nranks, -1, (unsigned long long)(it_checked + 1), sx.timeout_ns, 1)) atomicOr(flags, FLAG_COMM);
+        const double* t = sx.res_table + 2 * (long long)((it_checked + 1) & 3) * sx.nblocks_global;
+        double tot = 0.0, tot0 = 0.0;
+        for (int q = 0; q < sx.nblocks_global; q++) { tot += __ldcg(t + 2 * q); tot0 += __ldcg(t + 2 * q + 1); }   // rank order of main.cpp:381-392
+        if (tot / tot0 < sx.tol) { *sx.stop_iter = it_checked; *stop = 1; }
+    }
+    __threadfence();
+    *reinterpret_cast<volatile int*>(sx.go) = launch_no;
+}
+
+// ------------------------------------------------------------------ one strip, one step
+// `reload(k, strip)` re-derives the strip's identity after the row loop (from blockIdx or from the tile list), so
+// that neither it nor anything computed from it has to stay in a register across the rows.
+template <bool FAITHFUL, bool TPG, bool AXI, bool HOOKS, bool PUSH, class Reload>
+__device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, const PutArgs& put, const StepVar& sv, MarchSmem& sm, int k_in, int strip_in, Reload reload) {
+    const int lane = threadIdx.x;
+    int k = k_in, strip = strip_in;
     const BlockDev& b = a.blocks[k];
-    if (strip >= b.tiles_x * b.tiles_y) return;    // CTA-uniform
     MarchCtx m;
-    m.k = k; m.ncx = b.ncx; m.ncy = b.ncy; m.pitch = b.pitch; m.plane = b.plane; m.lane = lane;
-    const int c0 = (strip % b.tiles_x) * MCELLS;   // first updated cell column
-    const int j0 = (strip / b.tiles_x) * a.march_rows;
+    m.k = k; m.ncx = b.ncx; m.ncy = b.ncy; m.pitch = b.pitch; m.plane = (int)b.plane; m.lane = lane;
+    const int tx = strip % b.tiles_x, ty = strip / b.tiles_x;
+    const int c0 = tx * MCELLS;                    // first updated cell column
+    const int j0 = ty * a.march_rows;
     const int j1 = min(j0 + a.march_rows, m.ncy);
     m.c = c0 - 1 + CPL * lane;                     // this lane's first cell column (-1 and ncx are the ghost columns)
 #pragma unroll
@@ -367,13 +441,37 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
         const int w = CPL * lane + e;              // column within the staged row: 0 and WCOLS-1 are the halo columns
         m.writer[e] = w >= 1 && w <= MCELLS && m.c + e < m.ncx;
     }
-    m.Sout = b.state[a.cur ^ 1];
+    m.Sout = b.state[sv.cur ^ 1];
+    unsigned flags = 0;
+    bool ok = true;
+
+    // perimeter of the block (CTA-uniform).  Everything here is recomputed after the rows instead of being kept
+    // alive across them: the row loop has no register to spare.
+    bool waited = false;
+    if constexpr (PUSH) {
+        if (a.wait_flags != nullptr) {
+            const bool rl = tx == 0 && b.nb_kind[SIDE_LEFT] == NB_REMOTE, rr = tx == b.tiles_x - 1 && b.nb_kind[SIDE_RIGHT] == NB_REMOTE;
+            const bool rb = ty == 0 && b.nb_kind[SIDE_BOTTOM] == NB_REMOTE, rt = ty == b.tiles_y - 1 && b.nb_kind[SIDE_TOP] == NB_REMOTE;
+            if (rl | rr | rb | rt) {
+                // this strip borders another rank: its ghost cells come out of the arena, ahead of the row copies
+                if (!wait_peers_warp(a.wait_flags, a.nranks, a.rank, a.wait_seq, a.timeout_ns)) flags |= FLAG_COMM;
+                waited = true;
+                const int c1 = min(c0 + MCELLS, m.ncx);
+                if (rl) pull_remote_side(a, sv, b, SIDE_LEFT, j0, j1);
+                if (rr) pull_remote_side(a, sv, b, SIDE_RIGHT, j0, j1);
+                if (rb) pull_remote_side(a, sv, b, SIDE_BOTTOM, c0, c1);
+                if (rt) pull_remote_side(a, sv, b, SIDE_TOP, c0, c1);
+                fence_proxy_async_global();
+                __syncwarp();
+            }
+        }
+    }
 
     // ---- TMA row ring.  Array row `arow` holds cell row arow-1, node row arow-1 and the metric of cell
     // row arow-1; this strip reads array rows j0 (cell row below) .. j1+1 (cell row above the last).
     // Ring use n holds array rows j0+2n, j0+2n+1 (rows past the array end are zero-filled by TMA).
     const void* tmap = static_cast<const char*>(a.tmaps) + (size_t)k * 128;
-    const int plane0 = a.cur ? 4 : 0;              // first of the 7 planes read this step
+    const int plane0 = sv.cur ? 4 : 0;             // first of the 7 planes read this step
     const int col0 = COL0 + c0 - 1;                // even: the 16-byte rule of tiled copies
     const int arow_end = j1 + 1;
     auto stage_rows = [&](int n, int slot) {       // lane 0 only
@@ -388,28 +486,33 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
         for (int s = 0; s < MARCH_STAGES; s++) mbar_init(&sm.bar[s], 1);
         mbar_init_fence();
         tmap_acquire(tmap);
+        if constexpr (PUSH) fence_proxy_async_global();   // the state was written by other CTAs' generic stores (persistent launch)
 #pragma unroll
         for (int s = 0; s < MARCH_STAGES; s++) stage_rows(s, s);
     }
     __syncwarp();
     // this lane's first column of the state planes / node planes in stage 0, row 0
-    const double* rs = &sm.ring[0][a.cur ? 3 : 0][0][CPL * lane];
-    const double* rn = &sm.ring[0][a.cur ? 0 : 4][0][CPL * lane];
+    const double* rs = &sm.ring[0][sv.cur ? 3 : 0][0][CPL * lane];
+    const double* rn = &sm.ring[0][sv.cur ? 0 : 4][0][CPL * lane];
 
-    // global dt = max over blocks (main.cpp:270-292); the table was written by the ghost kernel
+    // global dt = max over blocks (main.cpp:270-292); the table was written by the ghost kernel (first step of a
+    // batch) or by the strips holding cell (0,0) of every block in the previous step, on any rank
+    if constexpr (PUSH) {
+        if (a.wait_flags != nullptr && !waited) {
+            if (!wait_peers_warp(a.wait_flags, a.nranks, a.rank, a.wait_seq, a.timeout_ns)) flags |= FLAG_COMM;
+        }
+    }
     double dt = 0.0;
     if (a.dt_ready) {
-        dt = __ldcg(a.dt_used);                    // reduced by the ghost kernel
+        dt = __ldcg(sv.dt_used);                   // reduced by the ghost kernel
     } else {
-        for (int t = lane; t < a.nblocks_global; t += 32) dt = fmax(dt, __ldcg(a.dt_table + t));
+        for (int t = lane; t < a.nblocks_global; t += 32) dt = fmax(dt, __ldcg(sv.dt_table + t));
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) dt = fmax(dt, __shfl_xor_sync(0xffffffffu, dt, s));
-        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) *a.dt_used = dt;   // for the step's history record
+        if (k == 0 && strip == 0 && lane == 0) *sv.dt_used = dt;   // for the step's history record
     }
     m.dt = dt;
 
-    unsigned flags = 0;
-    bool ok = true;
     // ---- prologue (ring use 0): cell rows j0-1 (row 0) and j0 (row 1), node row j0, bottom-face fluxes of row j0
     RowState A, B;
     ok &= mbar_wait(&sm.bar[0], 0);
@@ -474,11 +577,215 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
     }
     if (isnan(sq[0]) || isnan(sq[1]) || isnan(sq[2]) || isnan(sq[3])) flags |= FLAG_NAN;   // SpatialDiscretization.cpp:1008
     if (!ok) flags |= FLAG_NAN | 0x80000000u;      // a staged row never arrived
+    reload(k, strip);
+    const BlockDev& bb = a.blocks[k];
     if (lane < 4) {
         const double s = lane == 0 ? sq[0] : lane == 1 ? sq[1] : lane == 2 ? sq[2] : sq[3];
-        a.partials[4 * (long long)(b.tile0 + strip) + lane] = s;
+        sv.partials[4 * (long long)(bb.tile0 + strip) + lane] = s;
+    }
+
+    if constexpr (PUSH) {
+        const int ntx = bb.tiles_x, nty = bb.tiles_y;
+        const int ex = strip % ntx, ey = strip / ntx;
+        const bool tl = ex == 0, tr = ex == ntx - 1, tb = ey == 0, tt = ey == nty - 1;
+        if (tl | tr | tb | tt) {
+            const int e_c0 = ex * MCELLS, e_c1 = min(e_c0 + MCELLS, bb.ncx);
+            const int e_j0 = ey * a.march_rows, e_j1 = min(e_j0 + a.march_rows, bb.ncy);
+            __syncwarp();                          // the strip's new cells are visible to every lane
+            if (tl) push_side<FAITHFUL>(a, g, put, sv, bb, SIDE_LEFT, e_j0, e_j1);
+            if (tr) push_side<FAITHFUL>(a, g, put, sv, bb, SIDE_RIGHT, e_j0, e_j1);
+            if (tb) push_side<FAITHFUL>(a, g, put, sv, bb, SIDE_BOTTOM, e_c0, e_c1);
+            if (tt) push_side<FAITHFUL>(a, g, put, sv, bb, SIDE_TOP, e_c0, e_c1);
+            bool put_something = false;
+            if (put.peer_mode) {
+                put_something = (tl && bb.nb_kind[SIDE_LEFT] == NB_REMOTE) || (tr && bb.nb_kind[SIDE_RIGHT] == NB_REMOTE) ||
+                                (tb && bb.nb_kind[SIDE_BOTTOM] == NB_REMOTE) || (tt && bb.nb_kind[SIDE_TOP] == NB_REMOTE) || strip == 0;
+            }
+            if (strip == 0 && lane == 0) {
+                // find_dt of the NEW state from cell (0,0) (main.cpp:19-37), for the next step on every rank
+                const double dtb = block_dt_value(bb.state[sv.cur ^ 1], bb.plane, bb.pitch, bb.min_face, g.gamRs, g.cfl);
+                if (isnan(dtb)) flags |= FLAG_NAN;
+                if (put.peer_mode) {
+                    for (int r = 0; r < put.nranks; r++) put.dt_dst[r][sv.parity * put.dt_stride + bb.gid] = dtb;
+                } else {
+                    sv.dt_next[bb.gid] = dtb;
+                }
+            }
+            if (put_something) {
+                // all stores of this strip are ordered before its ticket; the last perimeter strip of the launch
+                // raises this rank's flag in every peer's arena (release at system scope)
+                __threadfence_system();
+                __syncwarp();
+                if (lane == 0) {
+                    if (atomicAdd(put.ticket, 1u) == put.expected - 1) {
+                        *put.ticket = 0u;
+                        __threadfence_system();
+                        for (int r = 0; r < put.nranks; r++)
+                            if (r != put.rank) st_release_sys(put.flag_dst[r], sv.seq);
+                    }
+                }
+            }
+        }
     }
     if (flags) atomicOr(a.flags, flags);
+}
+
+// The finalize role inside the fused step kernel: CTA `k` (one warp) runs the previous step's bookkeeping for
+// owned block k, reusing the row ring's shared memory as the reduction scratch.
+__device__ __forceinline__ void march_finalize_role(const FinalizeArgs& fin, MarchSmem& sm, int k) {
+    static_assert(sizeof(sm.ring) >= 256 * 4 * sizeof(double) + 16, "reduction scratch does not fit the ring");
+    double (*red)[4] = reinterpret_cast<double (*)[4]>(&sm.ring[0][0][0][0]);
+    bool* last = reinterpret_cast<bool*>(&sm.G[0][0]);
+    finalize_block(fin, k, red, last);
+}
+
+__device__ __forceinline__ int2 tile_from_list(const int2* list, int t) {
+    int2 r;   // volatile: a reload after the row loop must not be folded into the load before it
+    asm volatile("ld.global.nc.v2.s32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(list + t));
+    return r;
+}
+
+// One launch = one step.  PUSH (the fused step): [stop test across ranks] + bookkeeping of the previous step + every
+// strip of every owned block.  Single rank: grid (most strips of a block, [1 +] owned blocks), row 0 being the
+// bookkeeping row when a step is pending; across ranks: grid (nfin + strips), strips in tile-list order - those that
+// border another rank first, so that their puts travel while the interior strips run.
+template <bool FAITHFUL, bool TPG, bool AXI, bool HOOKS, bool PUSH>
+__global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) march_kernel(const StepArgs a, const Gas g, const PutArgs put, const FinalizeArgs fin) {
+    __shared__ __align__(128) MarchSmem sm;
+    StepVar sv;
+    sv.cur = a.cur; sv.dt_table = a.dt_table; sv.dt_next = a.dt_next; sv.dt_used = a.dt_used; sv.partials = a.partials;
+    sv.parity = put.parity; sv.seq = put.seq;
+    if constexpr (PUSH) {
+        const StopArgs& sx = fin.stop_x;
+        if (sx.enabled) {
+            // across ranks: nothing of this launch runs before its stop decision (made by the first CTA)
+            if (blockIdx.x == 0 && blockIdx.y == 0) {
+                if (threadIdx.x == 0) stop_test(sx, a.launch_no >= 3 ? sx.iter0 + a.launch_no - 3 : -1, const_cast<int*>(a.stop), a.flags, a.launch_no);
+            } else if (threadIdx.x == 0) {
+                const unsigned long long t0 = global_ns();
+                while (*reinterpret_cast<volatile int*>(sx.go) < a.launch_no) {
+                    if ((long long)(global_ns() - t0) > sx.timeout_ns) { atomicOr(a.flags, FLAG_COMM); break; }
+                    __nanosleep(100);
+                }
+                __threadfence();
+            }
+            __syncwarp();
+        }
+        if (*reinterpret_cast<volatile const int*>(a.stop)) return;
+        if (a.tile_list != nullptr) {
+            if ((int)blockIdx.x < a.nfin) { march_finalize_role(fin, sm, blockIdx.x); return; }
+            const int t = (int)blockIdx.x - a.nfin;
+            if (t >= a.tile_count) return;
+            const int2 tl = tile_from_list(a.tile_list, t);
+            march_tile<FAITHFUL, TPG, AXI, HOOKS, PUSH>(a, g, put, sv, sm, tl.x, tl.y, [&](int& k, int& strip) {
+                const int2 r = tile_from_list(a.tile_list, (int)blockIdx.x - a.nfin);
+                k = r.x; strip = r.y;
+            });
+        } else {
+            const int fy = a.nfin ? 1 : 0;
+            if ((int)blockIdx.y < fy) {
+                if ((int)blockIdx.x < a.nfin) march_finalize_role(fin, sm, blockIdx.x);
+                return;
+            }
+            const int k = (int)blockIdx.y - fy;
+            if ((int)blockIdx.x >= a.blocks[k].tiles_x * a.blocks[k].tiles_y) return;    // CTA-uniform
+            march_tile<FAITHFUL, TPG, AXI, HOOKS, PUSH>(a, g, put, sv, sm, k, blockIdx.x, [&](int& k2, int& strip2) {
+                k2 = (int)blockIdx.y - (a.nfin ? 1 : 0); strip2 = blockIdx.x;
+            });
+        }
+    } else {
+        if (*a.stop) return;
+        if (a.tile_list != nullptr) {              // subset launch
+            if ((int)blockIdx.x >= a.tile_count) return;
+            const int2 t = __ldg(a.tile_list + blockIdx.x);
+            if (t.y >= a.blocks[t.x].tiles_x * a.blocks[t.x].tiles_y) return;
+            march_tile<FAITHFUL, TPG, AXI, HOOKS, PUSH>(a, g, put, sv, sm, t.x, t.y, [&](int& k, int& strip) {
+                const int2 r = tile_from_list(a.tile_list, blockIdx.x);
+                k = r.x; strip = r.y;
+            });
+        } else {
+            const int k = blockIdx.y;              // grid.y = owned blocks, grid.x covers the block with most strips
+            if ((int)blockIdx.x >= a.blocks[k].tiles_x * a.blocks[k].tiles_y) return;    // CTA-uniform
+            march_tile<FAITHFUL, TPG, AXI, HOOKS, PUSH>(a, g, put, sv, sm, k, blockIdx.x, [&](int& k2, int& strip2) { k2 = blockIdx.y; strip2 = blockIdx.x; });
+        }
+    }
+}
+
+// ------------------------------------------------------------------ persistent launch (small meshes)
+// Grid barrier of a cooperative launch: every CTA is one warp.  Bounded (FLAG_COMM), like every wait here.
+__device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned target) {
+    bool ok = true;
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        if (ld_acquire_gpu(bar) < target) {
+            const unsigned long long t0 = global_ns();
+            while (ld_acquire_gpu(bar) < target) {
+                if ((long long)(global_ns() - t0) > 4000000000ll) { ok = false; break; }
+            }
+        }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    return ok;
+}
+
+// A batch of a.coop_steps steps of a mesh whose strips are all resident at once (the shipped cases hold ~50 k
+// cells: a step is a few microseconds of work and would otherwise be bound by launch latency, main.cpp:263-532
+// as ONE launch).  CTA i < nowned: the bookkeeping of block i, one step behind the strips; the other CTAs keep
+// one strip each for the whole batch.  Between steps: one grid barrier - the perimeter strips have pushed the
+// new state's ghost ring and dt by then.  Same strips, same arithmetic, same summation order as the launch-per-step
+// path: the results are bit-identical.
+template <bool FAITHFUL, bool TPG, bool AXI>
+__global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) march_persist_kernel(const StepArgs a, const Gas g, const FinalizeArgs fin,
+                                                                                                double* dt_used_alt, double* partials_alt) {
+    __shared__ __align__(128) MarchSmem sm;
+    if (*a.stop) return;
+    const bool fin_role = (int)blockIdx.x < a.nowned;
+    int k = 0, strip = 0;
+    if (!fin_role) {
+        const int2 tl = __ldg(a.tile_list + ((int)blockIdx.x - a.nowned));
+        k = tl.x; strip = tl.y;
+    }
+    PutArgs put;
+    put.peer_mode = 0; put.parity = 0; put.seq = 0; put.nranks = 1; put.rank = 0; put.expected = 0;
+    put.dt_dst = nullptr; put.flag_dst = nullptr; put.ticket = nullptr; put.local_flags = nullptr; put.dt_stride = 0; put.timeout_ns = 0; put.dg = 0;
+    int done = 0;
+    bool stopped = false;
+    for (int s = 0; s < a.coop_steps; s++) {
+        const int odd = s & 1;
+        if (fin_role) {
+            if (s > 0) {
+                FinalizeArgs f = fin;              // step s-1
+                f.partials = odd ? fin.partials : partials_alt;
+                f.dt_used = odd ? fin.dt_used : dt_used_alt;
+                march_finalize_role(f, sm, blockIdx.x);
+            }
+        } else {
+            StepVar sv;
+            sv.cur = a.cur ^ odd;
+            sv.dt_table = odd ? a.dt_next : a.dt_table;
+            sv.dt_next = odd ? const_cast<double*>(a.dt_table) : a.dt_next;
+            sv.dt_used = odd ? dt_used_alt : a.dt_used;
+            sv.partials = odd ? partials_alt : a.partials;
+            sv.parity = 0; sv.seq = 0;
+            march_tile<FAITHFUL, TPG, AXI, false, true>(a, g, put, sv, sm, k, strip, [&](int& k2, int& strip2) {
+                const int2 r = tile_from_list(a.tile_list, (int)blockIdx.x - a.nowned);
+                k2 = r.x; strip2 = r.y;
+            });
+        }
+        done = s + 1;
+        if (!grid_barrier(a.grid_bar, (unsigned)(s + 1) * gridDim.x)) { if (threadIdx.x == 0) atomicOr(a.flags, FLAG_COMM); break; }
+        if (*reinterpret_cast<volatile const int*>(a.stop)) { stopped = true; break; }
+    }
+    // the last step's bookkeeping
+    if (fin_role && !stopped && done > 0) {
+        const int odd = (done - 1) & 1;
+        FinalizeArgs f = fin;
+        f.partials = odd ? partials_alt : fin.partials;
+        f.dt_used = odd ? dt_used_alt : fin.dt_used;
+        march_finalize_role(f, sm, blockIdx.x);
+    }
 }
 
 }  // namespace par2d

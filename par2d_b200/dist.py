@@ -119,8 +119,13 @@ class DistSolver:
         err = self.lib.last_error()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)            # all or nobody
         if int(ok.item()) == 1:
-            self.transport = "peer"
-            return
+            # every rank is connected: the strip decomposition (summation order of the norms) must agree
+            ok[0] = 1 if self.lib.peer_check(h) == 0 else 0
+            err = self.lib.last_error()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 1:
+                self.transport = "peer"
+                return
         self.lib.peer_disconnect(h)
         msg = f"peer-mapped exchange unavailable ({err.decode() if err else 'a peer failed'})"
         if strict:
@@ -144,14 +149,18 @@ class DistSolver:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
 
-    def advance(self, nsteps: int, check: bool = True) -> List[StepInfo]:
-        """Advance nsteps on every rank (collective); returns this rank's log records (local sums)."""
+    def advance(self, nsteps: int, check: bool = True, stop_on_tol: bool = False) -> List[StepInfo]:
+        """Advance nsteps on every rank (collective); returns this rank's log records (local sums).
+        stop_on_tol (peer transport): every rank stops after the iteration whose GLOBAL relres fell below
+        cfg.tol (main.cpp:506-531), decided on the device from the sums of all ranks."""
         if self.transport == "peer":
             info = (StepInfo * nsteps)()
-            rc = self.lib.step(self.solver.handle, nsteps, 0, info)
+            rc = self.lib.step(self.solver.handle, nsteps, int(stop_on_tol), info)
             if check:
                 self.lib.check(rc, "step")
-            return list(info)
+            return [i for i in info if i.iter >= 0]
+        if stop_on_tol:
+            raise ValueError("stop_on_tol across ranks needs the peer transport")
         self.queue_steps(nsteps)
         return self.collect(nsteps, check=check)
 
@@ -170,10 +179,9 @@ class DistSolver:
             self.lib.check(rc, "step_collect")
         return list(info)
 
-    def step(self, nsteps: int, check: bool = True):
-        """Advance nsteps; returns (dt[nsteps], relres[nsteps]) with relres summed over ALL blocks
-        in global block order on every rank."""
-        info = self.advance(nsteps, check=check)
+    def global_relres(self, nsteps: int) -> np.ndarray:
+        """relres of the last nsteps steps with the per-block sums of ALL ranks added in global block order
+        (the rank-order gather of main.cpp:379-392), identical on every rank and for any number of ranks."""
         hist = self.solver.block_history(nsteps)            # (nsteps, nowned, 2)
         table = torch.zeros(nsteps, self.nblocks, 2, dtype=torch.float64)
         for k, g in enumerate(self.solver.owned):
@@ -187,7 +195,13 @@ class DistSolver:
         for g in range(self.nblocks):                                     # rank order of main.cpp:381-392
             num += table[:, g, 0]
             den += table[:, g, 1]
-        return np.array([i.dt for i in info]), num / den
+        return num / den
+
+    def step(self, nsteps: int, check: bool = True, stop_on_tol: bool = False):
+        """Advance nsteps; returns (dt[n], relres[n]) with relres summed over ALL blocks in global block
+        order on every rank (n < nsteps if the run stopped on the tolerance)."""
+        info = self.advance(nsteps, check=check, stop_on_tol=stop_on_tol)
+        return np.array([i.dt for i in info]), self.global_relres(len(info))
 
     def get_state(self, b: int) -> np.ndarray:
         return self.solver.get_state(b)

@@ -1,0 +1,92 @@
+"""Single-process multi-GPU driver: N contexts, one per GPU, connected through peer-mapped arenas.
+
+The Python twin of ``par2d_fv --gpus N`` (par2d_b200/csrc/host/main.cpp): replaces the reference's
+rank setup (FV/main.cpp:68-74,125-142) without a second process - par2d_peer_connect_local enables
+peer access between the devices, every batch is queued on all contexts (par2d_step_async) before any
+is waited for (par2d_step_wait), the residual is gathered in global block order (main.cpp:379-392) and
+the tolerance break (main.cpp:506-531) is decided on the device from the sums of all contexts.
+Context r runs on ``devices[r % len(devices)]``: with fewer devices than contexts several contexts
+share a GPU (their kernels run side by side) - that is how the exchange protocol is tested on a
+one-GPU box.  No torch, no torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import Config, StepInfo
+from .host import Case
+from .solver import Solver, default_config
+
+
+class LocalMultiSolver:
+    def __init__(self, case: Case, cfg: Optional[Config] = None, nranks: int = 2, devices: Optional[Sequence[int]] = None, lib=None):
+        self.lib = lib or _capi.load_gpu()
+        cfg = (cfg or default_config(self.lib)).copy()
+        if devices is None:
+            n = C.c_int32()
+            self.lib.check(self.lib.device_count(C.byref(n)), "device_count")
+            devices = list(range(n.value))
+        self.nranks = nranks
+        self.owners = case.partition(nranks)
+        self.nblocks = case.nblocks
+        self.solvers: List[Solver] = []
+        for r in range(nranks):
+            c = cfg.copy()
+            c.rank, c.nranks, c.device = r, nranks, devices[r % len(devices)]
+            self.solvers.append(Solver(case, c, lib=self.lib, owners=self.owners))
+        arr = (C.c_void_p * nranks)(*[s.handle for s in self.solvers])
+        self.lib.check(self.lib.peer_connect_local(arr, nranks), "peer_connect_local")
+        self.connected = True
+
+    def _of(self, b: int) -> Solver:
+        return self.solvers[self.owners[b]]
+
+    def step(self, nsteps: int, stop_on_tol: bool = False):
+        """Advance nsteps on every context; returns (dt[n], relres[n]) with relres over ALL blocks in
+        global block order; n < nsteps if the run stopped on the tolerance."""
+        for s in self.solvers:
+            self.lib.check(self.lib.step_async(s.handle, nsteps, int(stop_on_tol)), "step_async")
+        infos = []
+        for s in self.solvers:
+            info = (StepInfo * max(nsteps, 1))()
+            self.lib.check(self.lib.step_wait(s.handle, info), "step_wait")
+            infos.append([i for i in info[:nsteps] if i.iter >= 0])
+        done = len(infos[0])
+        assert all(len(i) == done for i in infos), "the contexts stopped after different iterations"
+        table = np.zeros((done, self.nblocks, 2))
+        for s in self.solvers:
+            if done:
+                hist = s.block_history(done)
+                for k, g in enumerate(s.owned):
+                    table[:, g, :] = hist[:, k, :]
+        num, den = np.zeros(done), np.zeros(done)
+        for g in range(self.nblocks):          # rank order of main.cpp:381-392
+            num += table[:, g, 0]
+            den += table[:, g, 1]
+        self.infos = infos
+        return np.array([i.dt for i in infos[0]]), (num / den if done else num)
+
+    def get_state(self, b: int) -> np.ndarray:
+        return self._of(b).get_state(b)
+
+    def set_state(self, b: int, unk: np.ndarray):
+        self._of(b).set_state(b, unk)
+
+    def get_residual(self, b: int) -> np.ndarray:
+        return self._of(b).get_residual(b)
+
+    @property
+    def iteration(self) -> int:
+        return self.solvers[0].iteration
+
+    def close(self):
+        if self.connected:
+            for s in self.solvers:
+                self.lib.peer_disconnect(s.handle)
+            self.connected = False
+        for s in self.solvers:
+            s.close()

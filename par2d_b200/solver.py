@@ -59,6 +59,22 @@ class Solver:
         unk = np.ascontiguousarray(unk, dtype=np.float64).reshape(ny - 1, nx - 1, 4)
         self.lib.check(self.lib.set_state(self._h, b, unk.ctypes.data_as(_DP)), "set_state")
 
+    def get_states(self, blocks=None):
+        """All (or the given) owned blocks in one batched transfer (par2d_get_states): {block: (ny-1, nx-1, 4)}."""
+        blocks = list(self.owned if blocks is None else blocks)
+        out = {b: np.empty((self.shapes[b][1] - 1, self.shapes[b][0] - 1, 4), dtype=np.float64) for b in blocks}
+        ids = (C.c_int32 * len(blocks))(*blocks)
+        ptrs = (_DP * len(blocks))(*[out[b].ctypes.data_as(_DP) for b in blocks])
+        self.lib.check(self.lib.get_states(self._h, len(blocks), ids, ptrs), "get_states")
+        return out
+
+    def set_states(self, states: dict):
+        blocks = list(states)
+        arrs = [np.ascontiguousarray(states[b], dtype=np.float64) for b in blocks]
+        ids = (C.c_int32 * len(blocks))(*blocks)
+        ptrs = (_DP * len(blocks))(*[a.ctypes.data_as(_DP) for a in arrs])
+        self.lib.check(self.lib.set_states(self._h, len(blocks), ids, ptrs), "set_states")
+
     def get_residual(self, b: int) -> np.ndarray:
         nx, ny = self.shapes[b]
         out = np.empty((ny - 1, nx - 1, 4), dtype=np.float64)

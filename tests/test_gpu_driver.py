@@ -57,6 +57,63 @@ def test_driver_restart_and_second_order(tmp_path):
         r, _, _ = read_solution(str(tmp_path / "rest" / f"solution.b{b + 1}.tec"), nx, ny)
         assert np.array_equal(a, r), f"block {b}: restart + 20 differs from 40 straight"
     out = _run(tmp_path / "dg", "--case", case_path("Case_ffstep8"), "--niter", "30", "--accur", "1", "--saveiter", "0")
-    assert os.path.exists(tmp_path / "dg" / "solution.b001.it00030.tec") and "RelativeTotalResisual" in out
-    with open(tmp_path / "dg" / "solution.b003.it00030.tec") as f:
+    # print_state_DGP1's layout: <out>/time/solution.b%03d.it%05d.tec, initial state labelled 0 (FileIO.cpp:121-128)
+    assert os.path.exists(tmp_path / "dg" / "time" / "solution.b001.it00000.tec")
+    assert os.path.exists(tmp_path / "dg" / "time" / "solution.b001.it00030.tec") and "RelativeTotalResisual" in out
+    with open(tmp_path / "dg" / "time" / "solution.b003.it00030.tec") as f:
         assert f.readlines()[2].startswith("ZONE I=101, J=71, DATAPACKING=POINT, STRANDID=30, SOLUTIONTIME=")
+
+
+def test_driver_periodic_saves(tmp_path):
+    """saveiter > 0 with a batch size that divides it (the shipped defaults are 100 / 1000): the reference saves after
+    every iteration m > 0 with m % saveiter == 0 (main.cpp:484), i.e. the state after m + 1 steps, and labels the
+    second-order branch's files with m (they are all kept: FileIO.cpp:127)."""
+    case = case_path("Case_ffstep8")
+    out = _run(tmp_path / "d", "--case", case, "--niter", "25", "--accur", "1", "--saveiter", "10", "--batch", "5", "--printiter", "7")
+    assert out.count("RelativeTotalResisual") == 4          # iterations 0, 7, 14, 21
+    names = sorted(os.listdir(tmp_path / "d" / "time"))
+    # labels: 0 (initial), 10 and 20 (periodic), 25 (final: the loop variable's exit value, main.cpp:541-545)
+    assert [n for n in names if n.startswith("solution.b001.")] == [
+        "solution.b001.it00000.tec", "solution.b001.it00010.tec", "solution.b001.it00020.tec", "solution.b001.it00025.tec"]
+    # the file labelled 10 holds the state after 11 steps
+    _run(tmp_path / "e", "--case", case, "--niter", "11", "--accur", "1", "--saveiter", "0", "--batch", "11")
+    with open(tmp_path / "d" / "time" / "solution.b002.it00010.tec") as f:
+        per = f.readlines()[3:]
+    with open(tmp_path / "e" / "time" / "solution.b002.it00011.tec") as f:
+        fin = f.readlines()[3:]
+    assert per == fin
+    # first-order files are overwritten in place (FileIO.cpp:84): trimming the batches at the save points must not
+    # change where the run ends up
+    _run(tmp_path / "p", "--case", case, "--niter", "23", "--faithful", "--saveiter", "10", "--batch", "5")
+    _run(tmp_path / "q", "--case", case, "--niter", "23", "--faithful", "--saveiter", "0", "--batch", "23")
+    c = Case.load(case)
+    nx, ny = c.shape(2)
+    a, _, _ = read_solution(str(tmp_path / "p" / "solution.b3.tec"), nx, ny)
+    b, _, _ = read_solution(str(tmp_path / "q" / "solution.b3.tec"), nx, ny)
+    assert np.array_equal(a, b)
+    with open(tmp_path / "p" / "res.tec") as f, open(tmp_path / "q" / "res.tec") as g:
+        assert f.read() == g.read()
+
+
+def test_driver_multi_context(tmp_path):
+    """par2d_fv --gpus N: one process, N contexts (sharing the GPUs present), blocks partitioned, peer-mapped halo
+    exchange, residual gathered in global block order, tolerance stop decided across contexts: res.tec and every
+    solution file byte-identical to the one-context run."""
+    case = case_path("Case_spikefine24")
+    _run(tmp_path / "one", "--case", case, "--niter", "60", "--saveiter", "0", "--batch", "25")
+    for n in (2, 3):
+        out = _run(tmp_path / f"m{n}", "--case", case, "--niter", "60", "--saveiter", "0", "--batch", "25", "--gpus", str(n))
+        assert f"24 blocks on {n} contexts" in out
+        for name in ["res.tec"] + [f"solution.b{b + 1}.tec" for b in range(24)]:
+            with open(tmp_path / "one" / name, "rb") as f, open(tmp_path / f"m{n}" / name, "rb") as g:
+                assert f.read() == g.read(), (n, name)
+    # tolerance break in the middle of a batch on 2 contexts == on one
+    case = case_path("Case_ffstep8")
+    _run(tmp_path / "t1", "--case", case, "--niter", "40", "--saveiter", "0", "--tol", "0.9996", "--batch", "16")
+    _run(tmp_path / "t2", "--case", case, "--niter", "40", "--saveiter", "0", "--tol", "0.9996", "--batch", "16", "--gpus", "2")
+    with open(tmp_path / "t1" / "res.tec") as f:
+        lines = f.read().splitlines()
+    assert len(lines) == 1 + 3          # header + iterations 0, 1, 2
+    for name in ["res.tec"] + [f"solution.b{b + 1}.tec" for b in range(8)]:
+        with open(tmp_path / "t1" / name, "rb") as f, open(tmp_path / "t2" / name, "rb") as g:
+            assert f.read() == g.read(), name

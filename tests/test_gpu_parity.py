@@ -318,24 +318,27 @@ def test_full_size_fast_vs_faithful(gpu):
     assert all(a.dt == b.dt for a, b in zip(fi[:1], si[:1]))
 
 
-def test_overlapped_batches_change_nothing(gpu, monkeypatch):
-    """PAR2D_SINGLE_OVERLAP=1: meshes of 2 M cells and more run par2d_step batches with the ghost fill and the
-    bookkeeping on a side stream beside the interior strips (capi.cu::queue_batch_overlapped; opt-in, it buys nothing
-    under the power cap).  State, dt and residual history must equal the serial order bit for bit, over several
-    batches, in both arithmetic modes."""
+def test_fused_step_equals_separate_launches_bitwise(gpu, monkeypatch):
+    """The fused step (one launch: bookkeeping of the previous step + strips, the perimeter strips pushing the new
+    state's ghost ring and dt; march.cuh) against the order it replaces (PAR2D_NO_OVERLAP=1: ghost kernel, then march
+    kernel): state, dt and residual history bit for bit over several batches, in both arithmetic modes, on a mesh
+    large enough for the launch-per-step path (2 M cells)."""
     for mode in (MODE_FAST, MODE_FAITHFUL):
         runs = []
-        for overlap in ("1", "0"):
-            monkeypatch.setenv("PAR2D_SINGLE_OVERLAP", overlap)
+        for serial in ("0", "1"):
+            monkeypatch.setenv("PAR2D_NO_OVERLAP", serial)
             case = Case.synthetic_ramp(2048, 1056, 2, 2)
             s = Solver(case, make_cfg(gpu, 1, 1.4, mode), lib=gpu)
             u = s.get_state(1)
             u[200:260, 300:380, 0] *= 1.3          # a disturbance, so that the blocks really exchange something
             s.set_state(1, u)
             info = s.step(5) + s.step(1) + s.step(4)
-            runs.append(([s.get_state(b) for b in range(4)], [(i.iter, i.dt, i.relres, i.ressumsum) for i in info]))
+            runs.append(([s.get_state(b) for b in range(4)], [(i.iter, i.dt, i.relres, i.ressumsum) for i in info],
+                         [s.get_residual(b) for b in range(4)]))
             s.close()
         for a, b in zip(runs[0][0], runs[1][0]):
+            assert np.array_equal(a, b)
+        for a, b in zip(runs[0][2], runs[1][2]):
             assert np.array_equal(a, b)
         assert runs[0][1] == runs[1][1] and len(runs[0][1]) == 10
 
