@@ -235,6 +235,12 @@ int par2d_peer_disconnect(par2d_ctx* ctx);
 /* After every rank has returned from par2d_peer_connect (host barrier): verifies that all ranks cut their blocks
  * into the same strips, i.e. add the residual norms in the same order. */
 int par2d_peer_check(par2d_ctx* ctx);
+/* Diagnostic: this rank's view of the exchange after a batch (e.g. after PAR2D_ERR_COMM): flags_out[nranks*16] =
+ * the flag groups of its arena (slot 0: exchange events completed by each rank, slot 1: iterations whose residual
+ * sums each rank has published, slot 15: rows per strip), res_out[4*nblocks*2] = the residual table, counters_out[6]
+ * = {exchange events produced, launch whose stop decision is made, stop word, stop iteration, iteration counter,
+ * history records}.  Any pointer may be NULL. */
+int par2d_peer_snapshot(par2d_ctx* ctx, uint64_t* flags_out, double* res_out, int64_t* counters_out);
 /* The same connection for n contexts of ONE process (ctxs[r] = rank r of n, one per GPU; replaces the rank setup of
  * FV/main.cpp:68-74,125-142 for a single-process multi-GPU host): enables peer access between the devices and
  * hands every context the others' arenas directly - no handle exchange, no second process. */

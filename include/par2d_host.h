@@ -44,6 +44,18 @@ int par2d_case_synthetic_ramp_ranked(int32_t ncx, int32_t ncy, int32_t nbx, int3
  * indexing bit-exactly against the unsplit run. */
 int par2d_case_split(const par2d_case* single, int32_t nbx, int32_t nby, par2d_case** out);
 
+/* GridPart-compatible decomposer (GridPart/main.c): reads <dir>/gridin.conn (block count; per source block
+ * "ixm ixp iym iyp" - neighbour block >= 0 or minus the side's BC code - then "ipart jpart") and <dir>/gridin.dat
+ * (per block "ni nj", then ni*nj lines "x y", j outer) and cuts every source block into ipart x jpart sub-blocks
+ * that share a node line, numbered (source block, jblock, iblock), conn tuples across source blocks as
+ * GridPart/main.c:182-226 resolves them.  j split: ceil(nj/jpart - 1e-8) nodes.  i split: isteps == NULL applies
+ * the same rule; the committed GridPart source instead hard-codes the node table {0, 99, 178, 257, 356}
+ * (main.c:103-108) - pass it as isteps[nisteps] to reproduce that binary. */
+int par2d_gridpart(const char* dir, const int32_t* isteps, int32_t nisteps, par2d_case** out);
+/* Writes a case in the byte format of GridPart's own output (header lines npartb/ipartb/ngrid, "%le %le \n"
+ * coordinates, grid.conn), 0-based. */
+int par2d_case_write_gridpart(const par2d_case* c, const char* dir);
+
 /* Writes grid.conn + subgrids/ in the reference format (y written without the
  * shift, %.16e).  one_based selects the Case_ffstep8 naming. */
 int par2d_case_write(const par2d_case* c, const char* dir, int32_t one_based);

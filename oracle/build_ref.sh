@@ -7,6 +7,10 @@
 #   _ref/MPI2DFV          run-time configurable binary (ORACLE_NITER/IAXI/IGAM/ACCUR)
 #   _ref/MPI2DFV_strict   header differs from the reference's only in NITER
 #   _ref/libpar2d_ref.so  reference functions behind extern "C" (ref_wrap.cpp)
+#   _ref/GridPart         the reference's grid partitioner, unmodified (GridPart/main.c: its i split is the
+#                         hard-coded node table istepmanual[] = {0, 99, 178, 257, 356})
+#   _ref/GridPart_auto    the same source with the automatic i split it keeps in comments restored by sed
+#                         (generated copy under _ref/gen_gridpart/, a build artefact like the headers above)
 # Usage: oracle/build_ref.sh [build|verify]
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
@@ -43,6 +47,17 @@ build() {
         "$REF/main.cpp" $srcs -o "$OUT/MPI2DFV_strict"
     g++ $CXXFLAGS -fPIC -shared -I"$HERE" -I"$HERE/shim" -include "$OUT/gen_rt/Indexing.h" -I"$REF" \
         "$HERE/ref_wrap.cpp" $srcs -o "$OUT/libpar2d_ref.so"
+    GP="$(dirname "$REF")/GridPart/main.c"
+    if [ -f "$GP" ]; then
+        mkdir -p "$OUT/gen_gridpart"
+        gcc -O2 -w "$GP" -o "$OUT/GridPart" -lm
+        sed -e 's|istep = -999;|istep = ceil((double)ni[b]/ipart[b] - 1e-8);|' \
+            -e 's|int istart = istepmanual\[iblock\];//istep\*iblock;|int istart = istep*iblock;|' \
+            -e 's|int iend = istepmanual\[iblock+1\];//MIN(ni\[b\]-1, istep\*(iblock+1));|int iend = MIN(ni[b]-1, istep*(iblock+1));|' \
+            "$GP" > "$OUT/gen_gridpart/main.c"
+        grep -q 'int istart = istep\*iblock;' "$OUT/gen_gridpart/main.c" && grep -q 'int iend = MIN(ni\[b\]-1, istep\*(iblock+1));' "$OUT/gen_gridpart/main.c"
+        gcc -O2 -w "$OUT/gen_gridpart/main.c" -o "$OUT/GridPart_auto" -lm
+    fi
     echo "build_ref: built $(ls "$OUT" | tr '\n' ' ')"
 }
 

@@ -103,6 +103,7 @@ GPU_ONLY_API = {
     "peer_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "peer_disconnect": (C.c_int, [C.c_void_p]),
     "peer_check": (C.c_int, [C.c_void_p]),
+    "peer_snapshot": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), _DP, C.POINTER(C.c_int64)]),
     "peer_connect_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32]),
     "step_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "step_wait": (C.c_int, [C.c_void_p, C.POINTER(StepInfo)]),
@@ -129,6 +130,8 @@ HOST_API = {
                                                    C.POINTER(C.c_void_p)]),
     "par2d_case_split": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "par2d_case_write": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
+    "par2d_gridpart": (C.c_int, [C.c_char_p, _IP, C.c_int32, C.POINTER(C.c_void_p)]),
+    "par2d_case_write_gridpart": (C.c_int, [C.c_void_p, C.c_char_p]),
     "par2d_case_num_blocks": (C.c_int32, [C.c_void_p]),
     "par2d_case_num_cells": (C.c_int64, [C.c_void_p]),
     "par2d_case_block": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(BlockDesc)]),
@@ -175,6 +178,10 @@ _cache = {}
 def load_gpu() -> _Lib:
     """The product CUDA library.  No fallback: raises if it has not been built."""
     if "gpu" not in _cache:
+        # Kernels of contexts that share a process wait for each other (par2d_peer_connect_local): no kernel may be
+        # loaded lazily while another one spins.  par2d_create preloads what it launches; eager module loading (only
+        # effective if CUDA is not initialised yet) covers the rest.
+        os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
         # PAR2D_GPU_LIB: A/B builds of the same CUDA library (tools/build_variants.sh), measurements only
         _cache["gpu"] = _Lib(os.environ.get("PAR2D_GPU_LIB", GPU_LIB), "par2d_", [SOLVER_API, GPU_ONLY_API])
     return _cache["gpu"]

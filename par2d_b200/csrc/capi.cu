@@ -673,6 +673,8 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
     c->kt = cfg->mode == PAR2D_MODE_FAITHFUL ? kernels_faithful() : kernels_fast();
     c->dg = cfg->accur == 1;
     c->device = dev;
+    c->kt->preload(c->tpg, c->axi);   // every kernel this ctx can launch is resident before anything of it runs (lazy loading, see there)
+    preload_common();
     {
         // Rows per warp strip.  A strip is marched by ONE warp, row after row (~1 us per row), so small meshes
         // need short strips to expose enough warps (the shipped cases hold ~50 k cells: 64-row strips would be
@@ -1403,6 +1405,24 @@ int par2d_peer_check(par2d_ctx* c) {
     if (!c || !c->peer_connected) return fail(PAR2D_ERR_COMM, "peer_check: not connected");
     if (use_device(c)) return PAR2D_ERR_CUDA;
     return check_peers(c);
+}
+
+int par2d_peer_snapshot(par2d_ctx* c, uint64_t* flags_out, double* res_out, int64_t* counters_out) {
+    if (!c || !c->arena) return fail(PAR2D_ERR_COMM, "peer_snapshot: this ctx has no arena");
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    if (flags_out) CU_TRY(cudaMemcpy(flags_out, c->arena + c->lay.flags_off, sizeof(uint64_t) * 16 * c->cfg.nranks, cudaMemcpyDeviceToHost));
+    if (res_out) CU_TRY(cudaMemcpy(res_out, c->arena + c->lay.res_off, sizeof(double) * 8 * c->nblocks, cudaMemcpyDeviceToHost));
+    if (counters_out) {
+        int go = 0, stop = 0, pos = 0;
+        long long sit = 0, it = 0;
+        CU_TRY(cudaMemcpy(&go, c->go, sizeof go, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(&stop, c->stop, sizeof stop, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(&pos, c->hist_pos, sizeof pos, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(&sit, c->stop_iter, sizeof sit, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(&it, c->d_iter, sizeof it, cudaMemcpyDeviceToHost));
+        counters_out[0] = (int64_t)c->seq; counters_out[1] = go; counters_out[2] = stop; counters_out[3] = sit; counters_out[4] = it; counters_out[5] = pos;
+    }
+    return 0;
 }
 
 int par2d_peer_connect_local(par2d_ctx** ctxs, int32_t n) {

@@ -39,6 +39,10 @@ struct Block {
     int bid[4] = {-1, -1, -1, -1}; // bottom,right,top,left
     int bbound[4] = {-1, -1, -1, -1};
     int owner = 0;
+    // GridPart provenance (par2d_gridpart): partition counts and this block's position in its source block, for
+    // the header lines of the block file; and the y coordinates as they stand in the file (without the load shift)
+    int npart[2] = {1, 1}, ipart[2] = {0, 0};
+    std::vector<double> yfile;
 };
 
 bool file_exists(const std::string& p) {
@@ -255,6 +259,144 @@ int par2d_case_split(const par2d_case* single, int32_t nbx, int32_t nby, par2d_c
             b.bbound[PAR2D_TOP] = at_t ? src.bbound[PAR2D_TOP] : -1;
         }
     *out = cs.release();
+    return 0;
+}
+
+// GridPart (GridPart/main.c): reads <dir>/gridin.conn - the block count, then per source block "ixm ixp iym iyp"
+// (a neighbour block >= 0, or minus the boundary-condition code of that side) and "ipart jpart" (:23-40) - and
+// <dir>/gridin.dat - per block "ni nj" and ni*nj lines "x y", j outer (:43-74) - and cuts every source block into
+// ipart x jpart sub-blocks that share a node line with their neighbours (:132-145).  Sub-blocks are numbered in the
+// order (source block, jblock, iblock) (:85-94); a side on the source block's boundary takes the neighbouring
+// source block's facing sub-block (:182-226) or the side's code.
+// The j split is step = ceil(nj/jpart - 1e-8) nodes (:128).  The i split of the committed source is a hard-coded
+// table of node indices, istepmanual[] = {0, 99, 178, 257, 356} (:103-108,134,136; the automatic rule is commented
+// out): pass that table as isteps[] to reproduce it, or NULL for the automatic ceil rule in both directions.
+int par2d_gridpart(const char* dir, const int32_t* isteps, int32_t nisteps, par2d_case** out) {
+    if (!dir || !out) return host_fail(PAR2D_ERR_ARG, "gridpart: null argument");
+    const std::string root(dir);
+    FILE* fc = fopen((root + "/gridin.conn").c_str(), "r");
+    if (!fc) return host_fail(PAR2D_ERR_ARG, "cannot open %s/gridin.conn", dir);
+    int nblock = 0;
+    if (fscanf(fc, "%d", &nblock) != 1 || nblock < 1) { fclose(fc); return host_fail(PAR2D_ERR_ARG, "bad block count in %s/gridin.conn", dir); }
+    std::vector<int> ixm(nblock), ixp(nblock), iym(nblock), iyp(nblock), ipart(nblock), jpart(nblock);
+    for (int b = 0; b < nblock; b++) {
+        if (fscanf(fc, " %d %d %d %d%*[^\n]", &ixm[b], &ixp[b], &iym[b], &iyp[b]) != 4 || fscanf(fc, " %d %d%*[^\n]", &ipart[b], &jpart[b]) != 2 ||
+            ipart[b] < 1 || jpart[b] < 1) {
+            fclose(fc);
+            return host_fail(PAR2D_ERR_ARG, "bad record of block %d in %s/gridin.conn", b, dir);
+        }
+    }
+    fclose(fc);
+    FILE* fg = fopen((root + "/gridin.dat").c_str(), "r");
+    if (!fg) return host_fail(PAR2D_ERR_ARG, "cannot open %s/gridin.dat", dir);
+    std::vector<int> ni(nblock), nj(nblock);
+    std::vector<std::vector<double>> X(nblock), Y(nblock);
+    for (int b = 0; b < nblock; b++) {
+        if (fscanf(fg, "%d %d", &ni[b], &nj[b]) != 2 || ni[b] < 2 || nj[b] < 2) { fclose(fg); return host_fail(PAR2D_ERR_ARG, "bad node counts of block %d in %s/gridin.dat", b, dir); }
+        X[b].resize((size_t)ni[b] * nj[b]);
+        Y[b].resize((size_t)ni[b] * nj[b]);
+        for (size_t p = 0; p < X[b].size(); p++)
+            if (fscanf(fg, "%lE %lE ", &X[b][p], &Y[b][p]) != 2) { fclose(fg); return host_fail(PAR2D_ERR_ARG, "short node list of block %d in %s/gridin.dat", b, dir); }
+    }
+    fclose(fg);
+    // the consistency checks of GridPart/main.c:112-127 (it exits with status 100)
+    for (int b = 0; b < nblock; b++) {
+        const int nbx[2] = {ixm[b], ixp[b]}, nby[2] = {iym[b], iyp[b]};
+        for (int n : nbx)
+            if (n >= 0 && (n >= nblock || nj[b] != nj[n] || jpart[b] != jpart[n])) return host_fail(PAR2D_ERR_ARG, "gridpart: blocks %d and %d do not match across their x face", b, n);
+        for (int n : nby)
+            if (n >= 0 && (n >= nblock || ni[b] != ni[n] || ipart[b] != ipart[n])) return host_fail(PAR2D_ERR_ARG, "gridpart: blocks %d and %d do not match across their y face", b, n);
+        if (isteps && (nisteps < ipart[b] + 1 || isteps[ipart[b]] > ni[b] - 1))
+            return host_fail(PAR2D_ERR_ARG, "gridpart: the manual i split does not fit block %d (%d nodes, %d parts)", b, ni[b], ipart[b]);
+    }
+    std::vector<int> first(nblock + 1, 0);    // blkind[b][j][i] = first[b] + j*ipart[b] + i
+    for (int b = 0; b < nblock; b++) first[b + 1] = first[b] + ipart[b] * jpart[b];
+    auto blkind = [&](int b, int j, int i) { return first[b] + j * ipart[b] + i; };
+    std::unique_ptr<par2d_case> cs(new par2d_case);
+    cs->blocks.resize((size_t)first[nblock]);
+    for (int b = 0; b < nblock; b++) {
+        const int istep = (int)ceil((double)ni[b] / ipart[b] - 1e-8), jstep = (int)ceil((double)nj[b] / jpart[b] - 1e-8);
+        for (int jb = 0; jb < jpart[b]; jb++)
+            for (int ib = 0; ib < ipart[b]; ib++) {
+                const int i0 = isteps ? isteps[ib] : istep * ib, i1 = isteps ? isteps[ib + 1] : std::min(ni[b] - 1, istep * (ib + 1));
+                const int j0 = jstep * jb, j1 = std::min(nj[b] - 1, jstep * (jb + 1));
+                if (i1 <= i0 || j1 <= j0) return host_fail(PAR2D_ERR_ARG, "gridpart: empty sub-block (%d,%d) of block %d", ib, jb, b);
+                const int me = blkind(b, jb, ib);
+                Block& k = cs->blocks[(size_t)me];
+                k.nx = i1 - i0 + 1;
+                k.ny = j1 - j0 + 1;
+                k.npart[0] = ipart[b]; k.npart[1] = jpart[b];
+                k.ipart[0] = ib; k.ipart[1] = jb;
+                k.x.resize((size_t)k.nx * k.ny);
+                k.y.resize(k.x.size());
+                k.yfile.resize(k.x.size());
+                for (int j = 0; j < k.ny; j++)
+                    for (int i = 0; i < k.nx; i++) {
+                        const size_t src = (size_t)(j0 + j) * ni[b] + i0 + i, dst = (size_t)j * k.nx + i;
+                        k.x[dst] = X[b][src];
+                        k.yfile[dst] = Y[b][src];
+                        k.y[dst] = Y[b][src] + kYShift;
+                    }
+                // (boundary code, neighbour block) per side, GridPart/main.c:170-226
+                int code[4] = {-1, -1, -1, -1}, nbk[4];
+                nbk[PAR2D_LEFT] = me - 1; nbk[PAR2D_RIGHT] = me + 1; nbk[PAR2D_BOTTOM] = me - ipart[b]; nbk[PAR2D_TOP] = me + ipart[b];
+                if (ib == 0) {
+                    if (ixm[b] >= 0) nbk[PAR2D_LEFT] = blkind(ixm[b], jb, ipart[ixm[b]] - 1);
+                    else { nbk[PAR2D_LEFT] = -1; code[PAR2D_LEFT] = -ixm[b]; }
+                }
+                if (ib == ipart[b] - 1) {
+                    if (ixp[b] >= 0) nbk[PAR2D_RIGHT] = blkind(ixp[b], jb, 0);
+                    else { nbk[PAR2D_RIGHT] = -1; code[PAR2D_RIGHT] = -ixp[b]; }
+                }
+                if (jb == 0) {
+                    if (iym[b] >= 0) nbk[PAR2D_BOTTOM] = blkind(iym[b], jpart[iym[b]] - 1, ib);
+                    else { nbk[PAR2D_BOTTOM] = -1; code[PAR2D_BOTTOM] = -iym[b]; }
+                }
+                if (jb == jpart[b] - 1) {
+                    if (iyp[b] >= 0) nbk[PAR2D_TOP] = blkind(iyp[b], 0, ib);
+                    else { nbk[PAR2D_TOP] = -1; code[PAR2D_TOP] = -iyp[b]; }
+                }
+                for (int sd = 0; sd < 4; sd++) { k.bid[sd] = nbk[sd]; k.bbound[sd] = code[sd]; }
+                // one code per face, counter-clockwise: bottom, right, top, left (:227-261)
+                k.ibound.clear();
+                k.ibound.insert(k.ibound.end(), k.nx - 1, code[PAR2D_BOTTOM]);
+                k.ibound.insert(k.ibound.end(), k.ny - 1, code[PAR2D_RIGHT]);
+                k.ibound.insert(k.ibound.end(), k.nx - 1, code[PAR2D_TOP]);
+                k.ibound.insert(k.ibound.end(), k.ny - 1, code[PAR2D_LEFT]);
+            }
+    }
+    *out = cs.release();
+    return 0;
+}
+
+// Writes a case in the byte format of GridPart's output (GridPart/main.c:100,152-166,264-265): grid.conn, and
+// subgrids/grid.block<b>.dat with the "npartb/ipartb/ngrid" header lines, coordinates as "%le %le \n" (6 digits -
+// what the reference's own case directories hold), the word BC and one code per face.
+int par2d_case_write_gridpart(const par2d_case* c, const char* dir) {
+    if (!c || !dir) return host_fail(PAR2D_ERR_ARG, "case_write_gridpart: null argument");
+    const std::string root(dir);
+    mkdir(root.c_str(), 0755);
+    mkdir((root + "/subgrids").c_str(), 0755);
+    FILE* fc = fopen((root + "/grid.conn").c_str(), "w");
+    if (!fc) return host_fail(PAR2D_ERR_ARG, "cannot write %s/grid.conn", dir);
+    fprintf(fc, "%d\n", (int)c->blocks.size());
+    for (size_t b = 0; b < c->blocks.size(); b++) {
+        const Block& k = c->blocks[b];
+        fprintf(fc, "%d: (%d,%d) (%d,%d) (%d,%d) (%d,%d)\n", (int)b, k.bbound[PAR2D_LEFT], k.bid[PAR2D_LEFT], k.bbound[PAR2D_RIGHT], k.bid[PAR2D_RIGHT],
+                k.bbound[PAR2D_BOTTOM], k.bid[PAR2D_BOTTOM], k.bbound[PAR2D_TOP], k.bid[PAR2D_TOP]);
+    }
+    fclose(fc);
+    for (size_t b = 0; b < c->blocks.size(); b++) {
+        const Block& k = c->blocks[b];
+        const std::string path = root + "/subgrids/grid.block" + std::to_string((int)b) + ".dat";
+        FILE* f = fopen(path.c_str(), "w");
+        if (!f) return host_fail(PAR2D_ERR_ARG, "cannot write %s", path.c_str());
+        fprintf(f, "npartb: %d %d \nipartb: %d %d \nngrid: %d %d \n", k.npart[0], k.npart[1], k.ipart[0], k.ipart[1], k.nx, k.ny);
+        for (size_t p = 0; p < k.x.size(); p++) fprintf(f, "%le %le \n", k.x[p], k.yfile.empty() ? k.y[p] - kYShift : k.yfile[p]);
+        fprintf(f, "BC\n");
+        for (int code : k.ibound) fprintf(f, "%d\n", code);
+        fclose(f);
+    }
     return 0;
 }
 

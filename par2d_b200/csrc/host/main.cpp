@@ -37,6 +37,9 @@ static void usage() {
 }
 
 int main(int argc, char** argv) {
+    // the contexts of one process wait for each other's kernels: none may be loaded lazily while another one spins
+    // (par2d_create preloads what it launches; this covers the rest)
+    setenv("CUDA_MODULE_LOADING", "EAGER", 0);
     std::string case_dir = "../Case", out_dir = "../Outputs", therm = "../therm_air.dat", restart_dir;
     long niter = 5000000;  // NITER, FV/Indexing.h:20
     int printiter = 1, saveiter = 1000, batch = 100, ngpus = 1, ndev_arg = -1;

@@ -251,6 +251,7 @@ __global__ void test_solve_kernel(Gas g, long long n, const double* dt_ycc, cons
 
 // ------------------------------------------------------------------ launch table of one arithmetic mode
 struct KernelTable {
+    void (*preload)(bool tpg, bool axi);
     void (*ghost)(cudaStream_t, const StepArgs&, const Gas&, int write_dt, const FinalizeArgs* pending);
     void (*pack)(cudaStream_t, const StepArgs&, const Gas&, const SendLine*, int nlines, int max_n, const PutArgs&);
     void (*march)(cudaStream_t, const StepArgs&, const Gas&, bool tpg, bool axi);
@@ -291,6 +292,28 @@ struct Launch {
         const dim3 grid = a.tile_list ? dim3(a.nfin + a.tile_count, 1) : dim3(a.max_tiles > a.nfin ? a.max_tiles : a.nfin, a.nowned + (a.nfin ? 1 : 0));
         if (tpg) { if (axi) march_kernel<FAITHFUL, true, true, false, true><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); else march_kernel<FAITHFUL, true, false, false, true><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); }
         else { if (axi) march_kernel<FAITHFUL, false, true, false, true><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); else march_kernel<FAITHFUL, false, false, false, true><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); }
+    }
+    // Loads every kernel a ctx of this gas model can launch.  With CUDA's lazy module loading the FIRST launch of a
+    // kernel may need the context to go idle - a deadlock if a kernel of another ctx of the same process is spinning
+    // on a flag that only the kernel being loaded would raise (par2d_peer_connect_local).  par2d_create calls this
+    // while nothing is running.
+    static void preload(bool tpg, bool axi) {
+        cudaFuncAttributes fa;
+        auto touch = [&](const void* f) { cudaFuncGetAttributes(&fa, f); };
+        touch((const void*)ghost_kernel<FAITHFUL>);
+        touch((const void*)pack_kernel<FAITHFUL>);
+        touch((const void*)stop_tail_kernel<FAITHFUL>);
+        touch((const void*)dg_ghost_kernel<FAITHFUL>);
+        touch((const void*)dg_limit_kernel<FAITHFUL>);
+        touch(coop_fn(tpg, axi));
+        if (tpg) {
+            if (axi) { touch((const void*)march_kernel<FAITHFUL, true, true, false, false>); touch((const void*)march_kernel<FAITHFUL, true, true, true, false>); touch((const void*)march_kernel<FAITHFUL, true, true, false, true>); touch((const void*)dg_cell_kernel<FAITHFUL, true, true>); }
+            else { touch((const void*)march_kernel<FAITHFUL, true, false, false, false>); touch((const void*)march_kernel<FAITHFUL, true, false, true, false>); touch((const void*)march_kernel<FAITHFUL, true, false, false, true>); touch((const void*)dg_cell_kernel<FAITHFUL, true, false>); }
+        } else {
+            if (axi) { touch((const void*)march_kernel<FAITHFUL, false, true, false, false>); touch((const void*)march_kernel<FAITHFUL, false, true, true, false>); touch((const void*)march_kernel<FAITHFUL, false, true, false, true>); touch((const void*)dg_cell_kernel<FAITHFUL, false, true>); }
+            else { touch((const void*)march_kernel<FAITHFUL, false, false, false, false>); touch((const void*)march_kernel<FAITHFUL, false, false, true, false>); touch((const void*)march_kernel<FAITHFUL, false, false, false, true>); touch((const void*)dg_cell_kernel<FAITHFUL, false, false>); }
+        }
+        cudaGetLastError();
     }
     static const void* coop_fn(bool tpg, bool axi) {
         if (tpg) return axi ? (const void*)march_persist_kernel<FAITHFUL, true, true> : (const void*)march_persist_kernel<FAITHFUL, true, false>;
@@ -353,7 +376,7 @@ struct Launch {
         else { if (axi) test_solve_kernel<FAITHFUL, false, true><<<grid, 128, 0, s>>>(g, n, dy, unk, res, dv); else test_solve_kernel<FAITHFUL, false, false><<<grid, 128, 0, s>>>(g, n, dy, unk, res, dv); }
     }
     static const KernelTable* table() {
-        static const KernelTable t = {&ghost, &pack, &march, &march_push, &coop_capacity, &march_coop, &stop_tail, &dg_ghost, &dg_cell, &dg_limit, &test_ldfss, &test_boundary, &test_update_state, &test_solve};
+        static const KernelTable t = {&preload, &ghost, &pack, &march, &march_push, &coop_capacity, &march_coop, &stop_tail, &dg_ghost, &dg_cell, &dg_limit, &test_ldfss, &test_boundary, &test_update_state, &test_solve};
         return &t;
     }
 };

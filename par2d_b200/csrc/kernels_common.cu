@@ -16,6 +16,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
     finalize_block(a, blockIdx.x, red, &last);
 }
 
+// see Launch::preload (kernels.cuh)
+void preload_common();
+
 void launch_finalize(cudaStream_t s, const FinalizeArgs& a) {
     finalize_kernel<<<a.nowned, 256, 0, s>>>(a);
 }
@@ -146,6 +149,18 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters,
 }
 void launch_fp64_probe(cudaStream_t s, double* out, int grid, int iters) {
     fp64_probe_kernel<<<grid, 256, 0, s>>>(out, iters, 0.5);
+}
+
+void preload_common() {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, (const void*)finalize_kernel);
+    cudaFuncGetAttributes(&fa, (const void*)aos_to_planes_kernel);
+    cudaFuncGetAttributes(&fa, (const void*)planes_to_aos_kernel);
+    cudaFuncGetAttributes(&fa, (const void*)fill_uniform_kernel);
+    cudaFuncGetAttributes(&fa, (const void*)nodes_to_planes_kernel);
+    cudaFuncGetAttributes(&fa, (const void*)cell_metric_kernel);
+    cudaFuncGetAttributes(&fa, (const void*)min_face_kernel);
+    cudaGetLastError();
 }
 
 }  // namespace par2d

@@ -118,6 +118,7 @@ __device__ __forceinline__ void finalize_block(const FinalizeArgs& a, int k, dou
 }
 #endif
 
+void preload_common();
 void launch_finalize(cudaStream_t s, const FinalizeArgs& a);
 void launch_aos_to_planes(cudaStream_t s, const BlockDev& b, int buf, const double* aos);
 void launch_planes_to_aos(cudaStream_t s, const BlockDev& b, int buf, double* aos);

@@ -38,6 +38,24 @@ class Case:
                   "case_synthetic_ramp")
         return cls(h)
 
+    @classmethod
+    def gridpart(cls, directory: str, isteps=None) -> "Case":
+        """GridPart's decomposition of <directory>/gridin.conn + gridin.dat (GridPart/main.c).  isteps: the manual
+        table of i node breaks of the committed GridPart source ([0, 99, 178, 257, 356]); None = the automatic
+        ceil rule in both directions."""
+        lib = _capi.load_host()
+        h = C.c_void_p()
+        if isteps is None:
+            arr, n = None, 0
+        else:
+            arr, n = (C.c_int32 * len(isteps))(*isteps), len(isteps)
+        lib.check(lib.par2d_gridpart(os.fsencode(directory), arr, n, C.byref(h)), "gridpart")
+        return cls(h)
+
+    def write_gridpart(self, directory: str):
+        """grid.conn + subgrids/ in the byte format of GridPart's own output."""
+        self._lib.check(self._lib.par2d_case_write_gridpart(self._h, os.fsencode(directory)), "case_write_gridpart")
+
     def split(self, nbx: int, nby: int) -> "Case":
         h = C.c_void_p()
         self._lib.check(self._lib.par2d_case_split(self._h, nbx, nby, C.byref(h)), "case_split")
