@@ -1071,6 +1071,7 @@ int par2d_get_residual(par2d_ctx* c, int32_t block, double* res) {
     // peer-mapped mode: the arenas hold the lines and dt of the state left by the last par2d_step
     // (after par2d_set_state, call par2d_step(ctx, 0, 0, NULL) on every rank to refresh them)
     flush_finalize(c);
+    CU_TRY(cudaMemsetAsync(c->stop, 0, sizeof(int), c->stream));   // a batch that stopped on the tolerance leaves the stop word set
     c->kt->ghost(c->stream, a, c->gas, c->peer_connected ? 0 : 1, nullptr);
     launch_step(c, a);
     const size_t bytes = sizeof(double) * 4 * (size_t)b.ncx * b.ncy;
@@ -1119,6 +1120,7 @@ int par2d_get_residual_dg(par2d_ctx* c, int32_t block, double* res, double* resx
     DgArgs d = dg_args(c, 0);
     d.res_out = out;
     d.res_block = k;
+    CU_TRY(cudaMemsetAsync(c->stop, 0, sizeof(int), c->stream));
     c->kt->dg_ghost(c->stream, a, c->gas, d, c->peer_connected ? 0 : 1);
     c->kt->dg_cell(c->stream, a, c->gas, d, c->tpg, c->axi);
     CU_TRY(cudaMemcpyAsync(res, out, sizeof(double) * n4, cudaMemcpyDeviceToHost, c->stream));

@@ -45,6 +45,19 @@ def case_path(name):
     return os.path.join(CASES, name)
 
 
+def overlay_case(base, overlay, dst):
+    """Case directory = tests/golden/cases/<base> with the files of tests/golden/cases/<overlay> laid over it."""
+    import shutil
+    shutil.copytree(case_path(base), dst)
+    for root, _, files in os.walk(case_path(overlay)):
+        for f in files:
+            if f == "README":
+                continue
+            rel = os.path.relpath(os.path.join(root, f), case_path(overlay))
+            shutil.copy(os.path.join(root, f), os.path.join(dst, rel))
+    return dst
+
+
 def load_golden(name, variant):
     return np.load(os.path.join(GOLDEN, f"golden_{name}_{variant}.npz"))
 

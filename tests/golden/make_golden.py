@@ -42,6 +42,9 @@ RUNS = [
     ("Case_rktnoz9", "axi_cpg", 1, 1.4, 200),
     ("Case_rktnoz9", "axi_tpg", 1, -1.4, 200),
     ("Case_spikefine24", "axi_cpg", 1, 1.4, 200),
+    # the reference's nested variant FV/Case_spikefine24/Case: BC 5 (Bernoulli inflow, BoundaryConditions.cpp:135-146)
+    # on the right side of blocks 11 and 15; assembled from the base case + the overlay directory
+    ("Case_spikefine24_bc5", "axi_cpg", 1, 1.4, 200),
 ]
 FULL_STATE = {(r[0], r[1]) for r in RUNS}
 
@@ -56,10 +59,19 @@ RUNS_DG = [
 def main():
     if not run_ref.available():
         raise SystemExit("oracle/_ref/MPI2DFV missing: run oracle/build_ref.sh first")
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
     for name, variant, iaxi, igam, steps in (RUNS if "--dg-only" not in sys.argv else []):
-        case = Case.load(os.path.join(CASES, name))
+        if only and name not in only:
+            continue
+        case_dir = os.path.join(CASES, name)
+        if name == "Case_spikefine24_bc5":
+            import tempfile
+            sys.path.insert(0, os.path.dirname(HERE))
+            from conftest import overlay_case
+            case_dir = overlay_case("Case_spikefine24", name, os.path.join(tempfile.mkdtemp(), "case"))
+        case = Case.load(case_dir)
         shapes = [case.shape(b) for b in range(case.nblocks)]
-        out = run_ref.run(os.path.join(CASES, name), THERM, shapes, steps, iaxi=iaxi, igam=igam)
+        out = run_ref.run(case_dir, THERM, shapes, steps, iaxi=iaxi, igam=igam)
         assert not out["failed"], out["stdout_tail"]
         assert len(out["relres"]) == steps and len(out["dt"]) == steps
         data = dict(relres=out["relres"], dt=out["dt"], steps=np.int64(steps), iaxi=np.int64(iaxi), igam=np.float64(igam))
@@ -70,7 +82,7 @@ def main():
         path = os.path.join(HERE, f"golden_{name}_{variant}.npz")
         np.savez_compressed(path, **data)
         print(f"{path}: {steps} steps, {os.path.getsize(path) / 1e6:.2f} MB, relres[-1]={out['relres'][-1]:.6e}")
-    for name, variant, iaxi, igam, steps in RUNS_DG:
+    for name, variant, iaxi, igam, steps in (RUNS_DG if not only else []):
         case = Case.load(os.path.join(CASES, name))
         shapes = [case.shape(b) for b in range(case.nblocks)]
         out = run_ref.run(os.path.join(CASES, name), THERM, shapes, steps, iaxi=iaxi, igam=igam, accur=1)
