@@ -14,7 +14,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import case_path, flux_scales, load_golden, make_cfg, random_faces, random_states, state_err
+from conftest import GOLDEN, case_path, flux_scales, load_golden, make_cfg, random_faces, random_states, state_err
 import pointwise as pw
 from par2d_b200 import MODE_FAITHFUL, MODE_FAST, Case, Solver
 
@@ -378,3 +378,42 @@ def test_degenerate_block_shapes_vs_oracle(gpu, oracle, tmp_path, ncx, ncy, mode
     assert [i.status for i in ig] == [i.status for i in io]
     assert state_err(sg.get_state(0), so.get_state(0)) < TOL_STATE
     assert max(abs(a.relres / b.relres - 1.0) for a, b in zip(ig, io)) < TOL_HIST
+
+
+# ------------------------------------------------------------------ BC 5 (Bernoulli inflow) at case level
+
+def test_bc5_residual_vs_the_references_calc_dudt(gpu, tmp_path):
+    """Block 11 of the reference's nested FV/Case_spikefine24/Case variant (BC 5 on its right side,
+    BoundaryConditions.cpp:135-146) with a subsonic, partly reversed state: the device residual against the
+    fixture written by the UNMODIFIED reference's calc_dudt (tests/test_oracle_cpu.py::test_bc5_residual_port_vs_
+    reference_bitwise) - bit for bit in the faithful mode (no pow() on this path), 1e-11 of the residual scale in the
+    fast one."""
+    from test_oracle_cpu import bc5_block_case
+    single, _, u = bc5_block_case(tmp_path)
+    want = np.load(os.path.join(GOLDEN, "ref_dudt_bc5_block11.npz"))["dudt"]
+    for mode in (MODE_FAITHFUL, MODE_FAST):
+        s = Solver(single, make_cfg(gpu, 1, 1.4, mode), lib=gpu)
+        s.set_state(0, u)
+        got = s.get_residual(0)
+        if mode == MODE_FAITHFUL:
+            assert np.array_equal(got, want)
+        else:
+            scale = np.abs(want).reshape(-1, 4).max(axis=0)
+            assert (np.abs(got - want).reshape(-1, 4).max(axis=0) / scale).max() < 1e-11
+        s.close()
+
+
+@pytest.mark.parametrize("mode", [MODE_FAST, MODE_FAITHFUL])
+def test_bc5_case_nstep_vs_reference_golden(gpu, tmp_path, mode):
+    """The nested variant run for 200 steps by the unmodified reference (24 blocks, BC 5 on blocks 11 and 15)."""
+    from conftest import overlay_case
+    g = load_golden("Case_spikefine24_bc5", "axi_cpg")
+    case = Case.load(overlay_case("Case_spikefine24", "Case_spikefine24_bc5", str(tmp_path / "case")))
+    assert 5 in set(case.ibound(11)) and 5 in set(case.ibound(15))
+    s = Solver(case, make_cfg(gpu, 1, 1.4, mode), lib=gpu)
+    info = s.step(int(g["steps"]))
+    worst = max(state_err(s.get_state(b), g[f"b{b}"]) for b in range(case.nblocks))
+    # (the far-field faces of this case go through pow(): faithful is 2 ulp from the reference there, not bitwise)
+    assert worst <= (1e-13 if mode == MODE_FAITHFUL else TOL_STATE), worst
+    assert np.abs(np.array([i.relres for i in info]) / g["relres"] - 1).max() < 2e-6
+    s.close()

@@ -215,3 +215,54 @@ def test_references_converged_state_sits_at_its_committed_residual(oracle):
     expect = g["res_tail_relres"][2] + slope                           # the state was written after update 497227
     assert abs(relres[0] - expect) < 2e-11, (relres, expect)
     assert abs((relres[1] - relres[0]) - slope) < 0.2 * abs(slope)     # and keeps converging at the same rate
+
+
+# ---- BC 5 (Bernoulli inflow, BoundaryConditions.cpp:135-146) through the residual ----------------------------
+
+def bc5_block_case(tmp_path):
+    """Block 11 of the reference's nested FV/Case_spikefine24/Case variant (BC code 5 on its right side) as a
+    stand-alone one-block case, with a seeded state that is subsonic and partly reversed next to that side, so that
+    both branches of the Bernoulli inflow reach the flux.  Returns (case, ibound, state)."""
+    from conftest import overlay_case
+    from test_oracle_dg_cpu import _single_block_case
+    full = Case.load(overlay_case("Case_spikefine24", "Case_spikefine24_bc5", str(tmp_path / "bc5_full")))
+    x, y = full.nodes(11)
+    ib = np.ascontiguousarray(full.ibound(11), dtype=np.int32)
+    ny, nx = x.shape
+    assert set(ib[nx - 1:nx - 1 + ny - 1]) == {5}
+    ib[ib < 0] = 3                                   # stand-alone: interior faces become plain extrapolation
+    single = _single_block_case(tmp_path / "bc5_single", x, y, ib)
+    rng = np.random.default_rng(2025)
+    u = np.empty((ny - 1, nx - 1, 4))
+    u[..., 0] = rng.uniform(0.008, 0.02, u.shape[:2])
+    u[..., 1] = rng.uniform(-150.0, 500.0, u.shape[:2])
+    u[..., 2] = rng.uniform(-120.0, 120.0, u.shape[:2])
+    u[..., 3] = rng.uniform(250.0, 420.0, u.shape[:2])
+    return single, ib, u
+
+
+def test_bc5_residual_port_vs_reference_bitwise(oracle, ref, tmp_path):
+    single, ib, u = bc5_block_case(tmp_path)
+    s = Solver(single, make_cfg(oracle), lib=oracle)
+    s.set_state(0, u)
+    mine = s.get_residual(0)
+    assert ref.ref_init(ref._build_dir, 1, C.c_double(1.4)) == 0
+    IP = C.POINTER(C.c_int32)
+    ref.ref_calc_dudt.argtypes = [C.c_int, C.c_int, DP, DP, IP, DP, DP, DP]
+    xs, ys = single.nodes(0)
+    ny, nx = xs.shape
+    cfg = make_cfg(oracle)
+    uFS = np.array(list(cfg.uFS))
+    u2, out = u.copy(), np.zeros_like(u)
+    ref.ref_calc_dudt(nx, ny, _dp(np.ascontiguousarray(xs)), _dp(np.ascontiguousarray(ys)), ib.ctypes.data_as(IP), _dp(uFS), _dp(u2), _dp(out))
+    assert np.array_equal(mine, out)
+    # the ghost values matter here: with code 3 (extrapolation) on that side the residual of the last column differs
+    ib3 = ib.copy()
+    ib3[ib3 == 5] = 3
+    out3 = np.zeros_like(u)
+    ref.ref_calc_dudt(nx, ny, _dp(np.ascontiguousarray(xs)), _dp(np.ascontiguousarray(ys)), ib3.ctypes.data_as(IP), _dp(uFS), _dp(u.copy()), _dp(out3))
+    assert np.abs(out[:, -1] - out3[:, -1]).max() > 1e-3 * np.abs(out[:, -1]).max()
+    fixture = os.path.join(GOLDEN, "ref_dudt_bc5_block11.npz")
+    if os.environ.get("PAR2D_REGEN_GOLDEN") or not os.path.exists(fixture):
+        np.savez_compressed(fixture, dudt=out)
+    assert np.array_equal(np.load(fixture)["dudt"], out)

@@ -14,6 +14,7 @@ ap.add_argument("--steps", type=int, default=20000)
 ap.add_argument("--batch", type=int, default=2000)
 ap.add_argument("--ref-iters", type=int, default=1500)
 ap.add_argument("--out", default=None)
+ap.add_argument("--no-ref", action="store_true", help="skip the reference CPU runs")
 args = ap.parse_args()
 gpu = _capi.load_gpu()
 import run_ref
@@ -31,7 +32,7 @@ for name, igam in (("Case_ffstep1", 1.4), ("Case_ffstep8", 1.4), ("Case_rktnoz9"
     dt = time.perf_counter() - t0
     row = {"case": name, "gas": "CPG" if igam > 0 else "TPG (NASA-7)", "blocks": case.nblocks, "cells": case.ncells, "steps": done,
            "gpu_us_per_step": 1e6 * dt / done, "gpu_cell_updates_per_s": case.ncells * done / dt, "relres_last": info[-1].relres}
-    if run_ref.available() and igam > 0:
+    if run_ref.available() and igam > 0 and not args.no_ref:
         shapes = [case.shape(b) for b in range(case.nblocks)]
         tw = run_ref.run(path, therm, shapes, 100)["wall"]
         tf = run_ref.run(path, therm, shapes, 100 + args.ref_iters)["wall"]
