@@ -172,7 +172,10 @@ int par2d_step(par2d_ctx* ctx, int32_t nsteps, int32_t stop_on_tol, par2d_step_i
 /* par2d_step in two halves: _async queues the whole batch on the ctx stream and returns, _wait blocks until it has
  * completed and fills info[nsteps of the _async call].  One host thread can so drive the contexts of several GPUs
  * (par2d_peer_connect_local): _async on every ctx, then _wait on every ctx - the batches of peer-mapped contexts
- * depend on each other's progress. */
+ * depend on each other's progress.  That only works while the whole batch of the first ctx fits the driver's launch
+ * queue (a few dozen steps): a thread that blocks in a launch for ctx 0 never queues what ctx 0's kernels wait for.
+ * For longer batches drive each ctx from its own host thread with par2d_step (par2d_fv --gpus N and
+ * par2d_b200/local.py do). */
 int par2d_step_async(par2d_ctx* ctx, int32_t nsteps, int32_t stop_on_tol);
 int par2d_step_wait(par2d_ctx* ctx, par2d_step_info* info);
 
@@ -274,6 +277,11 @@ int par2d_test_solve(const par2d_config* cfg, int64_t n, const double* dt_ycc /*
  * their durations and the launch count.  bench.py derives roofline.achieved from it. */
 int par2d_kernel_timing(par2d_ctx* ctx, int32_t enable);
 int par2d_kernel_time(par2d_ctx* ctx, double* total_ms, int64_t* launches);
+
+/* Diagnostic of the persistent launch (ctx created with PAR2D_PROFILE_PERSIST=1 in the environment): for each of the
+ * first nsteps steps of the last batch, out[3*s + {0: SM cycles the first strip spent marching, 1: ... waiting at the
+ * grid barrier, 2: cycles of the first bookkeeping CTA}]. */
+int par2d_persist_profile(par2d_ctx* ctx, int64_t* out, int32_t nsteps);
 
 /* Number of CUDA devices this process sees (the reference asks MPI_Comm_size, FV/main.cpp:70-71). */
 int par2d_device_count(int32_t* n);

@@ -113,6 +113,7 @@ GPU_ONLY_API = {
     "synchronize": (C.c_int, [C.c_void_p]),
     "probe_fp64": (C.c_int, [C.c_int32, _DP]),
     "device_count": (C.c_int, [_IP]),
+    "persist_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "kernel_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "kernel_time": (C.c_int, [C.c_void_p, _DP, C.POINTER(C.c_int64)]),
 }

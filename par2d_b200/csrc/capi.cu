@@ -162,6 +162,7 @@ struct par2d_ctx {
     std::vector<BlockDev> hblk;
     std::vector<double*> block_mem;       // one allocation per owned block: 11 planes [state A x4][x y metric][state B x4]
     std::vector<int*> block_ibound;
+    std::vector<double2*> block_fnorm;
     BlockDev* dblk = nullptr;
     void* dtmaps = nullptr;
 
@@ -178,7 +179,6 @@ struct par2d_ctx {
     unsigned* ticket = nullptr;
     double* res0 = nullptr;
     double* blk_norm = nullptr;
-    double* blk_sum = nullptr;
     unsigned* flag_hist = nullptr;
     std::vector<unsigned> h_flag_hist;
     double* blk_hist = nullptr;
@@ -228,9 +228,16 @@ struct par2d_ctx {
     int n_push_tiles = 0;
     unsigned n_put_tiles = 0;        // strips of a launch that put something into a peer's arena
     bool fused = true;               // PAR2D_NO_OVERLAP=1: put -> ghost -> march as separate launches (A/B runs)
+    bool small_mesh = false;         // the GLOBAL mesh is small enough that a step is bound by latency, not by HBM: fused / persistent steps
+    long long global_cells = 0;
+    // large meshes across ranks: the strips that put something run first on a high-priority side stream, followed there by
+    // the put of the NEW state's lines; the interior strips run beside them on the main stream (tuned launch-per-step kernel)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_ghost = nullptr, ev_edge = nullptr;
     // persistent launch: a whole batch of a small mesh in one cooperative kernel
     int2* d_all_tiles = nullptr;
     unsigned* grid_bar = nullptr;
+    long long* prof = nullptr;       // PAR2D_PROFILE_PERSIST=1: per-step cycle counts of the persistent launch (par2d_persist_profile)
     int coop_capacity = 0;
     bool persist = true;             // PAR2D_NO_PERSIST=1: one launch per step (A/B runs)
     long long partials_stride = 0;   // doubles between the two parities of the strip sums
@@ -257,7 +264,6 @@ struct par2d_ctx {
     StepArgs step_args(int update) const {
         StepArgs a;
         a.blocks = dblk;
-        a.gas_dev = gas_dev;
         a.nowned = nowned;
         a.nblocks_global = nblocks;
         a.cur = cur;
@@ -271,6 +277,8 @@ struct par2d_ctx {
         a.launch_no = 0;
         a.coop_steps = 1;
         a.grid_bar = grid_bar;
+        a.prof = prof;
+        a.gas_dev = gas_dev;
         a.dt_used = dt_used + (iter_queued & 1);
         a.partials = partials + (iter_queued & 1) * partials_stride;
         a.flags = flags;
@@ -312,7 +320,6 @@ struct par2d_ctx {
         f.ticket = ticket;
         f.dt_used = dt_used + (iter_queued & 1);
         f.blk_norm = blk_norm;
-        f.blk_sum = blk_sum;
         f.flag_hist = flag_hist;
         f.flags = flags;
         memset(&f.stop_x, 0, sizeof f.stop_x);
@@ -391,9 +398,9 @@ PutArgs put_args(const par2d_ctx* c);
 
 // peer-mapped mode: produce the next exchange event from the current state with a launch of its own (start of a
 // batch; every step of the second-order branch and of the serial A/B order)
-void queue_put(par2d_ctx* c) {
+void queue_put(par2d_ctx* c, cudaStream_t stream = nullptr) {
     c->seq++;
-    c->kt->pack(c->stream, c->step_args(1), c->gas, c->dlines_peer, c->nlines, c->max_line, put_args(c));
+    c->kt->pack(stream ? stream : c->stream, c->step_args(1), c->gas, c->dlines_peer, c->nlines, c->max_line, put_args(c));
 }
 
 // The bookkeeping of a step (finalize) is deferred into the NEXT step's ghost launch, where it overlaps
@@ -482,6 +489,34 @@ PutArgs put_args(const par2d_ctx* c) {
     put.expected = c->n_put_tiles;
     put.dg = c->dg ? 1 : 0;
     return put;
+}
+
+// Large mesh across ranks: the exchange event of the state being read was produced before this call.
+//   main stream : ghost (waits for the peers' flags; previous step's bookkeeping) ... march(interior strips) ... wait(edge) ->
+//   side stream :           wait(ghost) -> march(strips that border another rank) -> put(new state's edge lines + dt, flag)
+// so the NVLink stores, the flag latency and the skew between GPUs hide behind the interior strips, and every strip runs
+// the tuned launch-per-step kernel.
+void queue_step_overlapped(par2d_ctx* c) {
+    StepArgs a = c->step_args(1);
+    a.dt_ready = 1;
+    c->kt->ghost(c->stream, a, c->gas, 0, c->fin_pending ? &c->fin_args : nullptr);
+    c->fin_pending = false;
+    cudaEventRecord(c->ev_ghost, c->stream);
+    cudaStreamWaitEvent(c->side_stream, c->ev_ghost, 0);
+    time_begin(c);
+    StepArgs ae = a, ai = a;
+    ae.tile_list = c->d_push_tiles; ae.tile_count = (int)c->n_put_tiles;
+    ai.tile_list = c->d_push_tiles + c->n_put_tiles; ai.tile_count = c->n_push_tiles - (int)c->n_put_tiles;
+    c->kt->march(c->side_stream, ae, c->gas, c->tpg, c->axi);
+    c->kt->march(c->stream, ai, c->gas, c->tpg, c->axi);
+    c->fin_args = c->finalize_args(0);
+    c->fin_pending = true;
+    c->iter_queued++;
+    c->cur ^= 1;
+    queue_put(c, c->side_stream);      // reads the NEW state's edge cells (all in those strips) and cell (0,0) of every block
+    cudaEventRecord(c->ev_edge, c->side_stream);
+    cudaStreamWaitEvent(c->stream, c->ev_edge, 0);
+    time_end(c);
 }
 
 // The fused step (first-order path): ONE launch = the bookkeeping of the previous step (leading CTAs) + every strip;
@@ -688,7 +723,12 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
                                                     // multi-GPU job derives the same strips (and with them the same summation order)
         long long rows = global_cells / (MCELLS * want_strips);
         rows -= rows & 1;
-        c->march_rows = (int)std::min<long long>(64, std::max<long long>(4, rows));
+        c->march_rows = (int)std::min<long long>(64, std::max<long long>(2, rows));
+        c->global_cells = global_cells;
+        // below ~2 M cells a step is a few tens of microseconds: bound by launch and dependency latency, not by HBM
+        c->small_mesh = global_cells < (2ll << 20);
+        const char* sm = getenv("PAR2D_SMALL_MESH");   // A/B runs: force the choice (0 / 1)
+        if (sm) c->small_mesh = atoi(sm) != 0;
     }
     const char* mrows = getenv("PAR2D_MARCH_ROWS");
     if (mrows && atoi(mrows) > 0) c->march_rows = atoi(mrows);
@@ -743,6 +783,7 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
     c->hblk.resize(c->nowned);
     c->block_mem.assign(c->nowned, nullptr);
     c->block_ibound.assign(c->nowned, nullptr);
+    c->block_fnorm.assign(c->nowned, nullptr);
     long long max_cells = 0, max_nodes = 0;
     for (int k = 0; k < c->nowned; k++) {
         const int g = c->owned_gid[k];
@@ -765,6 +806,8 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
         CU_TRY(cudaMalloc(&c->block_ibound[k], sizeof(int) * nfaces));
         CU_TRY(cudaMemcpyAsync(c->block_ibound[k], d.ibound, sizeof(int) * nfaces, cudaMemcpyHostToDevice, c->stream));
         b.ibound = c->block_ibound[k];
+        CU_TRY(cudaMalloc(&c->block_fnorm[k], sizeof(double2) * nfaces));
+        b.fnorm = c->block_fnorm[k];
         b.ux = b.uy = b.uxt = b.uyt = nullptr;
         for (int s = 0; s < 4; s++) b.ghost2[s] = nullptr;
         b.dg_tile0 = b.dg_ntiles = 0;
@@ -840,6 +883,7 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
         CU_TRY(cudaMemcpyAsync(c->staging + nn, d.y, sizeof(double) * nn, cudaMemcpyHostToDevice, c->stream));
         launch_nodes_to_planes(c->stream, b, c->staging, c->staging + nn);
         launch_cell_metric(c->stream, b, c->axi ? 1 : 0);
+        launch_face_normals(c->stream, b, c->block_fnorm[k]);
         const long long cells = (long long)b.ncx * b.ncy;
         const int nparts = (int)std::min<long long>(1024, (cells + 255) / 256);
         launch_min_face(c->stream, b, dparts, nparts);
@@ -906,11 +950,12 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
         const char* np = getenv("PAR2D_NO_PERSIST");
         c->persist = !(np && atoi(np) != 0);
         c->coop_capacity = (cfg->nranks == 1 && !c->dg) ? c->kt->coop_capacity(c->tpg, c->axi) : 0;
+        const char* pp = getenv("PAR2D_PROFILE_PERSIST");
+        if (pp && atoi(pp) != 0) { CU_TRY(cudaMalloc(&c->prof, sizeof(long long) * 3 * 4096)); CU_TRY(cudaMemset(c->prof, 0, sizeof(long long) * 3 * 4096)); }
     }
     c->partials_stride = 4ll * c->total_tiles;
     CU_TRY(cudaMalloc(&c->gas_dev, sizeof(Gas)));
     CU_TRY(cudaMemcpyAsync(c->gas_dev, &c->gas, sizeof(Gas), cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(cudaMalloc(&c->blk_sum, sizeof(double) * 2 * c->nowned));
     CU_TRY(cudaMalloc(&c->grid_bar, sizeof(unsigned)));
     CU_TRY(cudaMalloc(&c->go, sizeof(int)));
     CU_TRY(cudaMalloc(&c->stop_iter, sizeof(long long)));
@@ -947,6 +992,7 @@ int par2d_destroy(par2d_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (double* p : c->block_mem) cudaFree(p);
     for (int* p : c->block_ibound) cudaFree(p);
+    for (double2* p : c->block_fnorm) cudaFree(p);
     par2d_peer_disconnect(c);
     for (Peer& p : c->peers) cudaFree(p.d_send);
     if (c->arena) cudaFree(c->arena); else cudaFree(c->dt_table);
@@ -954,7 +1000,8 @@ int par2d_destroy(par2d_ctx* c) {
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (int q = 0; q < 2; q++) { if (c->ev_ready[q]) cudaEventDestroy(c->ev_ready[q]); if (c->ev_free[q]) cudaEventDestroy(c->ev_free[q]); }
     cudaFree(c->staging2);
-    cudaFree(c->d_all_tiles); cudaFree(c->gas_dev); cudaFree(c->blk_sum); cudaFree(c->grid_bar); cudaFree(c->go); cudaFree(c->stop_iter); cudaFree(c->flag_hist);
+    cudaFree(c->prof);
+    cudaFree(c->d_all_tiles); cudaFree(c->gas_dev); cudaFree(c->grid_bar); cudaFree(c->go); cudaFree(c->stop_iter); cudaFree(c->flag_hist);
     for (double* m : c->dg_mem) cudaFree(m);
     cudaFree(c->dg_partials);
     cudaFree(c->dblk); cudaFree(c->dtmaps); cudaFree(c->partials); cudaFree(c->flags);
@@ -1149,9 +1196,15 @@ int par2d_step_async(par2d_ctx* c, int32_t nsteps, int32_t stop_on_tol) {
     c->batch_steps = nsteps;
     c->batch_seq0 = c->seq;
     c->batch_stop = stop_on_tol && c->peer_connected;
+    // Which step?  (the choice depends on the GLOBAL mesh and the arguments only, so every rank makes the same one)
+    //   small mesh, or a stop test across ranks : the fused step - one launch per step, or the whole batch in one
+    //                                             persistent launch (single rank) - built for latency
+    //   large mesh                              : the tuned launch-per-step kernel behind a ghost launch; across ranks
+    //                                             with the edge strips + put overlapped on a side stream
+    const bool use_fused = c->fused && !c->dg && (c->small_mesh || (stop_on_tol && c->peer_connected));
     if (c->peer_connected) {
         // collective batch, no host transport
-        if (c->fused && !c->dg) {
+        if (use_fused) {
             // the current state's lines + dt (a launch of its own: the state may come from par2d_set_state), the ghost
             // ring by the pull kernel, then one launch per step; the last step leaves the final state's lines in the arenas
             if (c->batch_stop) CU_TRY(cudaMemsetAsync(c->go, 0, sizeof(int), c->stream));
@@ -1159,6 +1212,9 @@ int par2d_step_async(par2d_ctx* c, int32_t nsteps, int32_t stop_on_tol) {
             StepArgs a0 = c->step_args(1);
             c->kt->ghost(c->stream, a0, c->gas, 0, nullptr);
             for (int s = 0; s < nsteps; s++) queue_step_fused(c, s + 1, stop_on_tol);
+        } else if (c->fused && !c->dg) {
+            queue_put(c);              // the first state's lines; every step then produces the next state's
+            for (int s = 0; s < nsteps; s++) queue_step_overlapped(c);
         } else {
             // every step is  put (edge lines + dt_b into the neighbours' arenas, flag) -> ghost (waits for the
             // flags) -> march [-> limiter]; the trailing put leaves the final state's lines for par2d_get_residual
@@ -1168,15 +1224,15 @@ int par2d_step_async(par2d_ctx* c, int32_t nsteps, int32_t stop_on_tol) {
             }
             queue_put(c);
         }
-    } else if (c->dg || !c->fused) {
+    } else if (!use_fused) {
         for (int s = 0; s < nsteps; s++) queue_step(c, stop_on_tol, true);
     } else if (nsteps > 0) {
         // ghost ring + per-block dt of the current state by the pull kernel (it may come from par2d_set_state); every
         // step after that pushes them for the next one
         StepArgs a0 = c->step_args(1);
         c->kt->ghost(c->stream, a0, c->gas, 1, nullptr);
-        const bool small = c->persist && c->coop_capacity >= c->total_tiles + c->nowned;
-        if (!(small && queue_batch_persistent(c, nsteps, stop_on_tol)))
+        const bool fits = c->persist && c->coop_capacity >= c->total_tiles + c->nowned;
+        if (!(fits && queue_batch_persistent(c, nsteps, stop_on_tol)))
             for (int s = 0; s < nsteps; s++) queue_step_fused(c, s + 1, stop_on_tol);
     }
     flush_finalize(c);
@@ -1353,6 +1409,13 @@ static int finish_connect(par2d_ctx* c) {
         CU_TRY(cudaMalloc(&c->d_push_tiles, sizeof(int2) * first.size()));
         CU_TRY(cudaMemcpy(c->d_push_tiles, first.data(), sizeof(int2) * first.size(), cudaMemcpyHostToDevice));
     }
+    if (!c->side_stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        CU_TRY(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, hi));   // edge strips + put ahead of interior strips
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_ghost, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming));
+    }
     c->peer_connected = true;
     return 0;
 }
@@ -1469,6 +1532,9 @@ int par2d_peer_disconnect(par2d_ctx* c) {
             if ((int)p != c->cfg.rank && c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
     c->peer_base.clear();
     c->peer_connected = false;
+    if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); c->side_stream = nullptr; }
+    if (c->ev_ghost) { cudaEventDestroy(c->ev_ghost); c->ev_ghost = nullptr; }
+    if (c->ev_edge) { cudaEventDestroy(c->ev_edge); c->ev_edge = nullptr; }
     cudaFree(c->d_push_tiles); cudaFree(c->dlines_peer); cudaFree(c->d_dt_dst); cudaFree(c->d_flag_dst); cudaFree(c->d_res_dst); cudaFree(c->d_rflag_dst);
     c->d_push_tiles = nullptr; c->dlines_peer = nullptr; c->d_dt_dst = nullptr; c->d_flag_dst = nullptr; c->d_res_dst = nullptr; c->d_rflag_dst = nullptr;
     return 0;
@@ -1590,6 +1656,14 @@ int par2d_test_solve(const par2d_config* cfg, int64_t n, const double* dt_ycc, c
     kt->test_solve(0, g, !(cfg->igam > 0), cfg->iaxi == 1, n, (double*)dy.p, (double*)du.p, (double*)dr.p, (double*)dd.p);
     CU_TRY(cudaDeviceSynchronize());
     CU_TRY(cudaMemcpy(dv, dd.p, 32 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int par2d_persist_profile(par2d_ctx* c, int64_t* out, int32_t nsteps) {
+    if (!c || !out || nsteps < 0 || nsteps > 4096) return fail(PAR2D_ERR_ARG, "persist_profile: bad argument");
+    if (!c->prof) return fail(PAR2D_ERR_ARG, "persist_profile: create the ctx with PAR2D_PROFILE_PERSIST=1 in the environment");
+    if (use_device(c)) return PAR2D_ERR_CUDA;
+    CU_TRY(cudaMemcpy(out, c->prof, sizeof(long long) * 3 * nsteps, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -39,6 +39,8 @@ struct BlockDev {
     double* state[2];   // 4 planes each
     double* nodes;      // 3 planes: x, y, cell metric
     const int* ibound;  // BC code per boundary face, CCW (SpatialDiscretization.cpp:27,45,64,84)
+    const double2* fnorm; // outward unit normal per boundary face, same CCW index (SpatialDiscretization.cpp:33-34,51-52,71-72,
+                        // 91-92 over MeshModule.cpp:52-81; the right side takes the normals of column 0, as the reference does)
     int nb_kind[4];     // NB_* per side
     int nb_block[4];    // owned-block index of a same-rank neighbour
     int nb_side[4];     // the neighbour's side that faces us
@@ -109,7 +111,6 @@ struct StopArgs {
 
 struct StepArgs {
     const BlockDev* blocks;
-    const Gas* gas_dev;      // the Gas constants in global memory (for the non-inlined boundary-condition code)
     int nowned;
     int nblocks_global;
     int cur;                 // state buffer read this step
@@ -146,6 +147,10 @@ struct StepArgs {
     int launch_no;           // 1-based launch number within the batch (stop test across ranks)
     int coop_steps;          // persistent launch: steps advanced inside the kernel (else 1)
     unsigned* grid_bar;      // persistent launch: grid barrier counter
+    const Gas* gas_dev;      // the Gas constants in global memory (for the non-inlined boundary-condition code)
+    long long* prof;         // diagnostics of the persistent launch (null in production), see march_persist_kernel
+    // (new members go at the END: the offsets of the members above are part of what the tuned launch-per-step kernel was
+    //  compiled against - ptxas schedules its row loop differently when they move, see march.cuh)
 };
 
 struct FinalizeArgs {
@@ -161,7 +166,6 @@ struct FinalizeArgs {
     unsigned* ticket;        // last-block-done counter
     const double* dt_used;   // StepArgs::dt_used of the step being finalised
     double* blk_norm;        // [nowned][4] per-block residual norms (scratch between the block CTAs and the last one)
-    double* blk_sum;         // [nowned][2] per-block sums of the step being finalised (scratch of the last CTA)
     double tol;
     int stop_on_tol;
     int hist_cap;

@@ -84,7 +84,10 @@ static __device__ __forceinline__ bool wait_peers_warp(const unsigned long long*
 
 // per-block time step from cell (0,0) of state S: find_dt, main.cpp:19-37 (the static min over the face
 // lengths is BlockDev::min_face)
-static __device__ __noinline__ double block_dt_value(const double* S, long long plane, int pitch, double min_face, double gamRs, double cfl) {
+#ifndef HALO_NOINLINE
+#define HALO_NOINLINE __noinline__
+#endif
+static __device__ HALO_NOINLINE double block_dt_value(const double* S, long long plane, int pitch, double min_face, double gamRs, double cfl) {
     const long long o = (long long)pitch + COL0;
     const double u = __ldcg(S + plane + o), v = __ldcg(S + 2 * plane + o), T = __ldcg(S + 3 * plane + o);
     const double v2 = u * u + v * v;
@@ -92,24 +95,29 @@ static __device__ __noinline__ double block_dt_value(const double* S, long long 
     return cfl * min_face / vmax;
 }
 
+// CCW index of boundary face n of a side = index into ibound[] and fnorm[] (SpatialDiscretization.cpp:27,45,64,84)
+__device__ __forceinline__ int face_index(int ncx, int ncy, int side, int n) {
+    switch (side) {
+        case SIDE_BOTTOM: return n;
+        case SIDE_RIGHT: return ncx + n;
+        case SIDE_TOP: return 2 * ncx + ncy - 1 - n;
+        default: return 2 * ncx + 2 * ncy - 1 - n;
+    }
+}
+
 // Ghost cell of boundary face n of side `side` of block b, computed from and written into the state buffer S
-// (generate_ghost_cells, SpatialDiscretization.cpp:17-99): outward normal (:33-34,51-52,71-72,91-92; the right
-// side reads the normal of column 0, as the reference does), boundary_state, the ghost's T clamp.  The ghost
-// keeps its present value if the boundary condition leaves it unwritten.  Arguments are pointers to GLOBAL
-// memory (a by-reference kernel parameter would be copied to the stack by every CTA).
-static __device__ __noinline__ void bc_ghost_fill(const Gas* gp, const BlockDev* bp, double* S, int side, int n) {
+// (generate_ghost_cells, SpatialDiscretization.cpp:17-99): outward normal (precomputed once, BlockDev::fnorm),
+// boundary_state, the ghost's T clamp.  The ghost keeps its present value if the boundary condition leaves it
+// unwritten.  Arguments are pointers to GLOBAL memory (a by-reference kernel parameter would be copied to the stack
+// by every CTA).  The derived interior quantities are only evaluated for the codes that read them (the far field
+// needs the sound speed and the pressure, the Bernoulli inflow the kinetic energy): walls and extrapolation, most
+// of every perimeter, cost neither a square root nor a division.
+static __device__ HALO_NOINLINE void bc_ghost_fill(const Gas* gp, const BlockDev* bp, double* S, int side, int n) {
     const Gas& g = *gp;
     const BlockDev& b = *bp;
-    const double* X = b.nodes;
-    const double* Y = b.nodes + b.plane;
-    long long p0, p1;
-    double sgn;
-    int code;
-    if (side == SIDE_BOTTOM) { p0 = (long long)b.pitch + COL0 + n; p1 = p0 + 1; sgn = 1.0; code = b.ibound[n]; }
-    else if (side == SIDE_RIGHT) { p0 = (long long)(n + 1) * b.pitch + COL0; p1 = p0 + b.pitch; sgn = 1.0; code = b.ibound[b.ncx + n]; }
-    else if (side == SIDE_TOP) { p0 = (long long)(b.ncy + 1) * b.pitch + COL0 + n; p1 = p0 + 1; sgn = -1.0; code = b.ibound[2 * b.ncx + b.ncy - 1 - n]; }
-    else { p0 = (long long)(n + 1) * b.pitch + COL0; p1 = p0 + b.pitch; sgn = -1.0; code = b.ibound[2 * b.ncx + 2 * b.ncy - 1 - n]; }
-    const FaceGeom fg = face_geom<true>(X[p0], Y[p0], X[p1], Y[p1]);   // O(perimeter): unit normal as MeshModule.cpp:52-81
+    const int f = face_index(b.ncx, b.ncy, side, n);
+    const int code = __ldg(b.ibound + f);
+    const double2 nrm = __ldg(b.fnorm + f);
     int c, r;
     edge_cell_pos(b.ncx, b.ncy, side, n, c, r);
     const long long io = (long long)r * b.pitch + c;
@@ -118,10 +126,10 @@ static __device__ __noinline__ void bc_ghost_fill(const Gas* gp, const BlockDev*
     double ui[4], gh[4];
 #pragma unroll
     for (int v = 0; v < 4; v++) { ui[v] = __ldcg(S + v * b.plane + io); gh[v] = __ldcg(S + v * b.plane + go); }
-    const double v2 = ui[1] * ui[1] + ui[2] * ui[2];
-    const double p = fmax(ui[0] * g.Rs * ui[3], 1.0);
-    const double aint = sqrt(g.gamRs * ui[3]);
-    boundary_state(g, code, sgn * fg.nx, sgn * fg.ny, ui, aint, p, v2, gh);
+    double v2 = 0.0, p = 0.0, aint = 0.0;
+    if (code == 1) { p = fmax(ui[0] * g.Rs * ui[3], 1.0); aint = sqrt(g.gamRs * ui[3]); }
+    if (code == 5) v2 = ui[1] * ui[1] + ui[2] * ui[2];
+    boundary_state(g, code, nrm.x, nrm.y, ui, aint, p, v2, gh);
 #pragma unroll
     for (int v = 0; v < 4; v++) __stcg(S + v * b.plane + go, gh[v]);
 }

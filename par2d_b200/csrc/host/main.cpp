@@ -11,8 +11,9 @@
 //            ACCUR = 1: <out>/time/solution.b%03d.it%05d.tec         (FV/FileIO.cpp:121-128)
 // The reference is one MPI rank per block (main.cpp:68-74,125-142); here ONE process drives --gpus N
 // GPUs: the blocks are partitioned over N contexts (par2d_case_partition), the contexts are connected
-// through peer-mapped arenas (par2d_peer_connect_local) and every batch is queued on all of them before
-// any is waited for (par2d_step_async / par2d_step_wait).  The residual is gathered in global block order
+// through peer-mapped arenas (par2d_peer_connect_local) and every batch is advanced by one host thread per
+// context (the contexts' kernels wait for each other: a single thread that blocks while queueing for one
+// context would never queue what that context waits for).  The residual is gathered in global block order
 // (main.cpp:379-392) and the tolerance break of multi-block runs (main.cpp:506-531) is decided on the
 // device from the sums of all contexts, so every GPU stops after the same iteration.
 #include <sys/stat.h>
@@ -23,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "par2d_gpu.h"
@@ -164,12 +166,21 @@ int main(int argc, char** argv) {
         }
         // the reference only tests the tolerance in multi-block runs (main.cpp:506)
         const int stop = nb > 1 ? 1 : 0;
-        for (int r = 0; r < ngpus && !rc; r++) rc = par2d_step_async(ctx[r], (int)n, stop);
-        if (rc) { printf("par2d_step_async: %s\n", par2d_last_error()); break; }
-        for (int r = 0; r < ngpus; r++) {
-            const int e = par2d_step_wait(ctx[r], info[r].data());
-            if (e && !rc) { rc = e; printf("Failed Assert on the device (context %d): %s\n", r, par2d_last_error()); }
+        std::vector<int> rcs(ngpus, 0);
+        std::vector<std::string> errs(ngpus);
+        auto advance = [&](int r) {
+            rcs[r] = par2d_step(ctx[r], (int)n, stop, info[r].data());
+            if (rcs[r]) errs[r] = par2d_last_error();      // the error text is per thread
+        };
+        if (ngpus == 1) {
+            advance(0);
+        } else {
+            std::vector<std::thread> workers;
+            for (int r = 0; r < ngpus; r++) workers.emplace_back(advance, r);
+            for (std::thread& w : workers) w.join();
         }
+        for (int r = 0; r < ngpus; r++)
+            if (rcs[r] && !rc) { rc = rcs[r]; printf("Failed Assert on the device (context %d): %s\n", r, errs[r].c_str()); }
         long done = 0;
         while (done < n && info[0][done].iter >= 0) done++;
         if (ngpus > 1 && done > 0) {

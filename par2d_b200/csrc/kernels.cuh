@@ -37,9 +37,7 @@ __global__ void __launch_bounds__(256) ghost_kernel(StepArgs a, Gas g, int write
     // rows 0..nfin-1 of the grid: the residual bookkeeping of the PREVIOUS step (nfin = owned blocks, or 0
     // when nothing is pending), overlapped with this step's ghost fill
     if ((int)blockIdx.y < nfin) {
-        __shared__ double red[256][4];
-        __shared__ bool last;
-        if (blockIdx.x == 0) finalize_block(fin, blockIdx.y, red, &last);
+        if (blockIdx.x == 0 && threadIdx.x < 32) finalize_block(fin, blockIdx.y);
         return;
     }
     if (a.wait_flags != nullptr) {
@@ -274,12 +272,8 @@ struct Launch {
     static void march_h(cudaStream_t s, const StepArgs& a, const Gas& g, bool tpg, bool axi) {
         const dim3 grid = a.tile_list ? dim3(a.tile_count, 1) : dim3(a.max_tiles, a.nowned);   // one warp strip per CTA
         if (a.tile_list && a.tile_count == 0) return;
-        PutArgs put;
-        FinalizeArgs fin;
-        memset(&put, 0, sizeof put);
-        memset(&fin, 0, sizeof fin);
-        if (tpg) { if (axi) march_kernel<FAITHFUL, true, true, HOOKS, false><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); else march_kernel<FAITHFUL, true, false, HOOKS, false><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); }
-        else { if (axi) march_kernel<FAITHFUL, false, true, HOOKS, false><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); else march_kernel<FAITHFUL, false, false, HOOKS, false><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); }
+        if (tpg) { if (axi) march_kernel<FAITHFUL, true, true, HOOKS><<<grid, MARCH_THREADS, 0, s>>>(a, g); else march_kernel<FAITHFUL, true, false, HOOKS><<<grid, MARCH_THREADS, 0, s>>>(a, g); }
+        else { if (axi) march_kernel<FAITHFUL, false, true, HOOKS><<<grid, MARCH_THREADS, 0, s>>>(a, g); else march_kernel<FAITHFUL, false, false, HOOKS><<<grid, MARCH_THREADS, 0, s>>>(a, g); }
     }
     // the production step (advancing, no residual dump) runs the instantiation without the test hooks
     static void march(cudaStream_t s, const StepArgs& a, const Gas& g, bool tpg, bool axi) {
@@ -290,8 +284,8 @@ struct Launch {
     static void march_push(cudaStream_t s, const StepArgs& a, const Gas& g, const PutArgs& put, const FinalizeArgs& fin, bool tpg, bool axi) {
         // across ranks: tile-list order; single rank: (strips of the largest block, [bookkeeping row +] owned blocks)
         const dim3 grid = a.tile_list ? dim3(a.nfin + a.tile_count, 1) : dim3(a.max_tiles > a.nfin ? a.max_tiles : a.nfin, a.nowned + (a.nfin ? 1 : 0));
-        if (tpg) { if (axi) march_kernel<FAITHFUL, true, true, false, true><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); else march_kernel<FAITHFUL, true, false, false, true><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); }
-        else { if (axi) march_kernel<FAITHFUL, false, true, false, true><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); else march_kernel<FAITHFUL, false, false, false, true><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); }
+        if (tpg) { if (axi) march_fused_kernel<FAITHFUL, true, true><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); else march_fused_kernel<FAITHFUL, true, false><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); }
+        else { if (axi) march_fused_kernel<FAITHFUL, false, true><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); else march_fused_kernel<FAITHFUL, false, false><<<grid, MARCH_THREADS, 0, s>>>(a, g, put, fin); }
     }
     // Loads every kernel a ctx of this gas model can launch.  With CUDA's lazy module loading the FIRST launch of a
     // kernel may need the context to go idle - a deadlock if a kernel of another ctx of the same process is spinning
@@ -307,11 +301,11 @@ struct Launch {
         touch((const void*)dg_limit_kernel<FAITHFUL>);
         touch(coop_fn(tpg, axi));
         if (tpg) {
-            if (axi) { touch((const void*)march_kernel<FAITHFUL, true, true, false, false>); touch((const void*)march_kernel<FAITHFUL, true, true, true, false>); touch((const void*)march_kernel<FAITHFUL, true, true, false, true>); touch((const void*)dg_cell_kernel<FAITHFUL, true, true>); }
-            else { touch((const void*)march_kernel<FAITHFUL, true, false, false, false>); touch((const void*)march_kernel<FAITHFUL, true, false, true, false>); touch((const void*)march_kernel<FAITHFUL, true, false, false, true>); touch((const void*)dg_cell_kernel<FAITHFUL, true, false>); }
+            if (axi) { touch((const void*)march_kernel<FAITHFUL, true, true, false>); touch((const void*)march_kernel<FAITHFUL, true, true, true>); touch((const void*)march_fused_kernel<FAITHFUL, true, true>); touch((const void*)dg_cell_kernel<FAITHFUL, true, true>); }
+            else { touch((const void*)march_kernel<FAITHFUL, true, false, false>); touch((const void*)march_kernel<FAITHFUL, true, false, true>); touch((const void*)march_fused_kernel<FAITHFUL, true, false>); touch((const void*)dg_cell_kernel<FAITHFUL, true, false>); }
         } else {
-            if (axi) { touch((const void*)march_kernel<FAITHFUL, false, true, false, false>); touch((const void*)march_kernel<FAITHFUL, false, true, true, false>); touch((const void*)march_kernel<FAITHFUL, false, true, false, true>); touch((const void*)dg_cell_kernel<FAITHFUL, false, true>); }
-            else { touch((const void*)march_kernel<FAITHFUL, false, false, false, false>); touch((const void*)march_kernel<FAITHFUL, false, false, true, false>); touch((const void*)march_kernel<FAITHFUL, false, false, false, true>); touch((const void*)dg_cell_kernel<FAITHFUL, false, false>); }
+            if (axi) { touch((const void*)march_kernel<FAITHFUL, false, true, false>); touch((const void*)march_kernel<FAITHFUL, false, true, true>); touch((const void*)march_fused_kernel<FAITHFUL, false, true>); touch((const void*)dg_cell_kernel<FAITHFUL, false, true>); }
+            else { touch((const void*)march_kernel<FAITHFUL, false, false, false>); touch((const void*)march_kernel<FAITHFUL, false, false, true>); touch((const void*)march_fused_kernel<FAITHFUL, false, false>); touch((const void*)dg_cell_kernel<FAITHFUL, false, false>); }
         }
         cudaGetLastError();
     }

@@ -9,18 +9,13 @@
 namespace par2d {
 
 // Stand-alone launch of the step bookkeeping (end of a batch; see finalize_block in kernels_common.cuh).
-__global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
+__global__ void __launch_bounds__(32) finalize_kernel(FinalizeArgs a) {
     if (*a.stop) return;
-    __shared__ double red[256][4];
-    __shared__ bool last;
-    finalize_block(a, blockIdx.x, red, &last);
+    finalize_block(a, blockIdx.x);
 }
 
-// see Launch::preload (kernels.cuh)
-void preload_common();
-
 void launch_finalize(cudaStream_t s, const FinalizeArgs& a) {
-    finalize_kernel<<<a.nowned, 256, 0, s>>>(a);
+    finalize_kernel<<<a.nowned, 32, 0, s>>>(a);
 }
 
 // AoS unk[(j*ncx+i)*4+k] (FV/Indexing.h:11) -> padded planes; applies the T clamp that
@@ -102,6 +97,29 @@ void launch_nodes_to_planes(cudaStream_t s, const BlockDev& b, const double* x, 
     nodes_to_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(b, x, y);
 }
 
+// Outward unit normals of the boundary faces, CCW like ibound[] (generate_ghost_cells, SpatialDiscretization.cpp:
+// 33-34,51-52,71-72,91-92): bottom +n(i,0), right +n of column 0 (the reference reads geofa[0,j], not column nx-1),
+// top -n(i,ny-1), left -n(0,j), n = (dy,-dx)/len as MeshModule.cpp:52-81 - IEEE operations, no contraction (this TU).
+__global__ void face_normals_kernel(BlockDev b, double2* out) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ncx = b.ncx, ncy = b.ncy;
+    if (f >= 2 * (ncx + ncy)) return;
+    const double* X = b.nodes;
+    const double* Y = b.nodes + b.plane;
+    long long p0, p1;
+    double sgn;
+    if (f < ncx) { p0 = (long long)b.pitch + COL0 + f; p1 = p0 + 1; sgn = 1.0; }
+    else if (f < ncx + ncy) { p0 = (long long)(f - ncx + 1) * b.pitch + COL0; p1 = p0 + b.pitch; sgn = 1.0; }
+    else if (f < 2 * ncx + ncy) { const int n = 2 * ncx + ncy - 1 - f; p0 = (long long)(ncy + 1) * b.pitch + COL0 + n; p1 = p0 + 1; sgn = -1.0; }
+    else { const int n = 2 * ncx + 2 * ncy - 1 - f; p0 = (long long)(n + 1) * b.pitch + COL0; p1 = p0 + b.pitch; sgn = -1.0; }
+    const FaceGeom fg = face_geom<true>(X[p0], Y[p0], X[p1], Y[p1]);
+    out[f] = make_double2(sgn * fg.nx, sgn * fg.ny);
+}
+void launch_face_normals(cudaStream_t s, const BlockDev& b, double2* out) {
+    const int n = 2 * (b.ncx + b.ncy);
+    face_normals_kernel<<<(n + 255) / 256, 256, 0, s>>>(b, out);
+}
+
 // min over cells of the two face lengths leaving node (i,j), seeded with 1.0
 // (main.cpp:26-32 over geofa[.,.,0] and geofa[.,.,3], MeshModule.cpp:56,74).  min is
 // order independent, so a parallel reduction reproduces the serial value exactly.
@@ -160,6 +178,7 @@ void preload_common() {
     cudaFuncGetAttributes(&fa, (const void*)nodes_to_planes_kernel);
     cudaFuncGetAttributes(&fa, (const void*)cell_metric_kernel);
     cudaFuncGetAttributes(&fa, (const void*)min_face_kernel);
+    cudaFuncGetAttributes(&fa, (const void*)face_normals_kernel);
     cudaGetLastError();
 }
 

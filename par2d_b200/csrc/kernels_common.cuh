@@ -4,14 +4,14 @@
 #include "common.cuh"
 namespace par2d {
 
-// Residual bookkeeping of one step (main.cpp:39-57,365-392,494).  Called by one CTA per owned block k (any
-// CTA size that divides 256: the stand-alone finalize_kernel uses 256 threads, the finalize role inside the
-// fused step kernel one warp): sums the block's strip partials in a FIXED order - 256 virtual threads take
-// the strips thread-strided, then a binary tree over the 256 sums, exactly the order of a 256-thread
-// shared-memory reduction whatever the real CTA size - and takes the square roots (main.cpp:53-56); the
-// last CTA to finish adds the blocks in block order and appends dt, sum ||res||, sum res0 and relres to the
-// device history.  No multiply-add is involved, so the result does not depend on the contraction mode of
-// the including TU.
+// Residual bookkeeping of one step (main.cpp:39-57,365-392,494).  Called by the first WARP of one CTA per owned
+// block k (the stand-alone finalize_kernel, the bookkeeping rows of the ghost kernel, the bookkeeping CTAs of the
+// fused / persistent step kernels): sums the block's strip partials in a FIXED order - lane l adds strips l, l+32,
+// l+64, ... in that order, then a xor-shuffle tree over the 32 lane sums - and takes the square roots
+// (main.cpp:53-56); the last CTA to finish adds the blocks in block order and appends dt, sum ||res||, sum res0 and
+// relres to the device history.  No multiply-add is involved, so the result does not depend on the contraction
+// mode of the including TU; one warp does all of it in ~2 us for the 100-strip blocks of the shipped cases, which
+// is what lets it ride inside a persistent launch without holding up the steps.
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long fin_ld_acquire_sys(const unsigned long long* p) {
     unsigned long long v;
@@ -22,87 +22,87 @@ __device__ __forceinline__ void fin_st_release_sys(unsigned long long* p, unsign
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__device__ __forceinline__ void finalize_block(const FinalizeArgs& a, int k, double (*red)[4], bool* last) {
-    const int tid = threadIdx.x, nt = blockDim.x;
+// Threads beyond the first warp of the CTA must not call this.
+__device__ __forceinline__ void finalize_block(const FinalizeArgs& a, int k) {
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
     const BlockDev& b = a.blocks[k];
-    double norm[4] = {0.0, 0.0, 0.0, 0.0};   // thread 0: the block's norms
+    double norm[4] = {0.0, 0.0, 0.0, 0.0};
     // first order: one group of 4 sums; second-order branch: three groups (dudt, duxdt, duydt) whose square roots
     // are added as main.cpp:360-364 does, ressum + (ressumx + ressumy)
     const int ngroups = a.dg_partials ? 3 : 1;
-    double parked[4] = {0.0, 0.0, 0.0, 0.0};   // thread 0: ressumx while ressumy is being reduced
+    double parked[4] = {0.0, 0.0, 0.0, 0.0};   // ressumx while ressumy is being reduced
     for (int grp = 0; grp < ngroups; grp++) {
         const int ntiles = a.dg_partials ? b.dg_ntiles : b.tiles_x * b.tiles_y;
-        __syncthreads();
-        for (int vt = tid; vt < 256; vt += nt) {
-            double s[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int t = vt; t < ntiles; t += 256) {
-                const double2* p = a.dg_partials ? reinterpret_cast<const double2*>(a.dg_partials + 12 * (long long)(b.dg_tile0 + t) + 4 * grp)
-                                                 : reinterpret_cast<const double2*>(a.partials + 4 * (long long)(b.tile0 + t));
-                const double2 p0 = __ldcg(p), p1 = __ldcg(p + 1);
-                s[0] += p0.x; s[1] += p0.y; s[2] += p1.x; s[3] += p1.y;
-            }
-            for (int v = 0; v < 4; v++) red[vt][v] = s[v];
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+        for (int t = lane; t < ntiles; t += 32) {
+            const double2* p = a.dg_partials ? reinterpret_cast<const double2*>(a.dg_partials + 12 * (long long)(b.dg_tile0 + t) + 4 * grp)
+                                             : reinterpret_cast<const double2*>(a.partials + 4 * (long long)(b.tile0 + t));
+            const double2 p0 = __ldcg(p), p1 = __ldcg(p + 1);
+            s[0] += p0.x; s[1] += p0.y; s[2] += p1.x; s[3] += p1.y;
         }
-        __syncthreads();
-        for (int w = 128; w > 0; w >>= 1) {
-            for (int vt = tid; vt < w; vt += nt)
-                for (int v = 0; v < 4; v++) red[vt][v] += red[vt + w][v];
-            __syncthreads();
-        }
-        if (tid == 0) {
-            for (int v = 0; v < 4; v++) {
-                const double rt = sqrt(red[0][v]);
-                if (grp == 0) norm[v] = rt;
-                else if (grp == 1) parked[v] = rt;
-                else norm[v] = norm[v] + (parked[v] + rt);
-            }
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+#pragma unroll
+            for (int w = 16; w > 0; w >>= 1) s[v] += __shfl_xor_sync(full, s[v], w);
+            const double rt = sqrt(s[v]);
+            if (grp == 0) norm[v] = rt;
+            else if (grp == 1) parked[v] = rt;
+            else norm[v] = norm[v] + (parked[v] + rt);
         }
     }
-    if (tid == 0) {
+    int last = 0;
+    if (lane == 0) {
         for (int v = 0; v < 4; v++) a.blk_norm[4 * k + v] = norm[v];
         __threadfence();
-        *last = atomicAdd(a.ticket, 1u) == (unsigned)(a.nowned - 1);
+        last = atomicAdd(a.ticket, 1u) == (unsigned)(a.nowned - 1);
     }
-    __syncthreads();
-    if (!*last) return;
+    last = __shfl_sync(full, last, 0);
+    if (!last) return;
     __threadfence();
-    // last CTA: per-block sums by one thread per block (the global loads overlap), then thread 0 adds the
+    // last CTA: per-block sums by one lane per block (the global loads overlap), then lane 0 adds the
     // blocks in block order (main.cpp:379-392 gathers in rank order)
     const long long it = *a.iter;
     const int pos = *a.hist_pos;
     const StopArgs& sx = a.stop_x;
     const int slot = (int)((it + 1) & 3);
-    for (int q = tid; q < a.nowned; q += nt) {
+    double tot = 0.0, tot0 = 0.0;
+    for (int q0 = 0; q0 < a.nowned; q0 += 32) {
+        const int q = q0 + lane;
         double sum = 0.0, sum0 = 0.0;
-        for (int v = 0; v < 4; v++) {
-            const double rs = __ldcg(a.blk_norm + 4 * q + v);
-            double r0 = a.res0[4 * q + v];
-            if (it == 0) r0 = rs;
-            if (r0 < 1e-16) r0 = fmax(rs, 1e-16);
-            a.res0[4 * q + v] = r0;
-            sum += rs;
-            sum0 += r0;
+        if (q < a.nowned) {
+            for (int v = 0; v < 4; v++) {
+                const double rs = __ldcg(a.blk_norm + 4 * q + v);
+                double r0 = a.res0[4 * q + v];
+                if (it == 0) r0 = rs;
+                if (r0 < 1e-16) r0 = fmax(rs, 1e-16);
+                a.res0[4 * q + v] = r0;
+                sum += rs;
+                sum0 += r0;
+            }
+            if (pos < a.hist_cap) {
+                a.blk_hist[2 * ((long long)pos * a.nowned + q) + 0] = sum;
+                a.blk_hist[2 * ((long long)pos * a.nowned + q) + 1] = sum0;
+            }
+            if (sx.enabled) {
+                // this block's sums into every rank's residual table (the gather of main.cpp:379-392, one-sided)
+                const long long o = 2 * ((long long)slot * sx.nblocks_global + a.blocks[q].gid);
+                for (int r = 0; r < sx.nranks; r++) { sx.res_dst[r][o] = sum; sx.res_dst[r][o + 1] = sum0; }
+            }
         }
-        if (pos < a.hist_cap) {
-            a.blk_hist[2 * ((long long)pos * a.nowned + q) + 0] = sum;
-            a.blk_hist[2 * ((long long)pos * a.nowned + q) + 1] = sum0;
-        }
-        a.blk_sum[2 * q] = sum;
-        a.blk_sum[2 * q + 1] = sum0;
-        if (sx.enabled) {
-            // this block's sums into every rank's residual table (the gather of main.cpp:379-392, one-sided)
-            const long long o = 2 * ((long long)slot * sx.nblocks_global + a.blocks[q].gid);
-            for (int r = 0; r < sx.nranks; r++) { sx.res_dst[r][o] = sum; sx.res_dst[r][o + 1] = sum0; }
+        const int n = min(32, a.nowned - q0);
+        for (int r = 0; r < n; r++) {           // block order
+            tot += __shfl_sync(full, sum, r);
+            tot0 += __shfl_sync(full, sum0, r);
         }
     }
     if (sx.enabled) __threadfence_system();
-    __syncthreads();
-    if (tid != 0) return;
+    __syncwarp();
+    if (lane != 0) return;
     if (sx.enabled) {
         for (int r = 0; r < sx.nranks; r++) fin_st_release_sys(sx.rflag_dst[r], (unsigned long long)(it + 1));
     }
-    double tot = 0.0, tot0 = 0.0;
-    for (int q = 0; q < a.nowned; q++) { tot += a.blk_sum[2 * q]; tot0 += a.blk_sum[2 * q + 1]; }
     const double relres = tot / tot0;
     if (pos < a.hist_cap) {
         double* h = a.step_hist + 4 * (long long)pos;
@@ -126,5 +126,6 @@ void launch_fill_uniform(cudaStream_t s, const BlockDev& b, int buf, const doubl
 void launch_nodes_to_planes(cudaStream_t s, const BlockDev& b, const double* x, const double* y);
 void launch_cell_metric(cudaStream_t s, const BlockDev& b, int axi);
 void launch_min_face(cudaStream_t s, const BlockDev& b, double* out, int nparts);
+void launch_face_normals(cudaStream_t s, const BlockDev& b, double2* out);
 void launch_fp64_probe(cudaStream_t s, double* out, int grid, int iters);
 }  // namespace par2d

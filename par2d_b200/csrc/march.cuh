@@ -53,6 +53,10 @@ namespace par2d {
 #ifndef MARCH_VOTE_J
 #define MARCH_VOTE_J 1       // the fully-upwind warp vote also on j-faces (0: i-faces only, A/B runs)
 #endif
+#ifndef PUSH_EXP
+#define PUSH_EXP 31     // diagnostics: bit mask of the fused step's pieces that are compiled in (1 bookkeeping role + stop test, 2 pull,
+                        // 4 epilogue, 8 flag wait, 16 proxy fence); anything but 31 gives wrong results and is for timing runs only
+#endif
 #ifndef MARCH_STAGES
 #define MARCH_STAGES 3    // ring stages of two rows each
 #endif
@@ -142,19 +146,24 @@ struct RowState {
     double yfb[CPL];         // mid-point radius of the cell's bottom face (lean path: ycc = (bottom + top)/2)
 };
 
-struct MarchCtx {
+// PlaneT: the type of the plane stride.  The tuned launch-per-step kernel keeps it in 64 bits (precomputed multiples
+// in registers); the fused kernel, which has fewer registers to spare across the row loop, in 32 (one IMAD.WIDE per
+// plane; < 2^31 doubles per plane is checked by par2d_create).
+template <class PlaneT>
+struct MarchCtxT {
     int k, c, ncx, ncy, pitch, lane;   // c = first cell column of this lane
-    int plane;                         // doubles per plane (< 2^31: par2d_create checks); 32 bits keep the store addressing to one IMAD.WIDE per plane
+    PlaneT plane;
     bool writer[CPL];
     double dt;
     double* Sout;
 };
+using MarchCtx = MarchCtxT<long long>;
 
 // Residual, norms, solve and new state of one cell from its four face fluxes (left, right, bottom, top).
 // (xa,ya)..(xd,yd) = nodes (c,j), (c+1,j), (c+1,j+1), (c,j+1)  (MeshModule.cpp:28-40).  Returns the new
 // state in out[4] when a.update.
-template <bool FAITHFUL, bool TPG, bool AXI, bool HOOKS>
-__device__ __forceinline__ void cell_update(const StepArgs& a, const Gas& g, const MarchCtx& m, int c, int j, const FaceState& cur, double T, double im,
+template <bool FAITHFUL, bool TPG, bool AXI, bool HOOKS, class CTX>
+__device__ __forceinline__ void cell_update(const StepArgs& a, const Gas& g, const CTX& m, int c, int j, const FaceState& cur, double T, double im,
                                             double xa, double ya, double xb, double yb, double xc, double yc_, double xd, double yd,
                                             const Flux& Fl, const Flux& Fr, const Flux& Gb, const Flux& Gt,
                                             double out[4], double& sq0, double& sq1, double& sq2, double& sq3, unsigned& flags, bool live = true,
@@ -247,8 +256,8 @@ __device__ __forceinline__ void cell_update(const StepArgs& a, const Gas& g, con
 // One row of a strip: consumes the carried state `lo` of cell row j and the staged row above it (srow/nrow
 // = this lane's first column of the state / node planes of that row in the ring), produces the carried
 // state `hi` of row j+1, updates this lane's cells of row j.
-template <bool FAITHFUL, bool TPG, bool AXI, bool HOOKS>
-__device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const MarchCtx& m, MarchSmem& sm, int j, const double* srow, const double* nrow,
+template <bool FAITHFUL, bool TPG, bool AXI, bool HOOKS, class CTX>
+__device__ __forceinline__ void march_row(const StepArgs& a, const Gas& g, const CTX& m, MarchSmem& sm, int j, const double* srow, const double* nrow,
                                           const RowState& lo, RowState& hi, double& sq0, double& sq1, double& sq2, double& sq3, unsigned& flags) {
     const int q = CPL * m.lane;                    // this lane's first column in the staged row
     unsigned flu[CPL];
@@ -351,23 +360,29 @@ struct StepVar {
     double* partials;        // this step's strip sums
     int parity;              // peer-mapped mode: parity of the exchange event this step produces
     unsigned long long seq;  //   ... and its number (the step consumes event StepArgs::wait_seq = seq-1)
+    int first;               // first step of this CTA in the launch: make the tensor map visible to the TMA unit
 };
 
 // ------------------------------------------------------------------ fused step: the perimeter of a block
+// Everything the fused step adds to a strip lives in NON-INLINED functions that take their arguments by value or as
+// pointers to global memory: the row loop of march_tile is tuned to the last register and the last branch, and ptxas
+// only keeps it that way (convergence of the warp proven, no register moves between the two rows of a trip) while
+// the strip's own code path contains no divergent loop and no spill-prone live range - measured: any of these
+// pieces inlined costs 8-10 % more instructions in the row loop and 27 % of the step.
+
 // One side of a perimeter strip after its rows are done (the strip's new cells sit in Sout, visible to the whole
 // warp): per edge cell n of [n0, n1)
 //   boundary-condition face : the ghost state of the NEW state -> ghost ring of Sout       (generate_ghost_cells)
 //   same-rank neighbour     : the new cell -> the neighbour block's ghost ring              (halo exchange, :263-269)
 //   off-rank neighbour      : the new cell -> the neighbour rank's arena over NVLink        (halo exchange, :236-259)
 // so that the next step finds its ghost ring complete without a ghost launch.
-template <bool FAITHFUL>
-__device__ __forceinline__ void push_side(const StepArgs& a, const Gas& g, const PutArgs& put, const StepVar& sv, const BlockDev& b, int side, int n0, int n1) {
+__device__ __forceinline__ void push_side(const BlockDev* blocks, const Gas* gas, const BlockDev& b, int out_buf, int parity, int side, int n0, int n1) {
     const int kind = b.nb_kind[side];
-    double* Sout = b.state[sv.cur ^ 1];
+    double* Sout = b.state[out_buf];
     for (int n = n0 + (int)threadIdx.x; n < n1; n += 32) {
         int c, r;
         if (kind == NB_NONE) {
-            bc_ghost_fill(a.gas_dev, &b, Sout, side, n);
+            bc_ghost_fill(gas, &b, Sout, side, n);
             continue;
         }
         edge_cell_pos(b.ncx, b.ncy, side, n, c, r);
@@ -376,39 +391,119 @@ __device__ __forceinline__ void push_side(const StepArgs& a, const Gas& g, const
 #pragma unroll
         for (int v = 0; v < 4; v++) u[v] = __ldcg(Sout + v * b.plane + io);
         if (kind == NB_LOCAL) {
-            const BlockDev& o = a.blocks[b.nb_block[side]];
+            const BlockDev& o = blocks[b.nb_block[side]];
             ghost_cell_pos(o.ncx, o.ncy, b.nb_side[side], n, c, r);
-            double* So = o.state[sv.cur ^ 1];
+            double* So = o.state[out_buf];
             const long long go = (long long)r * o.pitch + c;
             u[3] = fmax(u[3], 201.0);
 #pragma unroll
             for (int v = 0; v < 4; v++) __stcg(So + v * o.plane + go, u[v]);
         } else if (b.put_dst[side] != nullptr) {
             // one 32-byte AoS record per edge cell (usend[k + NVAR*j], SpatialDiscretization.cpp:241)
-            double2* d2 = reinterpret_cast<double2*>(b.put_dst[side] + sv.parity * b.put_stride[side] + 4 * (long long)n);
+            double2* d2 = reinterpret_cast<double2*>(b.put_dst[side] + parity * b.put_stride[side] + 4 * (long long)n);
             d2[0] = make_double2(u[0], u[1]);
             d2[1] = make_double2(u[2], u[3]);
         }
     }
 }
 
-// Multi-rank step: the off-rank faces of this strip.  The neighbours' edge lines were put into this rank's arena
-// (event a.wait_seq); copy them into the ghost ring of the state being read, ahead of the TMA copies that stage it.
-__device__ __forceinline__ void pull_remote_side(const StepArgs& a, const StepVar& sv, const BlockDev& b, int side, int n0, int n1) {
-    double* S = b.state[sv.cur];
-    const double* line0 = b.recv[side] + a.recv_off;   // parity of the consumed event
-    for (int n = n0 + (int)threadIdx.x; n < n1; n += 32) {
-        int c, r;
-        ghost_cell_pos(b.ncx, b.ncy, side, n, c, r);
-        const long long go = (long long)r * b.pitch + c;
-        const double* line = line0 + 4 * (long long)n;
-        const double2 lo = __ldcg(reinterpret_cast<const double2*>(line)), hi = __ldcg(reinterpret_cast<const double2*>(line) + 1);
-        __stcg(S + go, lo.x); __stcg(S + b.plane + go, lo.y); __stcg(S + 2 * b.plane + go, hi.x); __stcg(S + 3 * b.plane + go, fmax(hi.y, 201.0));
+// what the epilogue needs of PutArgs, by value
+struct PutLite {
+    int peer_mode, parity, nranks, rank;
+    unsigned long long seq;
+    double* const* dt_dst;
+    long long dt_stride;
+    unsigned long long* const* flag_dst;
+    unsigned* ticket;
+    unsigned expected;
+};
+
+// After the rows of a perimeter strip: ghost ring / edge lines of the NEW state, the block's dt, the put ticket.
+// Returns error bits.
+static __device__ __noinline__ unsigned tile_epilogue(const BlockDev* blocks, const Gas* gas, int k, int strip, int out_buf, int march_rows,
+                                                     double* dt_next, double gamRs, double cfl, PutLite put) {
+    const BlockDev& b = blocks[k];
+    const int lane = threadIdx.x;
+    unsigned flags = 0;
+    const int ex = strip % b.tiles_x, ey = strip / b.tiles_x;
+    const bool tl = ex == 0, tr = ex == b.tiles_x - 1, tb = ey == 0, tt = ey == b.tiles_y - 1;
+    const int c0 = ex * MCELLS, c1 = min(c0 + MCELLS, b.ncx);
+    const int j0 = ey * march_rows, j1 = min(j0 + march_rows, b.ncy);
+    __syncwarp();                                  // the strip's new cells are visible to every lane
+    if (tl) push_side(blocks, gas, b, out_buf, put.parity, SIDE_LEFT, j0, j1);
+    if (tr) push_side(blocks, gas, b, out_buf, put.parity, SIDE_RIGHT, j0, j1);
+    if (tb) push_side(blocks, gas, b, out_buf, put.parity, SIDE_BOTTOM, c0, c1);
+    if (tt) push_side(blocks, gas, b, out_buf, put.parity, SIDE_TOP, c0, c1);
+    bool put_something = false;
+    if (put.peer_mode) {
+        put_something = (tl && b.nb_kind[SIDE_LEFT] == NB_REMOTE) || (tr && b.nb_kind[SIDE_RIGHT] == NB_REMOTE) ||
+                        (tb && b.nb_kind[SIDE_BOTTOM] == NB_REMOTE) || (tt && b.nb_kind[SIDE_TOP] == NB_REMOTE) || strip == 0;
     }
+    if (strip == 0 && lane == 0) {
+        // find_dt of the NEW state from cell (0,0) (main.cpp:19-37), for the next step on every rank
+        const double dtb = block_dt_value(b.state[out_buf], b.plane, b.pitch, b.min_face, gamRs, cfl);
+        if (isnan(dtb)) flags |= FLAG_NAN;
+        if (put.peer_mode) {
+            for (int r = 0; r < put.nranks; r++) put.dt_dst[r][put.parity * put.dt_stride + b.gid] = dtb;
+        } else {
+            dt_next[b.gid] = dtb;
+        }
+    }
+    if (put_something) {
+        // all stores of this strip are ordered before its ticket; the last perimeter strip of the launch raises this
+        // rank's flag in every peer's arena (release at system scope)
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+            if (atomicAdd(put.ticket, 1u) == put.expected - 1) {
+                *put.ticket = 0u;
+                __threadfence_system();
+                for (int r = 0; r < put.nranks; r++)
+                    if (r != put.rank) st_release_sys(put.flag_dst[r], put.seq);
+            }
+        }
+    }
+    __syncwarp();
+    return flags;
 }
 
-// Stop test across ranks, first CTA of launch `launch_no` (see StopArgs): the launch would overwrite the state left
-// by iteration it-1 - it may only run if that iteration's global relres stayed above the tolerance.
+// Multi-rank step, before a strip's rows: the peers' exchange event (their edge lines and dts of the state being
+// read) must have arrived; a strip that borders another rank copies the received lines of its faces into the ghost
+// ring of that state, ahead of the TMA copies that stage it.  Returns error bits.
+static __device__ __noinline__ unsigned tile_prologue_multi(const BlockDev* blocks, int k, int strip, int in_buf, int march_rows, int pull,
+                                                           const unsigned long long* wait_flags, int nranks, int rank, unsigned long long wait_seq,
+                                                           long long timeout_ns, long long recv_off) {
+    unsigned flags = 0;
+    if (!wait_peers_warp(wait_flags, nranks, rank, wait_seq, timeout_ns)) flags |= FLAG_COMM;
+    if (pull) {
+        const BlockDev& b = blocks[k];
+        const int ex = strip % b.tiles_x, ey = strip / b.tiles_x;
+        const int c0 = ex * MCELLS, c1 = min(c0 + MCELLS, b.ncx);
+        const int j0 = ey * march_rows, j1 = min(j0 + march_rows, b.ncy);
+        double* S = b.state[in_buf];
+        for (int side = 0; side < 4; side++) {
+            const bool touches = side == SIDE_LEFT ? ex == 0 : side == SIDE_RIGHT ? ex == b.tiles_x - 1 : side == SIDE_BOTTOM ? ey == 0 : ey == b.tiles_y - 1;
+            if (!touches || b.nb_kind[side] != NB_REMOTE) continue;
+            const bool vertical = side == SIDE_LEFT || side == SIDE_RIGHT;
+            const int n0 = vertical ? j0 : c0, n1 = vertical ? j1 : c1;
+            const double* line0 = b.recv[side] + recv_off;   // parity of the consumed event
+            for (int n = n0 + (int)threadIdx.x; n < n1; n += 32) {
+                int c, r;
+                ghost_cell_pos(b.ncx, b.ncy, side, n, c, r);
+                const long long go = (long long)r * b.pitch + c;
+                const double* line = line0 + 4 * (long long)n;
+                const double2 lo = __ldcg(reinterpret_cast<const double2*>(line)), hi = __ldcg(reinterpret_cast<const double2*>(line) + 1);
+                __stcg(S + go, lo.x); __stcg(S + b.plane + go, lo.y); __stcg(S + 2 * b.plane + go, hi.x); __stcg(S + 3 * b.plane + go, fmax(hi.y, 201.0));
+            }
+        }
+        fence_proxy_async_global();
+    }
+    __syncwarp();
+    return flags;
+}
+
+// Stop test across ranks (see StopArgs), launch `launch_no`: the launch would overwrite the state left by iteration
+// it-1 - it may only run if that iteration's global relres stayed above the tolerance.
 __device__ __forceinline__ void stop_test(const StopArgs& sx, long long it_checked, int* stop, unsigned* flags, int launch_no) {
     if (it_checked >= 0 && !*stop) {
         if (!wait_peers(sx.local_flags, sx.nranks, -1, (unsigned long long)(it_checked + 1), sx.timeout_ns, 1)) atomicOr(flags, FLAG_COMM);
@@ -420,6 +515,19 @@ __device__ __forceinline__ void stop_test(const StopArgs& sx, long long it_check
     __threadfence();
     *reinterpret_cast<volatile int*>(sx.go) = launch_no;
 }
+// ... and what every other CTA of that launch does meanwhile: wait for the decision.  Returns the stop word.
+static __device__ __noinline__ int stop_gate(const int* go, int launch_no, const int* stop, unsigned* flags, long long timeout_ns) {
+    if (threadIdx.x == 0) {
+        const unsigned long long t0 = global_ns();
+        while (*reinterpret_cast<const volatile int*>(go) < launch_no) {
+            if ((long long)(global_ns() - t0) > timeout_ns) { atomicOr(flags, FLAG_COMM); break; }
+            __nanosleep(100);
+        }
+        __threadfence();
+    }
+    __syncwarp();
+    return *reinterpret_cast<const volatile int*>(stop);
+}
 
 // ------------------------------------------------------------------ one strip, one step
 // `reload(k, strip)` re-derives the strip's identity after the row loop (from blockIdx or from the tile list), so
@@ -429,7 +537,7 @@ __device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, cons
     const int lane = threadIdx.x;
     int k = k_in, strip = strip_in;
     const BlockDev& b = a.blocks[k];
-    MarchCtx m;
+    MarchCtxT<int> m;
     m.k = k; m.ncx = b.ncx; m.ncy = b.ncy; m.pitch = b.pitch; m.plane = (int)b.plane; m.lane = lane;
     const int tx = strip % b.tiles_x, ty = strip / b.tiles_x;
     const int c0 = tx * MCELLS;                    // first updated cell column
@@ -445,25 +553,14 @@ __device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, cons
     unsigned flags = 0;
     bool ok = true;
 
-    // perimeter of the block (CTA-uniform).  Everything here is recomputed after the rows instead of being kept
-    // alive across them: the row loop has no register to spare.
-    bool waited = false;
-    if constexpr (PUSH) {
+    // multi-rank: a strip that borders another rank pulls its ghost cells out of the arena BEFORE staging its rows;
+    // every other strip waits for the peers' event (their dts) while its first rows are in flight
+    bool pull = false;
+    if constexpr (PUSH && (PUSH_EXP & 2)) {
         if (a.wait_flags != nullptr) {
-            const bool rl = tx == 0 && b.nb_kind[SIDE_LEFT] == NB_REMOTE, rr = tx == b.tiles_x - 1 && b.nb_kind[SIDE_RIGHT] == NB_REMOTE;
-            const bool rb = ty == 0 && b.nb_kind[SIDE_BOTTOM] == NB_REMOTE, rt = ty == b.tiles_y - 1 && b.nb_kind[SIDE_TOP] == NB_REMOTE;
-            if (rl | rr | rb | rt) {
-                // this strip borders another rank: its ghost cells come out of the arena, ahead of the row copies
-                if (!wait_peers_warp(a.wait_flags, a.nranks, a.rank, a.wait_seq, a.timeout_ns)) flags |= FLAG_COMM;
-                waited = true;
-                const int c1 = min(c0 + MCELLS, m.ncx);
-                if (rl) pull_remote_side(a, sv, b, SIDE_LEFT, j0, j1);
-                if (rr) pull_remote_side(a, sv, b, SIDE_RIGHT, j0, j1);
-                if (rb) pull_remote_side(a, sv, b, SIDE_BOTTOM, c0, c1);
-                if (rt) pull_remote_side(a, sv, b, SIDE_TOP, c0, c1);
-                fence_proxy_async_global();
-                __syncwarp();
-            }
+            pull = (tx == 0 && b.nb_kind[SIDE_LEFT] == NB_REMOTE) || (tx == b.tiles_x - 1 && b.nb_kind[SIDE_RIGHT] == NB_REMOTE) ||
+                   (ty == 0 && b.nb_kind[SIDE_BOTTOM] == NB_REMOTE) || (ty == b.tiles_y - 1 && b.nb_kind[SIDE_TOP] == NB_REMOTE);
+            if (pull) flags |= tile_prologue_multi(a.blocks, k, strip, sv.cur, a.march_rows, 1, a.wait_flags, a.nranks, a.rank, a.wait_seq, a.timeout_ns, a.recv_off);
         }
     }
 
@@ -485,8 +582,8 @@ __device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, cons
 #pragma unroll
         for (int s = 0; s < MARCH_STAGES; s++) mbar_init(&sm.bar[s], 1);
         mbar_init_fence();
-        tmap_acquire(tmap);
-        if constexpr (PUSH) fence_proxy_async_global();   // the state was written by other CTAs' generic stores (persistent launch)
+        if (sv.first) tmap_acquire(tmap);
+        if constexpr (PUSH && (PUSH_EXP & 16)) fence_proxy_async_global();   // the state was written by other CTAs' generic stores (persistent launch)
 #pragma unroll
         for (int s = 0; s < MARCH_STAGES; s++) stage_rows(s, s);
     }
@@ -497,10 +594,9 @@ __device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, cons
 
     // global dt = max over blocks (main.cpp:270-292); the table was written by the ghost kernel (first step of a
     // batch) or by the strips holding cell (0,0) of every block in the previous step, on any rank
-    if constexpr (PUSH) {
-        if (a.wait_flags != nullptr && !waited) {
-            if (!wait_peers_warp(a.wait_flags, a.nranks, a.rank, a.wait_seq, a.timeout_ns)) flags |= FLAG_COMM;
-        }
+    if constexpr (PUSH && (PUSH_EXP & 8)) {
+        if (a.wait_flags != nullptr && !pull)
+            flags |= tile_prologue_multi(a.blocks, k, strip, sv.cur, a.march_rows, 0, a.wait_flags, a.nranks, a.rank, a.wait_seq, a.timeout_ns, a.recv_off);
     }
     double dt = 0.0;
     if (a.dt_ready) {
@@ -584,59 +680,23 @@ __device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, cons
         sv.partials[4 * (long long)(bb.tile0 + strip) + lane] = s;
     }
 
-    if constexpr (PUSH) {
-        const int ntx = bb.tiles_x, nty = bb.tiles_y;
-        const int ex = strip % ntx, ey = strip / ntx;
-        const bool tl = ex == 0, tr = ex == ntx - 1, tb = ey == 0, tt = ey == nty - 1;
-        if (tl | tr | tb | tt) {
-            const int e_c0 = ex * MCELLS, e_c1 = min(e_c0 + MCELLS, bb.ncx);
-            const int e_j0 = ey * a.march_rows, e_j1 = min(e_j0 + a.march_rows, bb.ncy);
-            __syncwarp();                          // the strip's new cells are visible to every lane
-            if (tl) push_side<FAITHFUL>(a, g, put, sv, bb, SIDE_LEFT, e_j0, e_j1);
-            if (tr) push_side<FAITHFUL>(a, g, put, sv, bb, SIDE_RIGHT, e_j0, e_j1);
-            if (tb) push_side<FAITHFUL>(a, g, put, sv, bb, SIDE_BOTTOM, e_c0, e_c1);
-            if (tt) push_side<FAITHFUL>(a, g, put, sv, bb, SIDE_TOP, e_c0, e_c1);
-            bool put_something = false;
-            if (put.peer_mode) {
-                put_something = (tl && bb.nb_kind[SIDE_LEFT] == NB_REMOTE) || (tr && bb.nb_kind[SIDE_RIGHT] == NB_REMOTE) ||
-                                (tb && bb.nb_kind[SIDE_BOTTOM] == NB_REMOTE) || (tt && bb.nb_kind[SIDE_TOP] == NB_REMOTE) || strip == 0;
-            }
-            if (strip == 0 && lane == 0) {
-                // find_dt of the NEW state from cell (0,0) (main.cpp:19-37), for the next step on every rank
-                const double dtb = block_dt_value(bb.state[sv.cur ^ 1], bb.plane, bb.pitch, bb.min_face, g.gamRs, g.cfl);
-                if (isnan(dtb)) flags |= FLAG_NAN;
-                if (put.peer_mode) {
-                    for (int r = 0; r < put.nranks; r++) put.dt_dst[r][sv.parity * put.dt_stride + bb.gid] = dtb;
-                } else {
-                    sv.dt_next[bb.gid] = dtb;
-                }
-            }
-            if (put_something) {
-                // all stores of this strip are ordered before its ticket; the last perimeter strip of the launch
-                // raises this rank's flag in every peer's arena (release at system scope)
-                __threadfence_system();
-                __syncwarp();
-                if (lane == 0) {
-                    if (atomicAdd(put.ticket, 1u) == put.expected - 1) {
-                        *put.ticket = 0u;
-                        __threadfence_system();
-                        for (int r = 0; r < put.nranks; r++)
-                            if (r != put.rank) st_release_sys(put.flag_dst[r], sv.seq);
-                    }
-                }
-            }
+    if constexpr (PUSH && (PUSH_EXP & 4)) {
+        const int ntx = bb.tiles_x, ex = strip % ntx, ey = strip / ntx;
+        if (ex == 0 || ex == ntx - 1 || ey == 0 || ey == bb.tiles_y - 1) {     // CTA-uniform: the strip touches the block's perimeter
+            PutLite pl;
+            pl.peer_mode = put.peer_mode; pl.parity = sv.parity; pl.nranks = put.nranks; pl.rank = put.rank; pl.seq = sv.seq;
+            pl.dt_dst = put.dt_dst; pl.dt_stride = put.dt_stride; pl.flag_dst = put.flag_dst; pl.ticket = put.ticket; pl.expected = put.expected;
+            flags |= tile_epilogue(a.blocks, a.gas_dev, k, strip, sv.cur ^ 1, a.march_rows, sv.dt_next, g.gamRs, g.cfl, pl);
         }
     }
     if (flags) atomicOr(a.flags, flags);
 }
 
 // The finalize role inside the fused step kernel: CTA `k` (one warp) runs the previous step's bookkeeping for
-// owned block k, reusing the row ring's shared memory as the reduction scratch.
+// owned block k.
 __device__ __forceinline__ void march_finalize_role(const FinalizeArgs& fin, MarchSmem& sm, int k) {
-    static_assert(sizeof(sm.ring) >= 256 * 4 * sizeof(double) + 16, "reduction scratch does not fit the ring");
-    double (*red)[4] = reinterpret_cast<double (*)[4]>(&sm.ring[0][0][0][0]);
-    bool* last = reinterpret_cast<bool*>(&sm.G[0][0]);
-    finalize_block(fin, k, red, last);
+    (void)sm;
+    finalize_block(fin, k);
 }
 
 __device__ __forceinline__ int2 tile_from_list(const int2* list, int t) {
@@ -645,69 +705,197 @@ __device__ __forceinline__ int2 tile_from_list(const int2* list, int t) {
     return r;
 }
 
-// One launch = one step.  PUSH (the fused step): [stop test across ranks] + bookkeeping of the previous step + every
-// strip of every owned block.  Single rank: grid (most strips of a block, [1 +] owned blocks), row 0 being the
-// bookkeeping row when a step is pending; across ranks: grid (nfin + strips), strips in tile-list order - those that
-// border another rank first, so that their puts travel while the interior strips run.
-template <bool FAITHFUL, bool TPG, bool AXI, bool HOOKS, bool PUSH>
-__global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) march_kernel(const StepArgs a, const Gas g, const PutArgs put, const FinalizeArgs fin) {
+// ------------------------------------------------------------------ the launch-per-step kernel (large meshes)
+// One warp strip per CTA; the ghost ring and the per-block dt come from the ghost kernel launched before it, the
+// bookkeeping rides in the NEXT ghost launch.  This kernel is deliberately kept apart from march_tile above although
+// the two run the same rows: its row loop is at the edge of the register file, and the schedule ptxas finds for it
+// depends on everything else in the kernel - measured on B200 with the very same loop instructions, 0.549 ms per
+// launch here against 0.580 (same code behind the march_tile interface) and 0.635 (fused step) on the benchmark mesh.
+template <bool FAITHFUL, bool TPG, bool AXI, bool HOOKS>
+__global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) march_kernel(const StepArgs a, const Gas g) {
+    __shared__ __align__(128) MarchSmem sm;
+    if (*a.stop) return;
+    const int lane = threadIdx.x;
+    int k, strip;
+    if (a.tile_list != nullptr) {                  // subset launch (edge strips first, interior strips beside the exchange)
+        if ((int)blockIdx.x >= a.tile_count) return;
+        const int2 t = __ldg(a.tile_list + blockIdx.x);
+        k = t.x; strip = t.y;
+    } else {
+        k = blockIdx.y;                            // grid.y = owned blocks, grid.x covers the block with most strips
+        strip = blockIdx.x;
+    }
+    const BlockDev& b = a.blocks[k];
+    if (strip >= b.tiles_x * b.tiles_y) return;    // CTA-uniform
+    MarchCtx m;
+    m.k = k; m.ncx = b.ncx; m.ncy = b.ncy; m.pitch = b.pitch; m.plane = b.plane; m.lane = lane;
+    const int c0 = (strip % b.tiles_x) * MCELLS;   // first updated cell column
+    const int j0 = (strip / b.tiles_x) * a.march_rows;
+    const int j1 = min(j0 + a.march_rows, m.ncy);
+    m.c = c0 - 1 + CPL * lane;                     // this lane's first cell column (-1 and ncx are the ghost columns)
+#pragma unroll
+    for (int e = 0; e < CPL; e++) {
+        const int w = CPL * lane + e;              // column within the staged row: 0 and WCOLS-1 are the halo columns
+        m.writer[e] = w >= 1 && w <= MCELLS && m.c + e < m.ncx;
+    }
+    m.Sout = b.state[a.cur ^ 1];
+
+    // ---- TMA row ring.  Array row `arow` holds cell row arow-1, node row arow-1 and the metric of cell
+    // row arow-1; this strip reads array rows j0 (cell row below) .. j1+1 (cell row above the last).
+    // Ring use n holds array rows j0+2n, j0+2n+1 (rows past the array end are zero-filled by TMA).
+    const void* tmap = static_cast<const char*>(a.tmaps) + (size_t)k * 128;
+    const int plane0 = a.cur ? 4 : 0;              // first of the 7 planes read this step
+    const int col0 = COL0 + c0 - 1;                // even: the 16-byte rule of tiled copies
+    const int arow_end = j1 + 1;
+    auto stage_rows = [&](int n, int slot) {       // lane 0 only
+        const int arow = j0 + 2 * n;
+        if (arow <= arow_end) {
+            mbar_expect_tx(&sm.bar[slot], STAGE_BYTES);
+            tma_load_3d(&sm.ring[slot][0][0][0], tmap, col0, arow, plane0, &sm.bar[slot]);
+        }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < MARCH_STAGES; s++) mbar_init(&sm.bar[s], 1);
+        mbar_init_fence();
+        tmap_acquire(tmap);
+#pragma unroll
+        for (int s = 0; s < MARCH_STAGES; s++) stage_rows(s, s);
+    }
+    __syncwarp();
+    // this lane's first column of the state planes / node planes in stage 0, row 0
+    const double* rs = &sm.ring[0][a.cur ? 3 : 0][0][CPL * lane];
+    const double* rn = &sm.ring[0][a.cur ? 0 : 4][0][CPL * lane];
+
+    // global dt = max over blocks (main.cpp:270-292); the table was written by the ghost kernel
+    double dt = 0.0;
+    if (a.dt_ready) {
+        dt = __ldcg(a.dt_used);                    // reduced by the ghost kernel
+    } else {
+        for (int t = lane; t < a.nblocks_global; t += 32) dt = fmax(dt, __ldcg(a.dt_table + t));
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) dt = fmax(dt, __shfl_xor_sync(0xffffffffu, dt, s));
+        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) *a.dt_used = dt;   // for the step's history record
+    }
+    m.dt = dt;
+
+    unsigned flags = 0;
+    bool ok = true;
+    // ---- prologue (ring use 0): cell rows j0-1 (row 0) and j0 (row 1), node row j0, bottom-face fluxes of row j0
+    RowState A, B;
+    ok &= mbar_wait(&sm.bar[0], 0);
+    {
+        unsigned fl0[CPL];
+        const int q = CPL * lane;
+        const double* s1 = rs + WCOLS;             // row 1 of stage 0
+        const double* n1 = rn + WCOLS;
+#pragma unroll
+        for (int e = 0; e < CPL; e++) {
+            fl0[e] = 0;
+            A.T[e] = s1[3 * PLANE_D + e];
+            A.s[e] = face_state<FAITHFUL, TPG>(g, s1[e], s1[PLANE_D + e], s1[2 * PLANE_D + e], A.T[e], fl0[e]);
+            A.x[e] = n1[e]; A.y[e] = n1[PLANE_D + e];
+            A.im[e] = n1[2 * PLANE_D + e];
+        }
+        A.x[CPL] = shfl_down1(A.x[0]); A.y[CPL] = shfl_down1(A.y[0]);
+#pragma unroll
+        for (int e = 0; e < CPL; e++) {
+            const FaceState lo = face_state<FAITHFUL, TPG>(g, rs[e], rs[PLANE_D + e], rs[2 * PLANE_D + e], rs[3 * PLANE_D + e], fl0[e]);
+            // j-face: left state = upper cell, right state = lower cell (SpatialDiscretization.cpp:556-625)
+            const FaceGeom g0 = face_geom<FAITHFUL>(A.x[e], A.y[e], A.x[e + 1], A.y[e + 1]);
+            A.yfb[e] = g0.yf;
+            const Flux G0 = ldfss<FAITHFUL, AXI, !FAITHFUL && MARCH_VOTE_J>(g0, A.s[e], lo);
+            sm.G[0][q + e] = G0.f0; sm.G[1][q + e] = G0.f1; sm.G[2][q + e] = G0.f2; sm.G[3][q + e] = G0.f3; sm.G[4][q + e] = G0.parr;
+            if (m.writer[e]) flags |= fl0[e];
+        }
+    }
+    double sq0 = 0.0, sq1 = 0.0, sq2 = 0.0, sq3 = 0.0;
+    // stage 0 is consumed: refill it
+    __syncwarp();
+    if (lane == 0) stage_rows(MARCH_STAGES, 0);
+
+    // ---- march, two rows per trip (the carried state swaps roles, no register moves between rows): rows
+    //      j, j+1 consume ring use n = (j-j0)/2 + 1, which is then refilled with use n + MARCH_STAGES
+    int n = 1, slot = 1 % MARCH_STAGES;
+    uint32_t ph = (1 / MARCH_STAGES) & 1;
+    int j = j0;
+#pragma unroll 1
+    for (; j + 1 < j1; j += 2) {
+        ok &= mbar_wait(&sm.bar[slot], ph);
+        const double* s0 = rs + slot * STAGE_D;
+        const double* n0 = rn + slot * STAGE_D;
+        march_row<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, sm, j, s0, n0, A, B, sq0, sq1, sq2, sq3, flags);
+        march_row<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, sm, j + 1, s0 + WCOLS, n0 + WCOLS, B, A, sq0, sq1, sq2, sq3, flags);
+        __syncwarp();                              // every lane has read this stage
+        if (lane == 0) stage_rows(n + MARCH_STAGES, slot);
+        n++;
+        if (++slot == MARCH_STAGES) { slot = 0; ph ^= 1u; }
+    }
+    if (j < j1) {
+        ok &= mbar_wait(&sm.bar[slot], ph);
+        march_row<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, sm, j, rs + slot * STAGE_D, rn + slot * STAGE_D, A, B, sq0, sq1, sq2, sq3, flags);
+    }
+
+    // ---- sum of squares of this strip, fixed order: lanes (xor tree)
+    double sq[4] = {sq0, sq1, sq2, sq3};
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) sq[v] += __shfl_xor_sync(0xffffffffu, sq[v], s);
+    }
+    if (isnan(sq[0]) || isnan(sq[1]) || isnan(sq[2]) || isnan(sq[3])) flags |= FLAG_NAN;   // SpatialDiscretization.cpp:1008
+    if (!ok) flags |= FLAG_NAN | 0x80000000u;      // a staged row never arrived
+    if (lane < 4) {
+        const double s = lane == 0 ? sq[0] : lane == 1 ? sq[1] : lane == 2 ? sq[2] : sq[3];
+        a.partials[4 * (long long)(b.tile0 + strip) + lane] = s;
+    }
+    if (flags) atomicOr(a.flags, flags);
+}
+
+
+// ------------------------------------------------------------------ the fused step kernel
+// One launch = one step: [stop test across ranks] + bookkeeping of the previous step + every strip of every owned
+// block, the perimeter strips pushing the new state's ghost ring / edge lines / dt (tile_epilogue).  Single rank:
+// grid (most strips of a block, [1 +] owned blocks), row 0 being the bookkeeping row when a step is pending; across
+// ranks: grid (nfin + strips), strips in tile-list order - those that border another rank first, so that their puts
+// travel while the interior strips run.
+template <bool FAITHFUL, bool TPG, bool AXI>
+__global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) march_fused_kernel(const StepArgs a, const Gas g, const PutArgs put, const FinalizeArgs fin) {
     __shared__ __align__(128) MarchSmem sm;
     StepVar sv;
     sv.cur = a.cur; sv.dt_table = a.dt_table; sv.dt_next = a.dt_next; sv.dt_used = a.dt_used; sv.partials = a.partials;
-    sv.parity = put.parity; sv.seq = put.seq;
-    if constexpr (PUSH) {
-        const StopArgs& sx = fin.stop_x;
-        if (sx.enabled) {
-            // across ranks: nothing of this launch runs before its stop decision (made by the first CTA)
-            if (blockIdx.x == 0 && blockIdx.y == 0) {
-                if (threadIdx.x == 0) stop_test(sx, a.launch_no >= 3 ? sx.iter0 + a.launch_no - 3 : -1, const_cast<int*>(a.stop), a.flags, a.launch_no);
-            } else if (threadIdx.x == 0) {
-                const unsigned long long t0 = global_ns();
-                while (*reinterpret_cast<volatile int*>(sx.go) < a.launch_no) {
-                    if ((long long)(global_ns() - t0) > sx.timeout_ns) { atomicOr(a.flags, FLAG_COMM); break; }
-                    __nanosleep(100);
-                }
-                __threadfence();
-            }
+    sv.parity = put.parity; sv.seq = put.seq; sv.first = 1;
+    const StopArgs& sx = fin.stop_x;
+    if ((PUSH_EXP & 1) && sx.enabled) {
+        // across ranks: nothing of this launch runs before its stop decision (made by the first CTA)
+        if (blockIdx.x == 0 && blockIdx.y == 0) {
+            if (threadIdx.x == 0) stop_test(sx, a.launch_no >= 3 ? sx.iter0 + a.launch_no - 3 : -1, const_cast<int*>(a.stop), a.flags, a.launch_no);
             __syncwarp();
-        }
-        if (*reinterpret_cast<volatile const int*>(a.stop)) return;
-        if (a.tile_list != nullptr) {
-            if ((int)blockIdx.x < a.nfin) { march_finalize_role(fin, sm, blockIdx.x); return; }
-            const int t = (int)blockIdx.x - a.nfin;
-            if (t >= a.tile_count) return;
-            const int2 tl = tile_from_list(a.tile_list, t);
-            march_tile<FAITHFUL, TPG, AXI, HOOKS, PUSH>(a, g, put, sv, sm, tl.x, tl.y, [&](int& k, int& strip) {
-                const int2 r = tile_from_list(a.tile_list, (int)blockIdx.x - a.nfin);
-                k = r.x; strip = r.y;
-            });
         } else {
-            const int fy = a.nfin ? 1 : 0;
-            if ((int)blockIdx.y < fy) {
-                if ((int)blockIdx.x < a.nfin) march_finalize_role(fin, sm, blockIdx.x);
-                return;
-            }
-            const int k = (int)blockIdx.y - fy;
-            if ((int)blockIdx.x >= a.blocks[k].tiles_x * a.blocks[k].tiles_y) return;    // CTA-uniform
-            march_tile<FAITHFUL, TPG, AXI, HOOKS, PUSH>(a, g, put, sv, sm, k, blockIdx.x, [&](int& k2, int& strip2) {
-                k2 = (int)blockIdx.y - (a.nfin ? 1 : 0); strip2 = blockIdx.x;
-            });
+            stop_gate(sx.go, a.launch_no, a.stop, a.flags, sx.timeout_ns);
         }
+    }
+    if (*reinterpret_cast<volatile const int*>(a.stop)) return;
+    if (a.tile_list != nullptr) {
+        if ((PUSH_EXP & 1) && (int)blockIdx.x < a.nfin) { march_finalize_role(fin, sm, blockIdx.x); return; }
+        const int t = (int)blockIdx.x - a.nfin;
+        if (t >= a.tile_count) return;
+        const int2 tl = tile_from_list(a.tile_list, t);
+        march_tile<FAITHFUL, TPG, AXI, false, true>(a, g, put, sv, sm, tl.x, tl.y, [&](int& k, int& strip) {
+            const int2 r = tile_from_list(a.tile_list, (int)blockIdx.x - a.nfin);
+            k = r.x; strip = r.y;
+        });
     } else {
-        if (*a.stop) return;
-        if (a.tile_list != nullptr) {              // subset launch
-            if ((int)blockIdx.x >= a.tile_count) return;
-            const int2 t = __ldg(a.tile_list + blockIdx.x);
-            if (t.y >= a.blocks[t.x].tiles_x * a.blocks[t.x].tiles_y) return;
-            march_tile<FAITHFUL, TPG, AXI, HOOKS, PUSH>(a, g, put, sv, sm, t.x, t.y, [&](int& k, int& strip) {
-                const int2 r = tile_from_list(a.tile_list, blockIdx.x);
-                k = r.x; strip = r.y;
-            });
-        } else {
-            const int k = blockIdx.y;              // grid.y = owned blocks, grid.x covers the block with most strips
-            if ((int)blockIdx.x >= a.blocks[k].tiles_x * a.blocks[k].tiles_y) return;    // CTA-uniform
-            march_tile<FAITHFUL, TPG, AXI, HOOKS, PUSH>(a, g, put, sv, sm, k, blockIdx.x, [&](int& k2, int& strip2) { k2 = blockIdx.y; strip2 = blockIdx.x; });
+        const int fy = a.nfin ? 1 : 0;
+        if ((int)blockIdx.y < fy) {
+            if ((PUSH_EXP & 1) && (int)blockIdx.x < a.nfin) march_finalize_role(fin, sm, blockIdx.x);
+            return;
         }
+        const int k = (int)blockIdx.y - fy;
+        if ((int)blockIdx.x >= a.blocks[k].tiles_x * a.blocks[k].tiles_y) return;    // CTA-uniform
+        march_tile<FAITHFUL, TPG, AXI, false, true>(a, g, put, sv, sm, k, blockIdx.x, [&](int& k2, int& strip2) {
+            k2 = (int)blockIdx.y - (a.nfin ? 1 : 0); strip2 = blockIdx.x;
+        });
     }
 }
 
@@ -752,8 +940,12 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
     put.dt_dst = nullptr; put.flag_dst = nullptr; put.ticket = nullptr; put.local_flags = nullptr; put.dt_stride = 0; put.timeout_ns = 0; put.dg = 0;
     int done = 0;
     bool stopped = false;
+    // a.prof (diagnostics, tools/diag_persist.py): per step, SM clock cycles of the first strip's march, of its wait
+    // at the grid barrier, and of the first bookkeeping CTA
+    const bool prof = a.prof != nullptr && threadIdx.x == 0 && ((int)blockIdx.x == a.nowned || blockIdx.x == 0);
     for (int s = 0; s < a.coop_steps; s++) {
         const int odd = s & 1;
+        const long long t0 = prof ? clock64() : 0;
         if (fin_role) {
             if (s > 0) {
                 FinalizeArgs f = fin;              // step s-1
@@ -768,14 +960,17 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
             sv.dt_next = odd ? const_cast<double*>(a.dt_table) : a.dt_next;
             sv.dt_used = odd ? dt_used_alt : a.dt_used;
             sv.partials = odd ? partials_alt : a.partials;
-            sv.parity = 0; sv.seq = 0;
+            sv.parity = 0; sv.seq = 0; sv.first = s == 0;
             march_tile<FAITHFUL, TPG, AXI, false, true>(a, g, put, sv, sm, k, strip, [&](int& k2, int& strip2) {
                 const int2 r = tile_from_list(a.tile_list, (int)blockIdx.x - a.nowned);
                 k2 = r.x; strip2 = r.y;
             });
         }
         done = s + 1;
+        const long long t1 = prof ? clock64() : 0;
+        if (prof && s < 4096) a.prof[3 * s + (fin_role ? 2 : 0)] = t1 - t0;
         if (!grid_barrier(a.grid_bar, (unsigned)(s + 1) * gridDim.x)) { if (threadIdx.x == 0) atomicOr(a.flags, FLAG_COMM); break; }
+        if (prof && !fin_role && s < 4096) a.prof[3 * s + 1] = clock64() - t1;
         if (*reinterpret_cast<volatile const int*>(a.stop)) { stopped = true; break; }
     }
     // the last step's bookkeeping

@@ -472,7 +472,6 @@ PAR2D_FN bool boundary_state(const Gas& g, int btype, double normx, double normy
                                                double out[4]) {
     const double uL = ui[1], vL = ui[2];
     const double vn = uL * normx + vL * normy;
-    const double mn = vn / a_int;
     if (btype == -1) btype = 3;
     if (btype == 0) btype = 4;
     bool wrote = true;
@@ -498,6 +497,7 @@ PAR2D_FN bool boundary_state(const Gas& g, int btype, double normx, double normy
         out[3] = ui[3];
     } else if (btype == 1) {
         const double gm1 = g.gam - 1;
+        const double mn = vn / a_int;      // only the far field reads the normal Mach number
         if (mn <= -1) {
             out[0] = g.uFS[0]; out[1] = g.uFS[1]; out[2] = g.uFS[2]; out[3] = g.uFS[3];
         } else if (mn <= 0 && mn > -1) {

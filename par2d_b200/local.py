@@ -2,8 +2,7 @@
 
 The Python twin of ``par2d_fv --gpus N`` (par2d_b200/csrc/host/main.cpp): replaces the reference's
 rank setup (FV/main.cpp:68-74,125-142) without a second process - par2d_peer_connect_local enables
-peer access between the devices, every batch is queued on all contexts (par2d_step_async) before any
-is waited for (par2d_step_wait), the residual is gathered in global block order (main.cpp:379-392) and
+peer access between the devices, every batch is advanced by one host thread per context, the residual is gathered in global block order (main.cpp:379-392) and
 the tolerance break (main.cpp:506-531) is decided on the device from the sums of all contexts.
 Context r runs on ``devices[r % len(devices)]``: with fewer devices than contexts several contexts
 share a GPU (their kernels run side by side) - that is how the exchange protocol is tested on a
@@ -12,6 +11,7 @@ one-GPU box.  No torch, no torch.distributed.
 from __future__ import annotations
 
 import ctypes as C
+from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -41,6 +41,7 @@ class LocalMultiSolver:
         arr = (C.c_void_p * nranks)(*[s.handle for s in self.solvers])
         self.lib.check(self.lib.peer_connect_local(arr, nranks), "peer_connect_local")
         self.connected = True
+        self._pool = ThreadPoolExecutor(max_workers=nranks)
 
     def _of(self, b: int) -> Solver:
         return self.solvers[self.owners[b]]
@@ -48,13 +49,17 @@ class LocalMultiSolver:
     def step(self, nsteps: int, stop_on_tol: bool = False):
         """Advance nsteps on every context; returns (dt[n], relres[n]) with relres over ALL blocks in
         global block order; n < nsteps if the run stopped on the tolerance."""
-        for s in self.solvers:
-            self.lib.check(self.lib.step_async(s.handle, nsteps, int(stop_on_tol)), "step_async")
-        infos = []
-        for s in self.solvers:
+        def run(s):
             info = (StepInfo * max(nsteps, 1))()
-            self.lib.check(self.lib.step_wait(s.handle, info), "step_wait")
-            infos.append([i for i in info[:nsteps] if i.iter >= 0])
+            rc = self.lib.step(s.handle, nsteps, int(stop_on_tol), info)
+            msg = self.lib.last_error() if rc else b""          # the error text is per thread
+            return rc, msg, [i for i in info[:nsteps] if i.iter >= 0]
+
+        results = list(self._pool.map(run, self.solvers))
+        for rc, msg, _ in results:
+            if rc:
+                raise _capi.Par2dError(rc, "step", msg.decode() if msg else "")
+        infos = [r[2] for r in results]
         done = len(infos[0])
         assert all(len(i) == done for i in infos), "the contexts stopped after different iterations"
         table = np.zeros((done, self.nblocks, 2))
@@ -90,3 +95,4 @@ class LocalMultiSolver:
             self.connected = False
         for s in self.solvers:
             s.close()
+        self._pool.shutdown()

@@ -167,6 +167,22 @@ def test_contexts_of_one_process_match_one_context_bitwise(gpu, what, nranks, mo
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("mode", [MODE_FAST, MODE_FAITHFUL])
+def test_large_mesh_strategy_across_contexts_bitwise(gpu, monkeypatch, mode):
+    """Large meshes across ranks run the tuned launch-per-step kernel with the strips that border another rank and
+    the put on a side stream beside the interior strips (capi.cu::queue_step_overlapped).  Forced here on a small
+    mesh (PAR2D_SMALL_MESH=0), three contexts sharing the GPU: bit-identical to one context."""
+    monkeypatch.setenv("PAR2D_SMALL_MESH", "0")
+    make = lambda: Case.synthetic_ramp(256, 192, 4, 4)
+    one = _single(gpu, make(), mode, [5, 1, 4])
+    many = _multi(gpu, make(), mode, [5, 1, 4], 3)
+    assert np.array_equal(one[1], many[1]) and np.array_equal(one[2], many[2]) and len(one[1]) == 10
+    for a, b in zip(one[0], many[0]):
+        assert np.array_equal(a, b)
+    for a, b in zip(one[3], many[3]):
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("nranks", [2, 3])
 def test_stop_across_contexts(gpu, nranks):
     """tol .9996 on the 8-block forward step: every context stops after iteration 2 (the decision is made on the

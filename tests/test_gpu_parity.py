@@ -327,6 +327,8 @@ def test_fused_step_equals_separate_launches_bitwise(gpu, monkeypatch):
         runs = []
         for serial in ("0", "1"):
             monkeypatch.setenv("PAR2D_NO_OVERLAP", serial)
+            monkeypatch.setenv("PAR2D_SMALL_MESH", "1")      # the fused step is the default for small meshes only
+            monkeypatch.setenv("PAR2D_NO_PERSIST", "1")
             case = Case.synthetic_ramp(2048, 1056, 2, 2)
             s = Solver(case, make_cfg(gpu, 1, 1.4, mode), lib=gpu)
             u = s.get_state(1)

@@ -7,7 +7,7 @@ for spec in "$@"; do
     if [[ "$spec" == *:* ]]; then envs="$(echo "${spec#*:}" | tr ',' ' ')"; fi
     lib="par2d_b200/csrc/build/variants/libpar2d_gpu_$name.so"
     if [ "$name" = default ]; then lib="par2d_b200/libpar2d_gpu.so"; fi
-    line=$(env $envs PAR2D_GPU_LIB="$PWD/$lib" timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | grep '^{' | tail -1)
+    line=$(env $envs PAR2D_GPU_LIB="$PWD/$lib" timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-gate --preheat-ms 400 --sustain-ms 400 2>&1 | grep '^{' | tail -1)
     python - "$spec" "$line" >> "$out" <<'PY'
 import json, sys
 try:
