@@ -279,8 +279,9 @@ int par2d_kernel_timing(par2d_ctx* ctx, int32_t enable);
 int par2d_kernel_time(par2d_ctx* ctx, double* total_ms, int64_t* launches);
 
 /* Diagnostic of the persistent launch (ctx created with PAR2D_PROFILE_PERSIST=1 in the environment): for each of the
- * first nsteps steps of the last batch, out[3*s + {0: SM cycles the first strip spent marching, 1: ... waiting at the
- * grid barrier, 2: cycles of the first bookkeeping CTA}]. */
+ * first nsteps steps of the last batch, out[12*s + {0: SM cycles the first strip spent in its step, 1: ... waiting at the
+ * grid barrier, 2: cycles of the first bookkeeping CTA, 3..6: inside the strip (7..10: inside its perimeter epilogue), cumulative from the wait for its first
+ * staged rows: that wait, + prologue and rows, + norms, + perimeter epilogue}]. */
 int par2d_persist_profile(par2d_ctx* ctx, int64_t* out, int32_t nsteps);
 
 /* Number of CUDA devices this process sees (the reference asks MPI_Comm_size, FV/main.cpp:70-71). */

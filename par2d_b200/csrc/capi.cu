@@ -951,7 +951,7 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
         c->persist = !(np && atoi(np) != 0);
         c->coop_capacity = (cfg->nranks == 1 && !c->dg) ? c->kt->coop_capacity(c->tpg, c->axi) : 0;
         const char* pp = getenv("PAR2D_PROFILE_PERSIST");
-        if (pp && atoi(pp) != 0) { CU_TRY(cudaMalloc(&c->prof, sizeof(long long) * 3 * 4096)); CU_TRY(cudaMemset(c->prof, 0, sizeof(long long) * 3 * 4096)); }
+        if (pp && atoi(pp) != 0) { CU_TRY(cudaMalloc(&c->prof, sizeof(long long) * 12 * 4096)); CU_TRY(cudaMemset(c->prof, 0, sizeof(long long) * 12 * 4096)); }
     }
     c->partials_stride = 4ll * c->total_tiles;
     CU_TRY(cudaMalloc(&c->gas_dev, sizeof(Gas)));
@@ -1663,7 +1663,7 @@ int par2d_persist_profile(par2d_ctx* c, int64_t* out, int32_t nsteps) {
     if (!c || !out || nsteps < 0 || nsteps > 4096) return fail(PAR2D_ERR_ARG, "persist_profile: bad argument");
     if (!c->prof) return fail(PAR2D_ERR_ARG, "persist_profile: create the ctx with PAR2D_PROFILE_PERSIST=1 in the environment");
     if (use_device(c)) return PAR2D_ERR_CUDA;
-    CU_TRY(cudaMemcpy(out, c->prof, sizeof(long long) * 3 * nsteps, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(out, c->prof, sizeof(long long) * 12 * nsteps, cudaMemcpyDeviceToHost));
     return 0;
 }
 

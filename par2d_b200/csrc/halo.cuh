@@ -112,17 +112,11 @@ __device__ __forceinline__ int face_index(int ncx, int ncy, int side, int n) {
 // by every CTA).  The derived interior quantities are only evaluated for the codes that read them (the far field
 // needs the sound speed and the pressure, the Bernoulli inflow the kinetic energy): walls and extrapolation, most
 // of every perimeter, cost neither a square root nor a division.
-static __device__ HALO_NOINLINE void bc_ghost_fill(const Gas* gp, const BlockDev* bp, double* S, int side, int n) {
+// everything but the two cheap codes: far field (1), back pressure (2), Bernoulli inflow (5), unknown codes
+static __device__ __noinline__ void bc_ghost_general(const Gas* gp, const BlockDev* bp, double* S, int code, int f, long long io, long long go) {
     const Gas& g = *gp;
     const BlockDev& b = *bp;
-    const int f = face_index(b.ncx, b.ncy, side, n);
-    const int code = __ldg(b.ibound + f);
     const double2 nrm = __ldg(b.fnorm + f);
-    int c, r;
-    edge_cell_pos(b.ncx, b.ncy, side, n, c, r);
-    const long long io = (long long)r * b.pitch + c;
-    ghost_cell_pos(b.ncx, b.ncy, side, n, c, r);
-    const long long go = (long long)r * b.pitch + c;
     double ui[4], gh[4];
 #pragma unroll
     for (int v = 0; v < 4; v++) { ui[v] = __ldcg(S + v * b.plane + io); gh[v] = __ldcg(S + v * b.plane + go); }
@@ -132,6 +126,35 @@ static __device__ HALO_NOINLINE void bc_ghost_fill(const Gas* gp, const BlockDev
     boundary_state(g, code, nrm.x, nrm.y, ui, aint, p, v2, gh);
 #pragma unroll
     for (int v = 0; v < 4; v++) __stcg(S + v * b.plane + go, gh[v]);
+}
+
+static __device__ HALO_NOINLINE void bc_ghost_fill(const Gas* gp, const BlockDev* bp, double* S, int side, int n) {
+    const BlockDev& b = *bp;
+    const int f = face_index(b.ncx, b.ncy, side, n);
+    int code = __ldg(b.ibound + f);
+    int c, r;
+    edge_cell_pos(b.ncx, b.ncy, side, n, c, r);
+    const long long io = (long long)r * b.pitch + c;
+    ghost_cell_pos(b.ncx, b.ncy, side, n, c, r);
+    const long long go = (long long)r * b.pitch + c;
+    if (code == -1) code = 3;                      // BoundaryConditions.cpp:76-77
+    if (code == 0) code = 4;
+    // The two codes that make up most of every perimeter, spelled with never-contracted operations (the same bits in
+    // both arithmetic modes, the reference's operation order) and kept short: this code runs once per step and
+    // strip, i.e. out of a cold instruction cache - measured, ~12 cycles per instruction instead of ~1
+    if (code == 3 || code == 4) {
+        double u0 = __ldcg(S + io), u1 = __ldcg(S + b.plane + io), u2 = __ldcg(S + 2 * b.plane + io), u3 = __ldcg(S + 3 * b.plane + io);
+        if (code == 4) {                           // slip wall: V - 2 (V.n) n, BoundaryConditions.cpp:79-88
+            const double2 nrm = __ldg(b.fnorm + f);
+            const double vn = __dadd_rn(__dmul_rn(u1, nrm.x), __dmul_rn(u2, nrm.y));
+            const double t = __dmul_rn(2.0, vn);
+            const double w1 = __dsub_rn(u1, __dmul_rn(t, nrm.x)), w2 = __dsub_rn(u2, __dmul_rn(t, nrm.y));
+            u1 = w1; u2 = w2;
+        }
+        __stcg(S + go, u0); __stcg(S + b.plane + go, u1); __stcg(S + 2 * b.plane + go, u2); __stcg(S + 3 * b.plane + go, fmax(u3, 201.0));
+        return;
+    }
+    bc_ghost_general(gp, bp, S, code, f, io, go);
 }
 
 }  // namespace par2d

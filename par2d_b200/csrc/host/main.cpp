@@ -108,6 +108,11 @@ int main(int argc, char** argv) {
         if (par2d_peer_connect_local(ctx.data(), ngpus)) { printf("par2d_peer_connect_local: %s\n", par2d_last_error()); return 1; }
         printf("%d blocks on %d contexts (%d device%s), halo exchange through peer-mapped arenas\n", nb, ngpus, std::min(ndev, ngpus), std::min(ndev, ngpus) > 1 ? "s" : "");
     }
+    if (ngpus > ndev && batch > 16) {
+        // contexts that share a GPU must not run far ahead of each other (their kernels wait for each other inside the
+        // same work queues): short batches
+        batch = 16;
+    }
     auto owner_ctx = [&](int b) { return ctx[ngpus > 1 ? blocks[b].owner : 0]; };
 
     if (!restart_dir.empty()) {

@@ -361,6 +361,7 @@ struct StepVar {
     int parity;              // peer-mapped mode: parity of the exchange event this step produces
     unsigned long long seq;  //   ... and its number (the step consumes event StepArgs::wait_seq = seq-1)
     int first;               // first step of this CTA in the launch: make the tensor map visible to the TMA unit
+    long long* prof;         // diagnostics: this strip's phase time stamps of this step (null in production)
 };
 
 // ------------------------------------------------------------------ fused step: the perimeter of a block
@@ -421,7 +422,8 @@ struct PutLite {
 // After the rows of a perimeter strip: ghost ring / edge lines of the NEW state, the block's dt, the put ticket.
 // Returns error bits.
 static __device__ __noinline__ unsigned tile_epilogue(const BlockDev* blocks, const Gas* gas, int k, int strip, int out_buf, int march_rows,
-                                                     double* dt_next, double gamRs, double cfl, PutLite put) {
+                                                     double* dt_next, double gamRs, double cfl, PutLite put, long long* prof) {
+    const long long tq = prof ? clock64() : 0;
     const BlockDev& b = blocks[k];
     const int lane = threadIdx.x;
     unsigned flags = 0;
@@ -430,10 +432,13 @@ static __device__ __noinline__ unsigned tile_epilogue(const BlockDev* blocks, co
     const int c0 = ex * MCELLS, c1 = min(c0 + MCELLS, b.ncx);
     const int j0 = ey * march_rows, j1 = min(j0 + march_rows, b.ncy);
     __syncwarp();                                  // the strip's new cells are visible to every lane
+    if (prof) prof[0] = clock64() - tq;
     if (tl) push_side(blocks, gas, b, out_buf, put.parity, SIDE_LEFT, j0, j1);
     if (tr) push_side(blocks, gas, b, out_buf, put.parity, SIDE_RIGHT, j0, j1);
+    if (prof) prof[1] = clock64() - tq;
     if (tb) push_side(blocks, gas, b, out_buf, put.parity, SIDE_BOTTOM, c0, c1);
     if (tt) push_side(blocks, gas, b, out_buf, put.parity, SIDE_TOP, c0, c1);
+    if (prof) prof[2] = clock64() - tq;
     bool put_something = false;
     if (put.peer_mode) {
         put_something = (tl && b.nb_kind[SIDE_LEFT] == NB_REMOTE) || (tr && b.nb_kind[SIDE_RIGHT] == NB_REMOTE) ||
@@ -464,6 +469,7 @@ static __device__ __noinline__ unsigned tile_epilogue(const BlockDev* blocks, co
         }
     }
     __syncwarp();
+    if (prof) prof[3] = clock64() - tq;
     return flags;
 }
 
@@ -611,7 +617,9 @@ __device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, cons
 
     // ---- prologue (ring use 0): cell rows j0-1 (row 0) and j0 (row 1), node row j0, bottom-face fluxes of row j0
     RowState A, B;
+    const long long tp0 = (PUSH && sv.prof) ? clock64() : 0;
     ok &= mbar_wait(&sm.bar[0], 0);
+    if (PUSH && sv.prof) sv.prof[0] = clock64() - tp0;    // wait for the first staged rows
     {
         unsigned fl0[CPL];
         const int q = CPL * lane;
@@ -664,6 +672,7 @@ __device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, cons
         march_row<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, sm, j, rs + slot * STAGE_D, rn + slot * STAGE_D, A, B, sq0, sq1, sq2, sq3, flags);
     }
 
+    if (PUSH && sv.prof) sv.prof[1] = clock64() - tp0;    // ... + prologue + rows
     // ---- sum of squares of this strip, fixed order: lanes (xor tree)
     double sq[4] = {sq0, sq1, sq2, sq3};
 #pragma unroll
@@ -680,15 +689,17 @@ __device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, cons
         sv.partials[4 * (long long)(bb.tile0 + strip) + lane] = s;
     }
 
+    if (PUSH && sv.prof) sv.prof[2] = clock64() - tp0;    // ... + norms, strip identity
     if constexpr (PUSH && (PUSH_EXP & 4)) {
         const int ntx = bb.tiles_x, ex = strip % ntx, ey = strip / ntx;
         if (ex == 0 || ex == ntx - 1 || ey == 0 || ey == bb.tiles_y - 1) {     // CTA-uniform: the strip touches the block's perimeter
             PutLite pl;
             pl.peer_mode = put.peer_mode; pl.parity = sv.parity; pl.nranks = put.nranks; pl.rank = put.rank; pl.seq = sv.seq;
             pl.dt_dst = put.dt_dst; pl.dt_stride = put.dt_stride; pl.flag_dst = put.flag_dst; pl.ticket = put.ticket; pl.expected = put.expected;
-            flags |= tile_epilogue(a.blocks, a.gas_dev, k, strip, sv.cur ^ 1, a.march_rows, sv.dt_next, g.gamRs, g.cfl, pl);
+            flags |= tile_epilogue(a.blocks, a.gas_dev, k, strip, sv.cur ^ 1, a.march_rows, sv.dt_next, g.gamRs, g.cfl, pl, sv.prof ? sv.prof + 4 : nullptr);
         }
     }
+    if (PUSH && sv.prof) sv.prof[3] = clock64() - tp0;    // ... + perimeter epilogue
     if (flags) atomicOr(a.flags, flags);
 }
 
@@ -864,7 +875,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
     __shared__ __align__(128) MarchSmem sm;
     StepVar sv;
     sv.cur = a.cur; sv.dt_table = a.dt_table; sv.dt_next = a.dt_next; sv.dt_used = a.dt_used; sv.partials = a.partials;
-    sv.parity = put.parity; sv.seq = put.seq; sv.first = 1;
+    sv.parity = put.parity; sv.seq = put.seq; sv.first = 1; sv.prof = nullptr;
     const StopArgs& sx = fin.stop_x;
     if ((PUSH_EXP & 1) && sx.enabled) {
         // across ranks: nothing of this launch runs before its stop decision (made by the first CTA)
@@ -961,6 +972,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
             sv.dt_used = odd ? dt_used_alt : a.dt_used;
             sv.partials = odd ? partials_alt : a.partials;
             sv.parity = 0; sv.seq = 0; sv.first = s == 0;
+            sv.prof = (prof && s < 4096) ? a.prof + 12 * s + 3 : nullptr;
             march_tile<FAITHFUL, TPG, AXI, false, true>(a, g, put, sv, sm, k, strip, [&](int& k2, int& strip2) {
                 const int2 r = tile_from_list(a.tile_list, (int)blockIdx.x - a.nowned);
                 k2 = r.x; strip2 = r.y;
@@ -968,9 +980,9 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
         }
         done = s + 1;
         const long long t1 = prof ? clock64() : 0;
-        if (prof && s < 4096) a.prof[3 * s + (fin_role ? 2 : 0)] = t1 - t0;
+        if (prof && s < 4096) a.prof[12 * s + (fin_role ? 2 : 0)] = t1 - t0;
         if (!grid_barrier(a.grid_bar, (unsigned)(s + 1) * gridDim.x)) { if (threadIdx.x == 0) atomicOr(a.flags, FLAG_COMM); break; }
-        if (prof && !fin_role && s < 4096) a.prof[3 * s + 1] = clock64() - t1;
+        if (prof && !fin_role && s < 4096) a.prof[12 * s + 1] = clock64() - t1;
         if (*reinterpret_cast<volatile const int*>(a.stop)) { stopped = true; break; }
     }
     // the last step's bookkeeping

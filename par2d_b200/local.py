@@ -40,6 +40,10 @@ class LocalMultiSolver:
             self.solvers.append(Solver(case, c, lib=self.lib, owners=self.owners))
         arr = (C.c_void_p * nranks)(*[s.handle for s in self.solvers])
         self.lib.check(self.lib.peer_connect_local(arr, nranks), "peer_connect_local")
+        # contexts that SHARE a GPU (tests on a one-GPU box) must not run far ahead of each other: a kernel spinning on a
+        # peer's flag can sit in front of the very kernel that would raise it in the GPU's work queues.  Short batches
+        # keep the queues shallow; with one GPU per context there is no such limit.
+        self.max_batch = 16 if len(set(devices[r % len(devices)] for r in range(nranks))) < nranks else None
         self.connected = True
         self._pool = ThreadPoolExecutor(max_workers=nranks)
 
@@ -49,6 +53,19 @@ class LocalMultiSolver:
     def step(self, nsteps: int, stop_on_tol: bool = False):
         """Advance nsteps on every context; returns (dt[n], relres[n]) with relres over ALL blocks in
         global block order; n < nsteps if the run stopped on the tolerance."""
+        if self.max_batch and nsteps > self.max_batch:
+            dts, rels = [], []
+            left = nsteps
+            while left > 0:
+                n = min(left, self.max_batch)
+                d, r = self.step(n, stop_on_tol)
+                dts += list(d)
+                rels += list(r)
+                left -= n
+                if len(d) < n or (stop_on_tol and len(r) and r[-1] < self.solvers[0].cfg.tol):
+                    break
+            return np.array(dts), np.array(rels)
+
         def run(s):
             info = (StepInfo * max(nsteps, 1))()
             rc = self.lib.step(s.handle, nsteps, int(stop_on_tol), info)

@@ -12,8 +12,8 @@ for name in sys.argv[1:] or ["Case_ffstep8"]:
     s = Solver(case, cfg, lib=gpu)
     s.step(200)
     t0 = time.perf_counter(); s.step(4000); dt = time.perf_counter() - t0
-    out = (C.c_int64 * (3 * 4000))()
+    out = (C.c_int64 * (12 * 4000))()
     gpu.check(gpu.persist_profile(s.handle, out, 4000), "persist_profile")
-    a = np.array(list(out)).reshape(-1, 3)[100:]
-    print(f"{name}: {1e6 * dt / 4000:.2f} us/step wall; cycles/step median: march {np.median(a[:,0]):.0f}  barrier wait {np.median(a[:,1]):.0f}  bookkeeping {np.median(a[:,2]):.0f}  (1.9 GHz: {np.median(a.sum(1)[:])/1900:.2f} us sum of first two: {np.median(a[:,0]+a[:,1])/1900:.2f} us)")
+    a = np.array(list(out)).reshape(-1, 12)[100:]
+    print(f"{name}: {1e6 * dt / 4000:.2f} us/step wall; cycles/step median: march {np.median(a[:,0]):.0f}  barrier wait {np.median(a[:,1]):.0f}  bookkeeping {np.median(a[:,2]):.0f}  | in strip (cumulative): wait rows {np.median(a[:,3]):.0f}  +rows {np.median(a[:,4]):.0f}  +norms {np.median(a[:,5]):.0f}  +epilogue {np.median(a[:,6]):.0f} | inside the epilogue (cumulative): entry+syncwarp {np.median(a[:,7]):.0f}  left/right {np.median(a[:,8]):.0f}  bottom/top {np.median(a[:,9]):.0f}  dt+ticket {np.median(a[:,10]):.0f}")
     s.close()
