@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(256) ghost_kernel(StepArgs a, Gas g, int write
     // rows 0..nfin-1 of the grid: the residual bookkeeping of the PREVIOUS step (nfin = owned blocks, or 0
     // when nothing is pending), overlapped with this step's ghost fill
     if ((int)blockIdx.y < nfin) {
-        if (blockIdx.x == 0 && threadIdx.x < 32) finalize_block(fin, blockIdx.y);
+        __shared__ __align__(16) double stage[FIN_CHUNK * 4];
+        if (blockIdx.x == 0) finalize_block(fin, blockIdx.y, stage);
         return;
     }
     if (a.wait_flags != nullptr) {
@@ -266,6 +267,10 @@ struct KernelTable {
     void (*test_solve)(cudaStream_t, const Gas&, bool tpg, bool axi, long long n, const double*, const double*, const double*, double*);
 };
 
+// the production step of PAR2D_MODE_FAST lives in a module of its own (kernels_march.cu)
+void launch_march_tuned(cudaStream_t s, const StepArgs& a, const Gas& g, bool tpg, bool axi);
+void preload_march_tuned();
+
 template <bool FAITHFUL>
 struct Launch {
     template <bool HOOKS>
@@ -277,8 +282,12 @@ struct Launch {
     }
     // the production step (advancing, no residual dump) runs the instantiation without the test hooks
     static void march(cudaStream_t s, const StepArgs& a, const Gas& g, bool tpg, bool axi) {
-        if (a.update && a.res_out == nullptr) march_h<false>(s, a, g, tpg, axi);
-        else march_h<true>(s, a, g, tpg, axi);
+        if (a.update && a.res_out == nullptr) {
+            if constexpr (FAITHFUL) march_h<false>(s, a, g, tpg, axi);
+            else launch_march_tuned(s, a, g, tpg, axi);
+        } else {
+            march_h<true>(s, a, g, tpg, axi);
+        }
     }
     // the fused step: bookkeeping of the previous step + all strips, perimeter strips pushing ghosts / edge lines / dt
     static void march_push(cudaStream_t s, const StepArgs& a, const Gas& g, const PutArgs& put, const FinalizeArgs& fin, bool tpg, bool axi) {
@@ -294,6 +303,7 @@ struct Launch {
     static void preload(bool tpg, bool axi) {
         cudaFuncAttributes fa;
         auto touch = [&](const void* f) { cudaFuncGetAttributes(&fa, f); };
+        if constexpr (!FAITHFUL) preload_march_tuned();
         touch((const void*)ghost_kernel<FAITHFUL>);
         touch((const void*)pack_kernel<FAITHFUL>);
         touch((const void*)stop_tail_kernel<FAITHFUL>);

@@ -9,13 +9,14 @@
 namespace par2d {
 
 // Stand-alone launch of the step bookkeeping (end of a batch; see finalize_block in kernels_common.cuh).
-__global__ void __launch_bounds__(32) finalize_kernel(FinalizeArgs a) {
+__global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
+    __shared__ __align__(16) double stage[FIN_CHUNK * 4];
     if (*a.stop) return;
-    finalize_block(a, blockIdx.x);
+    finalize_block(a, blockIdx.x, stage);
 }
 
 void launch_finalize(cudaStream_t s, const FinalizeArgs& a) {
-    finalize_kernel<<<a.nowned, 32, 0, s>>>(a);
+    finalize_kernel<<<a.nowned, 256, 0, s>>>(a);
 }
 
 // AoS unk[(j*ncx+i)*4+k] (FV/Indexing.h:11) -> padded planes; applies the T clamp that

@@ -4,7 +4,7 @@
 #include "common.cuh"
 namespace par2d {
 
-// Residual bookkeeping of one step (main.cpp:39-57,365-392,494).  Called by the first WARP of one CTA per owned
+// Residual bookkeeping of one step (main.cpp:39-57,365-392,494).  Done by the first WARP of one CTA per owned
 // block k (the stand-alone finalize_kernel, the bookkeeping rows of the ghost kernel, the bookkeeping CTAs of the
 // fused / persistent step kernels): sums the block's strip partials in a FIXED order - lane l adds strips l, l+32,
 // l+64, ... in that order, then a xor-shuffle tree over the 32 lane sums - and takes the square roots
@@ -22,8 +22,15 @@ __device__ __forceinline__ void fin_st_release_sys(unsigned long long* p, unsign
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Threads beyond the first warp of the CTA must not call this.
-__device__ __forceinline__ void finalize_block(const FinalizeArgs& a, int k) {
+// FIN_CHUNK strips are staged per pass when the calling CTA is larger than a warp (finalize_kernel, the bookkeeping
+// rows of the ghost kernel): every thread fetches strips into shared memory, the first warp then adds them in the
+// canonical order - the same bits as the warp-only form, but with the whole CTA's loads in flight (in situ the
+// partial sums come from HBM: a single warp walking 2208 strips of a 2048^2 block took 33 us, measured).
+constexpr int FIN_CHUNK = 1024;
+
+// stage: FIN_CHUNK*4 doubles of shared memory, or null when the caller is a single warp (then blockDim.x must be 32).
+// With staging ALL threads of the CTA must call; only the first warp returns with work done.
+__device__ __forceinline__ void finalize_block(const FinalizeArgs& a, int k, double* stage = nullptr) {
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
     const BlockDev& b = a.blocks[k];
@@ -34,13 +41,36 @@ __device__ __forceinline__ void finalize_block(const FinalizeArgs& a, int k) {
     double parked[4] = {0.0, 0.0, 0.0, 0.0};   // ressumx while ressumy is being reduced
     for (int grp = 0; grp < ngroups; grp++) {
         const int ntiles = a.dg_partials ? b.dg_ntiles : b.tiles_x * b.tiles_y;
+        const double* src = a.dg_partials ? a.dg_partials + 12 * (long long)b.dg_tile0 + 4 * grp : a.partials + 4 * (long long)b.tile0;
+        const int stride = a.dg_partials ? 12 : 4;
         double s[4] = {0.0, 0.0, 0.0, 0.0};
+        if (stage != nullptr) {
+            for (int base = 0; base < ntiles; base += FIN_CHUNK) {
+                const int n = min(FIN_CHUNK, ntiles - base);
+                __syncthreads();
+                for (int t = threadIdx.x; t < n; t += blockDim.x) {
+                    const double2* p = reinterpret_cast<const double2*>(src + (long long)stride * (base + t));
+                    const double2 p0 = __ldcg(p), p1 = __ldcg(p + 1);
+                    reinterpret_cast<double2*>(stage)[2 * t] = p0;
+                    reinterpret_cast<double2*>(stage)[2 * t + 1] = p1;
+                }
+                __syncthreads();
+                if (threadIdx.x < 32) {
+                    for (int t = lane; t < n; t += 32) {
+                        const double2 p0 = reinterpret_cast<const double2*>(stage)[2 * t], p1 = reinterpret_cast<const double2*>(stage)[2 * t + 1];
+                        s[0] += p0.x; s[1] += p0.y; s[2] += p1.x; s[3] += p1.y;
+                    }
+                }
+            }
+            if (threadIdx.x >= 32 && grp == ngroups - 1) return;
+            if (threadIdx.x >= 32) continue;
+        } else {
 #pragma unroll 4
-        for (int t = lane; t < ntiles; t += 32) {
-            const double2* p = a.dg_partials ? reinterpret_cast<const double2*>(a.dg_partials + 12 * (long long)(b.dg_tile0 + t) + 4 * grp)
-                                             : reinterpret_cast<const double2*>(a.partials + 4 * (long long)(b.tile0 + t));
-            const double2 p0 = __ldcg(p), p1 = __ldcg(p + 1);
-            s[0] += p0.x; s[1] += p0.y; s[2] += p1.x; s[3] += p1.y;
+            for (int t = lane; t < ntiles; t += 32) {
+                const double2* p = reinterpret_cast<const double2*>(src + (long long)stride * t);
+                const double2 p0 = __ldcg(p), p1 = __ldcg(p + 1);
+                s[0] += p0.x; s[1] += p0.y; s[2] += p1.x; s[3] += p1.y;
+            }
         }
 #pragma unroll
         for (int v = 0; v < 4; v++) {

@@ -369,7 +369,8 @@ struct StepVar {
 // pointers to global memory: the row loop of march_tile is tuned to the last register and the last branch, and ptxas
 // only keeps it that way (convergence of the warp proven, no register moves between the two rows of a trip) while
 // the strip's own code path contains no divergent loop and no spill-prone live range - measured: any of these
-// pieces inlined costs 8-10 % more instructions in the row loop and 27 % of the step.
+// pieces inlined costs 8-10 % more instructions in the row loop (and even so the fused kernel is ~10 % slower per
+// launch than the launch-per-step kernel below - which is why large meshes keep that one).
 
 // One side of a perimeter strip after its rows are done (the strip's new cells sit in Sout, visible to the whole
 // warp): per edge cell n of [n0, n1)
@@ -718,10 +719,13 @@ __device__ __forceinline__ int2 tile_from_list(const int2* list, int t) {
 
 // ------------------------------------------------------------------ the launch-per-step kernel (large meshes)
 // One warp strip per CTA; the ghost ring and the per-block dt come from the ghost kernel launched before it, the
-// bookkeeping rides in the NEXT ghost launch.  This kernel is deliberately kept apart from march_tile above although
-// the two run the same rows: its row loop is at the edge of the register file, and the schedule ptxas finds for it
-// depends on everything else in the kernel - measured on B200 with the very same loop instructions, 0.549 ms per
-// launch here against 0.580 (same code behind the march_tile interface) and 0.635 (fused step) on the benchmark mesh.
+// bookkeeping rides in the NEXT ghost launch.  Kept apart from march_tile above although the two run the same rows:
+// this row loop sits at the edge of the register file (128 registers at 16 warps per SM) and ptxas only finds its
+// 785-instruction, move-free schedule while nothing else shares the strip's code path - with ANY piece of the fused
+// step compiled in (a flag wait, the perimeter epilogue, even as non-inlined calls) the same PTX loop becomes
+// 846-865 instructions with 20-30 register moves, and the fused kernel measures 0.637 ms per launch against 0.576
+// here on the benchmark mesh (same box, same sustained conditions; tools/ab_large.sh).  Large meshes are bound by
+// this kernel, so they keep it; small meshes are bound by latency and take the fused step.
 template <bool FAITHFUL, bool TPG, bool AXI, bool HOOKS>
 __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) march_kernel(const StepArgs a, const Gas g) {
     __shared__ __align__(128) MarchSmem sm;

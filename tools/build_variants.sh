@@ -9,6 +9,7 @@ while [ $# -ge 2 ]; do
     name="$1"; flags="$2"; shift 2
     d="build/variants/$name"; mkdir -p "$d"
     $NV $flags -Xptxas -v -c kernels_fast.cu -o "$d/kernels_fast.o" 2> "$d/ptxas.txt" &
+    $NV $flags -c kernels_march.cu -o "$d/kernels_march.o" &
     $NV $flags -fmad=false -c kernels_faithful.cu -o "$d/kernels_faithful.o" &
     $NV $flags -fmad=false -c kernels_common.cu -o "$d/kernels_common.o" &
     $NV $flags -c capi.cu -o "$d/capi.o" &
