@@ -245,6 +245,52 @@ def parity_gate(gpu, world, rank, local, transport):
     return records
 
 
+def shipped_cases(gpu, world, rank, local, transport, steps=3000):
+    """BASELINE.json configs[0..3] on the same N ranks: us per step and cell-updates/s of the four shipped case
+    directories (43-55 k cells: a step is bound by latency, not by HBM - the small-mesh path: one persistent launch per
+    batch on one GPU, one fused launch per step across GPUs).  A case with fewer blocks than ranks is skipped."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from par2d_b200 import Case, Solver, default_config
+    multi = world > 1
+    rows = []
+    for name, igam in (("Case_ffstep1", 1.4), ("Case_ffstep8", 1.4), ("Case_rktnoz9", -1.4), ("Case_spikefine24", 1.4)):
+        case = Case.load(os.path.join(REPO, "tests", "golden", "cases", name))
+        if case.nblocks < world:
+            rows.append({"case": name, "blocks": case.nblocks, "skipped": f"{case.nblocks} block(s) cannot be spread over {world} ranks"})
+            continue
+        cfg = default_config(gpu)
+        cfg.device, cfg.igam = local, igam
+        if multi:
+            from par2d_b200.dist import DistSolver
+            s = DistSolver(case, cfg, lib=gpu, transport=transport)
+            adv = s.advance
+        else:
+            s = Solver(case, cfg, lib=gpu)
+            adv = s.step
+        adv(200)
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+        t0 = time.perf_counter()
+        left = steps
+        while left > 0:
+            info = adv(min(left, 1000))
+            left -= min(left, 1000)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if multi:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+        ok = all(i.status == 0 for i in info)
+        rows.append({"case": name, "gas": "CPG" if igam > 0 else "TPG (NASA-7)", "blocks": case.nblocks, "cells": case.ncells, "ranks": world,
+                     "steps": steps, "us_per_step": 1e6 * sec / steps, "cell_updates_per_s": case.ncells * steps / sec, "status_ok": ok,
+                     "timing": "host wall clock around batches of 1000 steps (each batch ends with a synchronise + history read-back), max over ranks"})
+        s.close()
+    return rows
+
+
 def run_gpu_arm(args):
     import numpy as np
     import torch
@@ -264,6 +310,7 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     gpu = _capi.load_gpu()      # raises when the CUDA library is missing: there is no fallback path
     gate = None if args.no_gate else parity_gate(gpu, world, rank, local, args.transport)
+    shipped = None if args.no_gate else shipped_cases(gpu, world, rank, local, args.transport)
     # weak scaling (default, the driver's contract): 8 blocks per GPU; --strong: the full 8 x 8 block mesh on any N
     nbx, nby = LAYOUT[8] if args.strong else LAYOUT[args.gpus]
     blk = args.block
@@ -329,8 +376,9 @@ def run_gpu_arm(args):
     timed(int(args.preheat_ms / per_step) + 1)
     gpu.check(gpu.kernel_timing(h, 1), "kernel_timing")
     elapsed_ms, info = timed(args.steps, chunk=args.steps)          # THE timed region: exactly K steps, one batch
-    kms, kn = C.c_double(), C.c_int64()
+    kms, kn, nlaunch = C.c_double(), C.c_int64(), C.c_int64()
     gpu.check(gpu.kernel_time(h, C.byref(kms), C.byref(kn)), "kernel_time")
+    gpu.check(gpu.launch_count(h, C.byref(nlaunch)), "launch_count")
     relres_last = (solver.global_relres(args.steps)[-1] if multi else info[-1].relres)
     n_sus = int(args.sustain_ms / per_step) + 1
     sus_ms, sus_info = timed(n_sus)
@@ -360,11 +408,11 @@ def run_gpu_arm(args):
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for b, buf in host_bufs.items():
-            gpu.check(gpu.set_state(h, b, C.cast(buf.data_ptr(), dp)), "set_state")
+        ids = (C.c_int32 * len(host_bufs))(*host_bufs.keys())
+        ptrs = (dp * len(host_bufs))(*[C.cast(buf.data_ptr(), dp) for buf in host_bufs.values()])
+        gpu.check(gpu.set_states(h, len(host_bufs), ids, ptrs), "set_states")     # copy of block i+1 overlaps the transpose of block i
         einfo = advance(args.steps)                    # per-step dt/relres records are copied back
-        for b, buf in host_bufs.items():
-            gpu.check(gpu.get_state(h, b, C.cast(buf.data_ptr(), dp)), "get_state")
+        gpu.check(gpu.get_states(h, len(host_bufs), ids, ptrs), "get_states")
         e1.record()
         sync_all()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -423,11 +471,13 @@ def run_gpu_arm(args):
                    "l2": "state per GPU 1.07 GB read + 1.07 GB written per step >> 126 MB L2; no flush needed",
                    "arith_mode": "PAR2D_MODE_FAITHFUL" if args.faithful else "PAR2D_MODE_FAST"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-        # peer transport: ghost + edge strips + interior strips + put per step; external: ghost + march + pack
-        "gpu_launches": (LAUNCHES_PER_STEP + (2 if transport == "peer" else 1 if multi else 0)) * args.steps + 1 + (1 if transport == "peer" else 0),
+        # counted by the library: every kernel rank 0 launched inside the timed region (large mesh: ghost + march per step,
+        # across ranks ghost + edge strips + interior strips + put; + the put and the bookkeeping launch that open / close the batch)
+        "gpu_launches": int(nlaunch.value),
         "relres_last": relres_last, "dt": info[-1].dt,
         "value_sustained": value_sustained, "sustained_steps": n_sus,
         "parity_gate": gate,
+        "shipped_cases": shipped,
     }
     print(json.dumps(line), flush=True)
     if multi:

@@ -277,6 +277,9 @@ int par2d_test_solve(const par2d_config* cfg, int64_t n, const double* dt_ycc /*
  * their durations and the launch count.  bench.py derives roofline.achieved from it. */
 int par2d_kernel_timing(par2d_ctx* ctx, int32_t enable);
 int par2d_kernel_time(par2d_ctx* ctx, double* total_ms, int64_t* launches);
+/* Kernel launches of every kind this ctx has issued since the last par2d_kernel_timing / par2d_launch_count call
+ * (bench.py's gpu_launches). */
+int par2d_launch_count(par2d_ctx* ctx, int64_t* n);
 
 /* Diagnostic of the persistent launch (ctx created with PAR2D_PROFILE_PERSIST=1 in the environment): for each of the
  * first nsteps steps of the last batch, out[12*s + {0: SM cycles the first strip spent in its step, 1: ... waiting at the

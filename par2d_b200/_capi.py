@@ -116,6 +116,7 @@ GPU_ONLY_API = {
     "persist_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "kernel_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "kernel_time": (C.c_int, [C.c_void_p, _DP, C.POINTER(C.c_int64)]),
+    "launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
 }
 
 # entry points only the oracle has (test hooks)

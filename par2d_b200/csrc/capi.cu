@@ -236,6 +236,8 @@ struct par2d_ctx {
     cudaEvent_t ev_ghost = nullptr, ev_edge = nullptr;
     // persistent launch: a whole batch of a small mesh in one cooperative kernel
     int2* d_all_tiles = nullptr;
+    GhostOp* d_ops = nullptr;        // fused step: ghost-cell records, grouped by strip (common.cuh)
+    int2* d_op_range = nullptr;
     unsigned* grid_bar = nullptr;
     long long* prof = nullptr;       // PAR2D_PROFILE_PERSIST=1: per-step cycle counts of the persistent launch (par2d_persist_profile)
     int coop_capacity = 0;
@@ -260,6 +262,7 @@ struct par2d_ctx {
     int ev_used = 0;
     double kernel_ms = 0.0;
     long long kernel_launches = 0;
+    long long launches = 0;        // every kernel launch of this ctx since the last par2d_kernel_timing call
 
     StepArgs step_args(int update) const {
         StepArgs a;
@@ -278,6 +281,8 @@ struct par2d_ctx {
         a.coop_steps = 1;
         a.grid_bar = grid_bar;
         a.prof = prof;
+        a.ops = d_ops;
+        a.op_range = d_op_range;
         a.gas_dev = gas_dev;
         a.dt_used = dt_used + (iter_queued & 1);
         a.partials = partials + (iter_queued & 1) * partials_stride;
@@ -392,7 +397,7 @@ int build_tensor_maps(par2d_ctx* c) {
     return 0;
 }
 
-void launch_step(par2d_ctx* c, const StepArgs& a) { c->kt->march(c->stream, a, c->gas, c->tpg, c->axi); }
+void launch_step(par2d_ctx* c, const StepArgs& a) { c->launches++; c->kt->march(c->stream, a, c->gas, c->tpg, c->axi); }
 
 PutArgs put_args(const par2d_ctx* c);
 
@@ -400,6 +405,7 @@ PutArgs put_args(const par2d_ctx* c);
 // batch; every step of the second-order branch and of the serial A/B order)
 void queue_put(par2d_ctx* c, cudaStream_t stream = nullptr) {
     c->seq++;
+    c->launches++;
     c->kt->pack(stream ? stream : c->stream, c->step_args(1), c->gas, c->dlines_peer, c->nlines, c->max_line, put_args(c));
 }
 
@@ -407,6 +413,7 @@ void queue_put(par2d_ctx* c, cudaStream_t stream = nullptr) {
 // the ghost fill; flush_finalize() launches it on its own at the end of a batch.
 void flush_finalize(par2d_ctx* c) {
     if (!c->fin_pending) return;
+    c->launches++;
     launch_finalize(c->stream, c->fin_args);
     c->fin_pending = false;
 }
@@ -428,9 +435,13 @@ DgArgs dg_args(const par2d_ctx* c, int update) {
 void queue_step_dg(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
     StepArgs a = c->step_args(1);
     const DgArgs d = dg_args(c, 1);
+    c->launches++;
     c->kt->dg_ghost(c->stream, a, c->gas, d, with_ghost_dt ? 1 : 0);
+    c->launches++;
     c->kt->dg_cell(c->stream, a, c->gas, d, c->tpg, c->axi);
+    c->launches++;
     c->kt->dg_limit(c->stream, a, d);
+    c->launches++;
     launch_finalize(c->stream, c->finalize_args(stop_on_tol));
     c->iter_queued++;
     c->cur ^= 1;
@@ -499,6 +510,7 @@ PutArgs put_args(const par2d_ctx* c) {
 void queue_step_overlapped(par2d_ctx* c) {
     StepArgs a = c->step_args(1);
     a.dt_ready = 1;
+    c->launches++;
     c->kt->ghost(c->stream, a, c->gas, 0, c->fin_pending ? &c->fin_args : nullptr);
     c->fin_pending = false;
     cudaEventRecord(c->ev_ghost, c->stream);
@@ -507,7 +519,9 @@ void queue_step_overlapped(par2d_ctx* c) {
     StepArgs ae = a, ai = a;
     ae.tile_list = c->d_push_tiles; ae.tile_count = (int)c->n_put_tiles;
     ai.tile_list = c->d_push_tiles + c->n_put_tiles; ai.tile_count = c->n_push_tiles - (int)c->n_put_tiles;
+    c->launches++;
     c->kt->march(c->side_stream, ae, c->gas, c->tpg, c->axi);
+    c->launches++;
     c->kt->march(c->stream, ai, c->gas, c->tpg, c->axi);
     c->fin_args = c->finalize_args(0);
     c->fin_pending = true;
@@ -544,6 +558,7 @@ void queue_step_fused(par2d_ctx* c, int launch_no, int stop_on_tol) {
     }
     const PutArgs put = put_args(c);
     time_begin(c);
+    c->launches++;
     c->kt->march_push(c->stream, a, c->gas, put, fin, c->tpg, c->axi);
     time_end(c);
     c->fin_args = c->finalize_args(stop_on_tol);
@@ -566,6 +581,7 @@ bool queue_batch_persistent(par2d_ctx* c, int nsteps, int stop_on_tol) {
     double* partials_alt = c->partials + ((c->iter_queued + 1) & 1) * c->partials_stride;
     if (cudaMemsetAsync(c->grid_bar, 0, sizeof(unsigned), c->stream) != cudaSuccess) return false;
     time_begin(c);
+    c->launches++;
     const cudaError_t e = c->kt->march_coop(c->stream, a, c->gas, fin, dt_used_alt, partials_alt, c->tpg, c->axi);
     time_end(c);
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
@@ -578,6 +594,7 @@ void queue_step(par2d_ctx* c, int stop_on_tol, bool with_ghost_dt) {
     if (c->dg) { queue_step_dg(c, stop_on_tol, with_ghost_dt); return; }
     StepArgs a = c->step_args(1);
     a.dt_ready = with_ghost_dt ? 0 : 1;
+    c->launches++;
     c->kt->ghost(c->stream, a, c->gas, with_ghost_dt ? 1 : 0, c->fin_pending ? &c->fin_args : nullptr);
     c->fin_pending = false;
     time_begin(c);
@@ -953,6 +970,75 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
         const char* pp = getenv("PAR2D_PROFILE_PERSIST");
         if (pp && atoi(pp) != 0) { CU_TRY(cudaMalloc(&c->prof, sizeof(long long) * 12 * 4096)); CU_TRY(cudaMemset(c->prof, 0, sizeof(long long) * 12 * 4096)); }
     }
+    {
+        // ghost-cell records of the fused step, grouped by the strip that holds the edge cell
+        std::vector<std::vector<GhostOp>> per_tile((size_t)c->total_tiles);
+        std::vector<int32_t> codes;
+        for (int k = 0; k < c->nowned; k++) {
+            const BlockDev& b = c->hblk[k];
+            const par2d_block_desc& d = blocks[c->owned_gid[k]];
+            const int ncx = b.ncx, ncy = b.ncy;
+            std::vector<double2> fn((size_t)2 * (ncx + ncy));
+            CU_TRY(cudaMemcpy(fn.data(), c->block_fnorm[k], sizeof(double2) * fn.size(), cudaMemcpyDeviceToHost));
+            for (int side = 0; side < 4; side++) {
+                if (b.nb_kind[side] == NB_REMOTE) continue;          // put by the strips themselves (push_side)
+                const int len = (side == SIDE_BOTTOM || side == SIDE_TOP) ? ncx : ncy;
+                for (int n = 0; n < len; n++) {
+                    int ec, er, gc, gr, f;
+                    switch (side) {
+                        case SIDE_BOTTOM: ec = COL0 + n; er = 1; gc = COL0 + n; gr = 0; f = n; break;
+                        case SIDE_RIGHT: ec = COL0 + ncx - 1; er = n + 1; gc = COL0 + ncx; gr = n + 1; f = ncx + n; break;
+                        case SIDE_TOP: ec = COL0 + n; er = ncy; gc = COL0 + n; gr = ncy + 1; f = 2 * ncx + ncy - 1 - n; break;
+                        default: ec = COL0; er = n + 1; gc = COL0 - 1; gr = n + 1; f = 2 * ncx + 2 * ncy - 1 - n; break;
+                    }
+                    GhostOp op;
+                    memset(&op, 0, sizeof op);
+                    const long long io = (long long)er * b.pitch + ec;
+                    op.src[0] = b.state[0] + io; op.src[1] = b.state[1] + io;
+                    op.src_plane = (int)b.plane;
+                    op.blk = k; op.f = f; op.code = d.ibound[f];
+                    if (b.nb_kind[side] == NB_LOCAL) {
+                        const BlockDev& o = c->hblk[b.nb_block[side]];
+                        int oc, orow;
+                        switch (b.nb_side[side]) {
+                            case SIDE_BOTTOM: oc = COL0 + n; orow = 0; break;
+                            case SIDE_RIGHT: oc = COL0 + o.ncx; orow = n + 1; break;
+                            case SIDE_TOP: oc = COL0 + n; orow = o.ncy + 1; break;
+                            default: oc = COL0 - 1; orow = n + 1; break;
+                        }
+                        const long long go = (long long)orow * o.pitch + oc;
+                        op.dst[0] = o.state[0] + go; op.dst[1] = o.state[1] + go;
+                        op.dst_plane = (int)o.plane;
+                        op.kind = 0;
+                    } else {
+                        const long long go = (long long)gr * b.pitch + gc;
+                        op.dst[0] = b.state[0] + go; op.dst[1] = b.state[1] + go;
+                        op.dst_plane = (int)b.plane;
+                        int code = op.code;
+                        if (code == -1) code = 3;                  // BoundaryConditions.cpp:76-77
+                        if (code == 0) code = 4;
+                        op.code = code;
+                        op.kind = code == 3 ? 0 : code == 4 ? 1 : code == 1 ? 3 : 2;
+                        op.nx = fn[(size_t)f].x; op.ny = fn[(size_t)f].y;
+                    }
+                    int tx, ty;
+                    if (side == SIDE_BOTTOM || side == SIDE_TOP) { tx = n / MCELLS; ty = side == SIDE_BOTTOM ? 0 : b.tiles_y - 1; }
+                    else { tx = side == SIDE_LEFT ? 0 : b.tiles_x - 1; ty = n / c->march_rows; }
+                    per_tile[(size_t)(b.tile0 + ty * b.tiles_x + tx)].push_back(op);
+                }
+            }
+        }
+        std::vector<GhostOp> ops;
+        std::vector<int2> range((size_t)c->total_tiles);
+        for (int t = 0; t < c->total_tiles; t++) {
+            range[(size_t)t] = make_int2((int)ops.size(), (int)per_tile[(size_t)t].size());
+            ops.insert(ops.end(), per_tile[(size_t)t].begin(), per_tile[(size_t)t].end());
+        }
+        CU_TRY(cudaMalloc(&c->d_ops, sizeof(GhostOp) * std::max<size_t>(ops.size(), 1)));
+        CU_TRY(cudaMalloc(&c->d_op_range, sizeof(int2) * range.size()));
+        CU_TRY(cudaMemcpy(c->d_ops, ops.data(), sizeof(GhostOp) * ops.size(), cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(c->d_op_range, range.data(), sizeof(int2) * range.size(), cudaMemcpyHostToDevice));
+    }
     c->partials_stride = 4ll * c->total_tiles;
     CU_TRY(cudaMalloc(&c->gas_dev, sizeof(Gas)));
     CU_TRY(cudaMemcpyAsync(c->gas_dev, &c->gas, sizeof(Gas), cudaMemcpyHostToDevice, c->stream));
@@ -1000,7 +1086,7 @@ int par2d_destroy(par2d_ctx* c) {
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (int q = 0; q < 2; q++) { if (c->ev_ready[q]) cudaEventDestroy(c->ev_ready[q]); if (c->ev_free[q]) cudaEventDestroy(c->ev_free[q]); }
     cudaFree(c->staging2);
-    cudaFree(c->prof);
+    cudaFree(c->prof); cudaFree(c->d_ops); cudaFree(c->d_op_range);
     cudaFree(c->d_all_tiles); cudaFree(c->gas_dev); cudaFree(c->grid_bar); cudaFree(c->go); cudaFree(c->stop_iter); cudaFree(c->flag_hist);
     for (double* m : c->dg_mem) cudaFree(m);
     cudaFree(c->dg_partials);
@@ -1119,6 +1205,7 @@ int par2d_get_residual(par2d_ctx* c, int32_t block, double* res) {
     // (after par2d_set_state, call par2d_step(ctx, 0, 0, NULL) on every rank to refresh them)
     flush_finalize(c);
     CU_TRY(cudaMemsetAsync(c->stop, 0, sizeof(int), c->stream));   // a batch that stopped on the tolerance leaves the stop word set
+    c->launches++;
     c->kt->ghost(c->stream, a, c->gas, c->peer_connected ? 0 : 1, nullptr);
     launch_step(c, a);
     const size_t bytes = sizeof(double) * 4 * (size_t)b.ncx * b.ncy;
@@ -1168,7 +1255,9 @@ int par2d_get_residual_dg(par2d_ctx* c, int32_t block, double* res, double* resx
     d.res_out = out;
     d.res_block = k;
     CU_TRY(cudaMemsetAsync(c->stop, 0, sizeof(int), c->stream));
+    c->launches++;
     c->kt->dg_ghost(c->stream, a, c->gas, d, c->peer_connected ? 0 : 1);
+    c->launches++;
     c->kt->dg_cell(c->stream, a, c->gas, d, c->tpg, c->axi);
     CU_TRY(cudaMemcpyAsync(res, out, sizeof(double) * n4, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaMemcpyAsync(resx, out + n4, sizeof(double) * n4, cudaMemcpyDeviceToHost, c->stream));
@@ -1210,6 +1299,7 @@ int par2d_step_async(par2d_ctx* c, int32_t nsteps, int32_t stop_on_tol) {
             if (c->batch_stop) CU_TRY(cudaMemsetAsync(c->go, 0, sizeof(int), c->stream));
             queue_put(c);
             StepArgs a0 = c->step_args(1);
+            c->launches++;
             c->kt->ghost(c->stream, a0, c->gas, 0, nullptr);
             for (int s = 0; s < nsteps; s++) queue_step_fused(c, s + 1, stop_on_tol);
         } else if (c->fused && !c->dg) {
@@ -1230,6 +1320,7 @@ int par2d_step_async(par2d_ctx* c, int32_t nsteps, int32_t stop_on_tol) {
         // ghost ring + per-block dt of the current state by the pull kernel (it may come from par2d_set_state); every
         // step after that pushes them for the next one
         StepArgs a0 = c->step_args(1);
+        c->launches++;
         c->kt->ghost(c->stream, a0, c->gas, 1, nullptr);
         const bool fits = c->persist && c->coop_capacity >= c->total_tiles + c->nowned;
         if (!(fits && queue_batch_persistent(c, nsteps, stop_on_tol)))
@@ -1238,6 +1329,7 @@ int par2d_step_async(par2d_ctx* c, int32_t nsteps, int32_t stop_on_tol) {
     flush_finalize(c);
     if (c->batch_stop && nsteps > 0) {
         const long long first = std::max<long long>(c->iter, c->iter + nsteps - 2);
+        c->launches++;
         c->kt->stop_tail(c->stream, stop_args(c), c->stop, c->flags, first, c->iter + nsteps - 1);
     }
     c->batch_open = true;
@@ -1304,6 +1396,7 @@ int par2d_step_begin(par2d_ctx* c) {
     PutArgs put;
     memset(&put, 0, sizeof put);
     put.dg = c->dg ? 1 : 0;
+    c->launches++;
     c->kt->pack(c->stream, c->step_args(1), c->gas, c->dlines, c->nlines, c->max_line, put);
     return 0;
 }
@@ -1560,6 +1653,14 @@ int par2d_kernel_timing(par2d_ctx* c, int32_t enable) {
     c->timing = enable != 0;
     c->kernel_ms = 0.0;
     c->kernel_launches = 0;
+    c->launches = 0;
+    return 0;
+}
+
+int par2d_launch_count(par2d_ctx* c, int64_t* n) {
+    if (!c || !n) return fail(PAR2D_ERR_ARG, "launch_count: null argument");
+    *n = c->launches;
+    c->launches = 0;
     return 0;
 }
 

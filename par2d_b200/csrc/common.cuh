@@ -57,6 +57,24 @@ struct BlockDev {
     int dg_tile0, dg_ntiles;  // this block's strips of the cell kernel (one record each in the [.][12] partial-sum array)
 };
 
+// One ghost cell of the NEW state, as the fused step's perimeter strips fill it (march.cuh, tile_epilogue): where the
+// edge cell sits, where its ghost goes (the block's own ring for a boundary-condition face, the same-rank neighbour's
+// ring for a shared face) and what happens in between.  Built once per ctx, grouped by strip: the whole perimeter
+// work of a strip is one short loop over its records - it runs once per step out of a cold instruction cache, so
+// every instruction it does not have counts (measured on the persistent launch: ~12 cycles per cold instruction).
+struct GhostOp {
+    double* src[2];          // the edge cell, plane 0, in state buffer 0 / 1
+    double* dst[2];          // the ghost cell, plane 0, in state buffer 0 / 1
+    int src_plane, dst_plane;  // doubles between planes of the two blocks
+    int kind;                // 0 copy (shared face; extrapolation, codes 3 and -1), 1 slip wall (codes 4 and 0), 3 far field (code 1),
+                             // 2 any other code
+    int blk;                 // kind 2: owned block, CCW face index and BC code
+    int f, code;
+    int pad[2];
+    double nx, ny;           // kind 1: outward unit normal (BlockDev::fnorm)
+};
+static_assert(sizeof(GhostOp) == 80 && sizeof(GhostOp) % 16 == 0, "GhostOp is read with 16-byte loads");
+
 // one edge line to pack for an off-rank neighbour (SpatialDiscretization.cpp:236-257)
 struct SendLine {
     int block;   // owned-block index
@@ -149,6 +167,8 @@ struct StepArgs {
     unsigned* grid_bar;      // persistent launch: grid barrier counter
     const Gas* gas_dev;      // the Gas constants in global memory (for the non-inlined boundary-condition code)
     long long* prof;         // diagnostics of the persistent launch (null in production), see march_persist_kernel
+    const GhostOp* ops;      // fused step: ghost-cell records of this rank, grouped by strip
+    const int2* op_range;    // [total_tiles] (first record, count) of strip tile0 + s
     // (new members go at the END: the offsets of the members above are part of what the tuned launch-per-step kernel was
     //  compiled against - ptxas schedules its row loop differently when they move, see march.cuh)
 };

@@ -65,7 +65,7 @@ __device__ __forceinline__ void finalize_block(const FinalizeArgs& a, int k, dou
             if (threadIdx.x >= 32 && grp == ngroups - 1) return;
             if (threadIdx.x >= 32) continue;
         } else {
-#pragma unroll 4
+#pragma unroll 8
             for (int t = lane; t < ntiles; t += 32) {
                 const double2* p = reinterpret_cast<const double2*>(src + (long long)stride * t);
                 const double2 p0 = __ldcg(p), p1 = __ldcg(p + 1);

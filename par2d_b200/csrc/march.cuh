@@ -372,40 +372,20 @@ struct StepVar {
 // pieces inlined costs 8-10 % more instructions in the row loop (and even so the fused kernel is ~10 % slower per
 // launch than the launch-per-step kernel below - which is why large meshes keep that one).
 
-// One side of a perimeter strip after its rows are done (the strip's new cells sit in Sout, visible to the whole
-// warp): per edge cell n of [n0, n1)
-//   boundary-condition face : the ghost state of the NEW state -> ghost ring of Sout       (generate_ghost_cells)
-//   same-rank neighbour     : the new cell -> the neighbour block's ghost ring              (halo exchange, :263-269)
-//   off-rank neighbour      : the new cell -> the neighbour rank's arena over NVLink        (halo exchange, :236-259)
-// so that the next step finds its ghost ring complete without a ghost launch.
+// One side of a perimeter strip that borders another RANK, after its rows are done (the strip's new cells sit in Sout,
+// visible to the whole warp): the new edge cells n of [n0, n1) straight into the neighbour rank's arena over NVLink, one
+// 32-byte AoS record per edge cell (usend[k + NVAR*j], SpatialDiscretization.cpp:236-259).
 __device__ __forceinline__ void push_side(const BlockDev* blocks, const Gas* gas, const BlockDev& b, int out_buf, int parity, int side, int n0, int n1) {
-    const int kind = b.nb_kind[side];
-    double* Sout = b.state[out_buf];
+    (void)blocks; (void)gas;
+    if (b.put_dst[side] == nullptr) return;
+    const double* Sout = b.state[out_buf];
     for (int n = n0 + (int)threadIdx.x; n < n1; n += 32) {
         int c, r;
-        if (kind == NB_NONE) {
-            bc_ghost_fill(gas, &b, Sout, side, n);
-            continue;
-        }
         edge_cell_pos(b.ncx, b.ncy, side, n, c, r);
         const long long io = (long long)r * b.pitch + c;
-        double u[4];
-#pragma unroll
-        for (int v = 0; v < 4; v++) u[v] = __ldcg(Sout + v * b.plane + io);
-        if (kind == NB_LOCAL) {
-            const BlockDev& o = blocks[b.nb_block[side]];
-            ghost_cell_pos(o.ncx, o.ncy, b.nb_side[side], n, c, r);
-            double* So = o.state[out_buf];
-            const long long go = (long long)r * o.pitch + c;
-            u[3] = fmax(u[3], 201.0);
-#pragma unroll
-            for (int v = 0; v < 4; v++) __stcg(So + v * o.plane + go, u[v]);
-        } else if (b.put_dst[side] != nullptr) {
-            // one 32-byte AoS record per edge cell (usend[k + NVAR*j], SpatialDiscretization.cpp:241)
-            double2* d2 = reinterpret_cast<double2*>(b.put_dst[side] + parity * b.put_stride[side] + 4 * (long long)n);
-            d2[0] = make_double2(u[0], u[1]);
-            d2[1] = make_double2(u[2], u[3]);
-        }
+        double2* d2 = reinterpret_cast<double2*>(b.put_dst[side] + parity * b.put_stride[side] + 4 * (long long)n);
+        d2[0] = make_double2(__ldcg(Sout + io), __ldcg(Sout + b.plane + io));
+        d2[1] = make_double2(__ldcg(Sout + 2 * b.plane + io), __ldcg(Sout + 3 * b.plane + io));
     }
 }
 
@@ -422,31 +402,74 @@ struct PutLite {
 
 // After the rows of a perimeter strip: ghost ring / edge lines of the NEW state, the block's dt, the put ticket.
 // Returns error bits.
-static __device__ __noinline__ unsigned tile_epilogue(const BlockDev* blocks, const Gas* gas, int k, int strip, int out_buf, int march_rows,
-                                                     double* dt_next, double gamRs, double cfl, PutLite put, long long* prof) {
+static __device__ __noinline__ unsigned tile_epilogue(const BlockDev* blocks, const Gas* gas, const GhostOp* ops, int op0, int nop, int k, int strip,
+                                                     int out_buf, int march_rows, double* dt_next, double gamRs, double cfl, PutLite put, long long* prof) {
     const long long tq = prof ? clock64() : 0;
-    const BlockDev& b = blocks[k];
     const int lane = threadIdx.x;
     unsigned flags = 0;
-    const int ex = strip % b.tiles_x, ey = strip / b.tiles_x;
-    const bool tl = ex == 0, tr = ex == b.tiles_x - 1, tb = ey == 0, tt = ey == b.tiles_y - 1;
-    const int c0 = ex * MCELLS, c1 = min(c0 + MCELLS, b.ncx);
-    const int j0 = ey * march_rows, j1 = min(j0 + march_rows, b.ncy);
     __syncwarp();                                  // the strip's new cells are visible to every lane
     if (prof) prof[0] = clock64() - tq;
-    if (tl) push_side(blocks, gas, b, out_buf, put.parity, SIDE_LEFT, j0, j1);
-    if (tr) push_side(blocks, gas, b, out_buf, put.parity, SIDE_RIGHT, j0, j1);
+    // boundary-condition faces and faces shared with a block of this rank: one record per ghost cell
+    for (int i = lane; i < nop; i += 32) {
+        const GhostOp* op = ops + op0 + i;
+        const int4 meta = __ldg(reinterpret_cast<const int4*>(&op->src_plane));     // src_plane, dst_plane, kind, blk
+        if (meta.z >= 2) {
+            const BlockDev& b = blocks[meta.w];
+            double* S = b.state[out_buf];
+            const int2 fc = __ldg(reinterpret_cast<const int2*>(&op->f));
+            if (meta.z == 3) {
+                // far field (code 1, BoundaryConditions.cpp:148-188) where the normal velocity is supersonic - the usual
+                // state of these faces: vn/a <= -1 takes the free stream, vn/a >= 1 the interior state.  For a > 0 the
+                // quotient's comparisons with -1 and 1 are exactly those of vn with -a and a, so no division is needed.
+                const double* src = out_buf ? op->src[1] : op->src[0];
+                double* dst = out_buf ? op->dst[1] : op->dst[0];
+                const double u0 = __ldcg(src), u1 = __ldcg(src + meta.x), u2 = __ldcg(src + 2 * (long long)meta.x), u3 = __ldcg(src + 3 * (long long)meta.x);
+                const double2 nrm = __ldg(reinterpret_cast<const double2*>(&op->nx));
+                const double vn = __dadd_rn(__dmul_rn(u1, nrm.x), __dmul_rn(u2, nrm.y));
+                const double aint = sqrt(__dmul_rn(gas->gamRs, u3));
+                if (aint > 0.0 && (vn <= -aint || vn >= aint)) {
+                    const bool in = vn <= -aint;
+                    __stcg(dst, in ? gas->uFS[0] : u0); __stcg(dst + meta.y, in ? gas->uFS[1] : u1);
+                    __stcg(dst + 2 * (long long)meta.y, in ? gas->uFS[2] : u2); __stcg(dst + 3 * (long long)meta.y, fmax(in ? gas->uFS[3] : u3, 201.0));
+                    continue;
+                }
+            }
+            bc_ghost_general(gas, &b, S, fc.y, fc.x, op->src[out_buf] - S, op->dst[out_buf] - S);
+            continue;
+        }
+        const double* src = out_buf ? op->src[1] : op->src[0];
+        double* dst = out_buf ? op->dst[1] : op->dst[0];
+        double u0 = __ldcg(src), u1 = __ldcg(src + meta.x), u2 = __ldcg(src + 2 * (long long)meta.x), u3 = __ldcg(src + 3 * (long long)meta.x);
+        if (meta.z == 1) {                         // slip wall: V - 2 (V.n) n, BoundaryConditions.cpp:79-88 (as bc_ghost_fill)
+            const double2 nrm = __ldg(reinterpret_cast<const double2*>(&op->nx));
+            const double vn = __dadd_rn(__dmul_rn(u1, nrm.x), __dmul_rn(u2, nrm.y));
+            const double t = __dmul_rn(2.0, vn);
+            const double w1 = __dsub_rn(u1, __dmul_rn(t, nrm.x)), w2 = __dsub_rn(u2, __dmul_rn(t, nrm.y));
+            u1 = w1; u2 = w2;
+        }
+        __stcg(dst, u0); __stcg(dst + meta.y, u1); __stcg(dst + 2 * (long long)meta.y, u2); __stcg(dst + 3 * (long long)meta.y, fmax(u3, 201.0));
+    }
     if (prof) prof[1] = clock64() - tq;
-    if (tb) push_side(blocks, gas, b, out_buf, put.parity, SIDE_BOTTOM, c0, c1);
-    if (tt) push_side(blocks, gas, b, out_buf, put.parity, SIDE_TOP, c0, c1);
-    if (prof) prof[2] = clock64() - tq;
     bool put_something = false;
     if (put.peer_mode) {
-        put_something = (tl && b.nb_kind[SIDE_LEFT] == NB_REMOTE) || (tr && b.nb_kind[SIDE_RIGHT] == NB_REMOTE) ||
-                        (tb && b.nb_kind[SIDE_BOTTOM] == NB_REMOTE) || (tt && b.nb_kind[SIDE_TOP] == NB_REMOTE) || strip == 0;
+        // faces shared with a block of another rank: the new edge cells straight into that rank's arena
+        const BlockDev& b = blocks[k];
+        const int ex = strip % b.tiles_x, ey = strip / b.tiles_x;
+        const bool tl = ex == 0, tr = ex == b.tiles_x - 1, tb = ey == 0, tt = ey == b.tiles_y - 1;
+        const int c0 = ex * MCELLS, c1 = min(c0 + MCELLS, b.ncx);
+        const int j0 = ey * march_rows, j1 = min(j0 + march_rows, b.ncy);
+        const bool rl = tl && b.nb_kind[SIDE_LEFT] == NB_REMOTE, rr = tr && b.nb_kind[SIDE_RIGHT] == NB_REMOTE;
+        const bool rb = tb && b.nb_kind[SIDE_BOTTOM] == NB_REMOTE, rt = tt && b.nb_kind[SIDE_TOP] == NB_REMOTE;
+        if (rl) push_side(blocks, gas, b, out_buf, put.parity, SIDE_LEFT, j0, j1);
+        if (rr) push_side(blocks, gas, b, out_buf, put.parity, SIDE_RIGHT, j0, j1);
+        if (rb) push_side(blocks, gas, b, out_buf, put.parity, SIDE_BOTTOM, c0, c1);
+        if (rt) push_side(blocks, gas, b, out_buf, put.parity, SIDE_TOP, c0, c1);
+        put_something = rl || rr || rb || rt || strip == 0;
     }
+    if (prof) prof[2] = clock64() - tq;
     if (strip == 0 && lane == 0) {
         // find_dt of the NEW state from cell (0,0) (main.cpp:19-37), for the next step on every rank
+        const BlockDev& b = blocks[k];
         const double dtb = block_dt_value(b.state[out_buf], b.plane, b.pitch, b.min_face, gamRs, cfl);
         if (isnan(dtb)) flags |= FLAG_NAN;
         if (put.peer_mode) {
@@ -651,26 +674,25 @@ __device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, cons
     __syncwarp();
     if (lane == 0) stage_rows(MARCH_STAGES, 0);
 
-    // ---- march, two rows per trip (the carried state swaps roles, no register moves between rows): rows
-    //      j, j+1 consume ring use n = (j-j0)/2 + 1, which is then refilled with use n + MARCH_STAGES
+    // ---- march, ONE row per trip (ring use n = (j-j0)/2 + 1 holds rows j, j+1 and is refilled with use n + MARCH_STAGES
+    //      once both are consumed).  The launch-per-step kernel below unrolls two rows per trip to save the register
+    //      moves of the carried state; here the code SIZE counts instead: the fused / persistent step runs everything
+    //      once per step, and a per-step code footprint beyond the SM's instruction cache makes every line of it miss
+    //      every step (measured on the persistent launch: ~40 cycles per instruction outside the loop).
     int n = 1, slot = 1 % MARCH_STAGES;
     uint32_t ph = (1 / MARCH_STAGES) & 1;
-    int j = j0;
 #pragma unroll 1
-    for (; j + 1 < j1; j += 2) {
-        ok &= mbar_wait(&sm.bar[slot], ph);
-        const double* s0 = rs + slot * STAGE_D;
-        const double* n0 = rn + slot * STAGE_D;
-        march_row<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, sm, j, s0, n0, A, B, sq0, sq1, sq2, sq3, flags);
-        march_row<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, sm, j + 1, s0 + WCOLS, n0 + WCOLS, B, A, sq0, sq1, sq2, sq3, flags);
-        __syncwarp();                              // every lane has read this stage
-        if (lane == 0) stage_rows(n + MARCH_STAGES, slot);
-        n++;
-        if (++slot == MARCH_STAGES) { slot = 0; ph ^= 1u; }
-    }
-    if (j < j1) {
-        ok &= mbar_wait(&sm.bar[slot], ph);
-        march_row<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, sm, j, rs + slot * STAGE_D, rn + slot * STAGE_D, A, B, sq0, sq1, sq2, sq3, flags);
+    for (int j = j0; j < j1; j++) {
+        const int r = (j - j0) & 1;                // row within the stage
+        if (r == 0) ok &= mbar_wait(&sm.bar[slot], ph);
+        march_row<FAITHFUL, TPG, AXI, HOOKS>(a, g, m, sm, j, rs + slot * STAGE_D + r * WCOLS, rn + slot * STAGE_D + r * WCOLS, A, B, sq0, sq1, sq2, sq3, flags);
+        A = B;
+        if (r == 1) {
+            __syncwarp();                          // every lane has read this stage
+            if (lane == 0) stage_rows(n + MARCH_STAGES, slot);
+            n++;
+            if (++slot == MARCH_STAGES) { slot = 0; ph ^= 1u; }
+        }
     }
 
     if (PUSH && sv.prof) sv.prof[1] = clock64() - tp0;    // ... + prologue + rows
@@ -692,12 +714,18 @@ __device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, cons
 
     if (PUSH && sv.prof) sv.prof[2] = clock64() - tp0;    // ... + norms, strip identity
     if constexpr (PUSH && (PUSH_EXP & 4)) {
-        const int ntx = bb.tiles_x, ex = strip % ntx, ey = strip / ntx;
-        if (ex == 0 || ex == ntx - 1 || ey == 0 || ey == bb.tiles_y - 1) {     // CTA-uniform: the strip touches the block's perimeter
+        const int2 rg = __ldg(a.op_range + bb.tile0 + strip);       // this strip's ghost-cell records
+        bool epi = rg.y > 0 || strip == 0;
+        if (put.peer_mode) {
+            const int ntx = bb.tiles_x, ex = strip % ntx, ey = strip / ntx;
+            epi = epi || ex == 0 || ex == ntx - 1 || ey == 0 || ey == bb.tiles_y - 1;
+        }
+        if (epi) {                                 // CTA-uniform: the strip touches the block's perimeter
             PutLite pl;
             pl.peer_mode = put.peer_mode; pl.parity = sv.parity; pl.nranks = put.nranks; pl.rank = put.rank; pl.seq = sv.seq;
             pl.dt_dst = put.dt_dst; pl.dt_stride = put.dt_stride; pl.flag_dst = put.flag_dst; pl.ticket = put.ticket; pl.expected = put.expected;
-            flags |= tile_epilogue(a.blocks, a.gas_dev, k, strip, sv.cur ^ 1, a.march_rows, sv.dt_next, g.gamRs, g.cfl, pl, sv.prof ? sv.prof + 4 : nullptr);
+            flags |= tile_epilogue(a.blocks, a.gas_dev, a.ops, rg.x, rg.y, k, strip, sv.cur ^ 1, a.march_rows, sv.dt_next, g.gamRs, g.cfl, pl,
+                                   sv.prof ? sv.prof + 4 : nullptr);
         }
     }
     if (PUSH && sv.prof) sv.prof[3] = clock64() - tp0;    // ... + perimeter epilogue
@@ -939,8 +967,10 @@ __device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned target) {
 // one strip each for the whole batch.  Between steps: one grid barrier - the perimeter strips have pushed the
 // new state's ghost ring and dt by then.  Same strips, same arithmetic, same summation order as the launch-per-step
 // path: the results are bit-identical.
+// (12 resident warps per SM suffice for the meshes that fit this launch at all; 168 registers instead of 128 spare
+//  the strip code its spills)
 template <bool FAITHFUL, bool TPG, bool AXI>
-__global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) march_persist_kernel(const StepArgs a, const Gas g, const FinalizeArgs fin,
+__global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : 12) march_persist_kernel(const StepArgs a, const Gas g, const FinalizeArgs fin,
                                                                                                 double* dt_used_alt, double* partials_alt) {
     __shared__ __align__(128) MarchSmem sm;
     if (*a.stop) return;
