@@ -1222,8 +1222,13 @@ int par2d_set_slopes(par2d_ctx* c, int32_t block, const double* ux, const double
     if (use_device(c)) return PAR2D_ERR_CUDA;
     const BlockDev& b = c->hblk[k];
     const size_t bytes = sizeof(double) * 4 * (size_t)b.ncx * b.ncy;
-    CU_TRY(cudaMemcpyAsync(b.ux, ux, bytes, cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(cudaMemcpyAsync(b.uy, uy, bytes, cudaMemcpyHostToDevice, c->stream));
+    // the reference's AoS layout -> the planes the kernels read
+    const double* in[2] = {ux, uy};
+    double* out[2] = {b.ux, b.uy};
+    for (int q = 0; q < 2; q++) {
+        CU_TRY(cudaMemcpyAsync(c->staging, in[q], bytes, cudaMemcpyHostToDevice, c->stream));
+        launch_slopes_transpose(c->stream, c->staging, out[q], (long long)b.ncx * b.ncy, 1);
+    }
     CU_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -1235,8 +1240,12 @@ int par2d_get_slopes(par2d_ctx* c, int32_t block, double* ux, double* uy) {
     if (use_device(c)) return PAR2D_ERR_CUDA;
     const BlockDev& b = c->hblk[k];
     const size_t bytes = sizeof(double) * 4 * (size_t)b.ncx * b.ncy;
-    CU_TRY(cudaMemcpyAsync(ux, b.ux, bytes, cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(cudaMemcpyAsync(uy, b.uy, bytes, cudaMemcpyDeviceToHost, c->stream));
+    double* out[2] = {ux, uy};
+    const double* in[2] = {b.ux, b.uy};
+    for (int q = 0; q < 2; q++) {
+        launch_slopes_transpose(c->stream, in[q], c->staging, (long long)b.ncx * b.ncy, 0);
+        CU_TRY(cudaMemcpyAsync(out[q], c->staging, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
     CU_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }

@@ -51,7 +51,8 @@ struct BlockDev {
     int tile0;          // first tile/strip of this block in the partial-sum array
     double min_face;    // static part of find_dt (main.cpp:26-32)
     // second-order branch (cfg.accur == 1, dg.cuh); null / 0 otherwise
-    double *ux, *uy;    // xi / eta slopes, AoS [(j*ncx+i)*4+k] (main.cpp:169-172)
+    double *ux, *uy;    // xi / eta slopes, SoA planes [k][j*ncx+i] (the reference's AoS (j*ncx+i)*4+k of main.cpp:169-172 is
+                        // transposed by par2d_set_slopes / par2d_get_slopes)
     double *uxt, *uyt;  // damped, not yet limited slopes of the step in flight
     double* ghost2[4];  // two Gauss-point ghost states per boundary face, [(2n+pt)*4+k]
     int dg_tile0, dg_ntiles;  // this block's strips of the cell kernel (one record each in the [.][12] partial-sum array)

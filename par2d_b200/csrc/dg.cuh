@@ -2,7 +2,8 @@
 // (FV/DGP1Tools.cpp, the ACCUR == 1 paths of FV/SpatialDiscretization.cpp:159-1050 and FV/main.cpp:300-463).
 //
 // Unknowns per cell: the mean (rho,u,v,T) in the padded state planes (common.cuh) plus xi / eta slopes in
-// AoS arrays ux/uy[(j*ncx+i)*4+k]; two Gauss points per face with LDFSS at each; the slopes' right-hand
+// SoA planes ux/uy[k*ncell + j*ncx+i] (the reference's AoS (j*ncx+i)*4+k is transposed at the ABI, so that a warp's
+// lanes read consecutive doubles); two Gauss points per face with LDFSS at each; the slopes' right-hand
 // sides carry the xi/eta moments of the face fluxes plus a volume integral; the slopes are damped (0.9) and
 // limited against the neighbouring means after every update.
 //
@@ -54,20 +55,22 @@ __device__ __forceinline__ double dg_gauss() { return 1.0 / sqrt(3.0); }   // fo
 // ~8 warps per SM: nothing else hides the latency of a row's first touch)
 __device__ __forceinline__ void dg_prefetch_cell(const BlockDev& b, int buf, int i, int j) {
     const double* S = b.state[buf] + (long long)(j + 1) * b.pitch + COL0 + i;
-    const long long e = 4 * ((long long)j * b.ncx + i);
+    const long long e = (long long)j * b.ncx + i, nc = (long long)b.ncx * b.ncy;
 #pragma unroll
-    for (int k = 0; k < 4; k++) asm volatile("prefetch.global.L1 [%0];" ::"l"(S + k * b.plane));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(b.ux + e));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(b.uy + e));
+    for (int k = 0; k < 4; k++) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(S + k * b.plane));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(b.ux + k * nc + e));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(b.uy + k * nc + e));
+    }
 }
 
 // mean + slopes + pressure of cell (i,j) (State::p of ElemVar, StateVariables.h:49-50)
 __device__ __forceinline__ void dg_load_cell(const Gas& g, const BlockDev& b, int buf, int i, int j, DgCell& c) {
     const double* S = b.state[buf];
     const long long o = (long long)(j + 1) * b.pitch + COL0 + i;
-    const long long e = 4 * ((long long)j * b.ncx + i);
+    const long long e = (long long)j * b.ncx + i, nc = (long long)b.ncx * b.ncy;
 #pragma unroll
-    for (int k = 0; k < 4; k++) { c.u[k] = S[k * b.plane + o]; c.ux[k] = b.ux[e + k]; c.uy[k] = b.uy[e + k]; }
+    for (int k = 0; k < 4; k++) { c.u[k] = S[k * b.plane + o]; c.ux[k] = b.ux[k * nc + e]; c.uy[k] = b.uy[k * nc + e]; }
     c.p = fmax(c.u[0] * g.Rs * c.u[3], 1.0);
 }
 
@@ -594,8 +597,8 @@ __global__ void __launch_bounds__(32 * DG_WARPS, DG_MINB) dg_cell_kernel(StepArg
     #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     So[q * b.plane + o] = nu[q];
-                    b.uxt[4 * e + q] = (me.ux[q] + dvx[q]) * DG_DAMP;
-                    b.uyt[4 * e + q] = (me.uy[q] + dvy[q]) * DG_DAMP;
+                    b.uxt[q * ((long long)ncx * b.ncy) + e] = (me.ux[q] + dvx[q]) * DG_DAMP;
+                    b.uyt[q * ((long long)ncx * b.ncy) + e] = (me.uy[q] + dvy[q]) * DG_DAMP;
                 }
             }
             flags |= fl2;
@@ -648,7 +651,7 @@ __global__ void __launch_bounds__(DG_THREADS) dg_limit_kernel(StepArgs a, DgArgs
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const double me = Snew[q * b.plane + om];
-        double ux = b.uxt[4 * e + q], uy = b.uyt[4 * e + q];
+        double ux = b.uxt[q * ncell + e], uy = b.uyt[q * ncell + e];
         double du;
         if (has_ip && has_im) du = DG_DUSCALE * ((Sold[q * b.plane + o_ip] - Snew[q * b.plane + o_im]) / 2.0);
         else if (!has_im) du = DG_DUSCALE * ((Sold[q * b.plane + o_ip] - me) / 1.0);
@@ -658,8 +661,8 @@ __global__ void __launch_bounds__(DG_THREADS) dg_limit_kernel(StepArgs a, DgArgs
         else if (!has_jm) du = DG_DUSCALE * ((Sold[q * b.plane + o_jp] - me) / 1.0);
         else du = DG_DUSCALE * ((me - Snew[q * b.plane + o_jm]) / 1.0);
         uy = dg_sign(uy) * fmin(fabs(uy), fabs(du));
-        b.ux[4 * e + q] = ux;
-        b.uy[4 * e + q] = uy;
+        b.ux[q * ncell + e] = ux;
+        b.uy[q * ncell + e] = uy;
     }
 }
 

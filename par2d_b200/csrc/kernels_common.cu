@@ -47,6 +47,22 @@ __global__ void fill_uniform_kernel(BlockDev b, int buf, double r, double u, dou
     const long long o = (long long)(j + 1) * b.pitch + COL0 + i;
     S[o] = r; S[b.plane + o] = u; S[2 * b.plane + o] = v; S[3 * b.plane + o] = fmax(T, 201.0);
 }
+// slopes of the second-order branch: the reference's AoS ux[(j*ncx+i)*4+k] (main.cpp:169-172) <-> SoA planes [k][j*ncx+i]
+__global__ void slopes_transpose_kernel(const double* __restrict__ in, double* __restrict__ out, long long ncell, int to_soa) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= ncell) return;
+    if (to_soa) {
+        const double2 lo = reinterpret_cast<const double2*>(in)[2 * e], hi = reinterpret_cast<const double2*>(in)[2 * e + 1];
+        out[e] = lo.x; out[ncell + e] = lo.y; out[2 * ncell + e] = hi.x; out[3 * ncell + e] = hi.y;
+    } else {
+        reinterpret_cast<double2*>(out)[2 * e] = make_double2(in[e], in[ncell + e]);
+        reinterpret_cast<double2*>(out)[2 * e + 1] = make_double2(in[2 * ncell + e], in[3 * ncell + e]);
+    }
+}
+void launch_slopes_transpose(cudaStream_t s, const double* in, double* out, long long ncell, int to_soa) {
+    slopes_transpose_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, s>>>(in, out, ncell, to_soa);
+}
+
 // node coordinates x[j*nx+i] -> padded planes (row j+1, column COL0+i)
 __global__ void nodes_to_planes_kernel(BlockDev b, const double* __restrict__ x, const double* __restrict__ y) {
     const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -180,6 +196,7 @@ void preload_common() {
     cudaFuncGetAttributes(&fa, (const void*)cell_metric_kernel);
     cudaFuncGetAttributes(&fa, (const void*)min_face_kernel);
     cudaFuncGetAttributes(&fa, (const void*)face_normals_kernel);
+    cudaFuncGetAttributes(&fa, (const void*)slopes_transpose_kernel);
     cudaGetLastError();
 }
 

@@ -156,6 +156,7 @@ void launch_fill_uniform(cudaStream_t s, const BlockDev& b, int buf, const doubl
 void launch_nodes_to_planes(cudaStream_t s, const BlockDev& b, const double* x, const double* y);
 void launch_cell_metric(cudaStream_t s, const BlockDev& b, int axi);
 void launch_min_face(cudaStream_t s, const BlockDev& b, double* out, int nparts);
+void launch_slopes_transpose(cudaStream_t s, const double* in, double* out, long long ncell, int to_soa);
 void launch_face_normals(cudaStream_t s, const BlockDev& b, double2* out);
 void launch_fp64_probe(cudaStream_t s, double* out, int grid, int iters);
 }  // namespace par2d
