@@ -239,6 +239,10 @@ struct par2d_ctx {
     GhostOp* d_ops = nullptr;        // fused step: ghost-cell records, grouped by strip (common.cuh)
     int2* d_op_range = nullptr;
     unsigned* grid_bar = nullptr;
+    // ... without a stop test: every step's strip sums / dt / error bits of a launch, and the per-block norms made of them
+    double *ring_partials = nullptr, *ring_dt = nullptr, *ring_norm = nullptr, *ring_r0 = nullptr;
+    unsigned* ring_flags = nullptr;
+    bool defer = true;               // PAR2D_NO_DEFER=1: bookkeeping CTAs inside the persistent launch (A/B runs)
     long long* prof = nullptr;       // PAR2D_PROFILE_PERSIST=1: per-step cycle counts of the persistent launch (par2d_persist_profile)
     int coop_capacity = 0;
     bool persist = true;             // PAR2D_NO_PERSIST=1: one launch per step (A/B runs)
@@ -570,7 +574,39 @@ void queue_step_fused(par2d_ctx* c, int launch_no, int stop_on_tol) {
 
 // Single rank, small mesh: the whole batch in one cooperative launch (march_persist_kernel).  Returns false when the
 // launch was refused (the caller then falls back to one launch per step - still the CUDA path).
-bool queue_batch_persistent(par2d_ctx* c, int nsteps, int stop_on_tol) {
+// Without a stop test the bookkeeping leaves the step loop (DeferArgs): launches of at most DEFER_CHUNK steps, each followed by
+// the three kernels that turn the kept strip sums into history records.  `done` = steps of this batch queued before.
+bool queue_batch_persistent(par2d_ctx* c, int nsteps, int stop_on_tol, int done = 0) {
+    const bool defer = c->defer && !stop_on_tol && nsteps >= 16;
+    if (defer && nsteps > DEFER_CHUNK) {
+        for (int s0 = 0; s0 < nsteps; s0 += DEFER_CHUNK) {
+            // (a refused launch after the first cannot happen for a reason the first did not have; the remaining steps then
+            //  run as fused launches, which continue the batch's history behind the records written so far)
+            if (!queue_batch_persistent(c, std::min(DEFER_CHUNK, nsteps - s0), 0, done + s0)) {
+                if (s0 == 0) return false;
+                for (int s = s0; s < nsteps; s++) queue_step_fused(c, s + 1, 0);
+                return true;
+            }
+        }
+        return true;
+    }
+    DeferArgs df;
+    memset(&df, 0, sizeof df);
+    if (defer) {
+        if (!c->ring_partials) {
+            const size_t n = (size_t)DEFER_CHUNK;
+            if (cudaMalloc(&c->ring_partials, sizeof(double) * n * (size_t)c->partials_stride) != cudaSuccess ||
+                cudaMalloc(&c->ring_dt, sizeof(double) * n) != cudaSuccess || cudaMalloc(&c->ring_flags, sizeof(unsigned) * n) != cudaSuccess ||
+                cudaMalloc(&c->ring_norm, sizeof(double) * n * 4 * c->nowned) != cudaSuccess || cudaMalloc(&c->ring_r0, sizeof(double) * n * 4 * c->nowned) != cudaSuccess) {
+                cudaGetLastError();
+                cudaFree(c->ring_partials); cudaFree(c->ring_dt); cudaFree(c->ring_flags); cudaFree(c->ring_norm); cudaFree(c->ring_r0);
+                c->ring_partials = c->ring_dt = c->ring_norm = c->ring_r0 = nullptr; c->ring_flags = nullptr;
+                c->defer = false;                  // no room for the rings: bookkeeping CTAs inside the launch, as with a stop test
+                return queue_batch_persistent(c, nsteps, stop_on_tol, done);
+            }
+        }
+        df.on = 1; df.stride = c->partials_stride; df.partials = c->ring_partials; df.dt = c->ring_dt; df.flags = c->ring_flags;
+    }
     StepArgs a = c->step_args(1);
     a.dt_ready = 0;
     a.coop_steps = nsteps;
@@ -579,12 +615,17 @@ bool queue_batch_persistent(par2d_ctx* c, int nsteps, int stop_on_tol) {
     const FinalizeArgs fin = c->finalize_args(stop_on_tol);
     double* dt_used_alt = c->dt_used + ((c->iter_queued + 1) & 1);
     double* partials_alt = c->partials + ((c->iter_queued + 1) & 1) * c->partials_stride;
-    if (cudaMemsetAsync(c->grid_bar, 0, sizeof(unsigned), c->stream) != cudaSuccess) return false;
+    if ((long long)(nsteps + 1) * (c->total_tiles + c->nowned) >= (1ll << 31)) return false;   // the barrier counts arrivals in 31 bits
+    if (cudaMemsetAsync(c->grid_bar, 0, sizeof(unsigned) * BAR_WORDS, c->stream) != cudaSuccess) return false;
     time_begin(c);
     c->launches++;
-    const cudaError_t e = c->kt->march_coop(c->stream, a, c->gas, fin, dt_used_alt, partials_alt, c->tpg, c->axi);
+    const cudaError_t e = c->kt->march_coop(c->stream, a, c->gas, fin, dt_used_alt, partials_alt, df, c->tpg, c->axi);
     time_end(c);
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    if (defer) {
+        c->launches += 3;
+        launch_finalize_deferred(c->stream, fin, df, nsteps, c->iter + done, done, c->ring_norm, c->ring_r0);
+    }
     c->iter_queued += nsteps;
     c->cur ^= (nsteps & 1);
     return true;
@@ -966,6 +1007,8 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
         c->fused = !(no && atoi(no) != 0);
         const char* np = getenv("PAR2D_NO_PERSIST");
         c->persist = !(np && atoi(np) != 0);
+        const char* nd = getenv("PAR2D_NO_DEFER");
+        c->defer = !(nd && atoi(nd) != 0);
         c->coop_capacity = (cfg->nranks == 1 && !c->dg) ? c->kt->coop_capacity(c->tpg, c->axi) : 0;
         const char* pp = getenv("PAR2D_PROFILE_PERSIST");
         if (pp && atoi(pp) != 0) { CU_TRY(cudaMalloc(&c->prof, sizeof(long long) * 12 * 4096)); CU_TRY(cudaMemset(c->prof, 0, sizeof(long long) * 12 * 4096)); }
@@ -1042,7 +1085,7 @@ int par2d_create(const par2d_config* cfg, int32_t nblocks, const par2d_block_des
     c->partials_stride = 4ll * c->total_tiles;
     CU_TRY(cudaMalloc(&c->gas_dev, sizeof(Gas)));
     CU_TRY(cudaMemcpyAsync(c->gas_dev, &c->gas, sizeof(Gas), cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(cudaMalloc(&c->grid_bar, sizeof(unsigned)));
+    CU_TRY(cudaMalloc(&c->grid_bar, sizeof(unsigned) * BAR_WORDS));
     CU_TRY(cudaMalloc(&c->go, sizeof(int)));
     CU_TRY(cudaMalloc(&c->stop_iter, sizeof(long long)));
     CU_TRY(cudaMemsetAsync(c->go, 0, sizeof(int), c->stream));
@@ -1087,6 +1130,7 @@ int par2d_destroy(par2d_ctx* c) {
     for (int q = 0; q < 2; q++) { if (c->ev_ready[q]) cudaEventDestroy(c->ev_ready[q]); if (c->ev_free[q]) cudaEventDestroy(c->ev_free[q]); }
     cudaFree(c->staging2);
     cudaFree(c->prof); cudaFree(c->d_ops); cudaFree(c->d_op_range);
+    cudaFree(c->ring_partials); cudaFree(c->ring_dt); cudaFree(c->ring_flags); cudaFree(c->ring_norm); cudaFree(c->ring_r0);
     cudaFree(c->d_all_tiles); cudaFree(c->gas_dev); cudaFree(c->grid_bar); cudaFree(c->go); cudaFree(c->stop_iter); cudaFree(c->flag_hist);
     for (double* m : c->dg_mem) cudaFree(m);
     cudaFree(c->dg_partials);

@@ -165,7 +165,7 @@ struct StepArgs {
     int nfin;                // leading CTAs of the launch that run the previous step's bookkeeping (0: none pending)
     int launch_no;           // 1-based launch number within the batch (stop test across ranks)
     int coop_steps;          // persistent launch: steps advanced inside the kernel (else 1)
-    unsigned* grid_bar;      // persistent launch: grid barrier counter
+    unsigned* grid_bar;      // persistent launch: grid barrier words (BAR_WORDS)
     const Gas* gas_dev;      // the Gas constants in global memory (for the non-inlined boundary-condition code)
     long long* prof;         // diagnostics of the persistent launch (null in production), see march_persist_kernel
     const GhostOp* ops;      // fused step: ghost-cell records of this rank, grouped by strip
@@ -195,6 +195,22 @@ struct FinalizeArgs {
     const unsigned* flags;
     StopArgs stop_x;         // stop test across ranks (peer-mapped mode); enabled = 0 otherwise
 };
+
+// Persistent launch without a stop test: the bookkeeping is taken out of the step loop.  The strips keep every step's
+// sums, dt and an error-bit snapshot; three short kernels after the launch turn them into the history records
+// (kernels_common.cu, launch_finalize_deferred) - same arithmetic, same order, identical bits.
+struct DeferArgs {
+    int on;
+    long long stride;        // doubles between the strip sums of consecutive steps (4 x total strips)
+    double* partials;        // [steps][total strips][4]
+    double* dt;              // [steps] the global dt of each step
+    unsigned* flags;         // [steps] device error bits as of the end of each step
+};
+constexpr int DEFER_CHUNK = 1024;   // steps per persistent launch in this mode
+
+// grid barrier of the persistent launch (march.cuh, grid_barrier): the arrival counter and 16 release words, one 128-byte line each
+constexpr int BAR_RELEASE_WORDS = 16;
+constexpr int BAR_WORDS = 32 * (1 + BAR_RELEASE_WORDS);
 
 __host__ __device__ inline int edge_cells(int ncx, int ncy, int side) {
     return (side == SIDE_BOTTOM || side == SIDE_TOP) ? ncx : ncy;

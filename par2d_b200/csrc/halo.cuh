@@ -87,12 +87,17 @@ static __device__ __forceinline__ bool wait_peers_warp(const unsigned long long*
 #ifndef HALO_NOINLINE
 #define HALO_NOINLINE __noinline__
 #endif
-static __device__ HALO_NOINLINE double block_dt_value(const double* S, long long plane, int pitch, double min_face, double gamRs, double cfl) {
-    const long long o = (long long)pitch + COL0;
-    const double u = __ldcg(S + plane + o), v = __ldcg(S + 2 * plane + o), T = __ldcg(S + 3 * plane + o);
+// The arithmetic is a function of its own (one machine code for every caller: identical bits from the ghost kernel and
+// from the fused step), so that a caller on a latency-critical path can request the three values early and use them late.
+static __device__ HALO_NOINLINE double block_dt_math(double u, double v, double T, double min_face, double gamRs, double cfl) {
     const double v2 = u * u + v * v;
     const double vmax = sqrt(v2) + sqrt(gamRs * T);
     return cfl * min_face / vmax;
+}
+static __device__ __forceinline__ double block_dt_value(const double* S, long long plane, int pitch, double min_face, double gamRs, double cfl) {
+    const long long o = (long long)pitch + COL0;
+    const double u = __ldcg(S + plane + o), v = __ldcg(S + 2 * plane + o), T = __ldcg(S + 3 * plane + o);
+    return block_dt_math(u, v, T, min_face, gamRs, cfl);
 }
 
 // CCW index of boundary face n of a side = index into ibound[] and fnorm[] (SpatialDiscretization.cpp:27,45,64,84)

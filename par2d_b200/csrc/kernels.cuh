@@ -256,7 +256,7 @@ struct KernelTable {
     void (*march)(cudaStream_t, const StepArgs&, const Gas&, bool tpg, bool axi);
     void (*march_push)(cudaStream_t, const StepArgs&, const Gas&, const PutArgs&, const FinalizeArgs&, bool tpg, bool axi);
     int (*coop_capacity)(bool tpg, bool axi);   // CTAs of the persistent kernel that are resident at once on the current device
-    cudaError_t (*march_coop)(cudaStream_t, const StepArgs&, const Gas&, const FinalizeArgs&, double* dt_used_alt, double* partials_alt, bool tpg, bool axi);
+    cudaError_t (*march_coop)(cudaStream_t, const StepArgs&, const Gas&, const FinalizeArgs&, double* dt_used_alt, double* partials_alt, const DeferArgs&, bool tpg, bool axi);
     void (*stop_tail)(cudaStream_t, const StopArgs&, int* stop, unsigned* flags, long long it_first, long long it_last);
     void (*dg_ghost)(cudaStream_t, const StepArgs&, const Gas&, const DgArgs&, int write_dt);
     void (*dg_cell)(cudaStream_t, const StepArgs&, const Gas&, const DgArgs&, bool tpg, bool axi);
@@ -331,9 +331,10 @@ struct Launch {
         if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_fn(tpg, axi), MARCH_THREADS, 0) != cudaSuccess) return 0;
         return per_sm * sms;
     }
-    static cudaError_t march_coop(cudaStream_t s, const StepArgs& a, const Gas& g, const FinalizeArgs& fin, double* dt_used_alt, double* partials_alt, bool tpg, bool axi) {
-        void* args[] = {(void*)&a, (void*)&g, (void*)&fin, (void*)&dt_used_alt, (void*)&partials_alt};
-        return cudaLaunchCooperativeKernel(coop_fn(tpg, axi), dim3(a.nowned + a.tile_count), dim3(MARCH_THREADS), args, 0, s);
+    static cudaError_t march_coop(cudaStream_t s, const StepArgs& a, const Gas& g, const FinalizeArgs& fin, double* dt_used_alt, double* partials_alt, const DeferArgs& df,
+                                  bool tpg, bool axi) {
+        void* args[] = {(void*)&a, (void*)&g, (void*)&fin, (void*)&dt_used_alt, (void*)&partials_alt, (void*)&df};
+        return cudaLaunchCooperativeKernel(coop_fn(tpg, axi), dim3((df.on ? 0 : a.nowned) + a.tile_count), dim3(MARCH_THREADS), args, 0, s);
     }
     static void stop_tail(cudaStream_t s, const StopArgs& sx, int* stop, unsigned* flags, long long it_first, long long it_last) {
         stop_tail_kernel<FAITHFUL><<<1, 1, 0, s>>>(sx, stop, flags, it_first, it_last);

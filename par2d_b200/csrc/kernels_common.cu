@@ -19,6 +19,74 @@ void launch_finalize(cudaStream_t s, const FinalizeArgs& a) {
     finalize_kernel<<<a.nowned, 256, 0, s>>>(a);
 }
 
+// ---- deferred bookkeeping of a persistent launch (DeferArgs): finalize_block, one step after the other, as three kernels
+// 1. the norms of every (step, block): the first part of finalize_block, one warp each
+__global__ void __launch_bounds__(32) fin_norms_kernel(FinalizeArgs a, DeferArgs df, double* norm_ring) {
+    const int step = blockIdx.x, k = blockIdx.y;
+    a.partials = df.partials + step * df.stride;
+    double norm[4];
+    finalize_block_norms(a, k, nullptr, norm);
+    if (threadIdx.x < 4) {
+        const double n = threadIdx.x == 0 ? norm[0] : threadIdx.x == 1 ? norm[1] : threadIdx.x == 2 ? norm[2] : norm[3];
+        norm_ring[4 * ((long long)step * a.nowned + k) + threadIdx.x] = n;
+    }
+}
+// 2. the res0 rules (main.cpp:365-374) are the one thing that runs from step to step: one thread per (block, variable)
+__global__ void fin_res0_kernel(FinalizeArgs a, int nsteps, long long it0, const double* __restrict__ norm_ring, double* __restrict__ r0_ring) {
+    const int n4 = 4 * a.nowned;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += gridDim.x * blockDim.x) {
+        double r0 = a.res0[e];
+        for (int s0 = 0; s0 < nsteps; s0 += 8) {
+            double rs[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) rs[u] = s0 + u < nsteps ? norm_ring[(long long)(s0 + u) * n4 + e] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (s0 + u < nsteps) {
+                    if (it0 + s0 + u == 0) r0 = rs[u];
+                    if (r0 < 1e-16) r0 = fmax(rs[u], 1e-16);
+                    r0_ring[(long long)(s0 + u) * n4 + e] = r0;
+                }
+            }
+        }
+        a.res0[e] = r0;
+    }
+}
+// 3. the history records: one thread per step adds the blocks in block order (main.cpp:379-392)
+__global__ void fin_hist_kernel(FinalizeArgs a, DeferArgs df, int nsteps, long long it0, int pos0, const double* __restrict__ norm_ring, const double* __restrict__ r0_ring) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsteps) return;
+    const int pos = pos0 + s;
+    double tot = 0.0, tot0 = 0.0;
+    for (int q = 0; q < a.nowned; q++) {
+        double sum = 0.0, sum0 = 0.0;
+        for (int v = 0; v < 4; v++) {
+            sum += norm_ring[4 * ((long long)s * a.nowned + q) + v];
+            sum0 += r0_ring[4 * ((long long)s * a.nowned + q) + v];
+        }
+        if (pos < a.hist_cap) {
+            a.blk_hist[2 * ((long long)pos * a.nowned + q) + 0] = sum;
+            a.blk_hist[2 * ((long long)pos * a.nowned + q) + 1] = sum0;
+        }
+        tot += sum;
+        tot0 += sum0;
+    }
+    const double relres = tot / tot0;
+    if (pos < a.hist_cap) {
+        double* h = a.step_hist + 4 * (long long)pos;
+        h[0] = df.dt[s]; h[1] = tot; h[2] = tot0; h[3] = relres;
+        a.flag_hist[pos] = s + 1 < nsteps ? df.flags[s] : *a.flags;
+    }
+    if (s == 0) { *a.iter = it0 + nsteps; *a.hist_pos = pos0 + nsteps; }
+}
+
+void launch_finalize_deferred(cudaStream_t s, const FinalizeArgs& a, const DeferArgs& df, int nsteps, long long it0, int pos0, double* norm_ring, double* r0_ring) {
+    fin_norms_kernel<<<dim3(nsteps, a.nowned), 32, 0, s>>>(a, df, norm_ring);
+    const int n4 = 4 * a.nowned;
+    fin_res0_kernel<<<(n4 + 127) / 128, 128, 0, s>>>(a, nsteps, it0, norm_ring, r0_ring);
+    fin_hist_kernel<<<(nsteps + 127) / 128, 128, 0, s>>>(a, df, nsteps, it0, pos0, norm_ring, r0_ring);
+}
+
 // AoS unk[(j*ncx+i)*4+k] (FV/Indexing.h:11) -> padded planes; applies the T clamp that
 // State::UpdateState performs on the initial state (main.cpp:226-238).
 __global__ void aos_to_planes_kernel(BlockDev b, int buf, const double* __restrict__ aos) {
@@ -189,6 +257,9 @@ void launch_fp64_probe(cudaStream_t s, double* out, int grid, int iters) {
 void preload_common() {
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, (const void*)finalize_kernel);
+    cudaFuncGetAttributes(&fa, (const void*)fin_norms_kernel);
+    cudaFuncGetAttributes(&fa, (const void*)fin_res0_kernel);
+    cudaFuncGetAttributes(&fa, (const void*)fin_hist_kernel);
     cudaFuncGetAttributes(&fa, (const void*)aos_to_planes_kernel);
     cudaFuncGetAttributes(&fa, (const void*)planes_to_aos_kernel);
     cudaFuncGetAttributes(&fa, (const void*)fill_uniform_kernel);

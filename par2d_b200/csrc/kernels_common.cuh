@@ -28,13 +28,16 @@ __device__ __forceinline__ void fin_st_release_sys(unsigned long long* p, unsign
 // partial sums come from HBM: a single warp walking 2208 strips of a 2048^2 block took 33 us, measured).
 constexpr int FIN_CHUNK = 1024;
 
+
 // stage: FIN_CHUNK*4 doubles of shared memory, or null when the caller is a single warp (then blockDim.x must be 32).
 // With staging ALL threads of the CTA must call; only the first warp returns with work done.
-__device__ __forceinline__ void finalize_block(const FinalizeArgs& a, int k, double* stage = nullptr) {
+// First part: the four residual norms of block k (main.cpp:39-57) from its strips' sums, in norm[] of every lane of the
+// first warp.  Returns false for the threads of a staged CTA that are done (everything but the first warp).
+__device__ __forceinline__ bool finalize_block_norms(const FinalizeArgs& a, int k, double* stage, double norm[4]) {
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
     const BlockDev& b = a.blocks[k];
-    double norm[4] = {0.0, 0.0, 0.0, 0.0};
+    norm[0] = norm[1] = norm[2] = norm[3] = 0.0;
     // first order: one group of 4 sums; second-order branch: three groups (dudt, duxdt, duydt) whose square roots
     // are added as main.cpp:360-364 does, ressum + (ressumx + ressumy)
     const int ngroups = a.dg_partials ? 3 : 1;
@@ -62,35 +65,70 @@ __device__ __forceinline__ void finalize_block(const FinalizeArgs& a, int k, dou
                     }
                 }
             }
-            if (threadIdx.x >= 32 && grp == ngroups - 1) return;
+            if (threadIdx.x >= 32 && grp == ngroups - 1) return false;
             if (threadIdx.x >= 32) continue;
         } else {
-#pragma unroll 8
-            for (int t = lane; t < ntiles; t += 32) {
-                const double2* p = reinterpret_cast<const double2*>(src + (long long)stride * t);
-                const double2 p0 = __ldcg(p), p1 = __ldcg(p + 1);
-                s[0] += p0.x; s[1] += p0.y; s[2] += p1.x; s[3] += p1.y;
+            // eight strips per lane requested together, then added in strip order: the trip count is the same for every
+            // lane and no pass waits for more than one round trip to L2 (a plain `for (t = lane; ...)` is compiled into a
+            // serial remainder loop of up to seven round trips ahead of the unrolled one)
+#pragma unroll 1
+            for (int base = 0; base < ntiles; base += 32 * 8) {
+                double2 p0[8], p1[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int t = base + 32 * u + lane;
+                    p0[u] = p1[u] = make_double2(0.0, 0.0);
+                    if (t < ntiles) {
+                        const double2* p = reinterpret_cast<const double2*>(src + (long long)stride * t);
+                        p0[u] = __ldcg(p); p1[u] = __ldcg(p + 1);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (base + 32 * u + lane < ntiles) { s[0] += p0[u].x; s[1] += p0[u].y; s[2] += p1[u].x; s[3] += p1[u].y; }
+                }
             }
+        }
+        // lane tree: the five levels as a LOOP over the four sums (this code runs once per step out of a cold instruction
+        // cache, where the bytes of code touched count, not the instructions executed); same operands, same order
+#pragma unroll 1
+        for (int w = 16; w > 0; w >>= 1) {
+#pragma unroll
+            for (int v = 0; v < 4; v++) s[v] += __shfl_xor_sync(full, s[v], w);
         }
 #pragma unroll
         for (int v = 0; v < 4; v++) {
-#pragma unroll
-            for (int w = 16; w > 0; w >>= 1) s[v] += __shfl_xor_sync(full, s[v], w);
             const double rt = sqrt(s[v]);
             if (grp == 0) norm[v] = rt;
             else if (grp == 1) parked[v] = rt;
             else norm[v] = norm[v] + (parked[v] + rt);
         }
     }
-    int last = 0;
-    if (lane == 0) {
+    return true;
+}
+
+__device__ __forceinline__ void finalize_block(const FinalizeArgs& a, int k, double* stage = nullptr, long long* fprof = nullptr) {
+    const long long fp0 = fprof ? clock64() : 0;   // diagnostics of the persistent launch (tools/diag_persist.py); null in production
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    double norm[4];
+    if (!finalize_block_norms(a, k, stage, norm)) return;
+    if (fprof) fprof[0] = clock64() - fp0;         // strip sums, lane tree, square roots
+    int last = 1;
+    if (a.nowned > 1) {                            // (a single block has nobody to wait for: no ticket, no fences)
+        if (lane == 0) {
+            for (int v = 0; v < 4; v++) a.blk_norm[4 * k + v] = norm[v];
+            __threadfence();
+            last = atomicAdd(a.ticket, 1u) == (unsigned)(a.nowned - 1);
+        }
+        last = __shfl_sync(full, last, 0);
+    } else if (lane == 0) {
         for (int v = 0; v < 4; v++) a.blk_norm[4 * k + v] = norm[v];
-        __threadfence();
-        last = atomicAdd(a.ticket, 1u) == (unsigned)(a.nowned - 1);
     }
-    last = __shfl_sync(full, last, 0);
+    if (fprof) { fprof[1] = clock64() - fp0; fprof[2] = last; }   // + fence, ticket
     if (!last) return;
-    __threadfence();
+    if (a.nowned > 1) __threadfence();
+    else __syncwarp();
     // last CTA: per-block sums by one lane per block (the global loads overlap), then lane 0 adds the
     // blocks in block order (main.cpp:379-392 gathers in rank order)
     const long long it = *a.iter;
@@ -129,6 +167,7 @@ __device__ __forceinline__ void finalize_block(const FinalizeArgs& a, int k, dou
     }
     if (sx.enabled) __threadfence_system();
     __syncwarp();
+    if (fprof) fprof[3] = clock64() - fp0;         // + fence, iteration counters, per-block sums
     if (lane != 0) return;
     if (sx.enabled) {
         for (int r = 0; r < sx.nranks; r++) fin_st_release_sys(sx.rflag_dst[r], (unsigned long long)(it + 1));
@@ -141,15 +180,19 @@ __device__ __forceinline__ void finalize_block(const FinalizeArgs& a, int k, dou
     }
     *a.iter = it + 1;
     *a.hist_pos = pos + 1;
-    *a.ticket = 0u;
+    if (a.nowned > 1) *a.ticket = 0u;
     // single rank: the local sums are the global ones (main.cpp:506-511); across ranks the test is made on the
     // published sums by the first CTA of a later launch (stop_test, march.cuh)
     if (a.stop_on_tol && !sx.enabled && relres < a.tol) *a.stop = 1;
+    if (fprof) fprof[4] = clock64() - fp0;         // + history record
 }
 #endif
 
 void preload_common();
 void launch_finalize(cudaStream_t s, const FinalizeArgs& a);
+// Deferred bookkeeping of `nsteps` steps whose strip sums, dts and error-bit snapshots were kept by a persistent launch
+// (DeferArgs): the same arithmetic in the same order as finalize_block, step after step, as three short kernels.
+void launch_finalize_deferred(cudaStream_t s, const FinalizeArgs& a, const DeferArgs& df, int nsteps, long long it0, int pos0, double* norm_ring, double* r0_ring);
 void launch_aos_to_planes(cudaStream_t s, const BlockDev& b, int buf, const double* aos);
 void launch_planes_to_aos(cudaStream_t s, const BlockDev& b, int buf, double* aos);
 void launch_fill_uniform(cudaStream_t s, const BlockDev& b, int buf, const double u[4]);

@@ -375,8 +375,7 @@ struct StepVar {
 // One side of a perimeter strip that borders another RANK, after its rows are done (the strip's new cells sit in Sout,
 // visible to the whole warp): the new edge cells n of [n0, n1) straight into the neighbour rank's arena over NVLink, one
 // 32-byte AoS record per edge cell (usend[k + NVAR*j], SpatialDiscretization.cpp:236-259).
-__device__ __forceinline__ void push_side(const BlockDev* blocks, const Gas* gas, const BlockDev& b, int out_buf, int parity, int side, int n0, int n1) {
-    (void)blocks; (void)gas;
+__device__ __forceinline__ void push_side(const BlockDev& b, int out_buf, int parity, int side, int n0, int n1) {
     if (b.put_dst[side] == nullptr) return;
     const double* Sout = b.state[out_buf];
     for (int n = n0 + (int)threadIdx.x; n < n1; n += 32) {
@@ -400,77 +399,102 @@ struct PutLite {
     unsigned expected;
 };
 
+// An L2 load that stays where it is written: the compiler otherwise sinks a load towards its first use, past branches
+// that do not need the value - and turns one round trip shared by several loads into one round trip each.
+__device__ __forceinline__ double ldcg_here(const double* p) {
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // After the rows of a perimeter strip: ghost ring / edge lines of the NEW state, the block's dt, the put ticket.
 // Returns error bits.
-static __device__ __noinline__ unsigned tile_epilogue(const BlockDev* blocks, const Gas* gas, const GhostOp* ops, int op0, int nop, int k, int strip,
+static __device__ __noinline__ unsigned tile_epilogue(const BlockDev* bk, const Gas* gas, const GhostOp* ops, int op0, int nop, int strip,
                                                      int out_buf, int march_rows, double* dt_next, double gamRs, double cfl, PutLite put, long long* prof) {
     const long long tq = prof ? clock64() : 0;
     const int lane = threadIdx.x;
     unsigned flags = 0;
     __syncwarp();                                  // the strip's new cells are visible to every lane
     if (prof) prof[0] = clock64() - tq;
-    // boundary-condition faces and faces shared with a block of this rank: one record per ghost cell
-    for (int i = lane; i < nop; i += 32) {
-        const GhostOp* op = ops + op0 + i;
-        const int4 meta = __ldg(reinterpret_cast<const int4*>(&op->src_plane));     // src_plane, dst_plane, kind, blk
-        if (meta.z >= 2) {
-            const BlockDev& b = blocks[meta.w];
-            double* S = b.state[out_buf];
-            const int2 fc = __ldg(reinterpret_cast<const int2*>(&op->f));
-            if (meta.z == 3) {
-                // far field (code 1, BoundaryConditions.cpp:148-188) where the normal velocity is supersonic - the usual
-                // state of these faces: vn/a <= -1 takes the free stream, vn/a >= 1 the interior state.  For a > 0 the
-                // quotient's comparisons with -1 and 1 are exactly those of vn with -a and a, so no division is needed.
-                const double* src = out_buf ? op->src[1] : op->src[0];
-                double* dst = out_buf ? op->dst[1] : op->dst[0];
-                const double u0 = __ldcg(src), u1 = __ldcg(src + meta.x), u2 = __ldcg(src + 2 * (long long)meta.x), u3 = __ldcg(src + 3 * (long long)meta.x);
-                const double2 nrm = __ldg(reinterpret_cast<const double2*>(&op->nx));
-                const double vn = __dadd_rn(__dmul_rn(u1, nrm.x), __dmul_rn(u2, nrm.y));
-                const double aint = sqrt(__dmul_rn(gas->gamRs, u3));
-                if (aint > 0.0 && (vn <= -aint || vn >= aint)) {
-                    const bool in = vn <= -aint;
-                    __stcg(dst, in ? gas->uFS[0] : u0); __stcg(dst + meta.y, in ? gas->uFS[1] : u1);
-                    __stcg(dst + 2 * (long long)meta.y, in ? gas->uFS[2] : u2); __stcg(dst + 3 * (long long)meta.y, fmax(in ? gas->uFS[3] : u3, 201.0));
-                    continue;
-                }
-            }
-            bc_ghost_general(gas, &b, S, fc.y, fc.x, op->src[out_buf] - S, op->dst[out_buf] - S);
-            continue;
-        }
-        const double* src = out_buf ? op->src[1] : op->src[0];
-        double* dst = out_buf ? op->dst[1] : op->dst[0];
-        double u0 = __ldcg(src), u1 = __ldcg(src + meta.x), u2 = __ldcg(src + 2 * (long long)meta.x), u3 = __ldcg(src + 3 * (long long)meta.x);
-        if (meta.z == 1) {                         // slip wall: V - 2 (V.n) n, BoundaryConditions.cpp:79-88 (as bc_ghost_fill)
+    // strip 0 holds cell (0,0) of its block: the three values find_dt reads there are requested NOW and used after the
+    // records - this code is a chain of L2 round trips, and every one that can overlap another must
+    double q1 = 0.0, q2 = 0.0, q3 = 0.0;
+    if (strip == 0) {                              // CTA-uniform
+        const BlockDev& b = *bk;
+        const double* S = b.state[out_buf];
+        const long long o = (long long)b.pitch + COL0;
+        q1 = ldcg_here(S + b.plane + o); q2 = ldcg_here(S + 2 * b.plane + o); q3 = ldcg_here(S + 3 * b.plane + o);
+    }
+    // boundary-condition faces and faces shared with a block of this rank: one record per ghost cell.  The loads of a
+    // record do not depend on its kind - the whole record in four 16-byte loads, then the edge cell - so lanes holding
+    // different kinds wait for ONE round trip to the record and ONE to the cell together (a branch per kind around its
+    // own loads made every kind present in the warp pay both round trips in turn: 6300 of the 13500 cycles of a corner
+    // strip's step on the shipped cases, profiles/r02_persistent_launch_profile.txt); the kinds then differ in a few
+    // arithmetic instructions only.
+    if (nop > 0) {
+        const double gRs = __ldg(&gas->gamRs);
+        const double fs0 = __ldg(&gas->uFS[0]), fs1 = __ldg(&gas->uFS[1]), fs2 = __ldg(&gas->uFS[2]), fs3 = __ldg(&gas->uFS[3]);
+#pragma unroll 1
+        for (int i = lane; i < nop; i += 32) {     // one trip for all but the corner strips of wide blocks: not unrolled, this code runs cold
+            const GhostOp* op = ops + op0 + i;
+            const ulonglong2 sp = __ldg(reinterpret_cast<const ulonglong2*>(&op->src[0]));
+            const ulonglong2 dp = __ldg(reinterpret_cast<const ulonglong2*>(&op->dst[0]));
+            const int4 meta = __ldg(reinterpret_cast<const int4*>(&op->src_plane));     // src_plane, dst_plane, kind, blk
             const double2 nrm = __ldg(reinterpret_cast<const double2*>(&op->nx));
+            const double* src = reinterpret_cast<const double*>(out_buf ? sp.y : sp.x);
+            double* dst = reinterpret_cast<double*>(out_buf ? dp.y : dp.x);
+            const double u0 = ldcg_here(src), u1 = ldcg_here(src + meta.x), u2 = ldcg_here(src + 2 * (long long)meta.x), u3 = ldcg_here(src + 3 * (long long)meta.x);
+            const int kind = meta.z;
+            // slip wall: V - 2 (V.n) n, BoundaryConditions.cpp:79-88 (never-contracted operations, as bc_ghost_fill)
             const double vn = __dadd_rn(__dmul_rn(u1, nrm.x), __dmul_rn(u2, nrm.y));
             const double t = __dmul_rn(2.0, vn);
             const double w1 = __dsub_rn(u1, __dmul_rn(t, nrm.x)), w2 = __dsub_rn(u2, __dmul_rn(t, nrm.y));
-            u1 = w1; u2 = w2;
+            double g0 = u0, g1 = kind == 1 ? w1 : u1, g2 = kind == 1 ? w2 : u2, g3 = u3;
+            bool general = kind == 2;
+            if (kind == 3) {
+                // far field (code 1, BoundaryConditions.cpp:148-188) where the normal velocity is supersonic - the usual
+                // state of these faces: vn/a <= -1 takes the free stream, vn/a >= 1 the interior state.  For a > 0 the
+                // quotient's comparisons with -1 and 1 are exactly those of vn with -a and a, so no division is needed.
+                const double aint = sqrt(__dmul_rn(gRs, u3));
+                if (aint > 0.0 && (vn <= -aint || vn >= aint)) {
+                    const bool in = vn <= -aint;
+                    g0 = in ? fs0 : u0; g1 = in ? fs1 : u1; g2 = in ? fs2 : u2; g3 = in ? fs3 : u3;
+                } else {
+                    general = true;
+                }
+            }
+            if (general) {                         // back pressure, Bernoulli inflow, subsonic far field, unknown codes
+                const BlockDev& b = *bk;           // a record's block (GhostOp::blk) is the block of the strip that holds it
+                double* S = b.state[out_buf];
+                const int2 fc = __ldg(reinterpret_cast<const int2*>(&op->f));
+                bc_ghost_general(gas, &b, S, fc.y, fc.x, src - S, dst - S);
+            } else {
+                __stcg(dst, g0); __stcg(dst + meta.y, g1); __stcg(dst + 2 * (long long)meta.y, g2); __stcg(dst + 3 * (long long)meta.y, fmax(g3, 201.0));
+            }
         }
-        __stcg(dst, u0); __stcg(dst + meta.y, u1); __stcg(dst + 2 * (long long)meta.y, u2); __stcg(dst + 3 * (long long)meta.y, fmax(u3, 201.0));
     }
     if (prof) prof[1] = clock64() - tq;
     bool put_something = false;
     if (put.peer_mode) {
         // faces shared with a block of another rank: the new edge cells straight into that rank's arena
-        const BlockDev& b = blocks[k];
+        const BlockDev& b = *bk;
         const int ex = strip % b.tiles_x, ey = strip / b.tiles_x;
         const bool tl = ex == 0, tr = ex == b.tiles_x - 1, tb = ey == 0, tt = ey == b.tiles_y - 1;
         const int c0 = ex * MCELLS, c1 = min(c0 + MCELLS, b.ncx);
         const int j0 = ey * march_rows, j1 = min(j0 + march_rows, b.ncy);
         const bool rl = tl && b.nb_kind[SIDE_LEFT] == NB_REMOTE, rr = tr && b.nb_kind[SIDE_RIGHT] == NB_REMOTE;
         const bool rb = tb && b.nb_kind[SIDE_BOTTOM] == NB_REMOTE, rt = tt && b.nb_kind[SIDE_TOP] == NB_REMOTE;
-        if (rl) push_side(blocks, gas, b, out_buf, put.parity, SIDE_LEFT, j0, j1);
-        if (rr) push_side(blocks, gas, b, out_buf, put.parity, SIDE_RIGHT, j0, j1);
-        if (rb) push_side(blocks, gas, b, out_buf, put.parity, SIDE_BOTTOM, c0, c1);
-        if (rt) push_side(blocks, gas, b, out_buf, put.parity, SIDE_TOP, c0, c1);
+        if (rl) push_side(b, out_buf, put.parity, SIDE_LEFT, j0, j1);
+        if (rr) push_side(b, out_buf, put.parity, SIDE_RIGHT, j0, j1);
+        if (rb) push_side(b, out_buf, put.parity, SIDE_BOTTOM, c0, c1);
+        if (rt) push_side(b, out_buf, put.parity, SIDE_TOP, c0, c1);
         put_something = rl || rr || rb || rt || strip == 0;
     }
     if (prof) prof[2] = clock64() - tq;
     if (strip == 0 && lane == 0) {
         // find_dt of the NEW state from cell (0,0) (main.cpp:19-37), for the next step on every rank
-        const BlockDev& b = blocks[k];
-        const double dtb = block_dt_value(b.state[out_buf], b.plane, b.pitch, b.min_face, gamRs, cfl);
+        const BlockDev& b = *bk;
+        const double dtb = block_dt_math(q1, q2, q3, b.min_face, gamRs, cfl);
         if (isnan(dtb)) flags |= FLAG_NAN;
         if (put.peer_mode) {
             for (int r = 0; r < put.nranks; r++) put.dt_dst[r][put.parity * put.dt_stride + b.gid] = dtb;
@@ -563,10 +587,12 @@ static __device__ __noinline__ int stop_gate(const int* go, int launch_no, const
 // `reload(k, strip)` re-derives the strip's identity after the row loop (from blockIdx or from the tile list), so
 // that neither it nor anything computed from it has to stay in a register across the rows.
 template <bool FAITHFUL, bool TPG, bool AXI, bool HOOKS, bool PUSH, class Reload>
-__device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, const PutArgs& put, const StepVar& sv, MarchSmem& sm, int k_in, int strip_in, Reload reload) {
+__device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, const PutArgs& put, const StepVar& sv, MarchSmem& sm, int k_in, int strip_in,
+                                           const BlockDev* bk_in, Reload reload) {
     const int lane = threadIdx.x;
     int k = k_in, strip = strip_in;
-    const BlockDev& b = a.blocks[k];
+    const BlockDev* bk = bk_in;                    // the strip's block descriptor: a.blocks + k, or the persistent launch's copy in shared memory
+    const BlockDev& b = *bk;
     MarchCtxT<int> m;
     m.k = k; m.ncx = b.ncx; m.ncy = b.ncy; m.pitch = b.pitch; m.plane = (int)b.plane; m.lane = lane;
     const int tx = strip % b.tiles_x, ty = strip / b.tiles_x;
@@ -705,8 +731,8 @@ __device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, cons
     }
     if (isnan(sq[0]) || isnan(sq[1]) || isnan(sq[2]) || isnan(sq[3])) flags |= FLAG_NAN;   // SpatialDiscretization.cpp:1008
     if (!ok) flags |= FLAG_NAN | 0x80000000u;      // a staged row never arrived
-    reload(k, strip);
-    const BlockDev& bb = a.blocks[k];
+    reload(k, strip, bk);
+    const BlockDev& bb = *bk;
     if (lane < 4) {
         const double s = lane == 0 ? sq[0] : lane == 1 ? sq[1] : lane == 2 ? sq[2] : sq[3];
         sv.partials[4 * (long long)(bb.tile0 + strip) + lane] = s;
@@ -724,7 +750,7 @@ __device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, cons
             PutLite pl;
             pl.peer_mode = put.peer_mode; pl.parity = sv.parity; pl.nranks = put.nranks; pl.rank = put.rank; pl.seq = sv.seq;
             pl.dt_dst = put.dt_dst; pl.dt_stride = put.dt_stride; pl.flag_dst = put.flag_dst; pl.ticket = put.ticket; pl.expected = put.expected;
-            flags |= tile_epilogue(a.blocks, a.gas_dev, a.ops, rg.x, rg.y, k, strip, sv.cur ^ 1, a.march_rows, sv.dt_next, g.gamRs, g.cfl, pl,
+            flags |= tile_epilogue(bk, a.gas_dev, a.ops, rg.x, rg.y, strip, sv.cur ^ 1, a.march_rows, sv.dt_next, g.gamRs, g.cfl, pl,
                                    sv.prof ? sv.prof + 4 : nullptr);
         }
     }
@@ -734,9 +760,9 @@ __device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, cons
 
 // The finalize role inside the fused step kernel: CTA `k` (one warp) runs the previous step's bookkeeping for
 // owned block k.
-__device__ __forceinline__ void march_finalize_role(const FinalizeArgs& fin, MarchSmem& sm, int k) {
+__device__ __forceinline__ void march_finalize_role(const FinalizeArgs& fin, MarchSmem& sm, int k, long long* fprof = nullptr) {
     (void)sm;
-    finalize_block(fin, k);
+    finalize_block(fin, k, nullptr, fprof);
 }
 
 __device__ __forceinline__ int2 tile_from_list(const int2* list, int t) {
@@ -924,9 +950,9 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
         const int t = (int)blockIdx.x - a.nfin;
         if (t >= a.tile_count) return;
         const int2 tl = tile_from_list(a.tile_list, t);
-        march_tile<FAITHFUL, TPG, AXI, false, true>(a, g, put, sv, sm, tl.x, tl.y, [&](int& k, int& strip) {
+        march_tile<FAITHFUL, TPG, AXI, false, true>(a, g, put, sv, sm, tl.x, tl.y, a.blocks + tl.x, [&](int& k, int& strip, const BlockDev*& bk) {
             const int2 r = tile_from_list(a.tile_list, (int)blockIdx.x - a.nfin);
-            k = r.x; strip = r.y;
+            k = r.x; strip = r.y; bk = a.blocks + r.x;
         });
     } else {
         const int fy = a.nfin ? 1 : 0;
@@ -936,29 +962,81 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : MARCH_MINB) marc
         }
         const int k = (int)blockIdx.y - fy;
         if ((int)blockIdx.x >= a.blocks[k].tiles_x * a.blocks[k].tiles_y) return;    // CTA-uniform
-        march_tile<FAITHFUL, TPG, AXI, false, true>(a, g, put, sv, sm, k, blockIdx.x, [&](int& k2, int& strip2) {
-            k2 = (int)blockIdx.y - (a.nfin ? 1 : 0); strip2 = blockIdx.x;
+        march_tile<FAITHFUL, TPG, AXI, false, true>(a, g, put, sv, sm, k, blockIdx.x, a.blocks + k, [&](int& k2, int& strip2, const BlockDev*& bk) {
+            k2 = (int)blockIdx.y - (a.nfin ? 1 : 0); strip2 = blockIdx.x; bk = a.blocks + k2;
         });
     }
 }
 
 // ------------------------------------------------------------------ persistent launch (small meshes)
 // Grid barrier of a cooperative launch: every CTA is one warp.  Bounded (FLAG_COMM), like every wait here.
-__device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned target) {
-    bool ok = true;
+//   bar[0]                      arrival counter (+1 per CTA and step; bit 31 = "the batch has converged", raised by a
+//                               bookkeeping CTA before it arrives)
+//   bar[32 * (1 + r)], r < 16   release words, one 128-byte line each: the number of the last completed step, with the
+//                               counter's bit 31 carried over
+// The last CTA to arrive (it knows from the value its own atomic returned) publishes the step number in the release
+// words; everybody else polls ONE of them, chosen by CTA index: the late arrivals' atomics do not queue behind ~1100
+// warps re-reading the counter's line, and the stop word of the batch travels in the same word, so that no CTA needs
+// another round trip to L2 to learn that the next step may start.  (Measured on the shipped cases: the poll rate and
+// where the pollers look are neutral; what costs is every FENCE, ~1000 cycles each.)
+// Returns 0 on a time-out, 1 to go on, 2 when the batch has converged.
+#ifndef BAR_RELEASE_ATOM
+#define BAR_RELEASE_ATOM 1   // 1: the arrival is ONE atom.release.gpu (SASS: MEMBAR.ALL.GPU + ATOMG); 0: fence.acq_rel.gpu + atomicAdd, whose
+                             //    fence also invalidates the SM's L1 (CCTL.IVALL) under the strips that still work there: 7.8 -> 7.5 us per step
+#endif
+#ifndef BAR_FORMAL
+#define BAR_FORMAL 0    // 1: every CTA leaves the barrier through an acquire fence and the last arrival fences before the release,
+                        //    as the PTX memory model asks for (A/B builds: +2000 cycles on every step of the shipped cases)
+#endif
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void bar_fence() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// `acquire`: the caller reads memory other CTAs wrote through L1 after the barrier (the bookkeeping CTAs: plain loads
+// of the iteration counters and res0) and needs the acquire fence that invalidates it.  A STRIP does not: everything it
+// reads of other CTAs' writes it reads at L2 - its rows by TMA (behind a proxy fence), the dt table and the cells of the
+// perimeter epilogue by ld.cg / ld.volatile - and what it reads through L1 (ghost-cell records, strip lists, gas
+// constants) never changes; its loads are issued after the flag load they depend on (a branch), and every arrival's
+// writes were performed at L2 before its arrival (release fence + atomic at L2).  A fence costs ~1000 cycles here, a
+// whole step of a shipped case ~14000: the strips leave on the relaxed load (measured 8.76 -> 7.8 us per step).
+__device__ __forceinline__ int grid_barrier(unsigned* bar, unsigned step_no, unsigned nctas, bool raise_stop, bool acquire, long long* bprof = nullptr) {
+    unsigned word = 0;
+    const long long tb = bprof ? clock64() : 0;    // diagnostics (tools/diag_persist.py); null in production
     __syncwarp();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
-        if (ld_acquire_gpu(bar) < target) {
-            const unsigned long long t0 = global_ns();
-            while (ld_acquire_gpu(bar) < target) {
-                if ((long long)(global_ns() - t0) > 4000000000ll) { ok = false; break; }
+        if (raise_stop) atomicOr(bar, 0x80000000u);
+        // release: what this CTA wrote is performed before its arrival
+#if BAR_RELEASE_ATOM
+        unsigned old;
+        asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
+#else
+        bar_fence();
+        if (bprof) bprof[0] = clock64() - tb;
+        const unsigned old = atomicAdd(bar, 1u);
+#endif
+        if (bprof) bprof[2] = clock64() - tb;
+        if ((old & 0x7fffffffu) == step_no * nctas - 1u) {
+            word = step_no | (old & 0x80000000u);
+            if (BAR_FORMAL || acquire) bar_fence();
+#pragma unroll
+            for (int r = 0; r < BAR_RELEASE_WORDS; r++) *reinterpret_cast<volatile unsigned*>(bar + 32 * (1 + r)) = word;
+        } else {
+            const unsigned* rel = bar + 32 * (1 + (int)(blockIdx.x % BAR_RELEASE_WORDS));
+            word = ld_relaxed_gpu(rel);
+            if ((word & 0x7fffffffu) < step_no) {
+                const unsigned long long t0 = global_ns();
+                unsigned spins = 0;
+                while (((word = ld_relaxed_gpu(rel)) & 0x7fffffffu) < step_no) {
+                    if ((++spins & 63u) == 0 && (long long)(global_ns() - t0) > 4000000000ll) { word = 0; break; }
+                }
             }
+            if (BAR_FORMAL || acquire) bar_fence();
         }
     }
-    ok = __all_sync(0xffffffffu, ok);
-    return ok;
+    word = __shfl_sync(0xffffffffu, word, 0);
+    return word == 0 ? 0 : (word & 0x80000000u) ? 2 : 1;
 }
 
 // A batch of a.coop_steps steps of a mesh whose strips are all resident at once (the shipped cases hold ~50 k
@@ -971,14 +1049,26 @@ __device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned target) {
 //  the strip code its spills)
 template <bool FAITHFUL, bool TPG, bool AXI>
 __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : 12) march_persist_kernel(const StepArgs a, const Gas g, const FinalizeArgs fin,
-                                                                                                double* dt_used_alt, double* partials_alt) {
+                                                                                                double* dt_used_alt, double* partials_alt, const DeferArgs df) {
     __shared__ __align__(128) MarchSmem sm;
+    // the strip's block descriptor, copied once: after every grid barrier (an acquire) a plain global load goes to L2
+    // again, and the descriptor's fields stand at the head of every step's chain (strip position -> first TMA copy)
+    __shared__ __align__(16) BlockDev sblk;
     if (*a.stop) return;
-    const bool fin_role = (int)blockIdx.x < a.nowned;
+    // df.on (no stop test in this batch): no bookkeeping CTAs - the strips keep every step's sums, dt and error bits, the
+    // history records are made after the launch (launch_finalize_deferred).  On the shipped cases the bookkeeping CTA of
+    // a block was the longest CTA of every step (one warp, code that runs once per step out of a cold instruction cache)
+    const int nfin = df.on ? 0 : a.nowned;
+    const bool fin_role = (int)blockIdx.x < nfin;
     int k = 0, strip = 0;
     if (!fin_role) {
-        const int2 tl = __ldg(a.tile_list + ((int)blockIdx.x - a.nowned));
+        const int2 tl = __ldg(a.tile_list + ((int)blockIdx.x - nfin));
         k = tl.x; strip = tl.y;
+        static_assert(sizeof(BlockDev) % 8 == 0, "BlockDev is copied in 8-byte words");
+        const unsigned long long* from = reinterpret_cast<const unsigned long long*>(a.blocks + k);
+        unsigned long long* to = reinterpret_cast<unsigned long long*>(&sblk);
+        for (int w = threadIdx.x; w < (int)(sizeof(BlockDev) / 8); w += 32) to[w] = from[w];
+        __syncwarp();
     }
     PutArgs put;
     put.peer_mode = 0; put.parity = 0; put.seq = 0; put.nranks = 1; put.rank = 0; put.expected = 0;
@@ -987,37 +1077,48 @@ __global__ void __launch_bounds__(MARCH_THREADS, FAITHFUL ? 1 : 12) march_persis
     bool stopped = false;
     // a.prof (diagnostics, tools/diag_persist.py): per step, SM clock cycles of the first strip's march, of its wait
     // at the grid barrier, and of the first bookkeeping CTA
-    const bool prof = a.prof != nullptr && threadIdx.x == 0 && ((int)blockIdx.x == a.nowned || blockIdx.x == 0);
+    const bool prof = a.prof != nullptr && threadIdx.x == 0 && ((int)blockIdx.x == nfin || blockIdx.x == 0);
+    // ... and, for step PROF_ALL_STEP alone, the same two numbers of EVERY CTA (upper half of the buffer)
+    constexpr int PROF_STEPS = 2048, PROF_ALL_STEP = 500;
+    const bool prof_all = a.prof != nullptr && threadIdx.x == 0 && 2 * gridDim.x <= 12 * PROF_STEPS;
     for (int s = 0; s < a.coop_steps; s++) {
         const int odd = s & 1;
-        const long long t0 = prof ? clock64() : 0;
+        const long long t0 = (prof || prof_all) ? clock64() : 0;
         if (fin_role) {
             if (s > 0) {
                 FinalizeArgs f = fin;              // step s-1
                 f.partials = odd ? fin.partials : partials_alt;
                 f.dt_used = odd ? fin.dt_used : dt_used_alt;
-                march_finalize_role(f, sm, blockIdx.x);
+                // diagnostics: phases of the bookkeeping of blocks 0 and 1, 8 slots per step behind the per-CTA records
+                long long* fp = (a.prof != nullptr && threadIdx.x == 0 && blockIdx.x < 2 && s < 1024) ? a.prof + 12 * PROF_STEPS + 8192 + 16 * s + 8 * blockIdx.x : nullptr;
+                march_finalize_role(f, sm, blockIdx.x, fp);
             }
         } else {
             StepVar sv;
             sv.cur = a.cur ^ odd;
             sv.dt_table = odd ? a.dt_next : a.dt_table;
             sv.dt_next = odd ? const_cast<double*>(a.dt_table) : a.dt_next;
-            sv.dt_used = odd ? dt_used_alt : a.dt_used;
-            sv.partials = odd ? partials_alt : a.partials;
+            sv.dt_used = df.on ? df.dt + s : odd ? dt_used_alt : a.dt_used;
+            sv.partials = df.on ? df.partials + s * df.stride : odd ? partials_alt : a.partials;
+            // error bits as of the end of the previous step, for its history record (per-step status)
+            if (df.on && s > 0 && blockIdx.x == 0 && threadIdx.x == 0) df.flags[s - 1] = __ldcg(a.flags);
             sv.parity = 0; sv.seq = 0; sv.first = s == 0;
-            sv.prof = (prof && s < 4096) ? a.prof + 12 * s + 3 : nullptr;
-            march_tile<FAITHFUL, TPG, AXI, false, true>(a, g, put, sv, sm, k, strip, [&](int& k2, int& strip2) {
-                const int2 r = tile_from_list(a.tile_list, (int)blockIdx.x - a.nowned);
-                k2 = r.x; strip2 = r.y;
+            sv.prof = (prof && s < PROF_STEPS) ? a.prof + 12 * s + 3 : nullptr;
+            march_tile<FAITHFUL, TPG, AXI, false, true>(a, g, put, sv, sm, k, strip, &sblk, [&](int& k2, int& strip2, const BlockDev*& bk) {
+                const int2 r = tile_from_list(a.tile_list, (int)blockIdx.x - (df.on ? 0 : a.nowned));
+                k2 = r.x; strip2 = r.y; bk = &sblk;
             });
         }
         done = s + 1;
-        const long long t1 = prof ? clock64() : 0;
-        if (prof && s < 4096) a.prof[12 * s + (fin_role ? 2 : 0)] = t1 - t0;
-        if (!grid_barrier(a.grid_bar, (unsigned)(s + 1) * gridDim.x)) { if (threadIdx.x == 0) atomicOr(a.flags, FLAG_COMM); break; }
-        if (prof && !fin_role && s < 4096) a.prof[12 * s + 1] = clock64() - t1;
-        if (*reinterpret_cast<volatile const int*>(a.stop)) { stopped = true; break; }
+        const long long t1 = (prof || prof_all) ? clock64() : 0;
+        if (prof && s < PROF_STEPS) a.prof[12 * s + (fin_role ? 2 : 0)] = t1 - t0;
+        // a bookkeeping CTA that finds the stop word set (by itself or by a CTA before it) says so on its way into the barrier
+        const bool raise = fin_role && s > 0 && *reinterpret_cast<volatile const int*>(a.stop) != 0;
+        const int go = grid_barrier(a.grid_bar, (unsigned)(s + 1), gridDim.x, raise, fin_role, (prof && !fin_role && s < PROF_STEPS) ? a.prof + 12 * s + 9 : nullptr);
+        if (go == 0) { if (threadIdx.x == 0) atomicOr(a.flags, FLAG_COMM); break; }
+        if (prof && !fin_role && s < PROF_STEPS) a.prof[12 * s + 1] = clock64() - t1;
+        if (prof_all && s == PROF_ALL_STEP) { a.prof[12 * PROF_STEPS + 2 * blockIdx.x] = t1 - t0; a.prof[12 * PROF_STEPS + 2 * blockIdx.x + 1] = clock64() - t1; }
+        if (go == 2) { stopped = true; break; }
     }
     // the last step's bookkeeping
     if (fin_role && !stopped && done > 0) {

@@ -58,6 +58,23 @@ def test_persistent_launch_bitwise(gpu, monkeypatch, name, igam, mode):
             assert np.array_equal(a, b), label
 
 
+@pytest.mark.parametrize("name,igam", [("Case_ffstep1", 1.4), ("Case_rktnoz9", -1.4)])
+def test_deferred_bookkeeping_bitwise(gpu, monkeypatch, name, igam):
+    """Without a stop test the persistent launch keeps every step's strip sums and the history records are made after
+    the launch (three short kernels), in launches of at most 1024 steps: 1100 + 5 + 30 steps give the records and the
+    state of the same batches with the bookkeeping CTAs inside the launch (PAR2D_NO_DEFER=1), bit for bit."""
+    monkeypatch.delenv("PAR2D_NO_PERSIST", raising=False)
+    monkeypatch.delenv("PAR2D_NO_OVERLAP", raising=False)
+    monkeypatch.delenv("PAR2D_NO_DEFER", raising=False)
+    deferred = _run(gpu, name, MODE_FAST, igam, [1100, 5, 30])
+    monkeypatch.setenv("PAR2D_NO_DEFER", "1")
+    inside = _run(gpu, name, MODE_FAST, igam, [1100, 5, 30])
+    assert len(deferred[1]) == 1135 and deferred[2] == 1135
+    assert deferred[1] == inside[1]
+    for a, b in zip(deferred[0], inside[0]):
+        assert np.array_equal(a, b)
+
+
 def test_persistent_launch_against_the_reference_golden(gpu):
     """The persistent launch in the bit-faithful mode reproduces the unmodified reference binary's state after 200
     steps of the 8-block forward step, bit for bit, in ONE kernel launch."""
