@@ -590,6 +590,7 @@ template <bool FAITHFUL, bool TPG, bool AXI, bool HOOKS, bool PUSH, class Reload
 __device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, const PutArgs& put, const StepVar& sv, MarchSmem& sm, int k_in, int strip_in,
                                            const BlockDev* bk_in, Reload reload) {
     const int lane = threadIdx.x;
+    const long long te = (PUSH && sv.prof) ? clock64() : 0;
     int k = k_in, strip = strip_in;
     const BlockDev* bk = bk_in;                    // the strip's block descriptor: a.blocks + k, or the persistent launch's copy in shared memory
     const BlockDev& b = *bk;
@@ -644,6 +645,7 @@ __device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, cons
         for (int s = 0; s < MARCH_STAGES; s++) stage_rows(s, s);
     }
     __syncwarp();
+    if (PUSH && sv.prof) sv.prof[6] = clock64() - te;     // entry -> first rows requested
     // this lane's first column of the state planes / node planes in stage 0, row 0
     const double* rs = &sm.ring[0][sv.cur ? 3 : 0][0][CPL * lane];
     const double* rn = &sm.ring[0][sv.cur ? 0 : 4][0][CPL * lane];
@@ -668,6 +670,7 @@ __device__ __forceinline__ void march_tile(const StepArgs& a, const Gas& g, cons
     // ---- prologue (ring use 0): cell rows j0-1 (row 0) and j0 (row 1), node row j0, bottom-face fluxes of row j0
     RowState A, B;
     const long long tp0 = (PUSH && sv.prof) ? clock64() : 0;
+    if (PUSH && sv.prof) sv.prof[-1] = tp0 - te;          // entry -> dt known, waiting for the rows
     ok &= mbar_wait(&sm.bar[0], 0);
     if (PUSH && sv.prof) sv.prof[0] = clock64() - tp0;    // wait for the first staged rows
     {
@@ -1013,7 +1016,6 @@ __device__ __forceinline__ int grid_barrier(unsigned* bar, unsigned step_no, uns
         asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
 #else
         bar_fence();
-        if (bprof) bprof[0] = clock64() - tb;
         const unsigned old = atomicAdd(bar, 1u);
 #endif
         if (bprof) bprof[2] = clock64() - tb;

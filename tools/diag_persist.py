@@ -21,7 +21,7 @@ for name in sys.argv[1:] or ["Case_ffstep8"]:
     m = lambda k: np.median(a[:, k])
     print(f"{name}: {1e6 * dt / NSTEP:.2f} us/step wall; cycles/step median: march {m(0):.0f}  barrier wait {m(1):.0f}  bookkeeping {m(2):.0f}  | in strip (cumulative): "
           f"wait rows {m(3):.0f}  +rows {m(4):.0f}  +norms {m(5):.0f}  +epilogue {m(6):.0f} | inside the epilogue (cumulative): entry+syncwarp {m(7):.0f}  "
-          f"ghost records {m(8):.0f}  dt+ticket {m(10):.0f} | inside the barrier (cumulative): fence {m(9):.0f}  +arrival atomic {m(11):.0f}")
+          f"ghost records {m(8):.0f}  dt+ticket {m(10):.0f} | before the rows: strip entry -> rows requested {m(9):.0f}  -> dt known {m(2):.0f} | barrier: arrival done after {m(11):.0f}")
     per = raw[12 * HALF:].reshape(-1, 2)
     n = int(np.count_nonzero(per[:, 0]))
     if n:
