@@ -51,7 +51,10 @@ namespace par2d {
 #define MARCH_YCC_FROM_FACES 1
 #endif
 #ifndef MARCH_VOTE_J
-#define MARCH_VOTE_J 1       // the fully-upwind warp vote also on j-faces (0: i-faces only, A/B runs)
+#define MARCH_VOTE_J 0       // the fully-upwind warp vote on i-faces only.  1: also on j-faces - which follow the walls and the
+                             // streamlines in every shipped case and in the benchmark, so their normal Mach number is subsonic,
+                             // the vote never passes and its test + branch is all cost: 0.5941/0.5862 -> 0.5735 ms per launch
+                             // (profiles/r02_ab_early_vote.txt)
 #endif
 #ifndef PUSH_EXP
 #define PUSH_EXP 31     // diagnostics: bit mask of the fused step's pieces that are compiled in (1 bookkeeping role + stop test, 2 pull,

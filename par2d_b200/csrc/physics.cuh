@@ -43,6 +43,12 @@ inline double __dsub_rn(double a, double b) { volatile double r = a - b; return 
                               // +x flow): 0 -> 0.5195 ms, 1 -> 0.5276 ms, 2 -> 0.5341 ms: every extra vote/branch on the
                               // general path costs more than the shortcut saves, so only the left-upwind case is voted
 #endif
+#ifndef LDFSS_VOTE_EARLY
+#define LDFSS_VOTE_EARLY 1    // the fully-upwind vote is taken on the un-normalised normal velocities, before the rsqrt (see ldfss)
+#endif
+#ifndef LDFSS_VOTE_MIN
+#define LDFSS_VOTE_MIN 1      // early vote on min(ml, mr): one square and one compare instead of two (0.5727 -> 0.5701 ms, two runs each)
+#endif
 #ifndef LDFSS_BRANCHFREE
 #define LDFSS_BRANCHFREE 1    // the subsonic diffusion term is evaluated without a branch and switched off by a select: measured
                               // +1.3% on B200 together with the warp vote (fully supersonic warps skip it anyway; fewer basic
@@ -457,6 +463,49 @@ PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) 
         o.f2 = yface * (fml * L.v + fmr * R.v + py_planar);
         o.f3 = yface * (fml * L.h0 + fmr * (R.h0));
     } else {
+#if defined(__CUDA_ARCH__) && LDFSS_UPWIND_VOTE && LDFSS_VOTE_EARLY
+        if constexpr (WARP_VOTE) {
+            // The vote BEFORE the rsqrt: xml >= 1  <=>  ml = len*(uL.n) >= len*ahalf  <=>  ml > 0 and ml^2 >= w, and a fully
+            // upwind flux needs neither the Mach numbers nor len*ahalf - la*xml IS ml.  A warp whose faces are all supersonic
+            // from the left skips the rsqrt series, the three products behind it and the split; the others pay two squares.
+            // Equal to the general path to rounding (2 ulp of the mass flux), not bit for bit: a face may be evaluated
+            // either way depending on the other 31 faces of its warp, so fast-mode results are decomposition-invariant
+            // to ~1e-15 relative, not bitwise (the faithful mode never comes here).
+            const double ahalf = L.a + R.a;
+            const double w = fma(fg.dx, fg.dx, fg.dy * fg.dy) * (ahalf * ahalf);
+            const double ml = fma(L.u, fg.dy, -L.v * fg.dx), mr = fma(R.u, fg.dy, -R.v * fg.dx);
+#if LDFSS_VOTE_MIN
+            const double mm = ml < mr ? ml : mr;
+            const bool up = mm > 0.0 && mm * mm >= w;
+#else
+            const bool up = ml > 0.0 && mr > 0.0 && ml * ml >= w && mr * mr >= w;
+#endif
+            if (__all_sync(0xffffffffu, up)) {
+                if constexpr (AXI) {
+                    const double fml = (fg.yf * L.rho) * ml;
+                    o.parr = -L.p * fg.dx;
+                    o.f0 = fml;
+                    o.f1 = fma(fml, L.u, (L.p * fg.yf) * fg.dy);
+                    o.f2 = fml * L.v;
+                    o.f3 = fml * L.h0;
+                } else {
+                    const double fml = L.rho * ml;
+                    o.parr = 0.0;
+                    o.f0 = fml;
+                    o.f1 = fma(fml, L.u, L.p * fg.dy);
+                    o.f2 = fma(fml, L.v, -L.p * fg.dx);
+                    o.f3 = fml * L.h0;
+                }
+                return o;
+            }
+            LdfssPre pre;
+            const double q = fast_rsqrt(w);
+            pre.la = w * q;
+            pre.xml = ml * q;
+            pre.xmr = mr * q;
+            return ldfss_lean_post<AXI, false>(fg, L, R, pre);
+        }
+#endif
         o = ldfss_lean_post<AXI, WARP_VOTE>(fg, L, R, ldfss_lean_pre(fg, L, R));
     }
     return o;

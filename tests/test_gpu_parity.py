@@ -203,7 +203,8 @@ def _perturbed(shape, seed):
 
 
 def _assert_residual_split_invariant(gpu, whole, parts, nbx, nby, mode, seed):
-    """calc_dudt on the same (random) field, unsplit vs split: every bit must agree, because ghost
+    """calc_dudt on the same (random) field, unsplit vs split: must agree (bit for bit away from block edges in the
+    bit-faithful mode, to 1e-13 of the residual scale in the fast mode), because ghost
     lines filled from neighbour blocks carry exactly the cells the unsplit stencil reads.  (N-step
     states are NOT comparable across decompositions by design: main.cpp:276 takes dt as the max
     over blocks of a per-block quantity.)"""
@@ -227,7 +228,11 @@ def _assert_residual_split_invariant(gpu, whole, parts, nbx, nby, mode, seed):
     for k, (j0, i0, h, w) in where.items():
         rb = b.get_residual(k)
         if mode == MODE_FAST:
-            assert np.array_equal(rb, ra[j0:j0 + h, i0:i0 + w]), f"block {k}"
+            # the fast mode evaluates a face either by the general LDFSS or - when all 32 faces of its warp are supersonic
+            # from the left - by the fully-upwind shortcut, which skips the rsqrt and rounds differently (physics.cuh,
+            # LDFSS_VOTE_EARLY): which faces share a warp depends on the decomposition, so the residual is
+            # decomposition-invariant to rounding, not bit for bit (the bit-faithful mode below is)
+            assert (np.abs(rb - ra[j0:j0 + h, i0:i0 + w]).reshape(-1, 4).max(axis=0) / scale).max() < 1e-13, f"block {k}"
         else:
             # the reference adds boundary-face fluxes after the interior ones
             # (SpatialDiscretization.cpp:481-625 then :643-977), so a cell on a block edge sums in a
@@ -298,7 +303,7 @@ def test_full_size_blocks_decomposition_invariance(gpu):
     """At the benchmark's block size (2048^2 cells per block, BASELINE.json configs[4]) the oracle
     needs minutes per step; instead check the size-independent property that the residual does not
     depend on the decomposition: one 4096x2048-cell block vs 2x1 blocks of 2048^2 vs 4x2 blocks of
-    1024^2, bit for bit."""
+    1024^2, to rounding (1e-13 of the residual scale: fast mode, see _assert_residual_split_invariant)."""
     whole = Case.synthetic_ramp(4096, 2048, 1, 1)
     _assert_residual_split_invariant(gpu, whole, Case.synthetic_ramp(4096, 2048, 2, 1), 2, 1, MODE_FAST, seed=5)
     _assert_residual_split_invariant(gpu, whole, Case.synthetic_ramp(4096, 2048, 4, 2), 4, 2, MODE_FAST, seed=5)
