@@ -126,7 +126,11 @@ static __device__ __noinline__ void bc_ghost_general(const Gas* gp, const BlockD
 #pragma unroll
     for (int v = 0; v < 4; v++) { ui[v] = __ldcg(S + v * b.plane + io); gh[v] = __ldcg(S + v * b.plane + go); }
     double v2 = 0.0, p = 0.0, aint = 0.0;
+#if defined(PAR2D_LEAN_BC)
+    if (code == 1) { p = fmax(ui[0] * g.Rs * ui[3], 1.0); aint = fast_sqrt(g.gamRs * ui[3]); }
+#else
     if (code == 1) { p = fmax(ui[0] * g.Rs * ui[3], 1.0); aint = sqrt(g.gamRs * ui[3]); }
+#endif
     if (code == 5) v2 = ui[1] * ui[1] + ui[2] * ui[2];
     boundary_state(g, code, nrm.x, nrm.y, ui, aint, p, v2, gh);
 #pragma unroll

@@ -531,6 +531,37 @@ PAR2D_FN void isentropic_ghost(double ref, double X, double gm1, double gam, dou
 #endif
 }
 
+#if defined(__CUDA_ARCH__) && defined(PAR2D_LEAN_BC)
+// The far field (code 1) of the fast mode's translation unit: the four cases of BoundaryConditions.cpp:150-190 with the
+// two subsonic ones merged, series reciprocals instead of divisions, one logarithm.  Short on purpose (see above).
+PAR2D_FN bool farfield_lean(const Gas& g, double normx, double normy, const double ui[4], double a_int, double p_int, double out[4]) {
+    const double vin = ui[1] * normx + ui[2] * normy;
+    const double ia = fast_rcp(a_int);
+    const double mn = vin * ia;
+    if (mn <= -1) {
+        out[0] = g.uFS[0]; out[1] = g.uFS[1]; out[2] = g.uFS[2]; out[3] = g.uFS[3];
+    } else if (mn >= 1) {
+        out[0] = ui[0]; out[1] = ui[1]; out[2] = ui[2]; out[3] = ui[3];
+    } else if (mn > -1 && mn < 1) {
+        const bool in = mn <= 0;                   // inflow: tangential velocity and reference density of the free stream
+        const double gm1 = g.gam - 1;
+        const double vfn = g.uFS[1] * normx + g.uFS[2] * normy;
+        const double bu = in ? g.uFS[1] : ui[1], bv = in ? g.uFS[2] : ui[2], bn = in ? vfn : vin;
+        const double vgn = 0.5 * (vin + vfn);
+        const double r = (a_int + 0.5 * gm1 * (vgn - vfn)) * ia;
+        const double lx = log(r * r);
+        const double rho = (in ? g.uFS[0] : ui[0]) * exp(gm1 * lx);
+        out[0] = rho;
+        out[1] = bu + (vgn - bn) * normx;
+        out[2] = bv + (vgn - bn) * normy;
+        out[3] = p_int * exp((g.gam * gm1) * lx) * fast_rcp(rho * g.Rs);
+    } else {
+        return false;                              // NaN normal Mach number
+    }
+    return true;
+}
+#endif
+
 PAR2D_FN bool boundary_state(const Gas& g, int btype, double normx, double normy,
                                                const double ui[4], double a_int, double p_int, double v2_int,
                                                double out[4]) {
@@ -559,6 +590,10 @@ PAR2D_FN bool boundary_state(const Gas& g, int btype, double normx, double normy
         out[1] = fmax(ui[1], 0.0);
         out[2] = ui[2];
         out[3] = ui[3];
+#if defined(__CUDA_ARCH__) && defined(PAR2D_LEAN_BC)
+    } else if (btype == 1) {
+        wrote = farfield_lean(g, normx, normy, ui, a_int, p_int, out);
+#else
     } else if (btype == 1) {
         const double gm1 = g.gam - 1;
         const double mn = vn / a_int;      // only the far field reads the normal Mach number
@@ -594,6 +629,7 @@ PAR2D_FN bool boundary_state(const Gas& g, int btype, double normx, double normy
         } else {
             wrote = false;  // NaN normal Mach number
         }
+#endif
     } else {
         wrote = false;  // unknown code: the reference falls through without writing
     }
