@@ -415,6 +415,61 @@ PAR2D_FN Flux ldfss_lean_post(const FaceGeom& fg, const FaceState& L, const Face
     return o;
 }
 
+// The early form of the fully-upwind test.  xml >= 1  <=>  ml = len*(uL.n) >= len*ahalf  <=>  ml > 0 and ml^2 >= w with
+// w = (len*ahalf)^2, and a fully upwind flux needs neither the Mach numbers nor len*ahalf - la*xml IS ml = uL dy - vL dx.
+// So the test needs no rsqrt, and a face that passes it none either (ldfss_upwind_left).  Equal to the general path to
+// rounding (2 ulp of the mass flux), not bit for bit: on the device a face is evaluated either way depending on the
+// other 31 faces of its warp, so fast-mode results are decomposition-invariant to ~1e-15 relative, not bitwise (the
+// faithful mode never comes here).  tests/test_host_physics_cpu.py checks both forms against each other on the host.
+struct LdfssEarly {
+    double w, ml, mr;        // (len*ahalf)^2 and the un-normalised normal velocities len*(u.n) of both sides
+    bool up;                 // both sides supersonic from the left
+};
+PAR2D_FN LdfssEarly ldfss_early(const FaceGeom& fg, const FaceState& L, const FaceState& R) {
+    LdfssEarly e;
+    const double ahalf = L.a + R.a;          // the lean FaceState carries a/2
+    e.w = fma(fg.dx, fg.dx, fg.dy * fg.dy) * (ahalf * ahalf);
+    e.ml = fma(L.u, fg.dy, -L.v * fg.dx);
+    e.mr = fma(R.u, fg.dy, -R.v * fg.dx);
+#if LDFSS_VOTE_MIN
+    const double mm = e.ml < e.mr ? e.ml : e.mr;
+    e.up = mm > 0.0 && mm * mm >= e.w;
+#else
+    e.up = e.ml > 0.0 && e.mr > 0.0 && e.ml * e.ml >= e.w && e.mr * e.mr >= e.w;
+#endif
+    return e;
+}
+// the flux of a face that is supersonic from the left on both sides: all/alr = 1/0, btl = btr = 0 in EulerFlux.cpp:146-186
+template <bool AXI>
+PAR2D_FN Flux ldfss_upwind_left(const FaceGeom& fg, const FaceState& L, double ml) {
+    Flux o;
+    if constexpr (AXI) {
+        const double fml = (fg.yf * L.rho) * ml;
+        o.parr = -L.p * fg.dx;
+        o.f0 = fml;
+        o.f1 = fma(fml, L.u, (L.p * fg.yf) * fg.dy);
+        o.f2 = fml * L.v;
+        o.f3 = fml * L.h0;
+    } else {
+        const double fml = L.rho * ml;
+        o.parr = 0.0;
+        o.f0 = fml;
+        o.f1 = fma(fml, L.u, L.p * fg.dy);
+        o.f2 = fma(fml, L.v, -L.p * fg.dx);
+        o.f3 = fml * L.h0;
+    }
+    return o;
+}
+// ... and the general path's inputs when the test fails: the rsqrt after all
+PAR2D_FN LdfssPre ldfss_pre_from_early(const LdfssEarly& e) {
+    LdfssPre pre;
+    const double q = fast_rsqrt(e.w);
+    pre.la = e.w * q;
+    pre.xml = e.ml * q;
+    pre.xmr = e.mr * q;
+    return pre;
+}
+
 // WARP_VOTE (device, lean path, all 32 lanes of the warp calling together): when EVERY face of the warp is
 // supersonic in the same direction the flux is fully upwind - cep = xml, cem = 0, pnet = pL (or the mirror
 // image) - and the split polynomials, their selects and the dead side's terms are skipped.  The result is
@@ -465,45 +520,11 @@ PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) 
     } else {
 #if defined(__CUDA_ARCH__) && LDFSS_UPWIND_VOTE && LDFSS_VOTE_EARLY
         if constexpr (WARP_VOTE) {
-            // The vote BEFORE the rsqrt: xml >= 1  <=>  ml = len*(uL.n) >= len*ahalf  <=>  ml > 0 and ml^2 >= w, and a fully
-            // upwind flux needs neither the Mach numbers nor len*ahalf - la*xml IS ml.  A warp whose faces are all supersonic
-            // from the left skips the rsqrt series, the three products behind it and the split; the others pay two squares.
-            // Equal to the general path to rounding (2 ulp of the mass flux), not bit for bit: a face may be evaluated
-            // either way depending on the other 31 faces of its warp, so fast-mode results are decomposition-invariant
-            // to ~1e-15 relative, not bitwise (the faithful mode never comes here).
-            const double ahalf = L.a + R.a;
-            const double w = fma(fg.dx, fg.dx, fg.dy * fg.dy) * (ahalf * ahalf);
-            const double ml = fma(L.u, fg.dy, -L.v * fg.dx), mr = fma(R.u, fg.dy, -R.v * fg.dx);
-#if LDFSS_VOTE_MIN
-            const double mm = ml < mr ? ml : mr;
-            const bool up = mm > 0.0 && mm * mm >= w;
-#else
-            const bool up = ml > 0.0 && mr > 0.0 && ml * ml >= w && mr * mr >= w;
-#endif
-            if (__all_sync(0xffffffffu, up)) {
-                if constexpr (AXI) {
-                    const double fml = (fg.yf * L.rho) * ml;
-                    o.parr = -L.p * fg.dx;
-                    o.f0 = fml;
-                    o.f1 = fma(fml, L.u, (L.p * fg.yf) * fg.dy);
-                    o.f2 = fml * L.v;
-                    o.f3 = fml * L.h0;
-                } else {
-                    const double fml = L.rho * ml;
-                    o.parr = 0.0;
-                    o.f0 = fml;
-                    o.f1 = fma(fml, L.u, L.p * fg.dy);
-                    o.f2 = fma(fml, L.v, -L.p * fg.dx);
-                    o.f3 = fml * L.h0;
-                }
-                return o;
-            }
-            LdfssPre pre;
-            const double q = fast_rsqrt(w);
-            pre.la = w * q;
-            pre.xml = ml * q;
-            pre.xmr = mr * q;
-            return ldfss_lean_post<AXI, false>(fg, L, R, pre);
+            // the vote BEFORE the rsqrt (see ldfss_early): a warp whose faces are all supersonic from the left skips the
+            // rsqrt series, the three products behind it and the split; the others pay one square and a compare
+            const LdfssEarly e = ldfss_early(fg, L, R);
+            if (__all_sync(0xffffffffu, e.up)) return ldfss_upwind_left<AXI>(fg, L, e.ml);
+            return ldfss_lean_post<AXI, false>(fg, L, R, ldfss_pre_from_early(e));
         }
 #endif
         o = ldfss_lean_post<AXI, WARP_VOTE>(fg, L, R, ldfss_lean_pre(fg, L, R));
@@ -516,24 +537,20 @@ PAR2D_FN Flux ldfss(const FaceGeom& fg, const FaceState& L, const FaceState& R) 
 // the ghost's UpdateState temperature clamp (SpatialDiscretization.cpp:39).  O(perimeter)
 // work, so a single (reference-ordered) formulation serves both modes.  Returns false when
 // the ghost must stay unwritten (NaN normal Mach number).
-// The isentropic pair of the subsonic far field (BoundaryConditions.cpp:163-187): rho = ref X^(gam-1), pg = p (rho/ref)^gam.
-// Reference order: two pow().  The translation unit of the fast mode (PAR2D_LEAN_BC, kernels_fast.cu) evaluates both from
-// ONE logarithm - pg = p X^(gam (gam-1)) - : ~150 instructions instead of ~500, on code that runs once per step and strip
-// out of a cold instruction cache (the persistent launch of the shipped nozzle / aerospike cases); equal to ~1e-16 relative.
+// The isentropic pair of the subsonic far field (BoundaryConditions.cpp:163-187) in the reference's order, two pow():
+// rho = ref X^(gam-1), pg = p (rho/ref)^gam.
 PAR2D_FN void isentropic_ghost(double ref, double X, double gm1, double gam, double p_int, double& rho, double& pg) {
-#if defined(__CUDA_ARCH__) && defined(PAR2D_LEAN_BC)
-    const double lx = log(X);
-    rho = ref * exp(gm1 * lx);
-    pg = p_int * exp((gam * gm1) * lx);
-#else
     rho = ref * pow(X, gm1);
     pg = p_int * pow(rho / ref, gam);
-#endif
 }
 
-#if defined(__CUDA_ARCH__) && defined(PAR2D_LEAN_BC)
-// The far field (code 1) of the fast mode's translation unit: the four cases of BoundaryConditions.cpp:150-190 with the
-// two subsonic ones merged, series reciprocals instead of divisions, one logarithm.  Short on purpose (see above).
+#if defined(PAR2D_LEAN_BC)
+// The far field (code 1) of the fast mode's translation unit (PAR2D_LEAN_BC, kernels_fast.cu): the four cases of
+// BoundaryConditions.cpp:150-190 with the two subsonic ones merged, series reciprocals instead of divisions, and the
+// isentropic pair from ONE logarithm - rho = ref exp((gam-1) ln X), pg = p exp(gam (gam-1) ln X) - : ~150 instructions
+// instead of ~500, on code that runs once per step and strip out of a cold instruction cache (the persistent launch of
+// the shipped nozzle / aerospike cases).  Equal to the reference-ordered form to ~1e-15 relative
+// (tests/test_host_physics_cpu.py on the host, test_gpu_parity.py on the device).
 PAR2D_FN bool farfield_lean(const Gas& g, double normx, double normy, const double ui[4], double a_int, double p_int, double out[4]) {
     const double vin = ui[1] * normx + ui[2] * normy;
     const double ia = fast_rcp(a_int);
@@ -590,7 +607,7 @@ PAR2D_FN bool boundary_state(const Gas& g, int btype, double normx, double normy
         out[1] = fmax(ui[1], 0.0);
         out[2] = ui[2];
         out[3] = ui[3];
-#if defined(__CUDA_ARCH__) && defined(PAR2D_LEAN_BC)
+#if defined(PAR2D_LEAN_BC)
     } else if (btype == 1) {
         wrote = farfield_lean(g, normx, normy, ui, a_int, p_int, out);
 #else

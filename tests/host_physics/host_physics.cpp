@@ -1,8 +1,9 @@
 // tests/host_physics/host_physics.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT.
 // The point-wise device functions of par2d_b200/csrc/physics.cuh compiled for the HOST (g++, no CUDA),
 // so that the formulas of both arithmetic modes can be checked against the oracle without a GPU.
-// Built twice by the Makefile next to it: HP_MODE=0 (fast formulas, FMA contraction on, like nvcc's
-// default) and HP_MODE=1 (reference-ordered formulas, contraction off).  Nothing in par2d_b200/ loads it.
+// Built three times by the Makefile next to it: HP_MODE=0 (fast formulas, FMA contraction on, like nvcc's
+// default), HP_MODE=1 (reference-ordered formulas, contraction off) and HP_MODE=2 (= 0 with PAR2D_LEAN_BC, the
+// far-field ghost code of the fast mode's translation unit).  Nothing in par2d_b200/ loads it.
 #include <cstdint>
 #include <cmath>
 #include "../../include/par2d_gpu.h"
@@ -77,7 +78,11 @@ int HP(test_boundary_state)(const par2d_config* cfg, int64_t n, const int32_t* b
         double ui[4] = {uInt[4 * i], uInt[4 * i + 1], uInt[4 * i + 2], fmax(uInt[4 * i + 3], 201.0)};
         const double v2 = ui[1] * ui[1] + ui[2] * ui[2];
         const double p = fmax(ui[0] * g.Rs * ui[3], 1.0);
+#if defined(PAR2D_LEAN_BC)
+        const double aint = fast_sqrt(g.gamRs * ui[3]);   // as bc_ghost_general does in that translation unit (halo.cuh)
+#else
         const double aint = sqrt(g.gamRs * ui[3]);
+#endif
         boundary_state(g, btype[i], norm[2 * i], norm[2 * i + 1], ui, aint, p, v2, uGhost + 4 * i);
     }
     return 0;
@@ -109,6 +114,40 @@ int HP(test_solve)(const par2d_config* cfg, int64_t n, const double* dt_ycc, con
     return 0;
 }
 
+}  // extern "C"
+
+#if HP_MODE == 0
+// The two forms of the lean LDFSS the device chooses between by warp vote (physics.cuh: ldfss_early): per face the test
+// `up`, the fully-upwind flux (ldfss_upwind_left, evaluated whether or not the test holds) and the general flux computed
+// from the same early quantities (ldfss_pre_from_early + ldfss_lean_post).  out[i*11 + {f0..f3, parr | f0..f3, parr | up}]
+template <bool TPG, bool AXI>
+static void upwind_n(const Gas& g, int64_t n, const double* face, const double* uL, const double* uR, double* out) {
+    for (int64_t i = 0; i < n; i++) {
+        unsigned fl = 0;
+        const double nx = face[4 * i], ny = face[4 * i + 1], len = face[4 * i + 2], yf = face[4 * i + 3];
+        FaceGeom fg;
+        fg.nx = nx; fg.ny = ny; fg.len = len; fg.yf = yf; fg.dx = -ny * len; fg.dy = nx * len; fg.rl = 0.0;
+        const FaceState L = face_state<false, TPG>(g, uL[4 * i], uL[4 * i + 1], uL[4 * i + 2], fmax(uL[4 * i + 3], 201.0), fl);
+        const FaceState R = face_state<false, TPG>(g, uR[4 * i], uR[4 * i + 1], uR[4 * i + 2], fmax(uR[4 * i + 3], 201.0), fl);
+        const LdfssEarly e = ldfss_early(fg, L, R);
+        const Flux a = ldfss_upwind_left<AXI>(fg, L, e.ml);
+        const Flux b = ldfss_lean_post<AXI, false>(fg, L, R, ldfss_pre_from_early(e));
+        double* o = out + 11 * i;
+        o[0] = a.f0; o[1] = a.f1; o[2] = a.f2; o[3] = a.f3; o[4] = a.parr;
+        o[5] = b.f0; o[6] = b.f1; o[7] = b.f2; o[8] = b.f3; o[9] = b.parr;
+        o[10] = e.up ? 1.0 : 0.0;
+    }
+}
+extern "C" int hp0_test_ldfss_upwind(const par2d_config* cfg, int64_t n, const double* face, const double* uL, const double* uR, double* out) {
+    const Gas g = make_gas(*cfg);
+    const bool tpg = !(cfg->igam > 0), axi = cfg->iaxi == 1;
+    if (tpg) { if (axi) upwind_n<true, true>(g, n, face, uL, uR, out); else upwind_n<true, false>(g, n, face, uL, uR, out); }
+    else { if (axi) upwind_n<false, true>(g, n, face, uL, uR, out); else upwind_n<false, false>(g, n, face, uL, uR, out); }
+    return 0;
+}
+#endif
+
+extern "C" {
 // cell_volume over n quads: xy[i*8 + {x1,y1,...,x4,y4}]
 int HP(test_volume)(int64_t n, const double* xy, double* vol) {
     for (int64_t i = 0; i < n; i++) {
